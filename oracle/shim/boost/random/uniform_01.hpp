@@ -1,0 +1,2 @@
+// TEST INFRASTRUCTURE ONLY: see ../random.hpp
+#include "../random.hpp"
