@@ -1,0 +1,181 @@
+"""GPU parity tests, dense 2-bit layout, through the C ABI (include/brr_gpu.h).
+
+Tier 1: computeNum / epsilon change per marker vs the reference's golden numbers (<= 1e-10 rel).
+Tier 2: 10-iteration replay of the reference chain consuming the recorded RNG table (<= 1e-8).
+Plus: CUDA path vs the C oracle on seeded random inputs, edge cases, async mode, block sizes.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from bayesrrcmd_b200 import Engine
+from helpers import Golden, check_iteration, num_tol, replay
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(g, layout="dense", **kw):
+    e = Engine(g.N, g.M, g.K, g.nG, layout=layout, **kw)
+    e.upload_bed(g.bed)
+    e.finalize()
+    e.set_model(g.S, g.groups)
+    return e
+
+
+@pytest.mark.parametrize("name", ["uk10k", "gauss", "missing_small"])
+def test_tier1_compute_num_and_delta(name):
+    g = Golden(name)
+    t = g.tier1()
+    e = make_engine(g)
+    lut = e.dense_lut()
+    eps = t["eps"]; en = np.linalg.norm(eps)
+    e.set_state(eps=eps)
+    for n, j in enumerate(t["cols"]):
+        for c in range(4):
+            if not np.isnan(t["lut"][n][c]):
+                assert abs(lut[j][c] - t["lut"][n][c]) <= 1e-12 * (1 + abs(lut[j][c])), (j, c)
+        b0, b1 = float(t["beta_old"][n]), float(t["beta_new"][n])
+        num = e.compute_num(int(j), b0)
+        assert abs(num - t["num_dense"][n]) <= num_tol(t["num_dense"][n], np.sqrt(g.N - 1.0), en), (j, num, t["num_dense"][n])
+    for n in range(len(t["delta_dense"])):
+        j = int(t["cols"][n])
+        e.set_state(eps=eps)
+        e.apply_delta(j, float(t["beta_old"][n]), float(t["beta_new"][n]))
+        got = e.get_state(beta=False, comp=False, acum=False)[0] - eps
+        assert np.max(np.abs(got - t["delta_dense"][n])) <= 1e-12
+
+
+def _replay_gpu(g, e, layout, iters, async_tokens=0):
+    chain = g.chain(layout)
+    e.set_state(eps=np.zeros(g.N), beta=np.zeros(g.M), comp=np.zeros(g.M), acum=np.zeros(g.M))
+    outs = []
+
+    def sweep(it, order, rand_uz, pi, sigmaG, sigmaE, eps_sum):
+        v, bs, out = e.sweep(order, rand_uz, pi, sigmaG, sigmaE, eps_sum, async_tokens)
+        outs.append(out)
+        return v, bs, out.eps_sum
+
+    return chain, replay(chain, iters, sweep, e.get_state, lambda x: e.set_state(eps=x)), outs
+
+
+@pytest.mark.parametrize("name,block", [("uk10k", 16), ("uk10k", 32), ("groups", 16), ("gauss", 8), ("missing_small", 16),
+                                        ("missing_small", 5), ("missing_small", 1)])
+def test_tier2_replay_reference_chain(name, block):
+    g = Golden(name)
+    e = make_engine(g, block_markers=block)
+    chain, it_res, outs = _replay_gpu(g, e, "dense", len(g.chain("dense")["mu"]))
+    for it, res in it_res:
+        check_iteration(chain, it, res, tol=1e-8)
+        assert outs[-1].n_nonskipped == chain["nonskipped"][it]
+        assert abs(outs[-1].eps_sqnorm - chain["chk_eps2"][it]) <= 1e-8 * chain["chk_eps2"][it]
+        assert abs(outs[-1].eps_sum - chain["chk_eps"][it]) <= 1e-8 * (1 + abs(chain["chk_eps"][it]))
+
+
+def _random_problem(seed, N, M, p_miss, nG=1, K=4):
+    rng = np.random.default_rng(seed)
+    maf = rng.uniform(0.02, 0.5, M)
+    geno = rng.binomial(2, maf[:, None], size=(M, N))
+    code = np.where(rng.random((M, N)) < p_miss, 1, np.array([3, 2, 0])[geno]).astype(np.uint8)
+    bed = np.zeros((M, (N + 3) // 4), dtype=np.uint8)
+    for k in range(4):
+        sub = code[:, k::4]
+        bed[:, :sub.shape[1]] |= (sub << (2 * k)).astype(np.uint8)
+    eps = rng.normal(size=N)
+    S = np.sort(rng.uniform(1e-4, 1e-1, size=(nG, K - 1)), axis=1)
+    groups = rng.integers(0, nG, M).astype(np.int32) if nG > 1 else None
+    pi = rng.dirichlet(np.r_[20.0, np.ones(K - 1)], size=nG)
+    sigmaG = rng.uniform(0.1, 0.9, nG)
+    return dict(rng=rng, bed=bed, eps=eps, S=S, groups=groups, pi=pi, sigmaG=sigmaG, sigmaE=0.6, N=N, M=M, K=K, nG=nG)
+
+
+@pytest.mark.parametrize("N,M,p_miss,nG,K,block,tokens", [
+    (64, 40, 0.0, 1, 4, 16, 0),        # smallest slice
+    (1000, 300, 0.01, 2, 3, 16, 0),
+    (5003, 200, 0.02, 1, 5, 32, 0),    # ragged N, several CTAs
+    (70001, 96, 0.001, 1, 4, 16, 0),   # every SM busy
+    (3000, 257, 0.01, 2, 4, 16, 20),   # asynchronous, 20 tokens (reference default)
+    (3000, 100, 0.0, 1, 2, 4, 0),      # K = 2
+])
+def test_sweep_matches_oracle_on_random_inputs(N, M, p_miss, nG, K, block, tokens):
+    O.build()
+    pr = _random_problem(N * 7 + M, N, M, p_miss, nG, K)
+    rng = pr["rng"]
+    e = Engine(N, M, K, nG, block_markers=block)
+    e.upload_bed(pr["bed"]); e.finalize(); e.set_model(pr["S"], pr["groups"])
+    beta = np.where(rng.random(M) < 0.3, rng.normal(size=M) * 0.05, 0.0)
+    comp = (beta != 0).astype(np.float64); acum = rng.random(M)
+    eps_o = pr["eps"].copy(); beta_o = beta.copy(); comp_o = comp.copy(); acum_o = acum.copy()
+    e.set_state(eps=pr["eps"], beta=beta, comp=comp, acum=acum)
+    for sweep_i in range(2):
+        order = rng.permutation(M).astype(np.uint32)
+        if sweep_i == 1:
+            order = order[: M - 7]          # a partial sweep is legal at this boundary
+        rand_uz = np.c_[rng.random(M), rng.normal(size=M)]
+        mdl = O.ModelArrays(N, pr["S"], pr["pi"], pr["sigmaG"], pr["sigmaE"])
+        v_o, bs_o, _ = O.sweep("dense", pr["bed"], M, order, rand_uz, mdl, pr["groups"], eps_o, beta_o, comp_o, acum_o,
+                               tokens=tokens)
+        v, bs, out = e.sweep(order, rand_uz, pr["pi"], pr["sigmaG"], pr["sigmaE"], 0.0, tokens)
+        eps, b, c, a = e.get_state()
+        assert (c == comp_o).all()
+        assert (v == v_o).all()
+        assert np.max(np.abs(b - beta_o)) <= 1e-9
+        assert np.max(np.abs(a - acum_o)) <= 1e-9
+        assert np.max(np.abs(eps - eps_o)) <= 1e-9
+        assert np.max(np.abs(bs - bs_o)) <= 1e-9 * (1 + np.abs(bs_o).max())
+        assert abs(out.eps_sqnorm - (eps_o ** 2).sum()) <= 1e-9 * (eps_o ** 2).sum()
+
+
+def test_empty_and_single_marker_sweeps():
+    pr = _random_problem(11, 777, 9, 0.05)
+    e = Engine(777, 9, 4, 1)
+    e.upload_bed(pr["bed"]); e.finalize(); e.set_model(pr["S"])
+    e.set_state(eps=pr["eps"])
+    rand_uz = np.c_[np.full(9, 0.5), np.zeros(9)]
+    v, bs, out = e.sweep(np.zeros(0, np.uint32), rand_uz, pr["pi"], pr["sigmaG"], 0.5)
+    assert v.sum() == 0 and out.n_blocks == 0
+    assert np.array_equal(e.get_state()[0], pr["eps"])
+    v, bs, out = e.sweep(np.array([3], np.uint32), rand_uz, pr["pi"], pr["sigmaG"], 0.5)
+    assert v.sum() == 1 and out.n_blocks == 1
+
+
+def test_mu_update_primitives():
+    pr = _random_problem(3, 4099, 4, 0.0)
+    e = Engine(4099, 4, 4, 1)
+    e.set_state(eps=pr["eps"])
+    s = e.eps_add_scalar(0.25)
+    ref = pr["eps"] + 0.25
+    assert abs(s - ref.sum()) <= 1e-10 * (1 + abs(ref.sum()))
+    assert np.array_equal(e.get_state()[0], ref)
+    s2, q2 = e.eps_reduce()
+    assert abs(q2 - (ref ** 2).sum()) <= 1e-10 * (ref ** 2).sum()
+
+
+def test_errors_are_reported_not_thrown():
+    from bayesrrcmd_b200 import BrrGpuError
+    pr = _random_problem(5, 300, 20, 0.0)
+    e = Engine(300, 20, 4, 1)
+    rand_uz = np.zeros((20, 2))
+    with pytest.raises(BrrGpuError, match="upload"):
+        e.sweep(np.arange(20, dtype=np.uint32), rand_uz, pr["pi"], pr["sigmaG"], 0.5)
+    e.upload_bed(pr["bed"]); e.finalize(); e.set_model(pr["S"])
+    with pytest.raises(BrrGpuError, match="twice"):
+        e.sweep(np.array([1, 1], np.uint32), rand_uz, pr["pi"], pr["sigmaG"], 0.5)
+    with pytest.raises(BrrGpuError, match="out of range"):
+        e.sweep(np.array([20], np.uint32), rand_uz, pr["pi"], pr["sigmaG"], 0.5)
+
+
+def test_synthetic_generator_matches_its_host_twin():
+    from bayesrrcmd_b200.capi import synth_bed_host
+    N, M = 5000, 64
+    e = Engine(N, M, 4, 1)
+    e.synth_dense(seed=42, p_missing=0.01)
+    e.finalize()
+    bed = synth_bed_host(42, N, 0, M, p_missing=0.01)
+    e2 = Engine(N, M, 4, 1)
+    e2.upload_bed(bed); e2.finalize()
+    assert (e.counts() == e2.counts()).all()
+    assert e.counts()[:, 3].sum() > 0
+    eps = np.random.default_rng(0).normal(size=N)
+    e.set_state(eps=eps); e2.set_state(eps=eps)
+    for j in (0, 17, 63):
+        assert e.compute_num(j, 0.1) == e2.compute_num(j, 0.1)

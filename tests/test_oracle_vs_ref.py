@@ -1,0 +1,66 @@
+"""CPU, only where oracle/_ref was built (this container): the C restatement against the live,
+unmodified reference object code on fresh random inputs."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import ref_lib as R
+
+pytestmark = pytest.mark.skipif(not R.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def _random_bed(rng, N, M, p_miss):
+    maf = rng.uniform(0.02, 0.5, M)
+    geno = rng.binomial(2, maf[:, None], size=(M, N))
+    code = np.where(rng.random((M, N)) < p_miss, 1, np.array([3, 2, 0])[geno]).astype(np.uint8)
+    bed = np.zeros((M, (N + 3) // 4), dtype=np.uint8)
+    for k in range(4):
+        sub = code[:, k::4]
+        bed[:, :sub.shape[1]] |= (sub << (2 * k)).astype(np.uint8)
+    return bed
+
+
+@pytest.mark.parametrize("N,p_miss", [(257, 0.0), (1001, 0.05)])
+def test_marker_ops_match_reference(N, p_miss):
+    O.build()
+    rng = np.random.default_rng(N)
+    bed = _random_bed(rng, N, 12, p_miss)
+    eps = rng.normal(size=N)
+    for j in range(12):
+        b0, b1 = (0.0 if j % 2 else rng.normal() * 0.1), rng.normal() * 0.1
+        cx = O.dense_column(bed[j], N)
+        assert np.max(np.abs(cx - R.dense_column(bed[j], N))) <= 1e-13
+        num, delta, _ = R.marker_ops(0, bed[j], N, eps, b0, b1)
+        assert abs(O.dense_compute_num(cx, eps, b0) - num) <= 1e-10 * abs(num) + 1e-12
+        stats, ones, twos, miss = O.ragged_marker(bed[j], N)
+        rs, ro, rt, rm = R.ragged_marker(bed[j], N)
+        assert np.allclose(stats, rs, rtol=1e-15, atol=0) and (ones == ro).all() and (twos == rt).all() and (miss == rm).all()
+        num, delta, es = R.marker_ops(1, bed[j], N, eps, b0, b1, float(eps.sum()))
+        assert abs(O.ragged_compute_num(stats, ones, twos, eps, b0, float(eps.sum())) - num) <= 1e-10 * abs(num) + 1e-12
+        e = eps.copy(); d = O.ragged_eps_update(stats, ones, twos, miss, e, b0, b1, 0.0)
+        assert np.max(np.abs((e - eps) - delta)) <= 1e-12 and abs(d - es) <= 1e-12
+
+
+def test_chain_matches_reference_with_missing_and_groups():
+    O.build()
+    rng = np.random.default_rng(5)
+    N, M = 501, 120
+    bed = _random_bed(rng, N, M, 0.02)
+    y = rng.normal(size=N).astype(np.float32)
+    groups = (np.arange(M) % 2).astype(np.int32)
+    S = np.array([[0.001, 0.01, 0.1], [0.002, 0.02, 0.2]])
+    for layout, name in ((0, "dense"), (1, "ragged")):
+        arr, _ = R.run_chain(bed, N, M, y, S, seed=3, iterations=4, layout=layout, groups=groups)
+        for it in range(4):
+            mdl = O.ModelArrays(N, S, arr["pi_in"][it], arr["sigmaG_in"][it], arr["sigmaE_in"][it])
+            eps = arr["eps_in"][it].copy(); beta = arr["beta_in"][it].copy()
+            comp = arr["comp_out"][it - 1].copy() if it else np.zeros(M)
+            acum = arr["acum_out"][it - 1].copy() if it else np.zeros(M)
+            v, bs, es = O.sweep(name, bed, M, arr["order"][it], arr["rand_uz"][it], mdl, groups, eps, beta, comp, acum,
+                                eps_sum=arr["epssum_in"][it])
+            assert np.max(np.abs(beta - arr["beta_out"][it])) <= 1e-11
+            assert (comp == arr["comp_out"][it]).all() and (v == arr["v_out"][it]).all()
+            assert np.max(np.abs(acum - arr["acum_out"][it])) <= 1e-11
+            assert np.max(np.abs(eps - arr["eps_out"][it])) <= 1e-10
+            assert np.max(np.abs(bs - arr["betasq_out"][it])) <= 1e-11
+            assert abs(es - arr["epssum_out"][it]) <= 1e-9
