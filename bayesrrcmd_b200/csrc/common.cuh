@@ -26,6 +26,20 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// acc += e if (q & mask) != 0, as ONE predicated DADD (the compiler otherwise emits DADD + 2 FSEL)
+__device__ __forceinline__ void add_if_bit(double &acc, double e, uint32_t q, uint32_t mask)
+{
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t;\n\t"
+        "and.b32 t, %2, %3;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "@p add.f64 %0, %0, %1;\n\t"
+        "}"
+        : "+d"(acc)
+        : "d"(e), "r"(q), "r"(mask));
+}
+
 // ---- grid-wide barrier: monotonically increasing arrival counter --------------------------------
 __device__ __forceinline__ void red_release_add(unsigned *p, unsigned v)
 {

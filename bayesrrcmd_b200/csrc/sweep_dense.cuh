@@ -247,8 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                         const double e = eps_s[t * UP8 + u];
 #pragma unroll
                         for (int a = 0; a < 4; ++a) {
-                            if (q1[a] & (1u << t)) s1[a] += e;
-                            if (q2[a] & (1u << t)) s2[a] += e;
+                            add_if_bit(s1[a], e, q1[a], 1u << t);
+                            add_if_bit(s2[a], e, q2[a], 1u << t);
                         }
                     }
                     if (anym) {
