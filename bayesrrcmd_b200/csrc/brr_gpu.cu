@@ -176,7 +176,8 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
         c->planes_bytes = size_t(M) * c->nCTA * 2 * c->PB;
         TRY_OR_DESTROY(dev_alloc(&c->planes, c->planes_bytes));
         TRY_OR_DESTROY(dev_alloc(&c->lut, size_t(M) * 4));
-        c->smem_bytes = sweep_smem_bytes(c->B, c->SL, c->PB);
+        c->smem_bytes = sweep_smem_bytes(kMaxB, c->SL, c->PB);      // room for any async token count
+        if (c->smem_bytes > size_t(prop.sharedMemPerBlockOptin)) c->smem_bytes = sweep_smem_bytes(c->B, c->SL, c->PB);
         CUDA_OR_DESTROY(cudaFuncSetAttribute(sweep_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
         int occ = 0;
         CUDA_OR_DESTROY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_dense_kernel, kThreads, c->smem_bytes));
@@ -436,13 +437,14 @@ static int launch_dense(brr_gpu_ctx *c)
     p.eps = c->eps; p.beta = c->beta; p.comp = c->comp; p.acum = c->acum;
     p.part_dot = c->part_dot; p.part_eps = c->part_eps; p.gram = c->gram; p.bar = c->bar; p.cta_red = c->cta_red;
     p.v = c->v; p.betasq = c->betasq; p.out_scalars = c->out_scalars; p.out_counts = c->out_counts;
-    if (p.B > c->B && sweep_smem_bytes(p.B, c->SL, c->PB) > c->smem_bytes)
+    if (sweep_smem_bytes(p.B, c->SL, c->PB) > c->smem_bytes)
         return fail(BRR_GPU_EINVAL, "async_tokens %u needs more shared memory than block_markers %u reserved", p.B, c->B);
     CUDA_TRY(cudaMemsetAsync(c->bar, 0, sizeof(unsigned) * 4, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->gram, 0, sizeof(int) * kGramBuffers * kMaxB * kMaxB * 4, c->stream));
     void *args[] = {&p};
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    CUDA_TRY(cudaLaunchCooperativeKernel((const void *)sweep_dense_kernel, dim3(c->nCTA), dim3(kThreads), args, c->smem_bytes, c->stream));
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void *)sweep_dense_kernel, dim3(c->nCTA), dim3(kThreads), args,
+                                         sweep_smem_bytes(p.B, c->SL, c->PB), c->stream));
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     c->launches += 1; c->last_launches = 1;
     return 0;

@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on the B200 engine.
+
+Metric (BASELINE.json): marker updates per second of the ppbayes Gibbs sweep (and seconds per sweep)
+on synthetic dense 2-bit genotypes N=500k x M=1M; achieved HBM GB/s vs the measured peak.
+
+A "step" is ONE full Gibbs sweep (= one AnalysisGraph::exec: M marker updates in a fresh random order,
+each = x_j.eps dot, mixture/beta draw, residual update).  The chain between sweeps (mu, sigmaE, sigmaG,
+pi draws) runs for real on the host, exactly as BayesRBase::runGibbs does, so the timed sweeps are
+sweeps 1+W .. W+K of a genuine chain started from the reference's initial state.
+
+    value  = M*K / (sum of the K sweep-kernel durations, CUDA events on the engine's stream; inputs staged in HBM)
+    e2e    = M*K / (sum of the K brr_gpu_sweep() wall times: pinned-host order + (u,z) table H2D, kernel,
+                    D2H of v/betasqnG/scalars and of beta, components, acum -- what exec() must leave in the Analysis)
+    N > 1:  individuals sharded over ranks (strong scaling: the total problem is fixed), max over ranks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20260101
+MAF_LO, MAF_HI, P_MISSING = 0.01, 0.5, 0.001
+S_CVA = np.array([[0.01, 0.001, 0.0001]])
+N_CAUSAL, H2 = 1000, 0.5
+V0E = S02E = V0G = S02G = 1e-4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-inds", type=int, default=int(os.environ.get("BRR_BENCH_N", 500000)))
+    ap.add_argument("--n-markers", type=int, default=int(os.environ.get("BRR_BENCH_M", 1000000)))
+    ap.add_argument("--block", type=int, default=int(os.environ.get("BRR_BENCH_BLOCK", 0)))
+    ap.add_argument("--cpu-markers", type=int, default=int(os.environ.get("BRR_BENCH_CPU_M", 384)))
+    ap.add_argument("--cpu-sweeps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def inv_scaled_chisq(rng, dof, scale):
+    # Distributions_boost::inv_scaled_chisq_rng (reference src/distributions_boost.cpp:45-60)
+    return 1.0 / rng.gamma(0.5 * dof, 1.0 / (0.5 * dof * scale))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_leg(n_inds, n_markers, eps_y, steps, warmup=0):
+    """The reference's own CPU implementation of the path (oracle/_ref, built from /root/reference with the
+    shipped -O3 -ffast-math flags), on a bounded sample: the first `n_markers` markers of the SAME synthetic
+    data set, all N individuals, dense layout, marker cache (Sequential graph: 1 core by construction)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_lib as R
+    from bayesrrcmd_b200.capi import synth_bed_host
+    fast = R.ref_available(fast=True)
+    if not fast and not R.ref_available():
+        return None
+    bed = synth_bed_host(SEED, n_inds, 0, n_markers, MAF_LO, MAF_HI, False, P_MISSING)
+    y = np.asarray(eps_y, dtype=np.float32)
+    _, t = R.run_chain(bed, n_inds, n_markers, y, S_CVA, seed=1, iterations=warmup + steps, layout=0, dump=False, fast=fast)
+    per_sweep = t["total_s"] / (warmup + steps)
+    return {"value": n_markers / per_sweep, "unit": "marker updates/s", "cores": 1, "kind": "reference",
+            "sample": "reference BayesRBase::runGibbs (dense, marker cache, Sequential graph), N=%d individuals x first %d "
+                      "markers of the bench data set, %d sweeps, %.3f s/sweep; linear in M: %.0f s per 1M-marker sweep"
+                      % (n_inds, n_markers, warmup + steps, per_sweep, per_sweep * 1e6 / n_markers),
+            "s_per_sweep_sample": per_sweep, "marker_build_s": t["build_s"]}
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    N, M = a.n_inds, a.n_markers
+    workload = "synthetic dense 2-bit N=%d x M=%d, MAF~U(%.2f,%.2f), %.1f%% missing, %d causal h2=%.1f, K=4 S=(0.01,0.001,0.0001)" % (
+        N, M, MAF_LO, MAF_HI, 100 * P_MISSING, N_CAUSAL, H2)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        rng = np.random.default_rng(SEED)
+        y = rng.standard_normal(N).astype(np.float32)
+        leg = cpu_reference_leg(N, a.cpu_markers, y, a.steps, a.warmup)
+        if leg is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+            return
+        line = {"impl": "reference", "metric": "marker updates/sec (ppbayes Gibbs sweep, dense)", "value": leg["value"],
+                "unit": "marker updates/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * leg["s_per_sweep_sample"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "sample": leg["sample"]},
+                "cpu_baseline": leg,
+                "e2e": {"value": leg["value"], "unit": "marker updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from bayesrrcmd_b200 import Engine
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    # ---- shard individuals over ranks (multiples of 64 rows so plane chunks stay aligned) -----------
+    per = ((N + world - 1) // world + 63) // 64 * 64
+    lo = min(N, rank * per); hi = min(N, lo + per)
+    n_loc = hi - lo
+    eng = Engine(n_loc, M, 4, 1, layout="dense", device=local_rank, block_markers=a.block, n_inds_total=N,
+                 rank=rank, world=world)
+    info = eng.info()
+    t0 = time.time()
+    eng.synth_dense(SEED, MAF_LO, MAF_HI, False, P_MISSING, ind_offset=lo)
+    counts = eng.counts()
+    if world > 1:
+        ct = torch.from_numpy(counts.astype(np.int64)).cuda()
+        dist.all_reduce(ct)
+        counts = ct.cpu().numpy().astype(np.uint32)
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.ipc_export())
+        eng.ipc_attach(handles)
+    eng.finalize(counts)
+    eng.set_model(S_CVA)
+    gen_s = time.time() - t0
+
+    # ---- phenotype: y = X beta + e with N_CAUSAL causal markers, h2 = 0.5, standardised like the reference
+    rng = np.random.default_rng(SEED)          # identical stream on every rank
+    causal = rng.choice(M, N_CAUSAL, replace=False)
+    bcausal = rng.standard_normal(N_CAUSAL) * np.sqrt(H2 / N_CAUSAL)
+    noise = rng.standard_normal(N) * np.sqrt(1.0 - H2)
+    eng.set_state(eps=noise[lo:hi], beta=np.zeros(M), comp=np.zeros(M), acum=np.zeros(M))
+    for j, b in zip(causal, bcausal):
+        eng.apply_delta(int(j), float(b), 0.0)            # eps += b * x_j
+    y = eng.get_state(beta=False, comp=False, acum=False)[0].astype(np.float32).astype(np.float64)   # VectorXf y
+    s1 = np.array([y.sum(), 0.0])
+    if world > 1:
+        t = torch.from_numpy(s1).cuda(); dist.all_reduce(t); s1 = t.cpu().numpy()
+    y = y - s1[0] / N
+    s2 = np.array([(y ** 2).sum()])
+    if world > 1:
+        t = torch.from_numpy(s2).cuda(); dist.all_reduce(t); s2 = t.cpu().numpy()
+    y = y / np.sqrt(s2[0] / (N - 1))
+    eng.set_state(eps=y)
+    y_full = y
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, y)
+        y_full = np.concatenate(parts)
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t); return float(t.item())
+
+    # ---- chain state as BayesRBase::init leaves it (reference src/BayesRBase.cpp:39-99) -------------
+    K = 4
+    pi = np.full((1, K), 0.5 / K); pi[0, 0] = 0.5
+    sigmaG = np.array([rng.random()])
+    sigmaE = allsum(float((y ** 2).sum())) / N * 0.5
+    mu = 0.0
+
+    kernel_ms, e2e_s, nonskipped, blocks = [], [], [], []
+    h2d = d2h = 0
+    sampler = None
+
+    def one_sweep(timed):
+        nonlocal mu, sigmaE, sigmaG, pi, h2d, d2h
+        s = allsum(eng.eps_add_scalar(mu))                      # updateMu (src/DenseBayesRRmz.cpp:36-42)
+        mu = rng.normal(s / N, np.sqrt(sigmaE / N))
+        eng.eps_add_scalar(-mu)
+        rand_uz = np.empty((M, 2)); rand_uz[:, 0] = rng.random(M); rand_uz[:, 1] = rng.standard_normal(M)
+        order = rng.permutation(M).astype(np.uint32)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        v, bs, out = eng.sweep(order, rand_uz, pi, sigmaG, sigmaE)     # the plugin call: host buffers in, host out
+        _, beta, comp, acum = eng.get_state(eps=False)
+        t1 = time.perf_counter()
+        if timed:
+            kernel_ms.append(out.kernel_ms); e2e_s.append(t1 - t0)
+            nonskipped.append(out.n_nonskipped); blocks.append(out.n_blocks)
+            h2d = order.nbytes + rand_uz.nbytes + pi.nbytes + sigmaG.nbytes
+            d2h = v.nbytes + bs.nbytes + 32 + beta.nbytes + comp.nbytes + acum.nbytes
+        sq = allsum(out.eps_sqnorm)
+        sigmaE = inv_scaled_chisq(rng, V0E + N, (sq + V0E * S02E) / (V0E + N))           # src/BayesRBase.cpp:238-239
+        m0 = v[0, 1:].sum()
+        sigmaG = np.array([inv_scaled_chisq(rng, V0G + m0, (bs[0] * m0 + V0G * S02G) / (V0G + m0))])   # :243-245
+        pi = rng.dirichlet(v[0] + 1.0)[None, :]                                          # :246
+        return out
+
+    for _ in range(a.warmup):
+        one_sweep(False)
+    launches0 = eng.launch_count()
+    if rank == 0:
+        sampler = ClockSampler(local_rank); sampler.start()
+    for _ in range(a.steps):
+        one_sweep(True)
+    launches = eng.launch_count() - launches0
+    if sampler:
+        sampler.stop_flag = True; sampler.join(timeout=2)
+
+    ksum = sum(kernel_ms) / 1e3; esum = sum(e2e_s)
+    if world > 1:
+        t = torch.tensor([ksum, esum], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ksum, esum = float(t[0]), float(t[1])
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    alg_bytes = ((n_loc + 3) // 4) * M                  # ceil(N_shard/4) genotype bytes per marker update
+    achieved = alg_bytes / (ksum / a.steps) / 1e9
+    line = {
+        "metric": "marker updates/sec (ppbayes Gibbs sweep, dense 2-bit, N=500k x M=1M)",
+        "value": M * a.steps / ksum, "unit": "marker updates/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * ksum / a.steps, "s_per_sweep": ksum / a.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "parallelism": "individuals sharded over %d GPU(s)" % world,
+                   "block_markers": info["block_markers"], "ctas": info["n_ctas"], "slice_inds": info["slice_inds"],
+                   "genotype_bytes_per_gpu": info["genotype_bytes"], "l2": "inputs (%.1f GB/GPU) are larger than L2" % (info["genotype_bytes"] / 1e9),
+                   "nonskipped_fraction": float(np.mean(nonskipped)) / M, "exchanges_per_sweep": int(np.mean(blocks)),
+                   "setup_s": gen_s},
+        "e2e": {"value": M * a.steps / esum, "unit": "marker updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "s_per_sweep": esum / a.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "sweep_dense_kernel",
+                     "algorithmic_bytes_per_launch": int(alg_bytes),
+                     "note": "dense 2-bit path is co-bounded by fp64 issue rate and per-block exchange latency (DESIGN.md)"},
+        "clocks": sampler.summary() if sampler else None,
+    }
+    if not a.no_cpu_baseline:
+        try:
+            leg = cpu_reference_leg(N, a.cpu_markers, y_full, a.cpu_sweeps)
+        except Exception as ex:      # the checker must never take the product's number down with it
+            leg = {"error": repr(ex)}
+        line["cpu_baseline"] = leg
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -87,6 +87,22 @@ def marker_ops(layout, bedcol, N, eps, beta_old, beta_new, eps_sum=0.0):
     return num.value, delta, es.value
 
 
+class _Quiet:
+    """The reference prints per-iteration progress to stdout; keep it out of callers' stdout."""
+
+    def __enter__(self):
+        import sys
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        C.CDLL(None).fflush(None)
+        os.dup2(self.saved, 1)
+        os.close(self.null); os.close(self.saved)
+
+
 def run_chain(bed, N, M, y, S, seed, iterations, layout=0, groups=None, dump=True, fast=False):
     """Run the reference's BayesRBase::runGibbs; returns (dict of per-iteration arrays, timings)."""
     S = np.ascontiguousarray(np.atleast_2d(S), dtype=np.float64)
@@ -111,7 +127,9 @@ def run_chain(bed, N, M, y, S, seed, iterations, layout=0, groups=None, dump=Tru
                   seed=seed, iterations=iterations, layout=layout,
                   dump=C.addressof(d) if dump else None)
     C.CDLL(None).srand(1)   # glibc rand() drives std::random_shuffle; fresh-process state
-    rc = load(fast).ref_run_chain(C.byref(a))
+    lib = load(fast)
+    with _Quiet():
+        rc = lib.ref_run_chain(C.byref(a))
     assert rc == 0, rc
     return arrays, dict(exec_s=a.execSeconds, total_s=a.totalSeconds, build_s=a.buildSeconds)
 
