@@ -8,7 +8,8 @@ import numpy as np
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libbrr_gpu.so")
 ABI_VERSION = 1
-LAYOUT_DENSE2BIT, LAYOUT_RAGGED = 0, 1
+LAYOUT_DENSE2BIT, LAYOUT_RAGGED, LAYOUT_EIGEN = 0, 1, 2
+_LAYOUTS = {"dense": 0, "ragged": 1, "eigen": 2}
 IPC_HANDLE_BYTES = 64
 
 # every symbol include/brr_gpu.h declares (tests check the library exports exactly these)
@@ -109,7 +110,7 @@ class Engine:
         self.N, self.M, self.K, self.nG = int(n_inds), int(n_markers), int(n_components), int(n_groups)
         self.layout = layout
         cfg = Config(abi_version=ABI_VERSION, device=device,
-                     layout=LAYOUT_DENSE2BIT if layout == "dense" else LAYOUT_RAGGED, n_inds=self.N,
+                     layout=_LAYOUTS[layout], n_inds=self.N,
                      n_inds_total=self.N if n_inds_total is None else int(n_inds_total), n_markers=self.M,
                      n_components=self.K, n_groups=self.nG, block_markers=block_markers, max_ctas=max_ctas,
                      rank=rank, world=world)

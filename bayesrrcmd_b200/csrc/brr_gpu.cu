@@ -105,7 +105,7 @@ extern "C" void brr_gpu_destroy(brr_gpu_ctx *c)
     void *ptrs[] = {c->planes, c->lut, c->counts_local, c->counts_global, c->group, c->cva, c->eps, c->beta, c->comp,
                     c->acum, c->order, c->rand_uz, c->pi, c->sigmaG, c->part_dot, c->part_eps, c->cta_red,
                     c->red_partial, c->gram, c->bar, c->v, c->betasq, c->out_scalars, c->out_counts,
-                    c->rag.offsets, c->rag.idx, c->rag.stats, c->rag.seg};
+                    c->rag.idx16, c->rag.cta_base, c->rag.stats, c->rag.seg};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_small) cudaFreeHost(c->h_small);
     if (c->h_counts) cudaFreeHost(c->h_counts);
@@ -142,7 +142,7 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
     if (cfg->n_components < 2 || cfg->n_components > (uint32_t)kMaxK) return fail(BRR_GPU_EINVAL, "n_components must be 2..%d", kMaxK);
     if (cfg->n_groups < 1 || cfg->n_groups * cfg->n_components > (uint32_t)kMaxGK) return fail(BRR_GPU_EINVAL, "n_groups*n_components must be 1..%d", kMaxGK);
     if (cfg->block_markers > (uint32_t)kMaxB) return fail(BRR_GPU_EINVAL, "block_markers must be <= %d", kMaxB);
-    if (cfg->layout != BRR_GPU_LAYOUT_DENSE2BIT && cfg->layout != BRR_GPU_LAYOUT_RAGGED) return fail(BRR_GPU_EINVAL, "unknown layout %d", cfg->layout);
+    if (cfg->layout < BRR_GPU_LAYOUT_DENSE2BIT || cfg->layout > BRR_GPU_LAYOUT_EIGEN) return fail(BRR_GPU_EINVAL, "unknown layout %d", cfg->layout);
     if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(BRR_GPU_EINVAL, "bad rank/world");
     if (cfg->n_inds_total < cfg->n_inds) return fail(BRR_GPU_EINVAL, "n_inds_total < n_inds");
 
@@ -188,6 +188,12 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
     } else {
         c->smem_bytes = ragged_smem_bytes(c->SL);
         CUDA_OR_DESTROY(cudaFuncSetAttribute(sweep_ragged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+        int occ = 0;
+        CUDA_OR_DESTROY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_ragged_kernel, kThreads, c->smem_bytes));
+        if (occ < 1 || uint32_t(occ) * c->numSMs < c->nCTA) {
+            int rc_ = fail(BRR_GPU_EINVAL, "ragged sweep kernel does not fit: %zu bytes of shared memory per CTA, %u CTAs", c->smem_bytes, c->nCTA);
+            brr_gpu_destroy(c); return rc_;
+        }
     }
     TRY_OR_DESTROY(dev_alloc(&c->counts_local, size_t(M) * 4));
     TRY_OR_DESTROY(dev_alloc(&c->counts_global, size_t(M) * 4));
@@ -294,7 +300,8 @@ extern "C" int brr_gpu_finalize_markers(brr_gpu_ctx *c, const uint32_t *global_c
         dense_lut_kernel<<<(M + 255) / 256, 256, 0, c->stream>>>(c->counts_global, M, c->cfg.n_inds_total, c->lut);
     } else {
         if (!c->rag.stats_given)
-            ragged_stats_kernel<<<(M + 255) / 256, 256, 0, c->stream>>>(c->counts_global, M, c->cfg.n_inds_total, c->rag.stats);
+            ragged_stats_kernel<<<(M + 255) / 256, 256, 0, c->stream>>>(c->counts_global, M, c->cfg.n_inds_total,
+                                                                        c->cfg.layout == BRR_GPU_LAYOUT_EIGEN, c->rag.stats);
     }
     ++c->launches;
     CUDA_TRY(cudaGetLastError());

@@ -46,10 +46,14 @@ typedef enum {
 typedef enum {
     BRR_GPU_LAYOUT_DENSE2BIT = 0, /* 2 bits per genotype; semantics of DenseMarker / DenseRKernel
                                      (src/densemarkerbuilder.cpp:23-60, src/densebayesrkernel.cpp) */
-    BRR_GPU_LAYOUT_RAGGED = 1     /* ascending index lists of ones / twos / missing; semantics of
+    BRR_GPU_LAYOUT_RAGGED = 1,    /* ascending index lists of ones / twos / missing; semantics of
                                      RaggedSparseMarker / RaggedBayesRKernel + SparseBayesRRG's
                                      analytically tracked sum(eps) (src/raggedbayesrkernel.cpp,
                                      src/sparsebayesrkernel.cpp, src/SparseBayesRRG.cpp:76-113) */
+    BRR_GPU_LAYOUT_EIGEN = 2      /* the same index lists with the semantics of EigenSparseMarker /
+                                     EigenBayesRKernel: missing genotypes imputed by the mean in the
+                                     statistics and in the dot (src/eigensparsemarkerbuilder.cpp:40-78,
+                                     src/eigenbayesrkernel.cpp:10-20) */
 } brr_gpu_layout;
 
 typedef struct brr_gpu_ctx brr_gpu_ctx;

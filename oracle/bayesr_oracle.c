@@ -287,39 +287,46 @@ int orc_sweep_dense(const uint8_t *bed, uint32_t M, const uint32_t *order, uint3
     return 0;
 }
 
-int orc_sweep_ragged(const uint8_t *bed, uint32_t M, const uint32_t *order, uint32_t n_order,
-                     const double *rand_uz, const orc_model *m, const int32_t *groups, uint32_t tokens,
-                     double *eps, double *eps_sum, double *beta, double *comp, double *acum, double *v,
-                     double *betasq)
+static int orc_sweep_sparse(int eigen, const uint8_t *bed, uint32_t M, const uint32_t *order, uint32_t n_order,
+                            const double *rand_uz, const orc_model *m, const int32_t *groups, uint32_t tokens,
+                            double *eps, double *eps_sum, double *beta, double *comp, double *acum, double *v,
+                            double *betasq)
 {
     const uint32_t N = m->N;
     const size_t cb = ((size_t)N + 3) / 4;
     const uint32_t T = tokens ? tokens : 1;
     int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * 3 * (size_t)N * T);
+    uint8_t *cls = (uint8_t *)malloc((size_t)N * T);
     double *stats = (double *)malloc(sizeof(double) * 4 * T);
     uint32_t *cnt = (uint32_t *)malloc(sizeof(uint32_t) * 3 * T);
     orc_draw *draws = (orc_draw *)malloc(sizeof(orc_draw) * T);
-    if (!idx || !stats || !cnt || !draws) return 1;
+    if (!idx || !cls || !stats || !cnt || !draws) return 1;
     for (uint32_t p = 0; p < n_order; p += T) {
         const uint32_t nb = (n_order - p < T) ? n_order - p : T;
         const double eps_sum_batch = *eps_sum;            /* readWithSharedLock, src/SparseBayesRRG.cpp:76-82 */
         for (uint32_t t = 0; t < nb; ++t) {
             const uint32_t j = order[p + t];
-            if (j >= M) { free(idx); free(stats); free(cnt); free(draws); return 2; }
+            if (j >= M) { free(idx); free(cls); free(stats); free(cnt); free(draws); return 2; }
             const int g = groups ? groups[j] : 0;
             int32_t *ones = idx + (size_t)3 * N * t, *twos = ones + N, *miss = twos + N;
+            uint8_t *c = cls + (size_t)N * t;
             orc_ragged_marker(bed + cb * j, N, stats + 4 * t, ones, &cnt[3 * t], twos, &cnt[3 * t + 1], miss,
                               &cnt[3 * t + 2]);
+            if (eigen) { orc_eigen_stats(bed + cb * j, N, stats + 4 * t); orc_decode_bed_column(bed + cb * j, N, c); }
             draws[t].beta_old = beta[j];
-            const double num = orc_ragged_compute_num(stats + 4 * t, ones, cnt[3 * t], twos, cnt[3 * t + 1], eps, N,
-                                                      beta[j], tokens ? eps_sum_batch : *eps_sum);
+            const double es = tokens ? eps_sum_batch : *eps_sum;
+            const double num = eigen ? orc_eigen_compute_num(stats + 4 * t, c, eps, N, beta[j], es)
+                                     : orc_ragged_compute_num(stats + 4 * t, ones, cnt[3 * t], twos, cnt[3 * t + 1], eps, N,
+                                                              beta[j], es);
             draws[t].comp = orc_sample_marker(m, g, num, beta[j], rand_uz[2 * (size_t)j], rand_uz[2 * (size_t)j + 1],
                                               &draws[t].beta_new, &draws[t].acum);
             if (tokens == 0) {
                 orc_commit(m, g, j, &draws[t], 1, beta, comp, acum, v, betasq);
-                if (!(draws[t].beta_old == 0.0 && draws[t].beta_new == 0.0))
-                    orc_ragged_eps_update(stats, ones, cnt[0], twos, cnt[1], miss, cnt[2], eps, N,
-                                          draws[t].beta_old, draws[t].beta_new, eps_sum);
+                if (!(draws[t].beta_old == 0.0 && draws[t].beta_new == 0.0)) {
+                    if (eigen) orc_eigen_eps_update(stats, c, eps, N, draws[t].beta_old, draws[t].beta_new, eps_sum);
+                    else orc_ragged_eps_update(stats, ones, cnt[0], twos, cnt[1], miss, cnt[2], eps, N,
+                                               draws[t].beta_old, draws[t].beta_new, eps_sum);
+                }
             }
         }
         if (tokens) {
@@ -328,14 +335,33 @@ int orc_sweep_ragged(const uint8_t *bed, uint32_t M, const uint32_t *order, uint
                 const int g = groups ? groups[j] : 0;
                 int32_t *ones = idx + (size_t)3 * N * t, *twos = ones + N, *miss = twos + N;
                 orc_commit(m, g, j, &draws[t], 0, beta, comp, acum, v, betasq);
-                if (!(draws[t].beta_old == 0.0 && draws[t].beta_new == 0.0))
-                    orc_ragged_eps_update(stats + 4 * t, ones, cnt[3 * t], twos, cnt[3 * t + 1], miss, cnt[3 * t + 2],
-                                          eps, N, draws[t].beta_old, draws[t].beta_new, eps_sum);
+                if (!(draws[t].beta_old == 0.0 && draws[t].beta_new == 0.0)) {
+                    if (eigen) orc_eigen_eps_update(stats + 4 * t, cls + (size_t)N * t, eps, N, draws[t].beta_old,
+                                                    draws[t].beta_new, eps_sum);
+                    else orc_ragged_eps_update(stats + 4 * t, ones, cnt[3 * t], twos, cnt[3 * t + 1], miss, cnt[3 * t + 2],
+                                               eps, N, draws[t].beta_old, draws[t].beta_new, eps_sum);
+                }
             }
         }
     }
-    free(idx); free(stats); free(cnt); free(draws);
+    free(idx); free(cls); free(stats); free(cnt); free(draws);
     return 0;
+}
+
+int orc_sweep_ragged(const uint8_t *bed, uint32_t M, const uint32_t *order, uint32_t n_order,
+                     const double *rand_uz, const orc_model *m, const int32_t *groups, uint32_t tokens,
+                     double *eps, double *eps_sum, double *beta, double *comp, double *acum, double *v,
+                     double *betasq)
+{
+    return orc_sweep_sparse(0, bed, M, order, n_order, rand_uz, m, groups, tokens, eps, eps_sum, beta, comp, acum, v, betasq);
+}
+
+int orc_sweep_eigen(const uint8_t *bed, uint32_t M, const uint32_t *order, uint32_t n_order,
+                    const double *rand_uz, const orc_model *m, const int32_t *groups, uint32_t tokens,
+                    double *eps, double *eps_sum, double *beta, double *comp, double *acum, double *v,
+                    double *betasq)
+{
+    return orc_sweep_sparse(1, bed, M, order, n_order, rand_uz, m, groups, tokens, eps, eps_sum, beta, comp, acum, v, betasq);
 }
 
 /* src/BayesRBase.cpp:85-89 */

@@ -96,6 +96,12 @@ int orc_sweep_ragged(const uint8_t *bed, uint32_t M, const uint32_t *order, uint
                      double *eps, double *eps_sum, double *beta, double *comp, double *acum, double *v,
                      double *betasq);
 
+/* Same for the eigen-sparse layout (src/eigenbayesrkernel.cpp, src/eigensparsemarkerbuilder.cpp). */
+int orc_sweep_eigen(const uint8_t *bed, uint32_t M, const uint32_t *order, uint32_t n_order,
+                    const double *rand_uz, const orc_model *m, const int32_t *groups, uint32_t tokens,
+                    double *eps, double *eps_sum, double *beta, double *comp, double *acum, double *v,
+                    double *betasq);
+
 /* src/BayesRBase.cpp:85-89: y (float32, file order) -> standardised eps; returns sigmaE init. */
 double orc_init_epsilon(const float *y, uint32_t N, double *eps);
 

@@ -48,6 +48,7 @@ def load():
                                         C.POINTER(Model), C.c_void_p, C.c_uint32] + [C.c_void_p] * 6
         lib.orc_sweep_ragged.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                          C.POINTER(Model), C.c_void_p, C.c_uint32] + [C.c_void_p] * 7
+        lib.orc_sweep_eigen.argtypes = lib.orc_sweep_ragged.argtypes
         lib.orc_init_epsilon.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         lib.orc_mu_mean_dense.argtypes = [C.c_void_p, C.c_uint32, C.c_double]
         lib.orc_mu_apply.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_double]
@@ -153,7 +154,8 @@ def sweep(layout, bed, M, order, rand_uz, model, groups, eps, beta, comp, acum, 
                                     tokens, _p(eps), _p(beta), _p(comp), _p(acum), _p(v), _p(bs))
     else:
         es = C.c_double(eps_sum)
-        rc = load().orc_sweep_ragged(_p(bed), M, _p(order), len(order), _p(rand_uz), C.byref(model.c), _p(g),
+        fn = load().orc_sweep_eigen if layout == "eigen" else load().orc_sweep_ragged
+        rc = fn(_p(bed), M, _p(order), len(order), _p(rand_uz), C.byref(model.c), _p(g),
                                      tokens, _p(eps), C.byref(es), _p(beta), _p(comp), _p(acum), _p(v), _p(bs))
         eps_sum = es.value
     assert rc == 0, rc

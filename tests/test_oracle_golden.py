@@ -18,7 +18,7 @@ def _replay_oracle(g, layout, iters, tokens=0):
 
     def sweep(it, order, rand_uz, pi, sigmaG, sigmaE, eps_sum):
         mdl = O.ModelArrays(g.N, g.S, pi, sigmaG, sigmaE)
-        return O.sweep("dense" if layout == "dense" else "ragged", g.bed, g.M, order, rand_uz, mdl, g.groups,
+        return O.sweep(layout, g.bed, g.M, order, rand_uz, mdl, g.groups,
                        st["eps"], st["beta"], st["comp"], st["acum"], tokens=tokens, eps_sum=eps_sum)
 
     def get_state():
@@ -32,13 +32,13 @@ def _replay_oracle(g, layout, iters, tokens=0):
 
 @pytest.mark.parametrize("name,layout,iters", [("uk10k", "dense", 3), ("uk10k", "ragged", 3), ("groups", "dense", 2),
                                                ("gauss", "dense", 2), ("missing_small", "dense", 6),
-                                               ("missing_small", "ragged", 6)])
+                                               ("missing_small", "ragged", 6), ("missing_small", "eigen", 6), ("uk10k", "eigen", 2)])
 def test_oracle_replays_reference_chain(name, layout, iters):
     g = Golden(name)
     chain, it_res = _replay_oracle(g, layout, iters)
     for it, res in it_res:
         check_iteration(chain, it, res, tol=1e-9)
-        if layout == "ragged":
+        if layout != "dense":
             assert abs(res["eps_sum"] - chain["epssum_out"][it]) <= 1e-9 * (1 + abs(chain["epssum_out"][it]))
 
 
