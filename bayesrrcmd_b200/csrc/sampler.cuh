@@ -46,19 +46,21 @@ struct Draw {
     int comp;       // chosen component, -1 = walk fell through (nothing assigned, :346-366)
 };
 
-// src/BayesRBase.cpp:325-366
-__device__ inline Draw sample_marker(const GroupConsts &gc, int g, int K, double num, double sigmaE,
-                                     double beta_old, double u, double z)
+// src/BayesRBase.cpp:325-366.  KT > 0: compile-time component count (arrays stay in registers).
+template <int KT>
+__device__ __forceinline__ Draw sample_marker_t(const GroupConsts &gc, int g, int Krt, double num, double sigmaE,
+                                                double beta_old, double u, double z)
 {
+    const int K = KT > 0 ? KT : Krt;
     const double *logPi = gc.logPi + g * K;
     const double *denom = gc.denom + g * K;
     const double *sdev = gc.sdev + g * K;
     const double *halfLog = gc.halfLog + g * K;
-    double logL[kMaxK], muk[kMaxK];
+    double logL[KT > 0 ? KT : kMaxK], muk[KT > 0 ? KT : kMaxK];
     muk[0] = 0.0;
     logL[0] = logPi[0];
     bool big = false;
-#pragma unroll 1
+#pragma unroll
     for (int k = 1; k < K; ++k) {
         muk[k] = num / denom[k];                                            // :325
         logL[k] = logPi[k] - halfLog[k] + 0.5 * (muk[k] * num) / sigmaE;   // :331-333
@@ -67,7 +69,7 @@ __device__ inline Draw sample_marker(const GroupConsts &gc, int g, int K, double
     double acum = 0.0;
     if (!big) {
         double s = 0.0;
-#pragma unroll 1
+#pragma unroll
         for (int l = 0; l < K; ++l) s += exp(logL[l] - logL[0]);
         acum = 1.0 / s;                                                     // :338
     }
@@ -75,7 +77,7 @@ __device__ inline Draw sample_marker(const GroupConsts &gc, int g, int K, double
     d.acum0 = acum;
     d.beta_new = beta_old;
     d.comp = -1;
-#pragma unroll 1
+#pragma unroll
     for (int k = 0; k < K; ++k) {
         if (u <= acum) {                                                    // :347
             d.beta_new = (k == 0) ? 0.0 : z * sdev[k] + muk[k];             // :350-352
@@ -84,16 +86,35 @@ __device__ inline Draw sample_marker(const GroupConsts &gc, int g, int K, double
         }
         if (k + 1 == K) break;     // reference reads logL[K] out of bounds; result unused
         bool b2 = false;
-#pragma unroll 1
+#pragma unroll
         for (int l = 1; l < K; ++l) b2 |= fabs(logL[l] - logL[k + 1]) > 700.0;   // :360
         if (!b2) {
             double s = 0.0;
-#pragma unroll 1
+#pragma unroll
             for (int l = 0; l < K; ++l) s += exp(logL[l] - logL[k + 1]);
             acum += 1.0 / s;                                                // :363
         }
     }
     return d;
+}
+
+__device__ inline Draw sample_marker(const GroupConsts &gc, int g, int K, double num, double sigmaE,
+                                     double beta_old, double u, double z)
+{
+    return sample_marker_t<0>(gc, g, K, num, sigmaE, beta_old, u, z);
+}
+
+// dispatch on the common component counts so that muk/logL live in registers
+__device__ __forceinline__ Draw sample_marker_k(const GroupConsts &gc, int g, int K, double num, double sigmaE,
+                                                double beta_old, double u, double z)
+{
+    switch (K) {
+    case 2: return sample_marker_t<2>(gc, g, K, num, sigmaE, beta_old, u, z);
+    case 3: return sample_marker_t<3>(gc, g, K, num, sigmaE, beta_old, u, z);
+    case 4: return sample_marker_t<4>(gc, g, K, num, sigmaE, beta_old, u, z);
+    case 5: return sample_marker_t<5>(gc, g, K, num, sigmaE, beta_old, u, z);
+    default: return sample_marker_t<0>(gc, g, K, num, sigmaE, beta_old, u, z);
+    }
 }
 
 } // namespace brr

@@ -372,15 +372,21 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             const uint32_t par = b & 1;
             const double *pd = p.part_dot + size_t(par) * p.nCTA * kMaxB;
             const double *pe = p.part_eps + size_t(par) * p.nCTA;
-            double acc = 0.0;
-            if (uint32_t(lane) < nb)
-                for (uint32_t c = warp; c < p.nCTA; c += kWarps) acc += ld_cg(pd + size_t(c) * kMaxB + lane);
-            sh.red_part[warp][lane] = acc;
-            if (lane == 0) {
-                double e = 0.0;
-                for (uint32_t c = warp; c < p.nCTA; c += kWarps) e += ld_cg(pe + c);
-                sh.red_part[warp][kMaxB] = e;
+            // all loads first (independent, L2 latency paid once), then a fixed-order sum
+            constexpr int kMaxPerWarp = 12;          // nCTA <= 16*12 = 192
+            double vals[kMaxPerWarp];
+#pragma unroll
+            for (int i = 0; i < kMaxPerWarp; ++i) {
+                const uint32_t c = warp + i * kWarps;
+                vals[i] = (c < p.nCTA && uint32_t(lane) < nb) ? ld_cg(pd + size_t(c) * kMaxB + lane) : 0.0;
             }
+            const double ev = (uint32_t(tid) < p.nCTA) ? ld_cg(pe + tid) : 0.0;
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < kMaxPerWarp; ++i) acc += vals[i];
+            sh.red_part[warp][lane] = acc;
+            const double es = warp_sum(ev);
+            if (lane == 0) sh.red_part[warp][kMaxB] = es;
             if (cta == 0 && !p.async_mode) {   // recycle the Gram buffer block b+3 will accumulate into
                 int *gz = p.gram + size_t((b + 3) % kGramBuffers) * (kMaxB * kMaxB * 4);
                 for (uint32_t i = tid; i < kMaxB * kMaxB * 4; i += kThreads) gz[i] = 0;
@@ -424,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             uint32_t done = 0;
             while (true) {
                 const bool live = act && uint32_t(k) >= done;
-                if (live) dr = sample_marker(sh.gc, g, K, d0 + corr + bo * NM1, p.sigmaE, bo, uu, zz);
+                if (live) dr = sample_marker_k(sh.gc, g, K, d0 + corr + bo * NM1, p.sigmaE, bo, uu, zz);
                 const bool ns = live && !(bo == 0.0 && dr.beta_new == 0.0);
                 const unsigned mask = __ballot_sync(0xffffffffu, ns);
                 if (p.async_mode || mask == 0) break;

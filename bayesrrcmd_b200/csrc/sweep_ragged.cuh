@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_ragged_kernel(const RaggedS
                 // missing individuals (eigen) carry the lazy offset too: count them via the imputed Zsum
                 const double listed = sh.dsum[k] + sh.off * m.zsum[k];
                 const double num = bo * NM1 - m.mean[k] * sh.eps_sum / m.sd[k] + listed / m.sd[k];   // sparsebayesrkernel.cpp:26
-                dr = sample_marker(sh.gc, g, K, num, p.sigmaE, bo, m.u[k], m.z[k]);
+                dr = sample_marker_k(sh.gc, g, K, num, p.sigmaE, bo, m.u[k], m.z[k]);
             }
             const bool nonskip = act && !(bo == 0.0 && dr.beta_new == 0.0);
             const unsigned mask = __ballot_sync(0xffffffffu, nonskip);
