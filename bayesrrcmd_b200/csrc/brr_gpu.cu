@@ -45,12 +45,12 @@ struct brr_gpu_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int numSMs = 0;
-    uint32_t nCTA = 0, SL = 0, PB = 0, B = 0;
+    uint32_t nCTA = 0, SL = 0, PW = 0, RS = 0, B = 0;
     size_t smem_bytes = 0;
 
-    // dense store
-    uint8_t *planes = nullptr;
-    size_t planes_bytes = 0;
+    // dense store: 2-bit codes, [M][nCTA][PW] words
+    uint32_t *codes = nullptr;
+    size_t codes_bytes = 0;
     double *lut = nullptr;
     uint32_t *counts_local = nullptr, *counts_global = nullptr;
     // ragged store
@@ -66,8 +66,9 @@ struct brr_gpu_ctx {
     double sigmaE = 0, eps_sum_in = 0;
     uint32_t n_order = 0, async_tokens = 0;
     // scratch + outputs
-    double *part_dot = nullptr, *part_eps = nullptr, *cta_red = nullptr, *red_partial = nullptr;
-    int *gram = nullptr;
+    double *part_dot = nullptr, *cta_red = nullptr, *red_partial = nullptr;
+    int *slots = nullptr;                   // dense sweep: rotating reduction slots + absmax + barrier, one allocation
+    unsigned long long *absmax = nullptr;
     unsigned *bar = nullptr;
     double *v = nullptr, *betasq = nullptr, *out_scalars = nullptr;
     unsigned *out_counts = nullptr;
@@ -102,9 +103,9 @@ extern "C" void brr_gpu_destroy(brr_gpu_ctx *c)
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    void *ptrs[] = {c->planes, c->lut, c->counts_local, c->counts_global, c->group, c->cva, c->eps, c->beta, c->comp,
-                    c->acum, c->order, c->rand_uz, c->pi, c->sigmaG, c->part_dot, c->part_eps, c->cta_red,
-                    c->red_partial, c->gram, c->bar, c->v, c->betasq, c->out_scalars, c->out_counts,
+    void *ptrs[] = {c->codes, c->lut, c->counts_local, c->counts_global, c->group, c->cva, c->eps, c->beta, c->comp,
+                    c->acum, c->order, c->rand_uz, c->pi, c->sigmaG, c->part_dot, c->cta_red,
+                    c->red_partial, c->slots, c->v, c->betasq, c->out_scalars, c->out_counts,
                     c->rag.idx16, c->rag.cta_base, c->rag.stats, c->rag.seg};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_small) cudaFreeHost(c->h_small);
@@ -119,17 +120,21 @@ static int choose_geometry(brr_gpu_ctx *c)
 {
     const brr_gpu_config &cfg = c->cfg;
     uint32_t maxCTA = cfg.max_ctas ? std::min<uint32_t>(cfg.max_ctas, c->numSMs) : c->numSMs;
-    c->B = cfg.block_markers ? cfg.block_markers : 16;
-    // slice = multiple of 64 individuals (plane chunk = 2*SL/8 bytes, a multiple of 16 for TMA bulk copies)
+    const bool dense = cfg.layout == BRR_GPU_LAYOUT_DENSE2BIT;
+    c->B = cfg.block_markers ? cfg.block_markers : (dense ? 64 : 16);
+    // slice = multiple of 64 individuals (one 64-individual MMA k-step pair = 4 code words = 16 bytes, the TMA granule)
     uint32_t per = (cfg.n_inds + maxCTA - 1) / maxCTA;
     uint32_t SL = ((per + 63) / 64) * 64;
-    const uint32_t minSL = 512;
+    const uint32_t minSL = 256;
     if (SL < minSL) SL = minSL;
     c->SL = SL;
     c->nCTA = (cfg.n_inds + SL - 1) / SL;
-    c->PB = SL / 8;
-    if (SL > 8192) return fail(BRR_GPU_EINVAL, "n_inds=%u needs %u individuals per CTA; at most 8192 (=%u per GPU) are supported: shard over more GPUs",
-                               cfg.n_inds, SL, 8192u * maxCTA);
+    c->PW = SL / 16;
+    c->RS = c->PW;
+    while (c->RS % 8 != 4) c->RS += 4;      // shared-memory row stride = 4 (mod 8) words: conflict-free fragment loads
+    const uint32_t maxSL = dense ? (uint32_t)kMaxSL : 8192u;
+    if (SL > maxSL) return fail(BRR_GPU_EINVAL, "n_inds=%u needs %u individuals per CTA; at most %u (=%u per GPU) are supported: shard over more GPUs",
+                                cfg.n_inds, SL, maxSL, maxSL * maxCTA);
     return 0;
 }
 
@@ -141,7 +146,10 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
     if (cfg->n_inds < 2 || cfg->n_markers < 1) return fail(BRR_GPU_EINVAL, "need n_inds >= 2 and n_markers >= 1");
     if (cfg->n_components < 2 || cfg->n_components > (uint32_t)kMaxK) return fail(BRR_GPU_EINVAL, "n_components must be 2..%d", kMaxK);
     if (cfg->n_groups < 1 || cfg->n_groups * cfg->n_components > (uint32_t)kMaxGK) return fail(BRR_GPU_EINVAL, "n_groups*n_components must be 1..%d", kMaxGK);
-    if (cfg->block_markers > (uint32_t)kMaxB) return fail(BRR_GPU_EINVAL, "block_markers must be <= %d", kMaxB);
+    {
+        const uint32_t maxb = cfg->layout == BRR_GPU_LAYOUT_DENSE2BIT ? kMaxB : kMaxW;
+        if (cfg->block_markers > maxb) return fail(BRR_GPU_EINVAL, "block_markers must be <= %u for this layout", maxb);
+    }
     if (cfg->layout < BRR_GPU_LAYOUT_DENSE2BIT || cfg->layout > BRR_GPU_LAYOUT_EIGEN) return fail(BRR_GPU_EINVAL, "unknown layout %d", cfg->layout);
     if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(BRR_GPU_EINVAL, "bad rank/world");
     if (cfg->n_inds_total < cfg->n_inds) return fail(BRR_GPU_EINVAL, "n_inds_total < n_inds");
@@ -173,11 +181,15 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
 
     const uint32_t M = cfg->n_markers, N = cfg->n_inds, K = cfg->n_components, nG = cfg->n_groups;
     if (cfg->layout == BRR_GPU_LAYOUT_DENSE2BIT) {
-        c->planes_bytes = size_t(M) * c->nCTA * 2 * c->PB;
-        TRY_OR_DESTROY(dev_alloc(&c->planes, c->planes_bytes));
+        c->codes_bytes = size_t(M) * c->nCTA * c->PW * 4;
+        TRY_OR_DESTROY(dev_alloc(&c->codes, c->codes_bytes / 4));
         TRY_OR_DESTROY(dev_alloc(&c->lut, size_t(M) * 4));
-        c->smem_bytes = sweep_smem_bytes(kMaxB, c->SL, c->PB);      // room for any async token count
-        if (c->smem_bytes > size_t(prop.sharedMemPerBlockOptin)) c->smem_bytes = sweep_smem_bytes(c->B, c->SL, c->PB);
+        c->smem_bytes = sweep_smem_bytes(c->RS);
+        if (c->smem_bytes > size_t(prop.sharedMemPerBlockOptin)) {
+            int rc_ = fail(BRR_GPU_EINVAL, "sweep kernel needs %zu bytes of shared memory per CTA (%u individuals per CTA); the device offers %zu: shard over more GPUs",
+                           c->smem_bytes, c->SL, size_t(prop.sharedMemPerBlockOptin));
+            brr_gpu_destroy(c); return rc_;
+        }
         CUDA_OR_DESTROY(cudaFuncSetAttribute(sweep_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
         int occ = 0;
         CUDA_OR_DESTROY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_dense_kernel, kThreads, c->smem_bytes));
@@ -185,7 +197,13 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
             int rc_ = fail(BRR_GPU_EINVAL, "sweep kernel does not fit: %zu bytes of shared memory per CTA, %u CTAs", c->smem_bytes, c->nCTA);
             brr_gpu_destroy(c); return rc_;
         }
+        const size_t slot_ints = size_t(kSlots) * kSlotInts + 8;     // + absmax (2 ints) + barrier counter + pad
+        TRY_OR_DESTROY(dev_alloc(&c->slots, slot_ints));
+        c->absmax = reinterpret_cast<unsigned long long *>(c->slots + size_t(kSlots) * kSlotInts);
+        c->bar = reinterpret_cast<unsigned *>(c->slots + size_t(kSlots) * kSlotInts + 2);
     } else {
+        TRY_OR_DESTROY(dev_alloc(&c->bar, 4));
+        c->slots = reinterpret_cast<int *>(c->bar);      // single owner pointer for destroy
         c->smem_bytes = ragged_smem_bytes(c->SL);
         CUDA_OR_DESTROY(cudaFuncSetAttribute(sweep_ragged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
         int occ = 0;
@@ -208,11 +226,8 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
     TRY_OR_DESTROY(dev_alloc(&c->pi, size_t(nG) * K));
     TRY_OR_DESTROY(dev_alloc(&c->sigmaG, nG));
     TRY_OR_DESTROY(dev_alloc(&c->part_dot, size_t(2) * c->nCTA * kMaxB));
-    TRY_OR_DESTROY(dev_alloc(&c->part_eps, size_t(2) * c->nCTA));
     TRY_OR_DESTROY(dev_alloc(&c->cta_red, size_t(2) * std::max<uint32_t>(c->nCTA, kRedBlocks)));
     TRY_OR_DESTROY(dev_alloc(&c->red_partial, size_t(2) * kRedBlocks));
-    TRY_OR_DESTROY(dev_alloc(&c->gram, size_t(kGramBuffers) * kMaxB * kMaxB * 4));
-    TRY_OR_DESTROY(dev_alloc(&c->bar, 4));
     TRY_OR_DESTROY(dev_alloc(&c->v, size_t(nG) * K));
     TRY_OR_DESTROY(dev_alloc(&c->betasq, nG));
     TRY_OR_DESTROY(dev_alloc(&c->out_scalars, 4));
@@ -256,9 +271,9 @@ extern "C" int brr_gpu_upload_dense2bit(brr_gpu_ctx *c, const uint8_t *bed, size
         if (e == cudaSuccess) {
             for (uint32_t y0 = 0; y0 < n; y0 += 65535) {
                 const uint32_t ny = std::min<uint32_t>(65535, n - y0);
-                bed_to_planes_kernel<<<dim3(c->nCTA, ny), 128, 0, c->stream>>>(stage + size_t(y0) * col_bytes, col_bytes,
-                                                                            first + done + y0, c->cfg.n_inds, c->nCTA,
-                                                                            c->SL, c->PB, c->planes);
+                bed_to_codes_kernel<<<dim3(c->nCTA, ny), 128, 0, c->stream>>>(stage + size_t(y0) * col_bytes, col_bytes,
+                                                                           first + done + y0, c->cfg.n_inds, c->nCTA,
+                                                                           c->SL, c->PW, c->codes);
                 ++c->launches;
             }
             e = cudaGetLastError();
@@ -269,7 +284,7 @@ extern "C" int brr_gpu_upload_dense2bit(brr_gpu_ctx *c, const uint8_t *bed, size
     }
     cudaFree(stage);
     const uint32_t wpb = 8;
-    count_classes_kernel<<<(count + wpb - 1) / wpb, wpb * 32, 0, c->stream>>>(c->planes, first, count, c->cfg.n_inds, c->nCTA, c->PB, c->counts_local);
+    count_classes_kernel<<<(count + wpb - 1) / wpb, wpb * 32, 0, c->stream>>>(c->codes, first, count, c->cfg.n_inds, c->nCTA, c->PW, c->counts_local);
     ++c->launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -413,7 +428,10 @@ extern "C" int brr_gpu_sweep_stage(brr_gpu_ctx *c, const uint32_t *marker_order,
     if (!marker_order || !rand_uz || !pi || !sigmaG) return fail(BRR_GPU_EINVAL, "null sweep input");
     const uint32_t M = c->cfg.n_markers, nG = c->cfg.n_groups, K = c->cfg.n_components;
     if (n_order > M) return fail(BRR_GPU_EINVAL, "n_order %u > n_markers %u", n_order, M);
-    if (async_tokens > (uint32_t)kMaxB) return fail(BRR_GPU_EINVAL, "async_tokens must be <= %d", kMaxB);
+    {
+        const uint32_t maxb = c->cfg.layout == BRR_GPU_LAYOUT_DENSE2BIT ? kMaxB : kMaxW;
+        if (async_tokens > maxb) return fail(BRR_GPU_EINVAL, "async_tokens must be <= %u for this layout", maxb);
+    }
     if (!(sigmaE > 0.0)) return fail(BRR_GPU_EINVAL, "sigmaE must be positive");
     {   // distinct, in-range marker ids
         std::vector<uint8_t> seen(M, 0);
@@ -437,21 +455,19 @@ static int launch_dense(brr_gpu_ctx *c)
 {
     DenseSweepParams p{};
     p.n_local = c->cfg.n_inds; p.n_total = c->cfg.n_inds_total; p.M = c->cfg.n_markers; p.K = c->cfg.n_components;
-    p.nG = c->cfg.n_groups; p.B = c->async_tokens ? c->async_tokens : c->B; p.nCTA = c->nCTA; p.SL = c->SL; p.PB = c->PB;
-    p.planes = c->planes; p.lut = c->lut; p.counts = c->counts_global; p.group = c->group;
+    p.nG = c->cfg.n_groups; p.B = c->async_tokens ? c->async_tokens : c->B; p.nCTA = c->nCTA; p.SL = c->SL; p.PW = c->PW; p.RS = c->RS;
+    p.codes = c->codes; p.lut = c->lut; p.counts = c->counts_global; p.group = c->group;
     p.order = c->order; p.n_order = c->n_order; p.rand_uz = c->rand_uz; p.pi = c->pi; p.sigmaG = c->sigmaG; p.cva = c->cva;
     p.sigmaE = c->sigmaE; p.async_mode = c->async_tokens ? 1u : 0u;
     p.eps = c->eps; p.beta = c->beta; p.comp = c->comp; p.acum = c->acum;
-    p.part_dot = c->part_dot; p.part_eps = c->part_eps; p.gram = c->gram; p.bar = c->bar; p.cta_red = c->cta_red;
+    p.slots = c->slots; p.absmax = c->absmax; p.bar = c->bar; p.cta_red = c->cta_red;
     p.v = c->v; p.betasq = c->betasq; p.out_scalars = c->out_scalars; p.out_counts = c->out_counts;
-    if (sweep_smem_bytes(p.B, c->SL, c->PB) > c->smem_bytes)
-        return fail(BRR_GPU_EINVAL, "async_tokens %u needs more shared memory than block_markers %u reserved", p.B, c->B);
-    CUDA_TRY(cudaMemsetAsync(c->bar, 0, sizeof(unsigned) * 4, c->stream));
-    CUDA_TRY(cudaMemsetAsync(c->gram, 0, sizeof(int) * kGramBuffers * kMaxB * kMaxB * 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->slots, 0, sizeof(int) * (size_t(kSlots) * kSlotInts + 8), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->out_counts, 0, sizeof(unsigned) * 4, c->stream));
     void *args[] = {&p};
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
     CUDA_TRY(cudaLaunchCooperativeKernel((const void *)sweep_dense_kernel, dim3(c->nCTA), dim3(kThreads), args,
-                                         sweep_smem_bytes(p.B, c->SL, c->PB), c->stream));
+                                         c->smem_bytes, c->stream));
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     c->launches += 1; c->last_launches = 1;
     return 0;
@@ -481,6 +497,8 @@ extern "C" int brr_gpu_sweep_fetch(brr_gpu_ctx *c, double *v, double *betasqn, b
     CUDA_TRY(cudaMemcpyAsync(c->h_counts, c->out_counts, sizeof(unsigned) * 4, cudaMemcpyDeviceToHost, c->stream));
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(BRR_GPU_ECUDA, "sweep failed: %s", cudaGetErrorString(e));
+    if (c->h_counts[2] != 0)
+        return fail(BRR_GPU_ESTATE, "sweep failed: the residual grew past the fixed-point range of the dot products inside one sweep (flags 0x%x)", c->h_counts[2]);
     if (v) memcpy(v, h, sizeof(double) * nG * K);
     if (betasqn) memcpy(betasqn, h + kMaxGK, sizeof(double) * nG);
     cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
@@ -512,7 +530,7 @@ extern "C" int brr_gpu_compute_num(brr_gpu_ctx *c, uint32_t marker, double beta_
     if (marker >= c->cfg.n_markers || !num_out) return fail(BRR_GPU_EINVAL, "bad marker / null output");
     const double NM1 = double(c->cfg.n_inds_total) - 1.0;
     if (c->cfg.layout == BRR_GPU_LAYOUT_DENSE2BIT) {
-        dense_dot_kernel<<<c->nCTA, 256, 0, c->stream>>>(c->planes, c->lut, marker, c->eps, c->cfg.n_inds, c->nCTA, c->SL, c->PB, c->cta_red);
+        dense_dot_kernel<<<c->nCTA, 256, 0, c->stream>>>(c->codes, c->lut, marker, c->eps, c->cfg.n_inds, c->nCTA, c->SL, c->PW, c->cta_red);
         ++c->launches;
         CUDA_TRY(cudaGetLastError());
         std::vector<double> h(c->nCTA);
@@ -532,8 +550,8 @@ extern "C" int brr_gpu_apply_delta(brr_gpu_ctx *c, uint32_t marker, double beta_
     if (!c->uploaded || !c->finalized) return fail(BRR_GPU_ESTATE, "upload and finalize the markers first");
     if (marker >= c->cfg.n_markers) return fail(BRR_GPU_EINVAL, "bad marker");
     if (c->cfg.layout == BRR_GPU_LAYOUT_DENSE2BIT) {
-        dense_axpy_kernel<<<(c->cfg.n_inds + 255) / 256, 256, 0, c->stream>>>(c->planes, c->lut, marker, beta_old - beta_new, c->eps,
-                                                                          c->cfg.n_inds, c->nCTA, c->SL, c->PB);
+        dense_axpy_kernel<<<(c->cfg.n_inds + 255) / 256, 256, 0, c->stream>>>(c->codes, c->lut, marker, beta_old - beta_new, c->eps,
+                                                                          c->cfg.n_inds, c->nCTA, c->SL, c->PW);
         ++c->launches;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -574,9 +592,9 @@ extern "C" int brr_gpu_synth_dense(brr_gpu_ctx *c, uint64_t seed, double maf_lo,
     if (rc) return rc;
     cudaError_t e = cudaMemcpyAsync(dthr, thr.data(), sizeof(uint32_t) * 3 * M, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) {
-        synth_planes_kernel<<<dim3(c->nCTA, std::min<uint32_t>(M, 4096)), 128, 0, c->stream>>>(seed, dthr, M, c->cfg.n_inds, ind_offset, c->nCTA, c->SL, c->PB, c->planes);
+        synth_codes_kernel<<<dim3(c->nCTA, std::min<uint32_t>(M, 4096)), 128, 0, c->stream>>>(seed, dthr, M, c->cfg.n_inds, ind_offset, c->nCTA, c->SL, c->PW, c->codes);
         const uint32_t wpb = 8;
-        count_classes_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, c->stream>>>(c->planes, 0, M, c->cfg.n_inds, c->nCTA, c->PB, c->counts_local);
+        count_classes_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, c->stream>>>(c->codes, 0, M, c->cfg.n_inds, c->nCTA, c->PW, c->counts_local);
         c->launches += 2;
         e = cudaGetLastError();
     }
@@ -614,7 +632,7 @@ extern "C" int brr_gpu_info(brr_gpu_ctx *c, uint32_t *n_ctas, uint32_t *slice_in
     if (n_ctas) *n_ctas = c->nCTA;
     if (slice_inds) *slice_inds = c->SL;
     if (block_markers) *block_markers = c->B;
-    if (genotype_bytes) *genotype_bytes = c->cfg.layout == BRR_GPU_LAYOUT_DENSE2BIT ? c->planes_bytes : c->rag.idx_bytes;
+    if (genotype_bytes) *genotype_bytes = c->cfg.layout == BRR_GPU_LAYOUT_DENSE2BIT ? c->codes_bytes : c->rag.idx_bytes;
     return 0;
 }
 

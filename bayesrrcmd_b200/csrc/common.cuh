@@ -7,10 +7,10 @@ namespace brr {
 
 constexpr int kThreads = 512;          // 16 warps per CTA, one CTA per SM
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxB = 32;              // markers per block (lanes of the sampling warp)
+constexpr int kMaxB = 64;              // dense: markers per block (two half-blocks of 32 sampling lanes)
+constexpr int kMaxW = 32;              // ragged: markers per window (lanes of the sampling warp)
 constexpr int kMaxK = 16;              // mixture components
 constexpr int kMaxGK = 256;            // n_groups * K held in shared memory
-constexpr int kGramBuffers = 4;        // rotating global Gram accumulators
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -97,17 +97,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned by
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
 }
 // global -> shared, 16-byte aligned on both sides, size a multiple of 16
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar)

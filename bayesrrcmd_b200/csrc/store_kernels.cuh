@@ -1,4 +1,4 @@
-// Kernels around the device-resident genotype store: PLINK -> bit planes, class counts, value
+// Kernels around the device-resident genotype store: PLINK -> 2-bit codes, class counts, value
 // tables, synthetic data, and the marker-level parity hooks (computeNum / epsilon change).
 #pragma once
 #include "common.cuh"
@@ -22,80 +22,72 @@ __host__ __device__ inline uint32_t synth_class(uint64_t seed, uint32_t marker, 
     return r < thr[0] ? 0u : (r < thr[1] ? 1u : 2u);
 }
 
-// Store layout: planes[((marker*nCTA + cta)*2 + plane)*PB + byte], bit i of a slice = individual
-// cta*SL + i.  P1 = {class 1 or missing}, P2 = {class 2 or missing}.
+// Store layout (HBM): codes[(marker*nCTA + cta)*PW + w] is a 32-bit word holding the 2-bit codes of the
+// 16 individuals cta*SL + 16w .. +15 (individual j of the word at bits 2j..2j+1); PW = SL/16 words per
+// (marker, CTA slice).  Code = allele count 0,1,2; 3 = missing.  Individuals past n_local get code 0.
+// The PLINK code (b1 b0) maps as 00->2, 10->1, 11->0, 01->missing (reference src/preprocessgraph.cpp:50-51,
+// src/densemarkerbuilder.cpp:30): new_hi = ~b1, new_lo = b1 ^ b0.
 
-// PLINK payload -> planes. grid = (nCTA, markers in chunk), threads over plane bytes.
-__global__ void bed_to_planes_kernel(const uint8_t *__restrict__ bed, size_t col_bytes, uint32_t first_marker,
-                                     uint32_t n_local, uint32_t nCTA, uint32_t SL, uint32_t PB,
-                                     uint8_t *__restrict__ planes)
+// PLINK payload -> codes. grid = (nCTA, markers in chunk), threads over words.
+__global__ void bed_to_codes_kernel(const uint8_t *__restrict__ bed, size_t col_bytes, uint32_t first_marker,
+                                    uint32_t n_local, uint32_t nCTA, uint32_t SL, uint32_t PW,
+                                    uint32_t *__restrict__ codes)
 {
     const uint32_t cta = blockIdx.x, mk = blockIdx.y;
     const uint8_t *col = bed + size_t(mk) * col_bytes;
-    uint8_t *dst = planes + (size_t(first_marker + mk) * nCTA + cta) * 2 * PB;
-    for (uint32_t u = threadIdx.x; u < PB; u += blockDim.x) {
-        const uint32_t i0 = cta * SL + 8 * u;
-        uint32_t p1 = 0, p2 = 0;
-        if (8 * u < SL && i0 < n_local) {
-            uint32_t two16 = col[i0 >> 2];
-            if ((i0 >> 2) + 1 < col_bytes) two16 |= uint32_t(col[(i0 >> 2) + 1]) << 8;
+    uint32_t *dst = codes + (size_t(first_marker + mk) * nCTA + cta) * PW;
+    for (uint32_t w = threadIdx.x; w < PW; w += blockDim.x) {
+        const uint32_t i0 = cta * SL + 16 * w;
+        uint32_t out = 0;
+        if (i0 < n_local) {
+            uint32_t raw = 0;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                if (i0 + t < n_local) {
-                    const uint32_t b0 = (two16 >> (2 * t)) & 1u, b1 = (two16 >> (2 * t + 1)) & 1u;
-                    // PLINK 00->2, 10->1 (b1=1,b0=0), 11->0, 01->missing (src/preprocessgraph.cpp:50-51)
-                    p1 |= (b0 ^ b1) << t;        // class 1 or missing
-                    p2 |= (b1 ^ 1u) << t;        // class 2 or missing
-                }
+            for (int k = 0; k < 4; ++k) {
+                const size_t byte = size_t(i0 >> 2) + k;
+                if (byte < col_bytes) raw |= uint32_t(col[byte]) << (8 * k);
             }
+            const uint32_t hi = raw & 0xAAAAAAAAu, lo = raw & 0x55555555u;
+            out = (~hi & 0xAAAAAAAAu) | ((lo ^ (hi >> 1)) & 0x55555555u);
+            const uint32_t valid = n_local - i0;                 // individuals of this word that exist
+            if (valid < 16) out &= (1u << (2 * valid)) - 1u;
         }
-        dst[u] = uint8_t(p1);
-        dst[PB + u] = uint8_t(p2);
+        dst[w] = out;
     }
 }
 
-// synthetic genotypes straight into the planes. grid = (nCTA, min(M, 65535)) with a marker loop.
-__global__ void synth_planes_kernel(uint64_t seed, const uint32_t *__restrict__ thr, uint32_t M, uint32_t n_local,
-                                    uint32_t ind_offset, uint32_t nCTA, uint32_t SL, uint32_t PB,
-                                    uint8_t *__restrict__ planes)
+// synthetic genotypes straight into the store. grid = (nCTA, min(M, 65535)) with a marker loop.
+__global__ void synth_codes_kernel(uint64_t seed, const uint32_t *__restrict__ thr, uint32_t M, uint32_t n_local,
+                                   uint32_t ind_offset, uint32_t nCTA, uint32_t SL, uint32_t PW,
+                                   uint32_t *__restrict__ codes)
 {
     const uint32_t cta = blockIdx.x;
     for (uint32_t mk = blockIdx.y; mk < M; mk += gridDim.y) {
-        uint8_t *dst = planes + (size_t(mk) * nCTA + cta) * 2 * PB;
+        uint32_t *dst = codes + (size_t(mk) * nCTA + cta) * PW;
         const uint32_t t3[3] = {thr[3 * mk], thr[3 * mk + 1], thr[3 * mk + 2]};
-        for (uint32_t u = threadIdx.x; u < PB; u += blockDim.x) {
-            const uint32_t i0 = cta * SL + 8 * u;
-            uint32_t p1 = 0, p2 = 0;
-            if (8 * u < SL) {
+        for (uint32_t w = threadIdx.x; w < PW; w += blockDim.x) {
+            const uint32_t i0 = cta * SL + 16 * w;
+            uint32_t out = 0;
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    if (i0 + t < n_local) {
-                        const uint32_t c = synth_class(seed, mk, ind_offset + i0 + t, t3);
-                        p1 |= uint32_t(c == 1u || c == 3u) << t;
-                        p2 |= uint32_t(c == 2u || c == 3u) << t;
-                    }
-                }
-            }
-            dst[u] = uint8_t(p1);
-            dst[PB + u] = uint8_t(p2);
+            for (int t = 0; t < 16; ++t)
+                if (i0 + t < n_local) out |= synth_class(seed, mk, ind_offset + i0 + t, t3) << (2 * t);
+            dst[w] = out;
         }
     }
 }
 
 // class counts of this shard: one warp per marker. counts[marker] = {n0, n1, n2, nmiss}
-__global__ void count_classes_kernel(const uint8_t *__restrict__ planes, uint32_t first, uint32_t count,
-                                     uint32_t n_local, uint32_t nCTA, uint32_t PB, uint32_t *__restrict__ counts)
+__global__ void count_classes_kernel(const uint32_t *__restrict__ codes, uint32_t first, uint32_t count,
+                                     uint32_t n_local, uint32_t nCTA, uint32_t PW, uint32_t *__restrict__ counts)
 {
     const uint32_t warps_per_block = blockDim.x / 32, lane = threadIdx.x & 31;
     const uint32_t mk = first + blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     if (mk >= first + count) return;
-    const uint32_t PW = PB / 4;
+    const uint32_t *base = codes + size_t(mk) * nCTA * PW;
     uint32_t n1 = 0, n2 = 0, nm = 0;
     for (uint32_t i = lane; i < nCTA * PW; i += 32) {
-        const uint32_t cta = i / PW, w = i % PW;
-        const uint32_t *base = reinterpret_cast<const uint32_t *>(planes + (size_t(mk) * nCTA + cta) * 2 * PB);
-        const uint32_t x1 = base[w], x2 = base[PW + w];
-        n1 += __popc(x1 & ~x2); n2 += __popc(x2 & ~x1); nm += __popc(x1 & x2);
+        const uint32_t x = base[i];
+        const uint32_t lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;
+        n1 += __popc(lo & ~hi); n2 += __popc(hi & ~lo); nm += __popc(lo & hi);
     }
     n1 = __reduce_add_sync(0xffffffffu, n1); n2 = __reduce_add_sync(0xffffffffu, n2); nm = __reduce_add_sync(0xffffffffu, nm);
     if (lane == 0) {
@@ -125,24 +117,31 @@ __global__ void dense_lut_kernel(const uint32_t *__restrict__ counts, uint32_t M
     lut[4 * size_t(mk) + 2] = c2 * sigma; lut[4 * size_t(mk) + 3] = cm * sigma;
 }
 
+__device__ __forceinline__ uint32_t code_of(const uint32_t *__restrict__ codes, uint32_t marker, uint32_t nCTA,
+                                            uint32_t SL, uint32_t PW, uint32_t gi)
+{
+    const uint32_t cta = gi / SL, i = gi - cta * SL;
+    return (codes[(size_t(marker) * nCTA + cta) * PW + (i >> 4)] >> (2 * (i & 15u))) & 3u;
+}
+
 // ---- marker-level parity hooks -------------------------------------------------------------------
 // DenseRKernel::computeNum without the beta_old*(N-1) term (reference src/densebayesrkernel.cpp:10-15):
-// one block per slice, deterministic block reduction, partial[cta] = sum_i lut[class_i] * eps_i.
-__global__ void dense_dot_kernel(const uint8_t *__restrict__ planes, const double *__restrict__ lut, uint32_t marker,
+// one block per slice, deterministic block reduction, partial[cta] = sum_i lut[code_i] * eps_i.
+__global__ void dense_dot_kernel(const uint32_t *__restrict__ codes, const double *__restrict__ lut, uint32_t marker,
                                  const double *__restrict__ eps, uint32_t n_local, uint32_t nCTA, uint32_t SL,
-                                 uint32_t PB, double *__restrict__ partial)
+                                 uint32_t PW, double *__restrict__ partial)
 {
     __shared__ double wsum[32];
     const uint32_t cta = blockIdx.x;
-    const uint8_t *p1 = planes + (size_t(marker) * nCTA + cta) * 2 * PB, *p2 = p1 + PB;
-    const double L0 = lut[4 * size_t(marker)], L1 = lut[4 * size_t(marker) + 1], L2 = lut[4 * size_t(marker) + 2],
-                 L3 = lut[4 * size_t(marker) + 3];
+    const uint32_t *row = codes + (size_t(marker) * nCTA + cta) * PW;
+    const double L[4] = {lut[4 * size_t(marker)], lut[4 * size_t(marker) + 1], lut[4 * size_t(marker) + 2],
+                         lut[4 * size_t(marker) + 3]};
     double acc = 0.0;
     for (uint32_t i = threadIdx.x; i < SL; i += blockDim.x) {
         const uint32_t gi = cta * SL + i;
         if (gi < n_local) {
-            const uint32_t b1 = (p1[i >> 3] >> (i & 7)) & 1u, b2 = (p2[i >> 3] >> (i & 7)) & 1u;
-            const double x = b1 ? (b2 ? L3 : L1) : (b2 ? L2 : L0);
+            const uint32_t c = (row[i >> 4] >> (2 * (i & 15u))) & 3u;
+            const double x = c == 0 ? L[0] : (c == 1 ? L[1] : (c == 2 ? L[2] : L[3]));
             acc += x * eps[gi];
         }
     }
@@ -157,16 +156,13 @@ __global__ void dense_dot_kernel(const uint8_t *__restrict__ planes, const doubl
 }
 
 // eps += dB * x_marker (dB = beta_old - beta_new; reference src/densebayesrkernel.cpp:17-20 + BayesRBase.cpp:376)
-__global__ void dense_axpy_kernel(const uint8_t *__restrict__ planes, const double *__restrict__ lut, uint32_t marker,
+__global__ void dense_axpy_kernel(const uint32_t *__restrict__ codes, const double *__restrict__ lut, uint32_t marker,
                                   double dB, double *__restrict__ eps, uint32_t n_local, uint32_t nCTA, uint32_t SL,
-                                  uint32_t PB)
+                                  uint32_t PW)
 {
     const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= n_local) return;
-    const uint32_t cta = gi / SL, i = gi % SL;
-    const uint8_t *p1 = planes + (size_t(marker) * nCTA + cta) * 2 * PB, *p2 = p1 + PB;
-    const uint32_t b1 = (p1[i >> 3] >> (i & 7)) & 1u, b2 = (p2[i >> 3] >> (i & 7)) & 1u;
-    eps[gi] += dB * lut[4 * size_t(marker) + (b1 | (b2 << 1))];
+    eps[gi] += dB * lut[4 * size_t(marker) + code_of(codes, marker, nCTA, SL, PW, gi)];
 }
 
 // eps += c, then per-block partial sums of eps and eps^2 (deterministic); c = 0 for a plain reduce

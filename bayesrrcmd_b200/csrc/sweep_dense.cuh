@@ -1,26 +1,35 @@
-// Persistent cooperative Gibbs-sweep kernel, dense 2-bit layout (sm_100a).
+// Persistent cooperative Gibbs-sweep kernel, dense 2-bit layout (sm_100a), version 2.
 //
 // One launch = one AnalysisGraph::exec (reference src/sequential.cpp:10-27 driving
 // src/BayesRBase.cpp:287-392 over all markers of the sweep, in the given order).
 //
 // Design
 //   * One CTA per SM, all co-resident (cooperative launch).  CTA c owns the individuals
-//     [c*SL, (c+1)*SL) and keeps their residuals eps in SHARED MEMORY for the whole sweep.
-//   * Genotypes live in HBM as two bit planes per (marker, CTA slice): P1 = {g==1 or missing},
-//     P2 = {g==2 or missing}.  A block of B markers (the next B of the permutation) is fetched with
-//     TMA 1-D bulk copies (cp.async.bulk + mbarrier), double buffered, one block ahead.
-//   * Per block every CTA computes, from its slice only:
-//       - B partial dots x_j . eps   (masked fp64 sums S1,S2,Smiss -> value-table combination),
-//       - the B x B integer Gram counts sum_i g_ij g_ik (+ the missing cross terms) by AND+POPC,
-//     publishes them (plain stores / integer REDs), and joins ONE grid-wide barrier.
-//   * After the barrier every CTA redundantly reduces the partials in a fixed order and one warp
-//     walks the block: lane k samples marker k with
+//     [c*SL, (c+1)*SL); their residuals eps live in REGISTERS (fp64, 8 per thread) for the whole sweep,
+//     plus an exact fixed-point copy in shared memory: q_i = rint(eps_i * 2^s) split into 8 signed
+//     base-256 digits ("limbs", int8).
+//   * Genotypes live in HBM as 2-bit codes (16 individuals per 32-bit word).  A block of 64 markers
+//     (the next 64 of the permutation) is fetched with TMA 1-D bulk copies (cp.async.bulk + mbarrier),
+//     double buffered, two blocks ahead.
+//   * All O(N) arithmetic runs on the tensor cores as INTEGER matrix products (mma.sync m16n8k32,
+//     u8 x u8 / u8 x s8 -> s32): a register-only 2-bit -> int8 expansion ((w >> 2c) & 0x03030303) feeds
+//       - the DOT pass:   64 markers x 8 limbs,   S[m][l] = sum_i g_mi * limb_l(q_i)
+//       - the GRAM pass:  64 x 64 marker pairs,   GG[j][k] = sum_i g_ji * g_ki   (upper triangle)
+//     Both are exact, so the per-CTA partial results are combined over CTAs (and GPUs) with integer
+//     reductions (RED.ADD) into a small rotating global slot: the result is bit-identical for every
+//     slicing of the individuals and needs no ordered floating-point reduction.
+//   * One grid-wide barrier per block.  The Gram pass of block b+1 runs between the arrival at the
+//     barrier of block b and the wait on it, so its cost hides the barrier latency.
+//   * After the barrier every CTA redundantly reconstructs the 64 dots x_j . eps and one warp walks the
+//     block (two half-blocks of 32 lanes): lane k samples marker k with
 //         num_k = x_k.eps_blockstart - sum_{j<k updated} (beta_j,new - beta_j,old) x_j.x_k + beta_old,k (N-1),
 //     which is exactly the dot against the residual the one-by-one loop would have seen.  Lanes
 //     speculate that no earlier marker of the block changes eps; each marker that does (not
 //     skipUpdate, src/BayesRBase.cpp:372) triggers one more SIMT round for the lanes behind it.
-//   * Finally every CTA applies eps += (beta_old - beta_new) x_j for the block's updated markers to
-//     its shared-memory slice (planes are still resident), and moves on.
+//   * Finally every thread applies eps += (beta_old - beta_new) x_j for the block's updated markers to
+//     its registers (codes are still resident in shared memory) and re-quantises its limbs.
+//   Missing genotypes (code 3) enter the integer products as the value 3 and are corrected exactly by a
+//   sparse side pass (sum of q over the missing individuals; cross counts with the other markers).
 //   Asynchronous mode (bounded staleness, src/BayesRBase.cpp:394-523 under src/parallelgraph.cpp):
 //   same pipeline with B = tokens and no Gram correction.
 #pragma once
@@ -29,11 +38,29 @@
 
 namespace brr {
 
+constexpr int kB = 64;                 // markers per block = tile structure of the MMA passes
+constexpr int kLimbs = 8;
+constexpr uint32_t kM3 = 0x03030303u;
+constexpr int kMissCap = 4096;         // entries of the per-block missing list (>= max slice length)
+constexpr int kMaxSL = 4096;           // individuals per CTA (2 register items of 4 per thread)
+constexpr int kScratchInts = 8192;     // 32 KB shared scratch
+constexpr int kHeadroomBits = 6;       // |eps| may grow 64x inside a sweep before the fixed point overflows
+
+// rotating global slot (int32 units)
+constexpr int kSlotA = 0;              // [64][64]: upper (j<k) = sum g'_j g'_k ; lower [k][j] = # both missing
+constexpr int kSlotY = 4096;           // [64][64]: Y[a][b] = sum over {i: b missing, a present} of g_a
+constexpr int kSlotDots = 8192;        // [64][8] limb sums
+constexpr int kSlotSm = 8704;          // [64][2] int64: sum of q over missing individuals (hi, lo parts)
+constexpr int kSlotEps = 8960;         // [2] int64: sum of q over all individuals (hi, lo parts)
+constexpr int kSlotFlag = 8964;        // != 0: some slice of the block has missing genotypes
+constexpr int kSlotInts = 8968;
+constexpr int kSlots = 4;
+
 struct DenseSweepParams {
     // geometry
-    uint32_t n_local, n_total, M, K, nG, B, nCTA, SL, PB;
+    uint32_t n_local, n_total, M, K, nG, B, nCTA, SL, PW, RS;   // PW = SL/16 words per row, RS = smem row stride (words)
     // store
-    const uint8_t *planes;   // [M][nCTA][2][PB]
+    const uint32_t *codes;   // [M][nCTA][PW]
     const double *lut;       // [M][4] values of class 0,1,2,missing
     const uint32_t *counts;  // [M][4] GLOBAL class counts
     const int32_t *group;    // [M] or nullptr
@@ -49,468 +76,643 @@ struct DenseSweepParams {
     // chain state
     double *eps, *beta, *comp, *acum;
     // scratch
-    double *part_dot;        // [2][nCTA][kMaxB]
-    double *part_eps;        // [2][nCTA]
-    int *gram;               // [kGramBuffers][kMaxB*kMaxB*4]
+    int *slots;              // [kSlots][kSlotInts], zero at launch
+    unsigned long long *absmax;   // bits of max |eps| (zero at launch)
     unsigned *bar;           // grid barrier arrival counter (zero at launch)
     double *cta_red;         // [nCTA][2]
     // outputs
     double *v;               // [nG][K]
     double *betasq;          // [nG]
     double *out_scalars;     // [0]=sum eps, [1]=||eps||^2
-    unsigned *out_counts;    // [0]=non-skipped markers, [1]=blocks
+    unsigned *out_counts;    // [0]=non-skipped markers, [1]=blocks, [2]=error flags
 };
 
 struct BlockMeta {
-    uint32_t id[kMaxB];
-    int32_t grp[kMaxB];
-    double beta_old[kMaxB], u[kMaxB], z[kMaxB];
-    double lut[kMaxB][4];
-    double sj[kMaxB], cj[kMaxB], ej[kMaxB];   // x = sj * (g - cj + ej*[missing])
-    double sumg[kMaxB], nmiss[kMaxB];         // global n1 + 2 n2, global missing count
+    uint32_t id[kB];
+    int32_t grp[kB];
+    double beta_old[kB], u[kB], z[kB];
+    double lut[kB][4];
+    double sj[kB], cj[kB], ej[kB];   // x = sj * (g - cj + ej*[missing])
+    double sumg[kB], nmiss[kB];      // global n1 + 2 n2, global missing count
 };
 
-struct SweepShared {   // fixed-size part; eps slice and plane buffers follow (dynamic)
+struct SweepShared {   // fixed-size part; limbs, code buffers, scratch and the missing list follow (dynamic)
     GroupConsts gc;
-    BlockMeta meta[2];
-    double G[kMaxB * kMaxB];
-    double dot_part[kWarps][4][3];
-    double red_part[kWarps][kMaxB + 1];
-    double dsum[kMaxB];
-    double dbeta[kMaxB];
-    double eps_sum_total;
-    double eps_sum_cta;
+    BlockMeta meta;
+    double d0[kB];
+    double dbeta[kB];
     double warp_tmp[kWarps];
     double betasq_s[kMaxGK];
     int v_s[kMaxGK];
-    int gram_s[kMaxB * kMaxB * 4];
-    uint32_t ns_list[kMaxB];
+    unsigned long long sm_s[kB][2];
+    unsigned long long epsq[2];      // this slice's sum of q, (hi, lo) parts
+    double eps_sum_total;
+    double scale, inv_scale;
+    uint32_t ns_list[kB];
     uint32_t n_ns;
     uint32_t n_nonskipped_total;
+    uint32_t miss_n, miss_stored;    // entries found / entries in the list for the block held in `miss_blk`
+    uint32_t miss_blk;
+    uint32_t has_missing;
+    uint32_t err;
     alignas(8) uint64_t mbar[2];
 };
 
-__host__ __device__ inline size_t sweep_smem_bytes(uint32_t B, uint32_t SL, uint32_t PB)
+__host__ __device__ inline size_t sweep_smem_bytes(uint32_t RS)
 {
-    size_t s = sizeof(SweepShared);
-    s = (s + 15) & ~size_t(15);
-    s += size_t(SL) * sizeof(double);           // eps slice, transposed [8][SL/8]
-    s += size_t(2) * B * 2 * PB;                // two plane buffers
+    size_t s = (sizeof(SweepShared) + 15) & ~size_t(15);
+    s += size_t(kLimbs) * RS * 16;              // limbs: [8][RS] uint4
+    s += size_t(2) * kB * RS * 4;               // two code buffers: [64][RS] words
+    s += size_t(kScratchInts) * 4;              // scratch
+    s += size_t(kMissCap) * 4;                  // missing list
     return s + 16;
 }
 
-__device__ __forceinline__ void load_meta_regs(const DenseSweepParams &p, uint32_t pos, uint32_t &id, int &grp,
-                                               double &bo, double &u, double &z, double lut[4], uint32_t cnt[4])
+// ---- tensor-core primitives ---------------------------------------------------------------------
+__device__ __forceinline__ void mma_u8u8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
-    id = p.order[pos];
-    grp = p.group ? p.group[id] : 0;
-    bo = p.beta[id];
-    u = p.rand_uz[2 * size_t(id)];
-    z = p.rand_uz[2 * size_t(id) + 1];
-    const double4 *l4 = reinterpret_cast<const double4 *>(p.lut + 4 * size_t(id));
-    const double4 l = *l4;
-    lut[0] = l.x; lut[1] = l.y; lut[2] = l.z; lut[3] = l.w;
-    const uint4 c = *reinterpret_cast<const uint4 *>(p.counts + 4 * size_t(id));
-    cnt[0] = c.x; cnt[1] = c.y; cnt[2] = c.z; cnt[3] = c.w;
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-__device__ __forceinline__ void store_meta(BlockMeta &m, int k, uint32_t id, int grp, double bo, double u, double z,
-                                           const double lut[4], const uint32_t cnt[4])
+// Gram pass: which 16x8 output tiles a warp role computes.  Tile (mi, nj) covers row markers
+// 16mi..16mi+15 and column markers 8nj..8nj+7; only tiles with some row < column are needed.
+__host__ __device__ constexpr int gram_role_mi(int role, int t)
 {
-    m.id[k] = id; m.grp[k] = grp; m.beta_old[k] = bo; m.u[k] = u; m.z[k] = z;
-    m.lut[k][0] = lut[0]; m.lut[k][1] = lut[1]; m.lut[k][2] = lut[2]; m.lut[k][3] = lut[3];
-    const double s = 0.5 * (lut[2] - lut[0]);       // value table is affine in the allele count
-    const double c = -lut[0] / s;
-    m.sj[k] = s; m.cj[k] = c; m.ej[k] = lut[3] / s + c;
-    m.sumg[k] = double(cnt[1]) + 2.0 * double(cnt[2]);
-    m.nmiss[k] = double(cnt[3]);
+    constexpr int tab[4][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 1, 1}, {1, 1, 1, 1, 2}, {2, 2, 2, 3, 3}};
+    return tab[role][t];
+}
+__host__ __device__ constexpr int gram_role_nj(int role, int t)
+{
+    constexpr int tab[4][5] = {{0, 1, 2, 3, 4}, {5, 6, 7, 6, 7}, {2, 3, 4, 5, 4}, {5, 6, 7, 6, 7}};
+    return tab[role][t];
+}
+
+// one warp, one role, its share of the 64-individual k-step pairs: acc[t] += tile t
+template <int ROLE>
+__device__ __forceinline__ void gram_role_pass(const uint32_t *__restrict__ pk, uint32_t RS, uint32_t NP, uint32_t kg,
+                                               uint32_t nkg, int lane, int (&acc)[5][4])
+{
+    const uint32_t gid = lane >> 2, tig = lane & 3;
+    for (uint32_t p = kg; p < NP; p += nkg) {
+        const uint32_t wo = 4 * p + tig;
+        uint32_t wa[4][2];      // A words of the m-tiles this role touches (rows gid, gid+8)
+        uint32_t wb[8];         // B words of the n-tiles this role touches (column gid)
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const int mi = gram_role_mi(ROLE, t), nj = gram_role_nj(ROLE, t);
+            bool first_m = true, first_n = true;
+#pragma unroll
+            for (int s = 0; s < t; ++s) { if (gram_role_mi(ROLE, s) == mi) first_m = false; if (gram_role_nj(ROLE, s) == nj) first_n = false; }
+            if (first_m) {
+                wa[mi][0] = pk[(16 * mi + gid) * RS + wo];
+                wa[mi][1] = pk[(16 * mi + gid + 8) * RS + wo];
+            }
+            if (first_n) wb[nj] = pk[(8 * nj + gid) * RS + wo];
+        }
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const int mi = gram_role_mi(ROLE, t), nj = gram_role_nj(ROLE, t);
+            const uint32_t w0 = wa[mi][0], w1 = wa[mi][1], wc = wb[nj];
+            mma_u8u8(acc[t], w0 & kM3, w1 & kM3, (w0 >> 2) & kM3, (w1 >> 2) & kM3, wc & kM3, (wc >> 2) & kM3);
+            mma_u8u8(acc[t], (w0 >> 4) & kM3, (w1 >> 4) & kM3, (w0 >> 6) & kM3, (w1 >> 6) & kM3, (wc >> 4) & kM3, (wc >> 6) & kM3);
+        }
+    }
+}
+
+// final owner (k-group 0) adds the other k-groups' copies and publishes the needed entries
+template <int ROLE>
+__device__ __forceinline__ void gram_role_publish(const int *__restrict__ scratch, uint32_t nkg, int lane, int (&acc)[5][4],
+                                                  int *__restrict__ slotA, uint32_t nb)
+{
+    const uint32_t gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+    for (int t = 0; t < 5; ++t)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int s = acc[t][r];
+            for (uint32_t g = 1; g < nkg; ++g) s += scratch[(((g - 1) * 4 + ROLE) * 20 + t * 4 + r) * 32 + lane];
+            const uint32_t row = 16 * gram_role_mi(ROLE, t) + gid + 8 * (r >> 1), col = 8 * gram_role_nj(ROLE, t) + 2 * tig + (r & 1);
+            if (row < col && col < nb && s != 0) atomicAdd(slotA + row * kB + col, s);
+        }
+}
+
+__device__ __forceinline__ void load_block_meta(const DenseSweepParams &p, BlockMeta &m, uint32_t pos, int k)
+{
+    const uint32_t id = p.order[pos];
+    m.id[k] = id; m.grp[k] = p.group ? p.group[id] : 0; m.beta_old[k] = p.beta[id];
+    m.u[k] = p.rand_uz[2 * size_t(id)]; m.z[k] = p.rand_uz[2 * size_t(id) + 1];
+    const double4 l = *reinterpret_cast<const double4 *>(p.lut + 4 * size_t(id));
+    m.lut[k][0] = l.x; m.lut[k][1] = l.y; m.lut[k][2] = l.z; m.lut[k][3] = l.w;
+    const uint4 c = *reinterpret_cast<const uint4 *>(p.counts + 4 * size_t(id));
+    const double s = 0.5 * (l.z - l.x);          // value table is affine in the allele count
+    const double cc = -l.x / s;
+    m.sj[k] = s; m.cj[k] = cc; m.ej[k] = l.w / s + cc;
+    m.sumg[k] = double(c.y) + 2.0 * double(c.z);
+    m.nmiss[k] = double(c.w);
+}
+
+// x_j . x_k for j < k from the reduced integer counts (A, Y in shared memory)
+__device__ __forceinline__ double gram_entry(const BlockMeta &m, const int *__restrict__ A, const int *__restrict__ Y,
+                                             bool has_missing, int j, int k, double Nt)
+{
+    double a = double(A[j * kB + k]), cy = 0.0, cz = 0.0, cw = 0.0;
+    if (has_missing) {
+        cw = double(A[k * kB + j]); cy = double(Y[j * kB + k]); cz = double(Y[k * kB + j]);
+        a = a - 3.0 * cy - 3.0 * cz - 9.0 * cw;
+    }
+    const double cj = m.cj[j], ck = m.cj[k], ej = m.ej[j], ek = m.ej[k];
+    double t = a - ck * m.sumg[j] - cj * m.sumg[k] + Nt * cj * ck;
+    t += ek * cy + ej * cz - cj * ek * m.nmiss[k] - ck * ej * m.nmiss[j] + ej * ek * cw;
+    return m.sj[j] * m.sj[k] * t;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSweepParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SweepShared &sh = *reinterpret_cast<SweepShared *>(smem_raw);
-    const size_t off_eps = (sizeof(SweepShared) + 15) & ~size_t(15);
-    double *eps_s = reinterpret_cast<double *>(smem_raw + off_eps);
-    unsigned char *planes_s = smem_raw + off_eps + size_t(p.SL) * sizeof(double);
+    const uint32_t RS = p.RS, PW = p.PW, SL = p.SL;
+    const size_t off0 = (sizeof(SweepShared) + 15) & ~size_t(15);
+    uint4 *limbs = reinterpret_cast<uint4 *>(smem_raw + off0);                       // [8][RS]
+    uint32_t *pkbuf = reinterpret_cast<uint32_t *>(smem_raw + off0 + size_t(kLimbs) * RS * 16);   // [2][64][RS]
+    int *scratch = reinterpret_cast<int *>(pkbuf + size_t(2) * kB * RS);
+    uint32_t *miss_list = reinterpret_cast<uint32_t *>(scratch + kScratchInts);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t gid = lane >> 2, tig = lane & 3;
     const uint32_t cta = blockIdx.x;
-    const uint32_t B = p.B, K = p.K, PB = p.PB, SL = p.SL;
-    const uint32_t UP8 = SL / 8;                     // 8-individual units (bytes of a plane) per slice
-    const uint32_t PW = SL / 32;                     // 32-bit words per plane per slice
-    const uint32_t chunk = 2 * PB;                   // bytes per (marker, CTA)
-    const double NM1 = double(p.n_total - 1);
+    const uint32_t B = p.B, K = p.K;
+    const uint32_t NP = SL / 64;                     // 64-individual k-step pairs per slice
+    const uint32_t NI = SL / 4;                      // register items (4 individuals each) per slice
+    const uint32_t CB = SL / 4;                      // bytes per (marker, CTA) row in HBM
+    const double NM1 = double(p.n_total - 1), Nt = double(p.n_total);
     const uint32_t nBlocks = (p.n_order + B - 1) / B;
-    const uint32_t slice0 = cta * SL;                // first individual of this slice
+    const uint32_t slice0 = cta * SL;
+    unsigned bar_gen = 0;
 
     // ---- prologue -----------------------------------------------------------------------------
-    // eps slice -> shared, transposed: individual i = 8u + t lives at eps_s[t*UP8 + u]
-    double my_sum = 0.0;
-    for (uint32_t i = tid; i < SL; i += kThreads) {
-        const uint32_t gi = slice0 + i;
-        const double e = (gi < p.n_local) ? p.eps[gi] : 0.0;
-        eps_s[(i & 7u) * UP8 + (i >> 3)] = e;
-        my_sum += e;
+    // eps -> registers.  item = 4w + c owns the individuals 16w + 4t + c, t = 0..3
+    double e[2][4];
+    double amax = 0.0;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const uint32_t item = tid + it * kThreads;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint32_t i = 16 * (item >> 2) + 4 * t + (item & 3u);
+            const uint32_t gi = slice0 + i;
+            e[it][t] = (item < NI && gi < p.n_local) ? p.eps[gi] : 0.0;
+            amax = fmax(amax, fabs(e[it][t]));
+        }
     }
     fill_group_consts(sh.gc, p.nG, K, NM1, p.sigmaE, p.pi, p.sigmaG, p.cva);
     for (int i = tid; i < kMaxGK; i += kThreads) { sh.v_s[i] = 0; sh.betasq_s[i] = 0.0; }
-    for (int i = tid; i < int(kMaxB * kMaxB * 4); i += kThreads) sh.gram_s[i] = 0;
+    for (uint32_t i = tid; i < 2 * kB * RS; i += kThreads) pkbuf[i] = 0;
     if (tid == 0) {
         mbar_init(&sh.mbar[0], 1); mbar_init(&sh.mbar[1], 1);
         mbar_fence_init();
-        sh.n_nonskipped_total = 0;
+        sh.n_nonskipped_total = 0; sh.n_ns = 0; sh.err = 0; sh.miss_blk = 0xffffffffu; sh.miss_n = 0; sh.miss_stored = 0;
+        sh.epsq[0] = 0; sh.epsq[1] = 0;
     }
-    my_sum = warp_sum(my_sum);
-    if (lane == 0) sh.warp_tmp[warp] = my_sum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0) sh.warp_tmp[warp] = amax;
     __syncthreads();
     if (tid == 0) {
-        double s = 0.0;
-        for (int w = 0; w < kWarps; ++w) s += sh.warp_tmp[w];
-        sh.eps_sum_cta = s;
+        double a = 0.0;
+        for (int w = 0; w < kWarps; ++w) a = fmax(a, sh.warp_tmp[w]);
+        atomicMax(p.absmax, (unsigned long long)__double_as_longlong(a));
     }
 
-    // TMA prefetch of one block of plane chunks (issued by warp 1)
+    // TMA prefetch of one block of code rows (issued by warp 1, two rows per lane); rows past the
+    // block's markers are zero-filled so that the fixed 64-row tile structure sees g = 0 there.
     auto prefetch = [&](uint32_t b) {
         const uint32_t nb = min(B, p.n_order - b * B);
-        uint64_t *bar = &sh.mbar[b & 1];
-        unsigned char *dst = planes_s + size_t(b & 1) * B * chunk;
-        if (lane == 0) mbar_arrive_expect_tx(bar, nb * chunk);
-        __syncwarp();
-        if (uint32_t(lane) < nb) {
-            const uint32_t id = p.order[b * B + lane];
-            const uint8_t *src = p.planes + (size_t(id) * p.nCTA + cta) * chunk;
-            bulk_g2s(dst + size_t(lane) * chunk, src, chunk, bar);
+        uint32_t *dst = pkbuf + size_t(b & 1) * kB * RS;
+        if (warp == 1) {
+            uint64_t *bar = &sh.mbar[b & 1];
+            fence_proxy_async();
+            if (lane == 0) mbar_arrive_expect_tx(bar, nb * CB);
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t r = lane + 32 * h;
+                if (r < nb) {
+                    const uint32_t id = p.order[b * B + r];
+                    bulk_g2s(dst + size_t(r) * RS, p.codes + (size_t(id) * p.nCTA + cta) * PW, CB, bar);
+                }
+            }
+        } else if (nb < B && warp >= 2) {
+            for (uint32_t i = (warp - 2) * 32 + lane; i < (B - nb) * PW; i += (kWarps - 2) * 32)
+                dst[size_t(nb + i / PW) * RS + i % PW] = 0;
+        }
+    };
+    if (nBlocks > 0) prefetch(0);
+    if (nBlocks > 1) prefetch(1);
+
+    grid_arrive(p.bar);
+    grid_wait(p.bar, (++bar_gen) * p.nCTA);
+    {   // common fixed-point scale: |q| <= 2^(62 - headroom) at the start of the sweep
+        const double a = __longlong_as_double((long long)__ldcg(p.absmax));
+        int ex = 0;
+        if (a > 0.0) frexp(a, &ex);
+        const int s = 62 - kHeadroomBits - ex;
+        if (tid == 0) { sh.scale = ldexp(1.0, s); sh.inv_scale = ldexp(1.0, -s); }
+    }
+    __syncthreads();
+    const double scale = sh.scale, inv_scale = sh.inv_scale;
+
+    // eps registers -> limbs in shared memory, and this slice's sum of q
+    auto quantize = [&]() {
+        long long shi = 0; unsigned long long slo = 0;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const uint32_t item = tid + it * kThreads;
+            if (item < NI) {
+                uint32_t lo[4], hi[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double x = e[it][t] * scale;
+                    if (!(fabs(x) < 4.0e18)) sh.err = 1u;                       // 2^62 = 4.6e18
+                    const long long q = __double2ll_rn(x);
+                    shi += q >> 32; slo += (unsigned long long)(q & 0xffffffffLL);
+                    const unsigned long long uq = ((unsigned long long)q + 0x8080808080808080ULL) ^ 0x8080808080808080ULL;
+                    lo[t] = (uint32_t)uq; hi[t] = (uint32_t)(uq >> 32);
+                }
+                const uint32_t w = item >> 2, c = item & 3u;
+                uint32_t *dst = reinterpret_cast<uint32_t *>(limbs) + c;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const uint32_t sel = uint32_t(l) | (uint32_t(4 + l) << 4);
+                    const uint32_t x01 = __byte_perm(lo[0], lo[1], sel), x23 = __byte_perm(lo[2], lo[3], sel);
+                    dst[(size_t(l) * RS + w) * 4] = __byte_perm(x01, x23, 0x5410);
+                    const uint32_t y01 = __byte_perm(hi[0], hi[1], sel), y23 = __byte_perm(hi[2], hi[3], sel);
+                    dst[(size_t(4 + l) * RS + w) * 4] = __byte_perm(y01, y23, 0x5410);
+                }
+            }
+        }
+        // block-wide integer sums (order independent)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            shi += __shfl_xor_sync(0xffffffffu, shi, o);
+            slo += __shfl_xor_sync(0xffffffffu, slo, o);
+        }
+        if (lane == 0) { atomicAdd(&sh.epsq[0], (unsigned long long)shi); atomicAdd(&sh.epsq[1], slo); }
+    };
+    quantize();
+
+    // ---- missing-genotype side pass --------------------------------------------------------------
+    // scan the rows [m_lo, m_hi) of a block buffer; list entries (m << 16 | slice-local individual)
+    auto scan_missing = [&](const uint32_t *pk, uint32_t m_lo, uint32_t m_hi) {
+        for (uint32_t idx = tid; idx < (m_hi - m_lo) * PW; idx += kThreads) {
+            const uint32_t m = m_lo + idx / PW, w = idx % PW;
+            const uint32_t x = pk[size_t(m) * RS + w];
+            uint32_t mm = x & (x >> 1) & 0x55555555u;
+            if (mm) {
+                uint32_t pos = atomicAdd(&sh.miss_n, (uint32_t)__popc(mm));
+                while (mm) {
+                    const int bit = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    if (pos < (uint32_t)kMissCap) miss_list[pos] = (m << 16) | (16 * w + (bit >> 1));
+                    ++pos;
+                }
+            }
+        }
+    };
+    // cross counts of the listed entries with every other marker of the block, into scratch (Y | Wlow)
+    auto cross_missing = [&](const uint32_t *pk, uint32_t n, uint32_t nb) {
+        int *Ys = scratch, *As = scratch + 4096;
+        for (uint32_t en = warp; en < n; en += kWarps) {
+            const uint32_t ent = miss_list[en], m = ent >> 16, i = ent & 0xffffu;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t a = lane + 32 * h;
+                if (a < nb && a != m) {
+                    const uint32_t code = (pk[size_t(a) * RS + (i >> 4)] >> (2 * (i & 15u))) & 3u;
+                    if (code == 3u) { if (a < m) atomicAdd(&As[m * kB + a], 1); }
+                    else if (code) atomicAdd(&Ys[a * kB + m], (int)code);
+                }
+            }
+        }
+    };
+
+    // Gram pass of block b: missing scan + cross counts + the 64x64 integer Gram, published into slot b%4
+    auto gram_pass = [&](uint32_t b) {
+        const uint32_t nb = min(B, p.n_order - b * B);
+        const uint32_t *pk = pkbuf + size_t(b & 1) * kB * RS;
+        int *slot = p.slots + size_t(b % kSlots) * kSlotInts;
+        mbar_wait(&sh.mbar[b & 1], (b >> 1) & 1);
+        if (tid == 0) { sh.miss_n = 0; sh.miss_blk = b; }
+        __syncthreads();
+        scan_missing(pk, 0, nb);
+        __syncthreads();
+        const uint32_t n_found = sh.miss_n;
+        if (tid == 0) sh.miss_stored = (n_found <= (uint32_t)kMissCap) ? n_found : 0xffffffffu;
+        if (n_found && tid == 0) atomicAdd(slot + kSlotFlag, 1);
+        const bool want_gram = !p.async_mode && nb > 1;
+        if (n_found && want_gram) {
+            for (int i = tid; i < kScratchInts; i += kThreads) scratch[i] = 0;
+            __syncthreads();
+            if (n_found <= (uint32_t)kMissCap) {
+                cross_missing(pk, n_found, nb);
+            } else {                                   // too many for one list: one marker at a time
+                for (uint32_t m = 0; m < nb; ++m) {
+                    __syncthreads();
+                    if (tid == 0) sh.miss_n = 0;
+                    __syncthreads();
+                    scan_missing(pk, m, m + 1);
+                    __syncthreads();
+                    cross_missing(pk, min(sh.miss_n, (uint32_t)kMissCap), nb);
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < 4096; i += kThreads) {
+                const int y = scratch[i], a = scratch[4096 + i];
+                if (y) atomicAdd(slot + kSlotY + i, y);
+                if (a) atomicAdd(slot + kSlotA + i, a);
+            }
+            __syncthreads();
+        }
+        if (want_gram) {
+            const uint32_t role = warp & 3, kg = warp >> 2, nkg = kWarps / 4;
+            int acc[5][4];
+#pragma unroll
+            for (int t = 0; t < 5; ++t) { acc[t][0] = 0; acc[t][1] = 0; acc[t][2] = 0; acc[t][3] = 0; }
+            switch (role) {
+            case 0: gram_role_pass<0>(pk, RS, NP, kg, nkg, lane, acc); break;
+            case 1: gram_role_pass<1>(pk, RS, NP, kg, nkg, lane, acc); break;
+            case 2: gram_role_pass<2>(pk, RS, NP, kg, nkg, lane, acc); break;
+            default: gram_role_pass<3>(pk, RS, NP, kg, nkg, lane, acc); break;
+            }
+            if (kg > 0) {
+                int *dst = scratch + ((kg - 1) * 4 + role) * 20 * 32;
+#pragma unroll
+                for (int t = 0; t < 5; ++t)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) dst[(t * 4 + r) * 32 + lane] = acc[t][r];
+            }
+            __syncthreads();
+            if (kg == 0) {
+                switch (role) {
+                case 0: gram_role_publish<0>(scratch, nkg, lane, acc, slot + kSlotA, nb); break;
+                case 1: gram_role_publish<1>(scratch, nkg, lane, acc, slot + kSlotA, nb); break;
+                case 2: gram_role_publish<2>(scratch, nkg, lane, acc, slot + kSlotA, nb); break;
+                default: gram_role_publish<3>(scratch, nkg, lane, acc, slot + kSlotA, nb); break;
+                }
+            }
+            __syncthreads();
         }
     };
 
     if (nBlocks > 0) {
-        if (warp == 1) prefetch(0);
-        if (warp == 2) {   // metadata of block 0
-            const uint32_t nb0 = min(B, p.n_order);
-            if (uint32_t(lane) < nb0) {
-                uint32_t id, cnt[4]; int grp; double bo, u, z, lut[4];
-                load_meta_regs(p, lane, id, grp, bo, u, z, lut, cnt);
-                store_meta(sh.meta[0], lane, id, grp, bo, u, z, lut, cnt);
-            }
-        }
+        if (uint32_t(tid) < min(B, p.n_order)) load_block_meta(p, sh.meta, tid, tid);
+        gram_pass(0);
     }
     __syncthreads();
-
-    // thread -> (t,u) positions of the shared eps slice it owns during the residual update
-    constexpr int kMaxR = 16;    // SL <= 16*512 = 8192 individuals per CTA
-    const int R = int((SL + kThreads - 1) / kThreads);
-
-    const uint32_t NG4 = (B + 3) / 4;                 // groups of 4 markers
-    const uint32_t NSEG = max(1u, uint32_t(kWarps) / NG4);
-    const uint32_t UPS = (UP8 + NSEG - 1) / NSEG;     // units per segment
-    const uint32_t NTP = NG4 * (NG4 + 1) / 2;         // 4x4 tile pairs of the Gram matrix
-    const uint32_t NSG = max(1u, (2u * kWarps + NTP - 1) / NTP);   // word segments per tile pair
-    const uint32_t WPS = (PW + NSG - 1) / NSG;
 
     for (uint32_t b = 0; b < nBlocks; ++b) {
         const uint32_t nb = min(B, p.n_order - b * B);
         const uint32_t buf = b & 1;
-        BlockMeta &meta = sh.meta[buf];
-        const unsigned char *pl = planes_s + size_t(buf) * B * chunk;
+        const uint32_t *pk = pkbuf + size_t(buf) * kB * RS;
+        int *slot = p.slots + size_t(b % kSlots) * kSlotInts;
+        BlockMeta &meta = sh.meta;
 
-        // ---- 1. prefetch block b+1 (planes by TMA, metadata into registers) ---------------------
-        uint32_t n_id = 0, n_cnt[4] = {0, 0, 0, 0}; int n_grp = 0; double n_bo = 0, n_u = 0, n_z = 0, n_lut[4] = {0, 0, 0, 0};
-        const bool has_next = (b + 1 < nBlocks);
-        const uint32_t nb_next = has_next ? min(B, p.n_order - (b + 1) * B) : 0;
-        if (has_next) {
-            if (warp == 1) prefetch(b + 1);
-            if (warp == 2 && uint32_t(lane) < nb_next)
-                load_meta_regs(p, (b + 1) * B + lane, n_id, n_grp, n_bo, n_u, n_z, n_lut, n_cnt);
-        }
-
-        // ---- 2. wait for this block's planes ---------------------------------------------------
-        mbar_wait(&sh.mbar[buf], (b >> 1) & 1);
-
-        // ---- 3. partial dots: warp = (marker group mg, unit segment sg) -------------------------
+        // ---- 1. dot pass: S[m][l] = sum_i g'_mi * limb_l(q_i); warp = k-group ------------------------
         {
-            const uint32_t mg = warp % NG4, sg = warp / NG4;
-            if (sg < NSEG) {
-                double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, sm[4] = {0, 0, 0, 0};
-                const uint32_t u0 = sg * UPS, u1 = min(UP8, u0 + UPS);
-                for (uint32_t u = u0 + lane; u < u1; u += 32) {
-                    uint32_t q1[4], q2[4], qm[4], anym = 0;
+            int acc[4][4];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        const uint32_t m = 4 * mg + a;
-                        uint32_t h1 = 0, h2 = 0;
-                        if (m < nb) { h1 = pl[(2 * m) * PB + u]; h2 = pl[(2 * m + 1) * PB + u]; }
-                        q1[a] = h1 & ~h2; q2[a] = h2 & ~h1; qm[a] = h1 & h2; anym |= qm[a];
+            for (int mi = 0; mi < 4; ++mi) { acc[mi][0] = 0; acc[mi][1] = 0; acc[mi][2] = 0; acc[mi][3] = 0; }
+            for (uint32_t pr = warp; pr < NP; pr += kWarps) {
+                const uint32_t wo = 4 * pr + tig;
+                const uint4 L = limbs[size_t(gid) * RS + wo];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    if (16u * mi < nb) {
+                        const uint32_t w0 = pk[(16 * mi + gid) * RS + wo], w1 = pk[(16 * mi + gid + 8) * RS + wo];
+                        mma_u8s8(acc[mi], w0 & kM3, w1 & kM3, (w0 >> 2) & kM3, (w1 >> 2) & kM3, L.x, L.y);
+                        mma_u8s8(acc[mi], (w0 >> 4) & kM3, (w1 >> 4) & kM3, (w0 >> 6) & kM3, (w1 >> 6) & kM3, L.z, L.w);
                     }
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const double e = eps_s[t * UP8 + u];
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            add_if_bit(s1[a], e, q1[a], 1u << t);
-                            add_if_bit(s2[a], e, q2[a], 1u << t);
-                        }
-                    }
-                    if (anym) {
-#pragma unroll 1
-                        for (int a = 0; a < 4; ++a) {
-                            uint32_t q = qm[a];
-                            while (q) {
-                                const int t = __ffs(q) - 1;
-                                q &= q - 1;
-                                sm[a] += eps_s[t * UP8 + u];
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const double r1 = warp_sum(s1[a]), r2 = warp_sum(s2[a]), r3 = warp_sum(sm[a]);
-                    if (lane == 0) { sh.dot_part[warp][a][0] = r1; sh.dot_part[warp][a][1] = r2; sh.dot_part[warp][a][2] = r3; }
                 }
             }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) scratch[(warp * 16 + mi * 4 + r) * 32 + lane] = acc[mi][r];
+            if (uint32_t(tid) < kB) { sh.sm_s[tid][0] = 0; sh.sm_s[tid][1] = 0; }
         }
-
-        // ---- 4. Gram counts by AND+POPC (synchronous mode only) --------------------------------
-        if (!p.async_mode && nb > 1) {
-            for (uint32_t task = warp; task < NTP * NSG; task += kWarps) {
-                const uint32_t tp = task % NTP, seg = task / NTP;
-                uint32_t ta = 0, rem = tp;                 // tp -> (ta <= tb)
-                while (rem >= NG4 - ta) { rem -= NG4 - ta; ++ta; }
-                const uint32_t tb = ta + rem;
-                if (4 * ta >= nb || 4 * tb >= nb) continue;
-                int gg[16], gm[16], mgc[16], mm[16];
+        __syncthreads();
+        {
+            // one output per thread: tile mi = tid/128, register r, lane l
+            int s = 0;
+            const int o = tid;      // (mi*4 + r)*32 + lane
 #pragma unroll
-                for (int i = 0; i < 16; ++i) { gg[i] = 0; gm[i] = 0; mgc[i] = 0; mm[i] = 0; }
-                const uint32_t w0 = seg * WPS, w1 = min(PW, w0 + WPS);
-                for (uint32_t w = w0 + lane; w < w1; w += 32) {
-                    uint32_t a1[4], a2[4], am[4], b1[4], b2[4], bm[4], anym = 0;
+            for (int w = 0; w < kWarps; ++w) s += scratch[w * 512 + o];
+            const int l5 = o & 31, r = (o >> 5) & 3, mi = o >> 7;
+            const uint32_t m = 16 * mi + (l5 >> 2) + 8 * (r >> 1), limb = 2 * (l5 & 3) + (r & 1);
+            if (s != 0 && m < nb) atomicAdd(slot + kSlotDots + m * kLimbs + limb, s);
+            if (tid == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotEps), sh.epsq[0]);
+                atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotEps) + 1, sh.epsq[1]);
+            }
+            // sum of q over the missing individuals of every marker (list built by this block's Gram pass)
+            const uint32_t stored = sh.miss_stored;
+            auto add_entry = [&](uint32_t ent) {
+                const uint32_t m2 = ent >> 16, i = ent & 0xffffu;
+                const uint32_t w = i >> 4, c = i & 3u, t = (i >> 2) & 3u;
+                const uint32_t *lw = reinterpret_cast<const uint32_t *>(limbs) + c;
+                unsigned long long uq = 0;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t mj = 4 * ta + i, mk = 4 * tb + i;
-                        uint32_t x1 = 0, x2 = 0, y1 = 0, y2 = 0;
-                        if (mj < nb) {
-                            x1 = reinterpret_cast<const uint32_t *>(pl + (2 * mj) * PB)[w];
-                            x2 = reinterpret_cast<const uint32_t *>(pl + (2 * mj + 1) * PB)[w];
-                        }
-                        if (mk < nb) {
-                            y1 = reinterpret_cast<const uint32_t *>(pl + (2 * mk) * PB)[w];
-                            y2 = reinterpret_cast<const uint32_t *>(pl + (2 * mk + 1) * PB)[w];
-                        }
-                        a1[i] = x1 & ~x2; a2[i] = x2 & ~x1; am[i] = x1 & x2;
-                        b1[i] = y1 & ~y2; b2[i] = y2 & ~y1; bm[i] = y1 & y2;
-                        anym |= am[i] | bm[i];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            gg[i * 4 + j] += __popc(a1[i] & b1[j]) + 2 * __popc((a1[i] & b2[j]) | (a2[i] & b1[j])) +
-                                             4 * __popc(a2[i] & b2[j]);
-                    if (anym) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                gm[i * 4 + j] += __popc(a1[i] & bm[j]) + 2 * __popc(a2[i] & bm[j]);
-                                mgc[i * 4 + j] += __popc(am[i] & b1[j]) + 2 * __popc(am[i] & b2[j]);
-                                mm[i * 4 + j] += __popc(am[i] & bm[j]);
-                            }
-                    }
+                for (int l = 0; l < kLimbs; ++l)
+                    uq |= (unsigned long long)((lw[(size_t(l) * RS + w) * 4] >> (8 * t)) & 0xffu) << (8 * l);
+                const long long q = (long long)((uq ^ 0x8080808080808080ULL) - 0x8080808080808080ULL);
+                atomicAdd(&sh.sm_s[m2][0], (unsigned long long)(q >> 32));
+                atomicAdd(&sh.sm_s[m2][1], (unsigned long long)(q & 0xffffffffLL));
+            };
+            if (stored != 0xffffffffu) {
+                for (uint32_t en = tid; en < stored; en += kThreads) add_entry(miss_list[en]);
+            } else {                                   // list overflowed: rescan, one marker at a time
+                for (uint32_t m2 = 0; m2 < nb; ++m2) {
+                    __syncthreads();
+                    if (tid == 0) sh.miss_n = 0;
+                    __syncthreads();
+                    scan_missing(pk, m2, m2 + 1);
+                    __syncthreads();
+                    const uint32_t n = min(sh.miss_n, (uint32_t)kMissCap);
+                    for (uint32_t en = tid; en < n; en += kThreads) add_entry(miss_list[en]);
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t mj = 4 * ta + i, mk = 4 * tb + j;
-                        const int r0 = __reduce_add_sync(0xffffffffu, gg[i * 4 + j]);
-                        const int r1 = __reduce_add_sync(0xffffffffu, gm[i * 4 + j]);
-                        const int r2 = __reduce_add_sync(0xffffffffu, mgc[i * 4 + j]);
-                        const int r3 = __reduce_add_sync(0xffffffffu, mm[i * 4 + j]);
-                        if (lane == 0 && mj < mk && mk < nb) {
-                            int *g = &sh.gram_s[(mj * kMaxB + mk) * 4];
-                            if (r0) atomicAdd(g + 0, r0);
-                            if (r1) atomicAdd(g + 1, r1);
-                            if (r2) atomicAdd(g + 2, r2);
-                            if (r3) atomicAdd(g + 3, r3);
-                        }
-                    }
             }
         }
         __syncthreads();
-
-        // ---- 5. publish this CTA's partials ----------------------------------------------------
-        {
-            const uint32_t par = b & 1;
-            if (uint32_t(tid) < nb) {
-                const uint32_t m = tid, mg = m / 4, a = m % 4;
-                double S1 = 0, S2 = 0, Sm = 0;
-                for (uint32_t sg = 0; sg < NSEG; ++sg) {
-                    const uint32_t w = sg * NG4 + mg;
-                    S1 += sh.dot_part[w][a][0]; S2 += sh.dot_part[w][a][1]; Sm += sh.dot_part[w][a][2];
-                }
-                const double *L = meta.lut[m];
-                const double y = (L[1] - L[0]) * S1 + (L[2] - L[0]) * S2 + (L[3] - L[0]) * Sm;
-                p.part_dot[(size_t(par) * p.nCTA + cta) * kMaxB + m] = y;
-            }
-            if (tid == 32) p.part_eps[size_t(par) * p.nCTA + cta] = sh.eps_sum_cta;
-            if (!p.async_mode && nb > 1) {
-                int *gg = p.gram + size_t(b % kGramBuffers) * (kMaxB * kMaxB * 4);
-                for (uint32_t i = tid; i < nb * kMaxB * 4; i += kThreads) {
-                    const int vv = sh.gram_s[i];
-                    if (vv) { atomicAdd(gg + i, vv); sh.gram_s[i] = 0; }
-                }
-            }
+        if (uint32_t(tid) < nb && (sh.sm_s[tid][0] | sh.sm_s[tid][1])) {
+            unsigned long long *g = reinterpret_cast<unsigned long long *>(slot + kSlotSm) + 2 * tid;
+            atomicAdd(g, sh.sm_s[tid][0]); atomicAdd(g + 1, sh.sm_s[tid][1]);
         }
 
-        // ---- 6. the one grid-wide exchange per block --------------------------------------------
+        // ---- 2. the one grid-wide exchange per block: arrive ... ------------------------------------
         grid_arrive(p.bar);
-        grid_wait(p.bar, (b + 1) * p.nCTA);
 
-        // ---- 7. reduce partials in a fixed order (identical in every CTA) ------------------------
-        {
-            const uint32_t par = b & 1;
-            const double *pd = p.part_dot + size_t(par) * p.nCTA * kMaxB;
-            const double *pe = p.part_eps + size_t(par) * p.nCTA;
-            // all loads first (independent, L2 latency paid once), then a fixed-order sum
-            constexpr int kMaxPerWarp = 12;          // nCTA <= 16*12 = 192
-            double vals[kMaxPerWarp];
-#pragma unroll
-            for (int i = 0; i < kMaxPerWarp; ++i) {
-                const uint32_t c = warp + i * kWarps;
-                vals[i] = (c < p.nCTA && uint32_t(lane) < nb) ? ld_cg(pd + size_t(c) * kMaxB + lane) : 0.0;
-            }
-            const double ev = (uint32_t(tid) < p.nCTA) ? ld_cg(pe + tid) : 0.0;
-            double acc = 0.0;
-#pragma unroll
-            for (int i = 0; i < kMaxPerWarp; ++i) acc += vals[i];
-            sh.red_part[warp][lane] = acc;
-            const double es = warp_sum(ev);
-            if (lane == 0) sh.red_part[warp][kMaxB] = es;
-            if (cta == 0 && !p.async_mode) {   // recycle the Gram buffer block b+3 will accumulate into
-                int *gz = p.gram + size_t((b + 3) % kGramBuffers) * (kMaxB * kMaxB * 4);
-                for (uint32_t i = tid; i < kMaxB * kMaxB * 4; i += kThreads) gz[i] = 0;
-            }
-        }
-        __syncthreads();
-        if (uint32_t(tid) <= kMaxB) {
-            double s = 0.0;
-            for (int w = 0; w < kWarps; ++w) s += sh.red_part[w][tid];
-            if (tid == kMaxB) sh.eps_sum_total = s; else sh.dsum[tid] = s;
-        }
+        // ---- 3. ... and hide its latency behind the Gram pass of the next block ----------------------
+        if (b > 0 && uint32_t(tid) < nb) load_block_meta(p, meta, b * B + tid, tid);     // meta of block b-1 is dead
+        if (b + 1 < nBlocks) gram_pass(b + 1);
+
+        // ---- 4. wait -----------------------------------------------------------------------------------
+        grid_wait(p.bar, (++bar_gen) * p.nCTA);
+
+        // ---- 5. read the reduced block back ----------------------------------------------------------------
+        const bool has_missing = __ldcg(slot + kSlotFlag) != 0;
         if (!p.async_mode && nb > 1) {
-            const int *gg = p.gram + size_t(b % kGramBuffers) * (kMaxB * kMaxB * 4);
-            const double Nt = double(p.n_total);
-            for (uint32_t pr = tid; pr < nb * nb; pr += kThreads) {
-                const uint32_t j = pr / nb, k = pr % nb;
-                if (j < k) {
-                    const int4 c = __ldcg(reinterpret_cast<const int4 *>(gg + (j * kMaxB + k) * 4));
-                    const double cj = meta.cj[j], ck = meta.cj[k], ej = meta.ej[j], ek = meta.ej[k];
-                    double t = double(c.x) - ck * meta.sumg[j] - cj * meta.sumg[k] + Nt * cj * ck;
-                    t += ek * double(c.y) + ej * double(c.z) - cj * ek * meta.nmiss[k] - ck * ej * meta.nmiss[j] +
-                         ej * ek * double(c.w);
-                    const double g = meta.sj[j] * meta.sj[k] * t;
-                    sh.G[j * kMaxB + k] = g;
-                    sh.G[k * kMaxB + j] = g;
-                }
+            const int4 *src = reinterpret_cast<const int4 *>(slot + kSlotA);
+            int4 *dst = reinterpret_cast<int4 *>(scratch);
+            const int n4 = has_missing ? 2048 : 1024;          // A, then Y
+            for (int i = tid; i < n4; i += kThreads) dst[i] = __ldcg(src + i);
+        }
+        if (tid == 0) {
+            const long long *eq = reinterpret_cast<const long long *>(slot + kSlotEps);
+            const long long hi = __ldcg(eq), lo = __ldcg(eq + 1);
+            sh.eps_sum_total = (double(hi) * 4294967296.0 + double(lo)) * inv_scale;
+        }
+        __syncthreads();
+        if (uint32_t(tid) < nb) {
+            const int4 *dp = reinterpret_cast<const int4 *>(slot + kSlotDots + tid * kLimbs);
+            const int4 d_lo = __ldcg(dp), d_hi = __ldcg(dp + 1);
+            const long long tlo = (long long)d_lo.x + ((long long)d_lo.y << 8) + ((long long)d_lo.z << 16) + ((long long)d_lo.w << 24);
+            const long long thi = (long long)d_hi.x + ((long long)d_hi.y << 8) + ((long long)d_hi.z << 16) + ((long long)d_hi.w << 24);
+            const double dprime = (double(thi) * 4294967296.0 + double(tlo)) * inv_scale;    // sum_i g'_i eps_i
+            double smd = 0.0;
+            if (has_missing) {
+                const long long *sp = reinterpret_cast<const long long *>(slot + kSlotSm) + 2 * tid;
+                smd = (double(__ldcg(sp)) * 4294967296.0 + double(__ldcg(sp + 1))) * inv_scale;
             }
+            const double *L = meta.lut[tid];
+            // x.eps = L0 sum(eps) + s (S1 + 2 S2) + (L3 - L0) Smissing ; the products saw missing as 3
+            sh.d0[tid] = L[0] * sh.eps_sum_total + meta.sj[tid] * (dprime - 3.0 * smd) + (L[3] - L[0]) * smd;
+        }
+        // recycle the slot of block b-1 (every CTA has read it before arriving at this block's barrier)
+        if (cta == b % p.nCTA) {
+            int4 *z = reinterpret_cast<int4 *>(p.slots + size_t((b + kSlots - 1) % kSlots) * kSlotInts);
+            for (int i = tid; i < kSlotInts / 4; i += kThreads) z[i] = make_int4(0, 0, 0, 0);
         }
         __syncthreads();
 
-        // ---- 8. the walk: one warp, lane = marker of the block ----------------------------------
+        // ---- 6. the walk: one warp, two half-blocks of 32 lanes ---------------------------------------------
         if (warp == 0) {
-            const int k = lane;
-            const bool act = uint32_t(k) < nb;
-            const double bo = act ? meta.beta_old[k] : 0.0;
-            const double uu = act ? meta.u[k] : 2.0, zz = act ? meta.z[k] : 0.0;
-            const int g = act ? meta.grp[k] : 0;
-            const double d0 = act ? (meta.lut[k][0] * sh.eps_sum_total + sh.dsum[k]) : 0.0;
-            double corr = 0.0;
-            Draw dr; dr.beta_new = bo; dr.acum0 = 0.0; dr.comp = -1;
-            uint32_t done = 0;
-            while (true) {
-                const bool live = act && uint32_t(k) >= done;
-                if (live) dr = sample_marker_k(sh.gc, g, K, d0 + corr + bo * NM1, p.sigmaE, bo, uu, zz);
-                const bool ns = live && !(bo == 0.0 && dr.beta_new == 0.0);
-                const unsigned mask = __ballot_sync(0xffffffffu, ns);
-                if (p.async_mode || mask == 0) break;
-                const int js = __ffs(mask) - 1;
-                const double dB = __shfl_sync(0xffffffffu, bo - dr.beta_new, js);   // eps += dB * x_js
-                if (k > js && act) corr += dB * sh.G[js * kMaxB + k];
-                done = js + 1;
-                if (done >= nb) break;
-            }
-            const double dB = act ? (bo - dr.beta_new) : 0.0;
-            const bool upd = act && dB != 0.0;
-            const bool nonskip = act && !(bo == 0.0 && dr.beta_new == 0.0);
-            if (act) sh.dbeta[k] = dB;
-            const unsigned um = __ballot_sync(0xffffffffu, upd);
-            if (upd) sh.ns_list[__popc(um & ((1u << k) - 1u))] = k;
-            const unsigned nsm = __ballot_sync(0xffffffffu, nonskip);
-            if (lane == 0) { sh.n_ns = __popc(um); sh.n_nonskipped_total += __popc(nsm); }
-            if (cta == 0 && act) {
-                const uint32_t id = meta.id[k];
-                if (!p.async_mode) p.acum[id] = dr.acum0;                  // src/BayesRBase.cpp:341
-                if (dr.comp >= 0) {
-                    p.beta[id] = dr.beta_new;                              // :350-352 / :492
-                    p.comp[id] = double(dr.comp);                          // :356 / :493
-                    atomicAdd(&sh.v_s[g * K + dr.comp], 1);                // :355 / :511
+            const int *As = scratch, *Ys = scratch + 4096;
+            uint32_t n_upd = 0, n_nonskip = 0;
+            for (uint32_t sub = 0; sub * 32 < nb; ++sub) {
+                const int k = sub * 32 + lane;
+                const bool act = uint32_t(k) < nb;
+                const double bo = act ? meta.beta_old[k] : 0.0;
+                const double uu = act ? meta.u[k] : 2.0, zz = act ? meta.z[k] : 0.0;
+                const int g = act ? meta.grp[k] : 0;
+                const double d0 = act ? sh.d0[k] : 0.0;
+                double corr = 0.0;
+                if (!p.async_mode && act)
+                    for (uint32_t q = 0; q < n_upd; ++q) {
+                        const int js = sh.ns_list[q];
+                        corr += sh.dbeta[js] * gram_entry(meta, As, Ys, has_missing, js, k, Nt);
+                    }
+                Draw dr; dr.beta_new = bo; dr.acum0 = 0.0; dr.comp = -1;
+                uint32_t done = 0;
+                while (true) {
+                    const bool live = act && uint32_t(lane) >= done;
+                    if (live) dr = sample_marker_k(sh.gc, g, K, d0 + corr + bo * NM1, p.sigmaE, bo, uu, zz);
+                    const bool ns = live && !(bo == 0.0 && dr.beta_new == 0.0);
+                    const unsigned mask = __ballot_sync(0xffffffffu, ns);
+                    if (p.async_mode || mask == 0) break;
+                    const int jl = __ffs(mask) - 1;
+                    const double dB = __shfl_sync(0xffffffffu, bo - dr.beta_new, jl);   // eps += dB * x_js
+                    if (lane > jl && act && dB != 0.0) corr += dB * gram_entry(meta, As, Ys, has_missing, sub * 32 + jl, k, Nt);
+                    done = jl + 1;
+                    if (sub * 32 + done >= nb) break;
                 }
-            }
-            if (cta == 0) {
-                for (uint32_t gi = 0; gi < p.nG; ++gi) {                   // :353 / :522
-                    const double b2 = (act && g == int(gi) && dr.comp > 0) ? dr.beta_new * dr.beta_new : 0.0;
-                    const double s = warp_sum(b2);
-                    if (lane == 0) sh.betasq_s[gi] += s;
+                const double dB = act ? (bo - dr.beta_new) : 0.0;
+                const bool upd = act && dB != 0.0;
+                const bool nonskip = act && !(bo == 0.0 && dr.beta_new == 0.0);
+                if (act) sh.dbeta[k] = dB;
+                const unsigned um = __ballot_sync(0xffffffffu, upd);
+                if (upd) sh.ns_list[n_upd + __popc(um & ((1u << lane) - 1u))] = k;
+                n_upd += __popc(um);
+                n_nonskip += __popc(__ballot_sync(0xffffffffu, nonskip));
+                if (cta == 0 && act) {
+                    const uint32_t id = meta.id[k];
+                    if (!p.async_mode) p.acum[id] = dr.acum0;                  // src/BayesRBase.cpp:341
+                    if (dr.comp >= 0) {
+                        p.beta[id] = dr.beta_new;                              // :350-352 / :492
+                        p.comp[id] = double(dr.comp);                          // :356 / :493
+                        atomicAdd(&sh.v_s[g * K + dr.comp], 1);                // :355 / :511
+                    }
                 }
+                if (cta == 0) {
+                    for (uint32_t gi = 0; gi < p.nG; ++gi) {                   // :353 / :522
+                        const double b2 = (act && g == int(gi) && dr.comp > 0) ? dr.beta_new * dr.beta_new : 0.0;
+                        const double s = warp_sum(b2);
+                        if (lane == 0) sh.betasq_s[gi] += s;
+                    }
+                }
+                __syncwarp();
             }
+            if (lane == 0) { sh.n_ns = n_upd; sh.n_nonskipped_total += n_nonskip; }
         }
         __syncthreads();
 
-        // ---- 9. residual update on the shared-memory slice -------------------------------------
-        {
-            const uint32_t n_ns = sh.n_ns;
-            double lsum = 0.0;
-            for (int r = 0; r < R && r < kMaxR; ++r) {
-                const uint32_t pos = tid + r * kThreads;          // position in eps_s
-                if (pos >= SL) break;
-                const uint32_t t = pos / UP8, u = pos - t * UP8;
-                const uint32_t gi = slice0 + 8 * u + t;
-                double e = eps_s[pos];
-                if (gi < p.n_local) {
+        // ---- 7. residual update in registers, re-quantise --------------------------------------------------
+        const uint32_t n_ns = sh.n_ns;
+        if (n_ns) {
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const uint32_t item = tid + it * kThreads;
+                if (item < NI) {
+                    const uint32_t w = item >> 2, c2 = 2 * (item & 3u);
                     for (uint32_t q = 0; q < n_ns; ++q) {
                         const uint32_t m = sh.ns_list[q];
-                        const uint32_t h1 = pl[(2 * m) * PB + u], h2 = pl[(2 * m + 1) * PB + u];
-                        const uint32_t code = ((h1 >> t) & 1u) | (((h2 >> t) & 1u) << 1);
-                        e += sh.dbeta[m] * meta.lut[m][code];             // eps += (beta_old-beta) * x
+                        const double dB = sh.dbeta[m];
+                        const uint32_t r = (pk[size_t(m) * RS + w] >> c2) & kM3;
+                        const double *L = meta.lut[m];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) e[it][t] += dB * L[(r >> (8 * t)) & 3u];   // eps += (beta_old-beta) * x
                     }
-                    if (n_ns) eps_s[pos] = e;
-                    lsum += e;
                 }
             }
-            lsum = warp_sum(lsum);
-            if (lane == 0) sh.warp_tmp[warp] = lsum;
+            if (tid == 0) { sh.epsq[0] = 0; sh.epsq[1] = 0; }
+            __syncthreads();
+            // individuals past n_local carry eps = 0 and code 0, so their lut[0] increments must not stick
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const uint32_t item = tid + it * kThreads;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t gi = slice0 + 16 * (item >> 2) + 4 * t + (item & 3u);
+                    if (gi >= p.n_local) e[it][t] = 0.0;
+                }
+            }
+            quantize();
         }
-        // metadata of the next block: registers -> shared (loads were issued at the top)
-        if (has_next && warp == 2 && uint32_t(lane) < nb_next)
-            store_meta(sh.meta[buf ^ 1], lane, n_id, n_grp, n_bo, n_u, n_z, n_lut, n_cnt);
         __syncthreads();
-        if (tid == 0) {
-            double s = 0.0;
-            for (int w = 0; w < kWarps; ++w) s += sh.warp_tmp[w];
-            sh.eps_sum_cta = s;
-        }
-        __syncthreads();
+
+        // ---- 8. this buffer is free: prefetch block b+2 into it ------------------------------------------
+        if (b + 2 < nBlocks) prefetch(b + 2);
     }
 
     // ---- epilogue: eps back to HBM, sweep scalars ------------------------------------------------
     double sq = 0.0;
-    for (uint32_t i = tid; i < SL; i += kThreads) {
-        const uint32_t gi = slice0 + i;
-        if (gi < p.n_local) {
-            const double e = eps_s[(i & 7u) * UP8 + (i >> 3)];
-            p.eps[gi] = e;
-            sq += e * e;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const uint32_t item = tid + it * kThreads;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint32_t gi = slice0 + 16 * (item >> 2) + 4 * t + (item & 3u);
+            if (item < NI && gi < p.n_local) { p.eps[gi] = e[it][t]; sq += e[it][t] * e[it][t]; }
         }
     }
     sq = warp_sum(sq);
@@ -519,12 +721,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     if (tid == 0) {
         double s = 0.0;
         for (int w = 0; w < kWarps; ++w) s += sh.warp_tmp[w];
-        p.cta_red[2 * cta + 0] = sh.eps_sum_cta;
+        // this slice's sum(eps) from the exact fixed-point sum
+        p.cta_red[2 * cta + 0] = (double((long long)sh.epsq[0]) * 4294967296.0 + double((long long)sh.epsq[1])) * inv_scale;
         p.cta_red[2 * cta + 1] = s;
+        if (sh.err) atomicOr(p.out_counts + 2, sh.err);
     }
     grid_arrive(p.bar);
     if (cta == 0) {
-        grid_wait(p.bar, (nBlocks + 1) * p.nCTA);
+        grid_wait(p.bar, (++bar_gen) * p.nCTA);
         if (warp == 0) {
             double s = 0.0, q = 0.0;
             for (uint32_t c = lane; c < p.nCTA; c += 32) { s += ld_cg(p.cta_red + 2 * c); q += ld_cg(p.cta_red + 2 * c + 1); }

@@ -52,7 +52,7 @@ struct RaggedSweepParams {
     double sigmaE, eps_sum_in;
     uint32_t async_mode;
     double *eps, *beta, *comp, *acum;
-    double *part_dot;              // [2][nCTA][kMaxB]
+    double *part_dot;              // [2][nCTA][kMaxW]
     unsigned *bar;
     double *cta_red;               // [nCTA][2]
     double *v, *betasq, *out_scalars;
@@ -60,20 +60,20 @@ struct RaggedSweepParams {
 };
 
 struct RaggedMeta {
-    uint32_t id[kMaxB];
-    int32_t grp[kMaxB];
-    double beta_old[kMaxB], u[kMaxB], z[kMaxB];
-    double mean[kMaxB], sd[kMaxB], zsum[kMaxB];
-    uint32_t s0[kMaxB], s1[kMaxB], s2[kMaxB], s3[kMaxB];   // this CTA's segment bounds
+    uint32_t id[kMaxW];
+    int32_t grp[kMaxW];
+    double beta_old[kMaxW], u[kMaxW], z[kMaxW];
+    double mean[kMaxW], sd[kMaxW], zsum[kMaxW];
+    uint32_t s0[kMaxW], s1[kMaxW], s2[kMaxW], s3[kMaxW];   // this CTA's segment bounds
 };
 
 struct RaggedShared {
     GroupConsts gc;
     RaggedMeta meta;
     double dot_part[kWarps][2];
-    double red_part[kWarps][kMaxB];
-    double dsum[kMaxB];
-    double dbeta[kMaxB];
+    double red_part[kWarps][kMaxW];
+    double dsum[kMaxW];
+    double dbeta[kMaxW];
     double warp_tmp[kWarps];
     double betasq_s[kMaxGK];
     int v_s[kMaxGK];
@@ -167,19 +167,19 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_ragged_kernel(const RaggedS
         }
         __syncthreads();
         if (uint32_t(tid) < nb)
-            p.part_dot[(size_t(pass & 1) * p.nCTA + cta) * kMaxB + tid] = sh.red_part[0][tid] + sh.red_part[1][tid];
+            p.part_dot[(size_t(pass & 1) * p.nCTA + cta) * kMaxW + tid] = sh.red_part[0][tid] + sh.red_part[1][tid];
         grid_arrive(p.bar);
         grid_wait(p.bar, (pass + 1) * p.nCTA);
         {
-            const double *pd = p.part_dot + size_t(pass & 1) * p.nCTA * kMaxB;
+            const double *pd = p.part_dot + size_t(pass & 1) * p.nCTA * kMaxW;
             double acc = 0.0;
             if (uint32_t(lane) < nb)
-                for (uint32_t c = warp; c < p.nCTA; c += kWarps) acc += ld_cg(pd + size_t(c) * kMaxB + lane);
+                for (uint32_t c = warp; c < p.nCTA; c += kWarps) acc += ld_cg(pd + size_t(c) * kMaxW + lane);
             __syncthreads();                  // red_part scratch rows were read above
             sh.red_part[warp][lane] = acc;
         }
         __syncthreads();
-        if (uint32_t(tid) < kMaxB) {
+        if (uint32_t(tid) < kMaxW) {
             double s = 0.0;
             for (int w = 0; w < kWarps; ++w) s += sh.red_part[w][tid];
             sh.dsum[tid] = s;
