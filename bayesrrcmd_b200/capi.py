@@ -21,7 +21,7 @@ SYMBOLS = [
     "brr_gpu_sweep", "brr_gpu_sweep_stage", "brr_gpu_sweep_run", "brr_gpu_sweep_fetch", "brr_gpu_compute_num",
     "brr_gpu_apply_delta", "brr_gpu_ipc_export", "brr_gpu_ipc_attach", "brr_gpu_block_stats", "brr_gpu_block_finish",
     "brr_gpu_num_blocks", "brr_gpu_stream", "brr_gpu_synth_dense", "brr_gpu_synth_bed_host", "brr_gpu_info",
-    "brr_gpu_launch_count",
+    "brr_gpu_launch_count", "brr_gpu_profile_cycles",
 ]
 
 
@@ -89,6 +89,7 @@ def load_library():
     lib.brr_gpu_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64)]
     lib.brr_gpu_launch_count.argtypes = [vp]
     lib.brr_gpu_launch_count.restype = C.c_uint64
+    lib.brr_gpu_profile_cycles.argtypes = [vp, vp, C.c_int]
     _lib = lib
     return lib
 
@@ -258,6 +259,15 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.brr_gpu_launch_count(self._h))
+
+    PROFILE_PHASES = ["dot", "dot_reduce", "gram_scan", "gram_cross", "gram_mma", "gram_reduce", "barrier_wait", "readback",
+                      "walk", "axpy", "quantize", "prologue", "walk_iters", "walk_solves", "walk_a", "gram_wait"]
+
+    def profile_cycles(self, reset=True):
+        """Phase cycle counters of the dense sweep kernel (needs BRR_GPU_PROFILE=1 at construction)."""
+        a = np.zeros(16, dtype=np.uint64)
+        self._check(self.lib.brr_gpu_profile_cycles(self._h, _ptr(a), int(reset)))
+        return dict(zip(self.PROFILE_PHASES, (int(x) for x in a)))
 
     def stream(self):
         return self.lib.brr_gpu_stream(self._h)

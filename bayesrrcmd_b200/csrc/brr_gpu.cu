@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -72,6 +73,7 @@ struct brr_gpu_ctx {
     unsigned *bar = nullptr;
     double *v = nullptr, *betasq = nullptr, *out_scalars = nullptr;
     unsigned *out_counts = nullptr;
+    unsigned long long *prof = nullptr;     // phase cycle counters (BRR_GPU_PROFILE=1)
     // pinned host mirrors for the small outputs
     double *h_small = nullptr;   // [kMaxGK + kMaxGK + 2 + 2*1024]
     unsigned *h_counts = nullptr;
@@ -105,7 +107,7 @@ extern "C" void brr_gpu_destroy(brr_gpu_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->codes, c->lut, c->counts_local, c->counts_global, c->group, c->cva, c->eps, c->beta, c->comp,
                     c->acum, c->order, c->rand_uz, c->pi, c->sigmaG, c->part_dot, c->cta_red,
-                    c->red_partial, c->slots, c->v, c->betasq, c->out_scalars, c->out_counts,
+                    c->red_partial, c->slots, c->v, c->betasq, c->out_scalars, c->out_counts, c->prof,
                     c->rag.idx16, c->rag.cta_base, c->rag.stats, c->rag.seg};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_small) cudaFreeHost(c->h_small);
@@ -232,6 +234,12 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
     TRY_OR_DESTROY(dev_alloc(&c->betasq, nG));
     TRY_OR_DESTROY(dev_alloc(&c->out_scalars, 4));
     TRY_OR_DESTROY(dev_alloc(&c->out_counts, 4));
+    if (const char *e = getenv("BRR_GPU_PROFILE")) {
+        if (e[0] == '1') {
+            TRY_OR_DESTROY(dev_alloc(&c->prof, 16));
+            CUDA_OR_DESTROY(cudaMemset(c->prof, 0, sizeof(unsigned long long) * 16));
+        }
+    }
     CUDA_OR_DESTROY(cudaMallocHost(reinterpret_cast<void **>(&c->h_small), sizeof(double) * (2 * kMaxGK + 8 + 2 * kRedBlocks)));
     CUDA_OR_DESTROY(cudaMallocHost(reinterpret_cast<void **>(&c->h_counts), sizeof(unsigned) * 8));
     CUDA_OR_DESTROY(cudaMemsetAsync(c->eps, 0, sizeof(double) * N, c->stream));
@@ -462,6 +470,7 @@ static int launch_dense(brr_gpu_ctx *c)
     p.eps = c->eps; p.beta = c->beta; p.comp = c->comp; p.acum = c->acum;
     p.slots = c->slots; p.absmax = c->absmax; p.bar = c->bar; p.cta_red = c->cta_red;
     p.v = c->v; p.betasq = c->betasq; p.out_scalars = c->out_scalars; p.out_counts = c->out_counts;
+    p.prof = c->prof;
     CUDA_TRY(cudaMemsetAsync(c->slots, 0, sizeof(int) * (size_t(kSlots) * kSlotInts + 8), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->out_counts, 0, sizeof(unsigned) * 4, c->stream));
     void *args[] = {&p};
@@ -637,6 +646,17 @@ extern "C" int brr_gpu_info(brr_gpu_ctx *c, uint32_t *n_ctas, uint32_t *slice_in
 }
 
 extern "C" uint64_t brr_gpu_launch_count(brr_gpu_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int brr_gpu_profile_cycles(brr_gpu_ctx *c, uint64_t *cycles16, int reset)
+{
+    CHECK_CTX(c);
+    if (!cycles16) return fail(BRR_GPU_EINVAL, "null output");
+    if (!c->prof) return fail(BRR_GPU_ESTATE, "phase profiling is off: set BRR_GPU_PROFILE=1 before brr_gpu_create");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(cycles16, c->prof, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost));
+    if (reset) CUDA_TRY(cudaMemset(c->prof, 0, sizeof(uint64_t) * 16));
+    return 0;
+}
 extern "C" void *brr_gpu_stream(brr_gpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 #include "ragged_host.inl"

@@ -15,6 +15,8 @@ struct GroupConsts {
     double denom[kMaxGK];    // (N-1) + sigmaE/sigmaG[g] * (1/cva[g][k-1])  k>=1 (:316-317)
     double sdev[kMaxGK];     // sqrt(sigmaE / denom)                        k>=1 (:352)
     double halfLog[kMaxGK];  // 0.5 * log(sigmaG/sigmaE*(N-1)*cva + 1)      k>=1 (:329,332)
+    double invDenom[kMaxGK]; // 1 / denom: the walk multiplies instead of dividing (1 ulp, see sample_marker_fast_t)
+    double halfInvSigmaE;    // 0.5 / sigmaE
 };
 
 // called by all threads of a CTA; every CTA computes the identical table
@@ -32,12 +34,14 @@ __device__ inline void fill_group_consts(GroupConsts &gc, int nG, int K, double 
             const double denom = NM1 + sigmaEOverSigmaG * (1.0 / c);
             const double logLScale = sG / sigmaE * NM1;
             gc.denom[i] = denom;
+            gc.invDenom[i] = 1.0 / denom;
             gc.sdev[i] = sqrt(sigmaE / denom);
             gc.halfLog[i] = 0.5 * log(logLScale * c + 1.0);
         } else {
-            gc.denom[i] = 1.0; gc.sdev[i] = 0.0; gc.halfLog[i] = 0.0;
+            gc.denom[i] = 1.0; gc.invDenom[i] = 1.0; gc.sdev[i] = 0.0; gc.halfLog[i] = 0.0;
         }
     }
+    if (threadIdx.x == 0) gc.halfInvSigmaE = 0.5 / sigmaE;
 }
 
 struct Draw {
@@ -53,7 +57,7 @@ __device__ __forceinline__ Draw sample_marker_t(const GroupConsts &gc, int g, in
 {
     const int K = KT > 0 ? KT : Krt;
     const double *logPi = gc.logPi + g * K;
-    const double *denom = gc.denom + g * K;
+    const double *invDenom = gc.invDenom + g * K;
     const double *sdev = gc.sdev + g * K;
     const double *halfLog = gc.halfLog + g * K;
     double logL[KT > 0 ? KT : kMaxK], muk[KT > 0 ? KT : kMaxK];
@@ -62,7 +66,7 @@ __device__ __forceinline__ Draw sample_marker_t(const GroupConsts &gc, int g, in
     bool big = false;
 #pragma unroll
     for (int k = 1; k < K; ++k) {
-        muk[k] = num / denom[k];                                            // :325
+        muk[k] = num * invDenom[k];                                         // :325 (same muk as the fast path and the walk's solve)
         logL[k] = logPi[k] - halfLog[k] + 0.5 * (muk[k] * num) / sigmaE;   // :331-333
         big |= fabs(logL[k] - logL[0]) > 700.0;                             // :335
     }
@@ -80,7 +84,7 @@ __device__ __forceinline__ Draw sample_marker_t(const GroupConsts &gc, int g, in
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         if (u <= acum) {                                                    // :347
-            d.beta_new = (k == 0) ? 0.0 : z * sdev[k] + muk[k];             // :350-352
+            d.beta_new = (k == 0) ? 0.0 : __fma_rn(z, sdev[k], muk[k]);     // :350-352
             d.comp = k;
             break;
         }
@@ -104,17 +108,80 @@ __device__ inline Draw sample_marker(const GroupConsts &gc, int g, int K, double
     return sample_marker_t<0>(gc, g, K, num, sigmaE, beta_old, u, z);
 }
 
+// The same draw with K exponentials instead of up to K*K: when no |logL_a - logL_b| can exceed the
+// reference's 700 guard (:335, :360), 1/sum_l exp(logL_l - logL_k) == exp(logL_k - logL_0) * acum0 up to
+// rounding, so the cumulative probabilities of components k >= 1 reuse the first pass.  acum0 (what the
+// reference stores in m_acum) is computed by the reference's own expression and is bit-identical; the
+// guarded (huge |num|) case falls back to the literal restatement above.  The two divisions per
+// component (num/denom, ./sigmaE) are multiplications by reciprocals hoisted into GroupConsts: the chain is
+// a latency-bound serial section, and a 1-ulp difference in muk / logL is far inside the 1e-8 replay gate.
+template <int KT>
+__device__ __forceinline__ Draw sample_marker_fast_t(const GroupConsts &gc, int g, int Krt, double num, double sigmaE,
+                                                     double beta_old, double u, double z)
+{
+    static_assert(KT >= 2, "compile-time component count required");
+    constexpr int K = KT;
+    const double *logPi = gc.logPi + g * K;
+    const double *invDenom = gc.invDenom + g * K;
+    const double *sdev = gc.sdev + g * K;
+    const double *halfLog = gc.halfLog + g * K;
+    const double hise = gc.halfInvSigmaE;
+    double logL[K], muk[K], ex[K];
+    muk[0] = 0.0;
+    logL[0] = logPi[0];
+    double mx = logL[0], mn = logL[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+        muk[k] = num * invDenom[k];                                         // :325 (num / denom, to 1 ulp)
+        logL[k] = logPi[k] - halfLog[k] + (muk[k] * num) * hise;           // :331-333
+        mx = fmax(mx, logL[k]); mn = fmin(mn, logL[k]);
+    }
+    if (!(mx - mn <= 700.0)) return sample_marker_t<KT>(gc, g, Krt, num, sigmaE, beta_old, u, z);
+    double s = 1.0;                                                          // exp(logL[0] - logL[0])
+    ex[0] = 1.0;
+#pragma unroll
+    for (int l = 1; l < K; ++l) ex[l] = exp(logL[l] - logL[0]);
+#pragma unroll
+    for (int l = 1; l < K; ++l) s += ex[l];
+    double acum = 1.0 / s;                                                  // :338
+    Draw d;
+    d.acum0 = acum;
+    d.beta_new = beta_old;
+    d.comp = -1;
+    const double p0 = acum;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (u <= acum) {                                                    // :347
+            d.beta_new = (k == 0) ? 0.0 : __fma_rn(z, sdev[k], muk[k]);     // :350-352
+            d.comp = k;
+            break;
+        }
+        if (k + 1 == K) break;
+        acum += ex[k + 1] * p0;                                             // :363
+    }
+    return d;
+}
+
 // dispatch on the common component counts so that muk/logL live in registers
 __device__ __forceinline__ Draw sample_marker_k(const GroupConsts &gc, int g, int K, double num, double sigmaE,
                                                 double beta_old, double u, double z)
 {
     switch (K) {
-    case 2: return sample_marker_t<2>(gc, g, K, num, sigmaE, beta_old, u, z);
-    case 3: return sample_marker_t<3>(gc, g, K, num, sigmaE, beta_old, u, z);
-    case 4: return sample_marker_t<4>(gc, g, K, num, sigmaE, beta_old, u, z);
-    case 5: return sample_marker_t<5>(gc, g, K, num, sigmaE, beta_old, u, z);
+    case 2: return sample_marker_fast_t<2>(gc, g, K, num, sigmaE, beta_old, u, z);
+    case 3: return sample_marker_fast_t<3>(gc, g, K, num, sigmaE, beta_old, u, z);
+    case 4: return sample_marker_fast_t<4>(gc, g, K, num, sigmaE, beta_old, u, z);
+    case 5: return sample_marker_fast_t<5>(gc, g, K, num, sigmaE, beta_old, u, z);
     default: return sample_marker_t<0>(gc, g, K, num, sigmaE, beta_old, u, z);
     }
+}
+
+// beta of a marker whose component is already known (the walk's triangular solve), :350-352
+__device__ __forceinline__ double beta_given_comp(const GroupConsts &gc, int g, int K, int comp, double num,
+                                                  double beta_old, double z)
+{
+    if (comp < 0) return beta_old;
+    if (comp == 0) return 0.0;
+    return __fma_rn(z, gc.sdev[g * K + comp], num * gc.invDenom[g * K + comp]);
 }
 
 } // namespace brr

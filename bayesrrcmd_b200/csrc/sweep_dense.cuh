@@ -41,14 +41,15 @@ namespace brr {
 constexpr int kB = 64;                 // markers per block = tile structure of the MMA passes
 constexpr int kLimbs = 8;
 constexpr uint32_t kM3 = 0x03030303u;
-constexpr int kMissCap = 4096;         // entries of the per-block missing list (>= max slice length)
+constexpr int kMissSeg = 256;          // missing-list entries per warp segment
+constexpr int kMissCap = kMissSeg * kWarps;
 constexpr int kMaxSL = 4096;           // individuals per CTA (2 register items of 4 per thread)
 constexpr int kScratchInts = 8192;     // 32 KB shared scratch
 constexpr int kHeadroomBits = 6;       // |eps| may grow 64x inside a sweep before the fixed point overflows
 
 // rotating global slot (int32 units)
 constexpr int kSlotA = 0;              // [64][64]: upper (j<k) = sum g'_j g'_k ; lower [k][j] = # both missing
-constexpr int kSlotY = 4096;           // [64][64]: Y[a][b] = sum over {i: b missing, a present} of g_a
+constexpr int kSlotY = 4096;           // [64][64]: YT[b][a] = sum over {i: b missing, a present} of g_a
 constexpr int kSlotDots = 8192;        // [64][8] limb sums
 constexpr int kSlotSm = 8704;          // [64][2] int64: sum of q over missing individuals (hi, lo parts)
 constexpr int kSlotEps = 8960;         // [2] int64: sum of q over all individuals (hi, lo parts)
@@ -85,13 +86,22 @@ struct DenseSweepParams {
     double *betasq;          // [nG]
     double *out_scalars;     // [0]=sum eps, [1]=||eps||^2
     unsigned *out_counts;    // [0]=non-skipped markers, [1]=blocks, [2]=error flags
+    unsigned long long *prof; // optional [kProfPhases]: SM cycles of CTA 0 per phase (nullptr = off)
 };
 
-struct BlockMeta {
+// phases of the block loop, as timed by thread 0 of CTA 0 when DenseSweepParams::prof is set
+enum { kProfDot = 0, kProfDotReduce, kProfGramScan, kProfGramCross, kProfGramMma, kProfGramReduce, kProfBarrier,
+       kProfReadback, kProfWalk, kProfAxpy, kProfQuantize, kProfPrologue, kProfWalkIters, kProfWalkSolves, kProfWalkA, kProfGramWait,
+       kProfPhases = 16 };
+
+struct alignas(16) BlockMeta {
     uint32_t id[kB];
     int32_t grp[kB];
-    double beta_old[kB], u[kB], z[kB];
+    double beta_old[kB];
+    double uz[kB][2];                // (u, z) of src/BayesRBase.cpp:343-344
     double lut[kB][4];
+    uint32_t cnt[kB][4];             // global class counts
+    // derived at read-back time
     double sj[kB], cj[kB], ej[kB];   // x = sj * (g - cj + ej*[missing])
     double sumg[kB], nmiss[kB];      // global n1 + 2 n2, global missing count
 };
@@ -101,19 +111,21 @@ struct SweepShared {   // fixed-size part; limbs, code buffers, scratch and the 
     BlockMeta meta;
     double d0[kB];
     double dbeta[kB];
+    double w_corr[kB];               // walk: corrections of the second half-block, betasq partials of warp 1
+    int w_comp[kB];                  // walk: tentative components
+    uint32_t w_nsm[2], w_chg[2], w_cnt[2], w_cnt2[2];
+    uint32_t ids[2][kB];             // marker ids of the blocks in the two code buffers
     double warp_tmp[kWarps];
     double betasq_s[kMaxGK];
     int v_s[kMaxGK];
-    unsigned long long sm_s[kB][2];
-    unsigned long long epsq[2];      // this slice's sum of q, (hi, lo) parts
+    unsigned long long wq[kWarps][2]; // per-warp sums of q over the slice, (hi, lo) parts
     double eps_sum_total;
     double scale, inv_scale;
     uint32_t ns_list[kB];
     uint32_t n_ns;
     uint32_t n_nonskipped_total;
-    uint32_t miss_n, miss_stored;    // entries found / entries in the list for the block held in `miss_blk`
-    uint32_t miss_blk;
-    uint32_t has_missing;
+    uint32_t miss_rowcnt[kWarps][4]; // missing-list entries of warp w for its rows w, w+16, w+32, w+48
+    uint32_t miss_any, miss_overflow;
     uint32_t err;
     alignas(8) uint64_t mbar[2];
 };
@@ -145,6 +157,11 @@ __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // Gram pass: which 16x8 output tiles a warp role computes.  Tile (mi, nj) covers row markers
 // 16mi..16mi+15 and column markers 8nj..8nj+7; only tiles with some row < column are needed.
@@ -208,19 +225,26 @@ __device__ __forceinline__ void gram_role_publish(const int *__restrict__ scratc
         }
 }
 
-__device__ __forceinline__ void load_block_meta(const DenseSweepParams &p, BlockMeta &m, uint32_t pos, int k)
+// per-marker inputs of a block: asynchronous gather into shared memory (thread k = marker k of the block) ...
+__device__ __forceinline__ void gather_block_meta(const DenseSweepParams &p, BlockMeta &m, uint32_t id, int k)
 {
-    const uint32_t id = p.order[pos];
-    m.id[k] = id; m.grp[k] = p.group ? p.group[id] : 0; m.beta_old[k] = p.beta[id];
-    m.u[k] = p.rand_uz[2 * size_t(id)]; m.z[k] = p.rand_uz[2 * size_t(id) + 1];
-    const double4 l = *reinterpret_cast<const double4 *>(p.lut + 4 * size_t(id));
-    m.lut[k][0] = l.x; m.lut[k][1] = l.y; m.lut[k][2] = l.z; m.lut[k][3] = l.w;
-    const uint4 c = *reinterpret_cast<const uint4 *>(p.counts + 4 * size_t(id));
-    const double s = 0.5 * (l.z - l.x);          // value table is affine in the allele count
-    const double cc = -l.x / s;
-    m.sj[k] = s; m.cj[k] = cc; m.ej[k] = l.w / s + cc;
-    m.sumg[k] = double(c.y) + 2.0 * double(c.z);
-    m.nmiss[k] = double(c.w);
+    m.id[k] = id;
+    cp_async16(&m.lut[k][0], p.lut + 4 * size_t(id));
+    cp_async16(&m.lut[k][2], p.lut + 4 * size_t(id) + 2);
+    cp_async16(&m.cnt[k][0], p.counts + 4 * size_t(id));
+    cp_async16(&m.uz[k][0], p.rand_uz + 2 * size_t(id));
+    cp_async8(&m.beta_old[k], p.beta + id);
+    if (p.group) cp_async4(&m.grp[k], p.group + id); else m.grp[k] = 0;
+}
+// ... and, once it has landed, what the walk derives from it
+__device__ __forceinline__ void derive_block_meta(BlockMeta &m, int k)
+{
+    const double l0 = m.lut[k][0], l2 = m.lut[k][2], l3 = m.lut[k][3];
+    const double s = 0.5 * (l2 - l0);          // value table is affine in the allele count
+    const double cc = -l0 / s;
+    m.sj[k] = s; m.cj[k] = cc; m.ej[k] = l3 / s + cc;
+    m.sumg[k] = double(m.cnt[k][1]) + 2.0 * double(m.cnt[k][2]);
+    m.nmiss[k] = double(m.cnt[k][3]);
 }
 
 // x_j . x_k for j < k from the reduced integer counts (A, Y in shared memory)
@@ -229,7 +253,7 @@ __device__ __forceinline__ double gram_entry(const BlockMeta &m, const int *__re
 {
     double a = double(A[j * kB + k]), cy = 0.0, cz = 0.0, cw = 0.0;
     if (has_missing) {
-        cw = double(A[k * kB + j]); cy = double(Y[j * kB + k]); cz = double(Y[k * kB + j]);
+        cw = double(A[k * kB + j]); cy = double(Y[k * kB + j]); cz = double(Y[j * kB + k]);     // Y is stored transposed
         a = a - 3.0 * cy - 3.0 * cz - 9.0 * cw;
     }
     const double cj = m.cj[j], ck = m.cj[k], ej = m.ej[j], ek = m.ej[k];
@@ -260,6 +284,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     const uint32_t nBlocks = (p.n_order + B - 1) / B;
     const uint32_t slice0 = cta * SL;
     unsigned bar_gen = 0;
+    const bool prof_on = (p.prof != nullptr) && cta == 0 && tid == 0;
+    long long t_prev = prof_on ? clock64() : 0;
+    auto PHASE = [&](int ph) {          // charge the cycles since the previous mark to phase `ph`
+        if (prof_on) { const long long t = clock64(); p.prof[ph] += (unsigned long long)(t - t_prev); t_prev = t; }
+    };
 
     // ---- prologue -----------------------------------------------------------------------------
     // eps -> registers.  item = 4w + c owns the individuals 16w + 4t + c, t = 0..3
@@ -278,12 +307,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     }
     fill_group_consts(sh.gc, p.nG, K, NM1, p.sigmaE, p.pi, p.sigmaG, p.cva);
     for (int i = tid; i < kMaxGK; i += kThreads) { sh.v_s[i] = 0; sh.betasq_s[i] = 0.0; }
+    if (tid < kWarps * 4) sh.miss_rowcnt[tid >> 2][tid & 3] = 0;
     for (uint32_t i = tid; i < 2 * kB * RS; i += kThreads) pkbuf[i] = 0;
     if (tid == 0) {
         mbar_init(&sh.mbar[0], 1); mbar_init(&sh.mbar[1], 1);
         mbar_fence_init();
-        sh.n_nonskipped_total = 0; sh.n_ns = 0; sh.err = 0; sh.miss_blk = 0xffffffffu; sh.miss_n = 0; sh.miss_stored = 0;
-        sh.epsq[0] = 0; sh.epsq[1] = 0;
+        sh.n_nonskipped_total = 0; sh.n_ns = 0; sh.err = 0; sh.miss_any = 0; sh.miss_overflow = 0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -310,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 const uint32_t r = lane + 32 * h;
                 if (r < nb) {
                     const uint32_t id = p.order[b * B + r];
+                    sh.ids[b & 1][r] = id;
                     bulk_g2s(dst + size_t(r) * RS, p.codes + (size_t(id) * p.nCTA + cta) * PW, CB, bar);
                 }
             }
@@ -368,42 +398,103 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             shi += __shfl_xor_sync(0xffffffffu, shi, o);
             slo += __shfl_xor_sync(0xffffffffu, slo, o);
         }
-        if (lane == 0) { atomicAdd(&sh.epsq[0], (unsigned long long)shi); atomicAdd(&sh.epsq[1], slo); }
+        if (lane == 0) { sh.wq[warp][0] = (unsigned long long)shi; sh.wq[warp][1] = slo; }
+    };
+    auto slice_q = [&](unsigned long long &hi, unsigned long long &lo) {     // this slice's sum of q (after a barrier)
+        hi = 0; lo = 0;
+        for (int w = 0; w < kWarps; ++w) { hi += sh.wq[w][0]; lo += sh.wq[w][1]; }
     };
     quantize();
 
     // ---- missing-genotype side pass --------------------------------------------------------------
-    // scan the rows [m_lo, m_hi) of a block buffer; list entries (m << 16 | slice-local individual)
-    auto scan_missing = [&](const uint32_t *pk, uint32_t m_lo, uint32_t m_hi) {
-        for (uint32_t idx = tid; idx < (m_hi - m_lo) * PW; idx += kThreads) {
-            const uint32_t m = m_lo + idx / PW, w = idx % PW;
-            const uint32_t x = pk[size_t(m) * RS + w];
-            uint32_t mm = x & (x >> 1) & 0x55555555u;
-            if (mm) {
-                uint32_t pos = atomicAdd(&sh.miss_n, (uint32_t)__popc(mm));
-                while (mm) {
-                    const int bit = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    if (pos < (uint32_t)kMissCap) miss_list[pos] = (m << 16) | (16 * w + (bit >> 1));
-                    ++pos;
+    // Each warp lists the missing entries (slice-local individual ids) of its rows into its private
+    // segment of the list: no atomics, deterministic.  all_rows: warp w scans rows w, w+16, w+32, w+48;
+    // else every warp scans its share of the words of the single row m_one (a row with more missing
+    // genotypes than a segment holds is handled that way, one row at a time).
+    auto scan_missing = [&](const uint32_t *pk, uint32_t nb, bool all_rows, uint32_t m_one) {
+        uint32_t *seg = miss_list + warp * kMissSeg;
+        uint32_t cnt = 0;
+        const uint32_t chunk = (PW + kWarps - 1) / kWarps;
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t m = all_rows ? uint32_t(warp + 16 * r) : m_one;
+            uint32_t c_r = 0;
+            if (m < nb && (all_rows || r == 0)) {
+                const uint32_t *row = pk + size_t(m) * RS;
+                const uint32_t w_lo = all_rows ? 0u : warp * chunk, w_hi = all_rows ? PW : min(PW, w_lo + chunk);
+                for (uint32_t w0 = w_lo; w0 < w_hi; w0 += 32) {
+                    const uint32_t w = w0 + lane;
+                    const uint32_t x = (w < w_hi) ? row[w] : 0u;
+                    uint32_t mm = x & (x >> 1) & 0x55555555u;
+                    const uint32_t n = __popc(mm);
+                    unsigned bal = __ballot_sync(0xffffffffu, n != 0);
+                    while (bal) {
+                        const int l = __ffs(bal) - 1;
+                        bal &= bal - 1;
+                        const uint32_t nl = __shfl_sync(0xffffffffu, n, l);
+                        if (lane == l) {
+                            uint32_t pos = cnt;
+                            while (mm) {
+                                const int bit = __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                if (pos < (uint32_t)kMissSeg) seg[pos] = 16 * w + (bit >> 1);
+                                ++pos;
+                            }
+                        }
+                        cnt += nl; c_r += nl;
+                    }
                 }
             }
+            if (lane == 0) sh.miss_rowcnt[warp][r] = c_r;
         }
+        if (lane == 0 && cnt) { sh.miss_any = 1; if (cnt > (uint32_t)kMissSeg) sh.miss_overflow = 1; }
+        __syncwarp();
     };
-    // cross counts of the listed entries with every other marker of the block, into scratch (Y | Wlow)
-    auto cross_missing = [&](const uint32_t *pk, uint32_t n, uint32_t nb) {
-        int *Ys = scratch, *As = scratch + 4096;
-        for (uint32_t en = warp; en < n; en += kWarps) {
-            const uint32_t ent = miss_list[en], m = ent >> 16, i = ent & 0xffffu;
+    // cross counts of this warp's listed entries of row m with every other marker of the block, straight
+    // into the global slot: YT[m][a] += g_a(i) (a present), Wlow[m][a] += 1 (a < m, a missing too)
+    auto cross_missing = [&](const uint32_t *pk, int *slot, uint32_t nb, uint32_t m, const uint32_t *ent, uint32_t n) {
+        int y[2] = {0, 0}, wv[2] = {0, 0};
+        for (uint32_t en = 0; en < n; en += 2) {
+            const uint32_t i0 = ent[en], i1 = (en + 1 < n) ? ent[en + 1] : 0xffffffffu;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint32_t a = lane + 32 * h;
                 if (a < nb && a != m) {
-                    const uint32_t code = (pk[size_t(a) * RS + (i >> 4)] >> (2 * (i & 15u))) & 3u;
-                    if (code == 3u) { if (a < m) atomicAdd(&As[m * kB + a], 1); }
-                    else if (code) atomicAdd(&Ys[a * kB + m], (int)code);
+                    const uint32_t c0 = (pk[size_t(a) * RS + (i0 >> 4)] >> (2 * (i0 & 15u))) & 3u;
+                    const uint32_t c1 = (i1 != 0xffffffffu) ? (pk[size_t(a) * RS + (i1 >> 4)] >> (2 * (i1 & 15u))) & 3u : 0u;
+                    y[h] += (c0 == 3u ? 0 : int(c0)) + (c1 == 3u ? 0 : int(c1));
+                    if (a < m) wv[h] += int(c0 == 3u) + int(c1 == 3u);
                 }
             }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t a = lane + 32 * h;
+            if (y[h]) atomicAdd(slot + kSlotY + m * kB + a, y[h]);
+            if (wv[h]) atomicAdd(slot + kSlotA + m * kB + a, wv[h]);
+        }
+    };
+    // sum of q over this warp's listed entries of row m -> global slot (exact, order independent)
+    auto missing_q_sum = [&](int *slot, uint32_t m, const uint32_t *ent, uint32_t n) {
+        long long shi = 0; unsigned long long slo = 0;
+        for (uint32_t en = lane; en < n; en += 32) {
+            const uint32_t i = ent[en];
+            const uint32_t w = i >> 4, c = i & 3u, t = (i >> 2) & 3u;
+            const uint32_t *lw = reinterpret_cast<const uint32_t *>(limbs) + c;
+            unsigned long long uq = 0;
+#pragma unroll
+            for (int l = 0; l < kLimbs; ++l)
+                uq |= (unsigned long long)((lw[(size_t(l) * RS + w) * 4] >> (8 * t)) & 0xffu) << (8 * l);
+            const long long q = (long long)((uq ^ 0x8080808080808080ULL) - 0x8080808080808080ULL);
+            shi += q >> 32; slo += (unsigned long long)(q & 0xffffffffLL);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            shi += __shfl_xor_sync(0xffffffffu, shi, o);
+            slo += __shfl_xor_sync(0xffffffffu, slo, o);
+        }
+        if (lane == 0 && n) {
+            unsigned long long *g = reinterpret_cast<unsigned long long *>(slot + kSlotSm) + 2 * m;
+            atomicAdd(g, (unsigned long long)shi); atomicAdd(g + 1, slo);
         }
     };
 
@@ -413,36 +504,34 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         const uint32_t *pk = pkbuf + size_t(b & 1) * kB * RS;
         int *slot = p.slots + size_t(b % kSlots) * kSlotInts;
         mbar_wait(&sh.mbar[b & 1], (b >> 1) & 1);
-        if (tid == 0) { sh.miss_n = 0; sh.miss_blk = b; }
+        if (tid == 0) { sh.miss_any = 0; sh.miss_overflow = 0; }
         __syncthreads();
-        scan_missing(pk, 0, nb);
+        PHASE(kProfGramWait);
+        scan_missing(pk, nb, true, 0);
         __syncthreads();
-        const uint32_t n_found = sh.miss_n;
-        if (tid == 0) sh.miss_stored = (n_found <= (uint32_t)kMissCap) ? n_found : 0xffffffffu;
-        if (n_found && tid == 0) atomicAdd(slot + kSlotFlag, 1);
+        PHASE(kProfGramScan);
+        const bool any_missing = sh.miss_any != 0, overflow = sh.miss_overflow != 0;
+        if (any_missing && tid == 0) atomicAdd(slot + kSlotFlag, 1);
         const bool want_gram = !p.async_mode && nb > 1;
-        if (n_found && want_gram) {
-            for (int i = tid; i < kScratchInts; i += kThreads) scratch[i] = 0;
-            __syncthreads();
-            if (n_found <= (uint32_t)kMissCap) {
-                cross_missing(pk, n_found, nb);
-            } else {                                   // too many for one list: one marker at a time
+        if (any_missing && want_gram) {
+            if (!overflow) {
+                uint32_t off = 0;
+                for (int r = 0; r < 4; ++r) {
+                    const uint32_t n = sh.miss_rowcnt[warp][r];
+                    if (n) cross_missing(pk, slot, nb, warp + 16 * r, miss_list + warp * kMissSeg + off, n);
+                    off += n;
+                }
+            } else {                                   // too many for the list: one row at a time
                 for (uint32_t m = 0; m < nb; ++m) {
                     __syncthreads();
-                    if (tid == 0) sh.miss_n = 0;
-                    __syncthreads();
-                    scan_missing(pk, m, m + 1);
-                    __syncthreads();
-                    cross_missing(pk, min(sh.miss_n, (uint32_t)kMissCap), nb);
+                    scan_missing(pk, nb, false, m);
+                    const uint32_t n = min(sh.miss_rowcnt[warp][0], (uint32_t)kMissSeg);
+                    if (n) cross_missing(pk, slot, nb, m, miss_list + warp * kMissSeg, n);
                 }
+                __syncthreads();
+                if (tid == 0) sh.miss_overflow = 1;      // tells the dot pass to rescan as well
             }
-            __syncthreads();
-            for (int i = tid; i < 4096; i += kThreads) {
-                const int y = scratch[i], a = scratch[4096 + i];
-                if (y) atomicAdd(slot + kSlotY + i, y);
-                if (a) atomicAdd(slot + kSlotA + i, a);
-            }
-            __syncthreads();
+            PHASE(kProfGramCross);
         }
         if (want_gram) {
             const uint32_t role = warp & 3, kg = warp >> 2, nkg = kWarps / 4;
@@ -463,6 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                     for (int r = 0; r < 4; ++r) dst[(t * 4 + r) * 32 + lane] = acc[t][r];
             }
             __syncthreads();
+            PHASE(kProfGramMma);
             if (kg == 0) {
                 switch (role) {
                 case 0: gram_role_publish<0>(scratch, nkg, lane, acc, slot + kSlotA, nb); break;
@@ -472,14 +562,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 }
             }
             __syncthreads();
+            PHASE(kProfGramReduce);
         }
     };
 
     if (nBlocks > 0) {
-        if (uint32_t(tid) < min(B, p.n_order)) load_block_meta(p, sh.meta, tid, tid);
+        if (uint32_t(tid) < min(B, p.n_order)) gather_block_meta(p, sh.meta, sh.ids[0][tid], tid);
         gram_pass(0);
     }
     __syncthreads();
+    PHASE(kProfPrologue);
 
     for (uint32_t b = 0; b < nBlocks; ++b) {
         const uint32_t nb = min(B, p.n_order - b * B);
@@ -509,9 +601,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) scratch[(warp * 16 + mi * 4 + r) * 32 + lane] = acc[mi][r];
-            if (uint32_t(tid) < kB) { sh.sm_s[tid][0] = 0; sh.sm_s[tid][1] = 0; }
         }
         __syncthreads();
+        PHASE(kProfDot);
         {
             // one output per thread: tile mi = tid/128, register r, lane l
             int s = 0;
@@ -521,82 +613,82 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             const int l5 = o & 31, r = (o >> 5) & 3, mi = o >> 7;
             const uint32_t m = 16 * mi + (l5 >> 2) + 8 * (r >> 1), limb = 2 * (l5 & 3) + (r & 1);
             if (s != 0 && m < nb) atomicAdd(slot + kSlotDots + m * kLimbs + limb, s);
-            if (tid == 0) {
-                atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotEps), sh.epsq[0]);
-                atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotEps) + 1, sh.epsq[1]);
+            if (warp == 0) {                      // lane 2w+h holds part h of warp w's sum of q
+                unsigned long long v = sh.wq[lane >> 1][lane & 1];
+#pragma unroll
+                for (int o2 = 2; o2 < 32; o2 <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+                if (lane < 2) atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotEps) + lane, v);
             }
             // sum of q over the missing individuals of every marker (list built by this block's Gram pass)
-            const uint32_t stored = sh.miss_stored;
-            auto add_entry = [&](uint32_t ent) {
-                const uint32_t m2 = ent >> 16, i = ent & 0xffffu;
-                const uint32_t w = i >> 4, c = i & 3u, t = (i >> 2) & 3u;
-                const uint32_t *lw = reinterpret_cast<const uint32_t *>(limbs) + c;
-                unsigned long long uq = 0;
-#pragma unroll
-                for (int l = 0; l < kLimbs; ++l)
-                    uq |= (unsigned long long)((lw[(size_t(l) * RS + w) * 4] >> (8 * t)) & 0xffu) << (8 * l);
-                const long long q = (long long)((uq ^ 0x8080808080808080ULL) - 0x8080808080808080ULL);
-                atomicAdd(&sh.sm_s[m2][0], (unsigned long long)(q >> 32));
-                atomicAdd(&sh.sm_s[m2][1], (unsigned long long)(q & 0xffffffffLL));
-            };
-            if (stored != 0xffffffffu) {
-                for (uint32_t en = tid; en < stored; en += kThreads) add_entry(miss_list[en]);
-            } else {                                   // list overflowed: rescan, one marker at a time
-                for (uint32_t m2 = 0; m2 < nb; ++m2) {
+            if (sh.miss_any) {
+                if (!sh.miss_overflow) {
+                    uint32_t off = 0;
+                    for (int r2 = 0; r2 < 4; ++r2) {
+                        const uint32_t n = sh.miss_rowcnt[warp][r2];
+                        if (n) missing_q_sum(slot, warp + 16 * r2, miss_list + warp * kMissSeg + off, n);
+                        off += n;
+                    }
+                } else {                               // list overflowed: rescan, one row at a time
+                    for (uint32_t m2 = 0; m2 < nb; ++m2) {
+                        __syncthreads();
+                        scan_missing(pk, nb, false, m2);
+                        const uint32_t n = min(sh.miss_rowcnt[warp][0], (uint32_t)kMissSeg);
+                        if (n) missing_q_sum(slot, m2, miss_list + warp * kMissSeg, n);
+                    }
                     __syncthreads();
-                    if (tid == 0) sh.miss_n = 0;
-                    __syncthreads();
-                    scan_missing(pk, m2, m2 + 1);
-                    __syncthreads();
-                    const uint32_t n = min(sh.miss_n, (uint32_t)kMissCap);
-                    for (uint32_t en = tid; en < n; en += kThreads) add_entry(miss_list[en]);
+                    if (tid == 0) { sh.miss_any = 1; sh.miss_overflow = 1; }
                 }
             }
-        }
-        __syncthreads();
-        if (uint32_t(tid) < nb && (sh.sm_s[tid][0] | sh.sm_s[tid][1])) {
-            unsigned long long *g = reinterpret_cast<unsigned long long *>(slot + kSlotSm) + 2 * tid;
-            atomicAdd(g, sh.sm_s[tid][0]); atomicAdd(g + 1, sh.sm_s[tid][1]);
         }
 
         // ---- 2. the one grid-wide exchange per block: arrive ... ------------------------------------
         grid_arrive(p.bar);
+        PHASE(kProfDotReduce);
 
         // ---- 3. ... and hide its latency behind the Gram pass of the next block ----------------------
-        if (b > 0 && uint32_t(tid) < nb) load_block_meta(p, meta, b * B + tid, tid);     // meta of block b-1 is dead
+        if (b > 0 && uint32_t(tid) < nb) gather_block_meta(p, meta, sh.ids[buf][tid], tid);   // meta of block b-1 is dead
         if (b + 1 < nBlocks) gram_pass(b + 1);
 
         // ---- 4. wait -----------------------------------------------------------------------------------
         grid_wait(p.bar, (++bar_gen) * p.nCTA);
+        PHASE(kProfBarrier);
 
-        // ---- 5. read the reduced block back ----------------------------------------------------------------
+        // ---- 5. read the reduced block back (all loads in flight at once) ----------------------------------
         const bool has_missing = __ldcg(slot + kSlotFlag) != 0;
-        if (!p.async_mode && nb > 1) {
+        const bool want_gram = !p.async_mode && nb > 1;
+        {
             const int4 *src = reinterpret_cast<const int4 *>(slot + kSlotA);
             int4 *dst = reinterpret_cast<int4 *>(scratch);
-            const int n4 = has_missing ? 2048 : 1024;          // A, then Y
-            for (int i = tid; i < n4; i += kThreads) dst[i] = __ldcg(src + i);
-        }
-        if (tid == 0) {
-            const long long *eq = reinterpret_cast<const long long *>(slot + kSlotEps);
-            const long long hi = __ldcg(eq), lo = __ldcg(eq + 1);
-            sh.eps_sum_total = (double(hi) * 4294967296.0 + double(lo)) * inv_scale;
-        }
-        __syncthreads();
-        if (uint32_t(tid) < nb) {
-            const int4 *dp = reinterpret_cast<const int4 *>(slot + kSlotDots + tid * kLimbs);
-            const int4 d_lo = __ldcg(dp), d_hi = __ldcg(dp + 1);
-            const long long tlo = (long long)d_lo.x + ((long long)d_lo.y << 8) + ((long long)d_lo.z << 16) + ((long long)d_lo.w << 24);
-            const long long thi = (long long)d_hi.x + ((long long)d_hi.y << 8) + ((long long)d_hi.z << 16) + ((long long)d_hi.w << 24);
-            const double dprime = (double(thi) * 4294967296.0 + double(tlo)) * inv_scale;    // sum_i g'_i eps_i
-            double smd = 0.0;
-            if (has_missing) {
-                const long long *sp = reinterpret_cast<const long long *>(slot + kSlotSm) + 2 * tid;
-                smd = (double(__ldcg(sp)) * 4294967296.0 + double(__ldcg(sp + 1))) * inv_scale;
+            const int n4 = want_gram ? (has_missing ? 2048 : 1024) : 0;          // A, then YT
+            int4 va[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int i = tid + t * kThreads; if (i < n4) va[t] = __ldcg(src + i); }
+            int4 d_lo = make_int4(0, 0, 0, 0), d_hi = d_lo;
+            long long sm_hi = 0, sm_lo = 0, e_hi = 0, e_lo = 0;
+            if (uint32_t(tid) < nb) {
+                const int4 *dp = reinterpret_cast<const int4 *>(slot + kSlotDots + tid * kLimbs);
+                d_lo = __ldcg(dp); d_hi = __ldcg(dp + 1);
+                if (has_missing) {
+                    const long long *sp = reinterpret_cast<const long long *>(slot + kSlotSm) + 2 * tid;
+                    sm_hi = __ldcg(sp); sm_lo = __ldcg(sp + 1);
+                }
+                const long long *eq = reinterpret_cast<const long long *>(slot + kSlotEps);
+                e_hi = __ldcg(eq); e_lo = __ldcg(eq + 1);
             }
-            const double *L = meta.lut[tid];
-            // x.eps = L0 sum(eps) + s (S1 + 2 S2) + (L3 - L0) Smissing ; the products saw missing as 3
-            sh.d0[tid] = L[0] * sh.eps_sum_total + meta.sj[tid] * (dprime - 3.0 * smd) + (L[3] - L[0]) * smd;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const int i = tid + t * kThreads; if (i < n4) dst[i] = va[t]; }
+            if (uint32_t(tid) < nb) {
+                cp_async_wait_all();
+                derive_block_meta(meta, tid);
+                const double eps_sum_total = (double(e_hi) * 4294967296.0 + double(e_lo)) * inv_scale;
+                const long long tlo = (long long)d_lo.x + ((long long)d_lo.y << 8) + ((long long)d_lo.z << 16) + ((long long)d_lo.w << 24);
+                const long long thi = (long long)d_hi.x + ((long long)d_hi.y << 8) + ((long long)d_hi.z << 16) + ((long long)d_hi.w << 24);
+                const double dprime = (double(thi) * 4294967296.0 + double(tlo)) * inv_scale;    // sum_i g'_i eps_i
+                const double smd = (double(sm_hi) * 4294967296.0 + double(sm_lo)) * inv_scale;
+                const double *L = meta.lut[tid];
+                // x.eps = L0 sum(eps) + s (S1 + 2 S2) + (L3 - L0) Smissing ; the products saw missing as 3
+                sh.d0[tid] = L[0] * eps_sum_total + meta.sj[tid] * (dprime - 3.0 * smd) + (L[3] - L[0]) * smd;
+            }
         }
         // recycle the slot of block b-1 (every CTA has read it before arriving at this block's barrier)
         if (cta == b % p.nCTA) {
@@ -604,67 +696,155 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             for (int i = tid; i < kSlotInts / 4; i += kThreads) z[i] = make_int4(0, 0, 0, 0);
         }
         __syncthreads();
+        PHASE(kProfReadback);
 
-        // ---- 6. the walk: one warp, two half-blocks of 32 lanes ---------------------------------------------
-        if (warp == 0) {
-            const int *As = scratch, *Ys = scratch + 4096;
-            uint32_t n_upd = 0, n_nonskip = 0;
-            for (uint32_t sub = 0; sub * 32 < nb; ++sub) {
-                const int k = sub * 32 + lane;
-                const bool act = uint32_t(k) < nb;
-                const double bo = act ? meta.beta_old[k] : 0.0;
-                const double uu = act ? meta.u[k] : 2.0, zz = act ? meta.z[k] : 0.0;
-                const int g = act ? meta.grp[k] : 0;
-                const double d0 = act ? sh.d0[k] : 0.0;
-                double corr = 0.0;
-                if (!p.async_mode && act)
-                    for (uint32_t q = 0; q < n_upd; ++q) {
-                        const int js = sh.ns_list[q];
-                        corr += sh.dbeta[js] * gram_entry(meta, As, Ys, has_missing, js, k, Nt);
-                    }
-                Draw dr; dr.beta_new = bo; dr.acum0 = 0.0; dr.comp = -1;
-                uint32_t done = 0;
-                while (true) {
-                    const bool live = act && uint32_t(lane) >= done;
-                    if (live) dr = sample_marker_k(sh.gc, g, K, d0 + corr + bo * NM1, p.sigmaE, bo, uu, zz);
-                    const bool ns = live && !(bo == 0.0 && dr.beta_new == 0.0);
-                    const unsigned mask = __ballot_sync(0xffffffffu, ns);
-                    if (p.async_mode || mask == 0) break;
-                    const int jl = __ffs(mask) - 1;
-                    const double dB = __shfl_sync(0xffffffffu, bo - dr.beta_new, jl);   // eps += dB * x_js
-                    if (lane > jl && act && dB != 0.0) corr += dB * gram_entry(meta, As, Ys, has_missing, sub * 32 + jl, k, Nt);
-                    done = jl + 1;
-                    if (sub * 32 + done >= nb) break;
-                }
-                const double dB = act ? (bo - dr.beta_new) : 0.0;
-                const bool upd = act && dB != 0.0;
-                const bool nonskip = act && !(bo == 0.0 && dr.beta_new == 0.0);
-                if (act) sh.dbeta[k] = dB;
-                const unsigned um = __ballot_sync(0xffffffffu, upd);
-                if (upd) sh.ns_list[n_upd + __popc(um & ((1u << lane) - 1u))] = k;
-                n_upd += __popc(um);
-                n_nonskip += __popc(__ballot_sync(0xffffffffu, nonskip));
-                if (cta == 0 && act) {
-                    const uint32_t id = meta.id[k];
-                    if (!p.async_mode) p.acum[id] = dr.acum0;                  // src/BayesRBase.cpp:341
-                    if (dr.comp >= 0) {
-                        p.beta[id] = dr.beta_new;                              // :350-352 / :492
-                        p.comp[id] = double(dr.comp);                          // :356 / :493
-                        atomicAdd(&sh.v_s[g * K + dr.comp], 1);                // :355 / :511
-                    }
-                }
-                if (cta == 0) {
-                    for (uint32_t gi = 0; gi < p.nG; ++gi) {                   // :353 / :522
-                        const double b2 = (act && g == int(gi) && dr.comp > 0) ? dr.beta_new * dr.beta_new : 0.0;
-                        const double s = warp_sum(b2);
-                        if (lane == 0) sh.betasq_s[gi] += s;
-                    }
-                }
-                __syncwarp();
+        // ---- 6. the walk: one warp, lane l owns markers l and l+32 of the block ----------------------------
+        // The one-by-one loop is reproduced exactly in three steps that iterate to a fixed point:
+        //   (a) every marker is sampled against its current dot (speculating no earlier marker changes eps);
+        //   (b) with the components fixed, the non-skipped markers (src/BayesRBase.cpp:372) are solved in
+        //       order: beta_j from its corrected dot, then the dots of all later markers are corrected by
+        //       (beta_old_j - beta_j) x_j.x_k.  This is a triangular solve with O(1) flops per step -- no exp;
+        //   (c) every marker whose dot moved is sampled again; if all components (hence all betas, bit for
+        //       bit) are confirmed, the state equals the sequential chain's, else (b) restarts with the new ones.
+        // Two warps: thread k < 64 samples marker k of the block; warp 0 runs the solve for both halves.
+        const bool walker = warp < 2;
+        const int wk = tid;                                   // marker of a walker thread
+        const bool act = walker && uint32_t(wk) < nb;
+        double bo = 0.0, uu = 2.0, zz = 0.0, base = 0.0; int gg = 0;
+        double bo1 = 0.0, zz1 = 0.0, base1 = 0.0; int gg1 = 0; bool act1 = false;    // warp 0: marker 32+lane
+        Draw dr; dr.beta_new = 0.0; dr.acum0 = 0.0; dr.comp = -1;
+        if (walker) {
+            // (a) on warps 0 and 1 ...
+            if (act) {
+                bo = meta.beta_old[wk]; uu = meta.uz[wk][0]; zz = meta.uz[wk][1]; gg = meta.grp[wk];
+                base = sh.d0[wk] + bo * NM1;
             }
-            if (lane == 0) { sh.n_ns = n_upd; sh.n_nonskipped_total += n_nonskip; }
+            if (warp == 0 && uint32_t(32 + lane) < nb) {
+                act1 = true; bo1 = meta.beta_old[32 + lane]; zz1 = meta.uz[32 + lane][1]; gg1 = meta.grp[32 + lane];
+                base1 = sh.d0[32 + lane] + bo1 * NM1;
+            }
+            dr.beta_new = bo;
+            if (act) dr = sample_marker_k(sh.gc, gg, K, base, p.sigmaE, bo, uu, zz);
+        } else if (want_gram) {
+            // ... while warps 2..15 turn the integer counts into the standardised Gram x_j.x_k (doubles, in place).
+            // Pairs are visited along diagonals k - j = d so that both A[j][k] and the transposed reads are
+            // bank-conflict free.
+            const int *As = scratch, *Ys = scratch + 4096;
+            constexpr int kStd = kThreads - 64;
+            constexpr int kPer = (32 * kB + kStd - 1) / kStd;
+            double gv[kPer];
+#pragma unroll
+            for (int t = 0; t < kPer; ++t) {
+                const int idx = (tid - 64) + t * kStd;
+                const int dd = (idx >> 6) + 1, x = idx & 63;
+                const bool lo = x < 64 - dd;
+                const int d = lo ? dd : 64 - dd, j = lo ? x : x - (64 - dd), k = j + d;
+                const bool ok = idx < 32 * kB && !(dd == 32 && !lo) && uint32_t(k) < nb;
+                gv[t] = ok ? gram_entry(meta, As, Ys, has_missing, j, k, Nt) : 0.0;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kStd) : "memory");
+            double *G = reinterpret_cast<double *>(scratch);
+#pragma unroll
+            for (int t = 0; t < kPer; ++t) {
+                const int idx = (tid - 64) + t * kStd;
+                const int dd = (idx >> 6) + 1, x = idx & 63;
+                const bool lo = x < 64 - dd;
+                const int d = lo ? dd : 64 - dd, j = lo ? x : x - (64 - dd), k = j + d;
+                const bool ok = idx < 32 * kB && !(dd == 32 && !lo) && uint32_t(k) < nb;
+                if (ok) G[j * kB + k] = gv[t];
+            }
         }
         __syncthreads();
+        PHASE(kProfWalkA);
+        if (walker) {
+            const double *G = reinterpret_cast<const double *>(scratch);
+            double corr_used = 0.0;
+            for (int iter = 0; iter < 2 * kB && !p.async_mode; ++iter) {
+                const unsigned nsm = __ballot_sync(0xffffffffu, act && !(bo == 0.0 && dr.beta_new == 0.0));
+                if (lane == 0) sh.w_nsm[warp] = nsm;
+                sh.w_comp[wk] = dr.comp;
+                asm volatile("bar.sync 2, 64;" ::: "memory");
+                const unsigned nsm0 = sh.w_nsm[0], nsm1 = sh.w_nsm[1];
+                if ((nsm0 | nsm1) == 0) break;
+                if (prof_on) { p.prof[kProfWalkIters] += 1; p.prof[kProfWalkSolves] += __popc(nsm0) + __popc(nsm1); }
+                double corr = 0.0;
+                if (warp == 0) {
+                    // (b) triangular solve over the non-skipped markers, in block order
+                    const int comp1 = sh.w_comp[32 + lane];
+                    double c0 = 0.0, c1 = 0.0;
+                    unsigned m = nsm0;
+                    while (m) {
+                        const int jl = __ffs(m) - 1;
+                        m &= m - 1;
+                        const double mine = bo - beta_given_comp(sh.gc, gg, K, dr.comp, base + c0, bo, zz);
+                        const double dB = __shfl_sync(0xffffffffu, mine, jl);          // eps += dB * x_j
+                        if (dB != 0.0) {
+                            if (act && lane > jl) c0 += dB * G[jl * kB + lane];
+                            if (act1) c1 += dB * G[jl * kB + 32 + lane];
+                        }
+                    }
+                    m = nsm1;
+                    while (m) {
+                        const int jl = __ffs(m) - 1;
+                        m &= m - 1;
+                        const double mine = bo1 - beta_given_comp(sh.gc, gg1, K, comp1, base1 + c1, bo1, zz1);
+                        const double dB = __shfl_sync(0xffffffffu, mine, jl);
+                        if (dB != 0.0 && act1 && lane > jl) c1 += dB * G[(32 + jl) * kB + 32 + lane];
+                    }
+                    corr = c0;
+                    sh.w_corr[32 + lane] = c1;
+                }
+                asm volatile("bar.sync 2, 64;" ::: "memory");
+                if (warp == 1) corr = sh.w_corr[wk];
+                // (c) re-sample where the dot moved; confirm the components
+                bool changed = false;
+                if (act && corr != corr_used) {
+                    const Draw nd = sample_marker_k(sh.gc, gg, K, base + corr, p.sigmaE, bo, uu, zz);
+                    changed = nd.comp != dr.comp;
+                    dr = nd;
+                    corr_used = corr;
+                }
+                const unsigned chg = __ballot_sync(0xffffffffu, changed);
+                if (lane == 0) sh.w_chg[warp] = chg;
+                asm volatile("bar.sync 2, 64;" ::: "memory");
+                if ((sh.w_chg[0] | sh.w_chg[1]) == 0) break;
+            }
+            const double dB = act ? (bo - dr.beta_new) : 0.0;
+            const bool upd = act && dB != 0.0;
+            const bool nonskip = act && !(bo == 0.0 && dr.beta_new == 0.0);
+            if (act) sh.dbeta[wk] = dB;
+            const unsigned um = __ballot_sync(0xffffffffu, upd);
+            const unsigned nsk = __ballot_sync(0xffffffffu, nonskip);
+            if (lane == 0) { sh.w_cnt[warp] = __popc(um); sh.w_cnt2[warp] = __popc(nsk); }
+            if (cta == 0 && act) {
+                const uint32_t id = meta.id[wk];
+                if (!p.async_mode) p.acum[id] = dr.acum0;                      // src/BayesRBase.cpp:341
+                if (dr.comp >= 0) {
+                    p.beta[id] = dr.beta_new;                                  // :350-352 / :492
+                    p.comp[id] = double(dr.comp);                              // :356 / :493
+                    atomicAdd(&sh.v_s[gg * K + dr.comp], 1);                   // :355 / :511
+                }
+            }
+            if (cta == 0) {                                                    // :353 / :522, fixed summation order
+                for (uint32_t g0 = 0; g0 < p.nG; g0 += kB) {
+                    const uint32_t ng = min((uint32_t)kB, p.nG - g0);
+                    for (uint32_t gi = 0; gi < ng; ++gi) {
+                        const double b2 = (act && gg == int(g0 + gi) && dr.comp > 0) ? dr.beta_new * dr.beta_new : 0.0;
+                        const double sgi = warp_sum(b2);
+                        if (lane == 0) { if (warp == 0) sh.d0[gi] = sgi; else sh.w_corr[gi] = sgi; }
+                    }
+                    asm volatile("bar.sync 2, 64;" ::: "memory");
+                    if (uint32_t(tid) < ng) sh.betasq_s[g0 + tid] += sh.d0[tid] + sh.w_corr[tid];
+                    asm volatile("bar.sync 2, 64;" ::: "memory");
+                }
+            }
+            asm volatile("bar.sync 2, 64;" ::: "memory");
+            const uint32_t off = warp ? sh.w_cnt[0] : 0u;
+            if (upd) sh.ns_list[off + __popc(um & ((1u << lane) - 1u))] = wk;
+            if (tid == 0) { sh.n_ns = sh.w_cnt[0] + sh.w_cnt[1]; sh.n_nonskipped_total += sh.w_cnt2[0] + sh.w_cnt2[1]; }
+        }
+        __syncthreads();
+        PHASE(kProfWalk);
 
         // ---- 7. residual update in registers, re-quantise --------------------------------------------------
         const uint32_t n_ns = sh.n_ns;
@@ -684,8 +864,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                     }
                 }
             }
-            if (tid == 0) { sh.epsq[0] = 0; sh.epsq[1] = 0; }
-            __syncthreads();
+            PHASE(kProfAxpy);
             // individuals past n_local carry eps = 0 and code 0, so their lut[0] increments must not stick
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
@@ -699,6 +878,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             quantize();
         }
         __syncthreads();
+        PHASE(kProfQuantize);
 
         // ---- 8. this buffer is free: prefetch block b+2 into it ------------------------------------------
         if (b + 2 < nBlocks) prefetch(b + 2);
@@ -722,7 +902,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         double s = 0.0;
         for (int w = 0; w < kWarps; ++w) s += sh.warp_tmp[w];
         // this slice's sum(eps) from the exact fixed-point sum
-        p.cta_red[2 * cta + 0] = (double((long long)sh.epsq[0]) * 4294967296.0 + double((long long)sh.epsq[1])) * inv_scale;
+        unsigned long long qhi, qlo;
+        slice_q(qhi, qlo);
+        p.cta_red[2 * cta + 0] = (double((long long)qhi) * 4294967296.0 + double((long long)qlo)) * inv_scale;
         p.cta_red[2 * cta + 1] = s;
         if (sh.err) atomicOr(p.out_counts + 2, sh.err);
     }

@@ -200,6 +200,11 @@ int brr_gpu_synth_bed_host(uint64_t seed, double maf_lo, double maf_hi, int log_
 int brr_gpu_info(brr_gpu_ctx *ctx, uint32_t *n_ctas, uint32_t *slice_inds, uint32_t *block_markers,
                  uint64_t *genotype_bytes);
 uint64_t brr_gpu_launch_count(brr_gpu_ctx *ctx);
+/* Phase breakdown of the dense sweep kernel (SM cycles of CTA 0, accumulated over sweeps), available when
+ * the environment has BRR_GPU_PROFILE=1 at brr_gpu_create: 16 counters in the order dot, dot-reduce,
+ * gram-scan, gram-cross, gram-mma, gram-reduce, barrier wait, readback, walk, axpy, quantize, prologue,
+ * walk iterations, walk solve steps (counts), walk first round, wait for the code rows.  reset != 0 clears them. */
+int brr_gpu_profile_cycles(brr_gpu_ctx *ctx, uint64_t *cycles16, int reset);
 
 #ifdef __cplusplus
 }
