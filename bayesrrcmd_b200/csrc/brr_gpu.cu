@@ -132,7 +132,7 @@ static int choose_geometry(brr_gpu_ctx *c)
     c->SL = SL;
     c->nCTA = (cfg.n_inds + SL - 1) / SL;
     c->PW = SL / 16;
-    c->RS = c->PW;
+    c->RS = c->PW + (dense ? kTailWords : 0u);
     while (c->RS % 8 != 4) c->RS += 4;      // shared-memory row stride = 4 (mod 8) words: conflict-free fragment loads
     const uint32_t maxSL = dense ? (uint32_t)kMaxSL : 8192u;
     if (SL > maxSL) return fail(BRR_GPU_EINVAL, "n_inds=%u needs %u individuals per CTA; at most %u (=%u per GPU) are supported: shard over more GPUs",
@@ -183,7 +183,7 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
 
     const uint32_t M = cfg->n_markers, N = cfg->n_inds, K = cfg->n_components, nG = cfg->n_groups;
     if (cfg->layout == BRR_GPU_LAYOUT_DENSE2BIT) {
-        c->codes_bytes = size_t(M) * c->nCTA * c->PW * 4;
+        c->codes_bytes = size_t(M) * c->nCTA * (c->PW + kTailWords) * 4;
         TRY_OR_DESTROY(dev_alloc(&c->codes, c->codes_bytes / 4));
         TRY_OR_DESTROY(dev_alloc(&c->lut, size_t(M) * 4));
         c->smem_bytes = sweep_smem_bytes(c->RS);
@@ -236,8 +236,8 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
     TRY_OR_DESTROY(dev_alloc(&c->out_counts, 4));
     if (const char *e = getenv("BRR_GPU_PROFILE")) {
         if (e[0] == '1') {
-            TRY_OR_DESTROY(dev_alloc(&c->prof, 16));
-            CUDA_OR_DESTROY(cudaMemset(c->prof, 0, sizeof(unsigned long long) * 16));
+            TRY_OR_DESTROY(dev_alloc(&c->prof, 24));
+            CUDA_OR_DESTROY(cudaMemset(c->prof, 0, sizeof(unsigned long long) * 24));
         }
     }
     CUDA_OR_DESTROY(cudaMallocHost(reinterpret_cast<void **>(&c->h_small), sizeof(double) * (2 * kMaxGK + 8 + 2 * kRedBlocks)));
@@ -292,8 +292,12 @@ extern "C" int brr_gpu_upload_dense2bit(brr_gpu_ctx *c, const uint8_t *bed, size
     }
     cudaFree(stage);
     const uint32_t wpb = 8;
+    {
+        const size_t n_rows = size_t(count) * c->nCTA;
+        build_row_tails_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, c->stream>>>(c->codes, size_t(first) * c->nCTA, n_rows, c->PW);
+    }
     count_classes_kernel<<<(count + wpb - 1) / wpb, wpb * 32, 0, c->stream>>>(c->codes, first, count, c->cfg.n_inds, c->nCTA, c->PW, c->counts_local);
-    ++c->launches;
+    c->launches += 2;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->uploaded = true;
@@ -603,8 +607,10 @@ extern "C" int brr_gpu_synth_dense(brr_gpu_ctx *c, uint64_t seed, double maf_lo,
     if (e == cudaSuccess) {
         synth_codes_kernel<<<dim3(c->nCTA, std::min<uint32_t>(M, 4096)), 128, 0, c->stream>>>(seed, dthr, M, c->cfg.n_inds, ind_offset, c->nCTA, c->SL, c->PW, c->codes);
         const uint32_t wpb = 8;
+        const size_t n_rows = size_t(M) * c->nCTA;
+        build_row_tails_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, c->stream>>>(c->codes, 0, n_rows, c->PW);
         count_classes_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, c->stream>>>(c->codes, 0, M, c->cfg.n_inds, c->nCTA, c->PW, c->counts_local);
-        c->launches += 2;
+        c->launches += 3;
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -651,6 +657,14 @@ extern "C" int brr_gpu_profile_cycles(brr_gpu_ctx *c, uint64_t *cycles16, int re
 {
     CHECK_CTX(c);
     if (!cycles16) return fail(BRR_GPU_EINVAL, "null output");
+    if (c->prof && getenv("BRR_GPU_PROFILE_FINE")) {      // developer aid: the 8 extra fine-grained counters
+        uint64_t fine[8];
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaMemcpy(fine, c->prof + 16, sizeof(fine), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[brr_gpu fine] dotred1=%llu dotred2=%llu dotred3=%llu rb1=%llu rb2=%llu\n", (unsigned long long)fine[0],
+                (unsigned long long)fine[1], (unsigned long long)fine[2], (unsigned long long)fine[3], (unsigned long long)fine[4]);
+        if (reset) CUDA_TRY(cudaMemset(c->prof + 16, 0, sizeof(fine)));
+    }
     if (!c->prof) return fail(BRR_GPU_ESTATE, "phase profiling is off: set BRR_GPU_PROFILE=1 before brr_gpu_create");
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaMemcpy(cycles16, c->prof, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost));

@@ -22,9 +22,15 @@ __host__ __device__ inline uint32_t synth_class(uint64_t seed, uint32_t marker, 
     return r < thr[0] ? 0u : (r < thr[1] ? 1u : 2u);
 }
 
-// Store layout (HBM): codes[(marker*nCTA + cta)*PW + w] is a 32-bit word holding the 2-bit codes of the
-// 16 individuals cta*SL + 16w .. +15 (individual j of the word at bits 2j..2j+1); PW = SL/16 words per
-// (marker, CTA slice).  Code = allele count 0,1,2; 3 = missing.  Individuals past n_local get code 0.
+// Store layout (HBM): one ROW per (marker, CTA slice), PWT = PW + 8 words, at codes[(marker*nCTA + cta)*PWT]:
+//   words [0, PW), PW = SL/16: word w holds the 2-bit codes of the 16 individuals cta*SL + 16w .. +15
+//     (individual j of the word at bits 2j..2j+1).  Code = allele count 0,1,2; 3 = missing.  Individuals
+//     past n_local get code 0.
+//   words [PW, PW+8): the row's missing list as 16 x uint16: [0] = number of missing genotypes in the row
+//     (the true count, may exceed 15), [1..15] = the first slice-local individual ids, ascending.
+//   A row is fetched by ONE TMA bulk copy; the list lets the sweep correct for missing genotypes without
+//   scanning the codes (rows with more than 15 are rescanned by the warp that owns them).
+constexpr uint32_t kTailWords = 8;
 // The PLINK code (b1 b0) maps as 00->2, 10->1, 11->0, 01->missing (reference src/preprocessgraph.cpp:50-51,
 // src/densemarkerbuilder.cpp:30): new_hi = ~b1, new_lo = b1 ^ b0.
 
@@ -35,7 +41,7 @@ __global__ void bed_to_codes_kernel(const uint8_t *__restrict__ bed, size_t col_
 {
     const uint32_t cta = blockIdx.x, mk = blockIdx.y;
     const uint8_t *col = bed + size_t(mk) * col_bytes;
-    uint32_t *dst = codes + (size_t(first_marker + mk) * nCTA + cta) * PW;
+    uint32_t *dst = codes + (size_t(first_marker + mk) * nCTA + cta) * (PW + kTailWords);
     for (uint32_t w = threadIdx.x; w < PW; w += blockDim.x) {
         const uint32_t i0 = cta * SL + 16 * w;
         uint32_t out = 0;
@@ -62,7 +68,7 @@ __global__ void synth_codes_kernel(uint64_t seed, const uint32_t *__restrict__ t
 {
     const uint32_t cta = blockIdx.x;
     for (uint32_t mk = blockIdx.y; mk < M; mk += gridDim.y) {
-        uint32_t *dst = codes + (size_t(mk) * nCTA + cta) * PW;
+        uint32_t *dst = codes + (size_t(mk) * nCTA + cta) * (PW + kTailWords);
         const uint32_t t3[3] = {thr[3 * mk], thr[3 * mk + 1], thr[3 * mk + 2]};
         for (uint32_t w = threadIdx.x; w < PW; w += blockDim.x) {
             const uint32_t i0 = cta * SL + 16 * w;
@@ -75,6 +81,42 @@ __global__ void synth_codes_kernel(uint64_t seed, const uint32_t *__restrict__ t
     }
 }
 
+// missing lists of the rows [first_row, first_row + n_rows): one warp per row, ordered compaction
+__global__ void build_row_tails_kernel(uint32_t *__restrict__ codes, size_t first_row, size_t n_rows, uint32_t PW)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t r = size_t(blockIdx.x) * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    uint32_t *row = codes + (first_row + r) * (PW + kTailWords);
+    uint16_t *tail = reinterpret_cast<uint16_t *>(row + PW);
+    uint32_t cnt = 0;
+    if (lane < 16) tail[lane] = 0;
+    __syncwarp();
+    for (uint32_t w0 = 0; w0 < PW; w0 += 32) {
+        const uint32_t w = w0 + lane;
+        const uint32_t x = (w < PW) ? row[w] : 0u;
+        uint32_t mm = x & (x >> 1) & 0x55555555u;
+        const uint32_t n = __popc(mm);
+        unsigned bal = __ballot_sync(0xffffffffu, n != 0);
+        while (bal) {
+            const int l = __ffs(bal) - 1;
+            bal &= bal - 1;
+            const uint32_t nl = __shfl_sync(0xffffffffu, n, l);
+            if (int(lane) == l) {
+                uint32_t pos = cnt;
+                while (mm) {
+                    const int bit = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    if (pos < 15) tail[1 + pos] = uint16_t(16 * w + (bit >> 1));
+                    ++pos;
+                }
+            }
+            cnt += nl;
+        }
+    }
+    if (lane == 0) tail[0] = uint16_t(cnt);
+}
+
 // class counts of this shard: one warp per marker. counts[marker] = {n0, n1, n2, nmiss}
 __global__ void count_classes_kernel(const uint32_t *__restrict__ codes, uint32_t first, uint32_t count,
                                      uint32_t n_local, uint32_t nCTA, uint32_t PW, uint32_t *__restrict__ counts)
@@ -82,13 +124,15 @@ __global__ void count_classes_kernel(const uint32_t *__restrict__ codes, uint32_
     const uint32_t warps_per_block = blockDim.x / 32, lane = threadIdx.x & 31;
     const uint32_t mk = first + blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     if (mk >= first + count) return;
-    const uint32_t *base = codes + size_t(mk) * nCTA * PW;
+    const uint32_t PWT = PW + kTailWords;
+    const uint32_t *base = codes + size_t(mk) * nCTA * PWT;
     uint32_t n1 = 0, n2 = 0, nm = 0;
-    for (uint32_t i = lane; i < nCTA * PW; i += 32) {
-        const uint32_t x = base[i];
-        const uint32_t lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;
-        n1 += __popc(lo & ~hi); n2 += __popc(hi & ~lo); nm += __popc(lo & hi);
-    }
+    for (uint32_t c = 0; c < nCTA; ++c)
+        for (uint32_t w = lane; w < PW; w += 32) {
+            const uint32_t x = base[size_t(c) * PWT + w];
+            const uint32_t lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;
+            n1 += __popc(lo & ~hi); n2 += __popc(hi & ~lo); nm += __popc(lo & hi);
+        }
     n1 = __reduce_add_sync(0xffffffffu, n1); n2 = __reduce_add_sync(0xffffffffu, n2); nm = __reduce_add_sync(0xffffffffu, nm);
     if (lane == 0) {
         counts[4 * size_t(mk) + 0] = n_local - n1 - n2 - nm;
@@ -121,7 +165,7 @@ __device__ __forceinline__ uint32_t code_of(const uint32_t *__restrict__ codes, 
                                             uint32_t SL, uint32_t PW, uint32_t gi)
 {
     const uint32_t cta = gi / SL, i = gi - cta * SL;
-    return (codes[(size_t(marker) * nCTA + cta) * PW + (i >> 4)] >> (2 * (i & 15u))) & 3u;
+    return (codes[(size_t(marker) * nCTA + cta) * (PW + kTailWords) + (i >> 4)] >> (2 * (i & 15u))) & 3u;
 }
 
 // ---- marker-level parity hooks -------------------------------------------------------------------
@@ -133,7 +177,7 @@ __global__ void dense_dot_kernel(const uint32_t *__restrict__ codes, const doubl
 {
     __shared__ double wsum[32];
     const uint32_t cta = blockIdx.x;
-    const uint32_t *row = codes + (size_t(marker) * nCTA + cta) * PW;
+    const uint32_t *row = codes + (size_t(marker) * nCTA + cta) * (PW + kTailWords);
     const double L[4] = {lut[4 * size_t(marker)], lut[4 * size_t(marker) + 1], lut[4 * size_t(marker) + 2],
                          lut[4 * size_t(marker) + 3]};
     double acc = 0.0;

@@ -41,7 +41,8 @@ namespace brr {
 constexpr int kB = 64;                 // markers per block = tile structure of the MMA passes
 constexpr int kLimbs = 8;
 constexpr uint32_t kM3 = 0x03030303u;
-constexpr int kMissSeg = 256;          // missing-list entries per warp segment
+constexpr int kMissSeg = 256;          // entries of a warp's missing-list scratch segment
+constexpr uint32_t kTail = 8;          // tail words of a code row: 16 x uint16 missing list (store_kernels.cuh)
 constexpr int kMissCap = kMissSeg * kWarps;
 constexpr int kMaxSL = 4096;           // individuals per CTA (2 register items of 4 per thread)
 constexpr int kScratchInts = 8192;     // 32 KB shared scratch
@@ -50,7 +51,7 @@ constexpr int kHeadroomBits = 6;       // |eps| may grow 64x inside a sweep befo
 // rotating global slot (int32 units)
 constexpr int kSlotA = 0;              // [64][64]: upper (j<k) = sum g'_j g'_k ; lower [k][j] = # both missing
 constexpr int kSlotY = 4096;           // [64][64]: YT[b][a] = sum over {i: b missing, a present} of g_a
-constexpr int kSlotDots = 8192;        // [64][8] limb sums
+constexpr int kSlotDots = 8192;        // [64][4] int64: limb sums packed in pairs (even limb + odd limb * 2^32)
 constexpr int kSlotSm = 8704;          // [64][2] int64: sum of q over missing individuals (hi, lo parts)
 constexpr int kSlotEps = 8960;         // [2] int64: sum of q over all individuals (hi, lo parts)
 constexpr int kSlotFlag = 8964;        // != 0: some slice of the block has missing genotypes
@@ -59,9 +60,9 @@ constexpr int kSlots = 4;
 
 struct DenseSweepParams {
     // geometry
-    uint32_t n_local, n_total, M, K, nG, B, nCTA, SL, PW, RS;   // PW = SL/16 words per row, RS = smem row stride (words)
+    uint32_t n_local, n_total, M, K, nG, B, nCTA, SL, PW, RS;   // PW = SL/16 code words per row (+8 tail words in HBM), RS = smem row stride (words)
     // store
-    const uint32_t *codes;   // [M][nCTA][PW]
+    const uint32_t *codes;   // [M][nCTA][PW + 8]  (store_kernels.cuh)
     const double *lut;       // [M][4] values of class 0,1,2,missing
     const uint32_t *counts;  // [M][4] GLOBAL class counts
     const int32_t *group;    // [M] or nullptr
@@ -92,7 +93,7 @@ struct DenseSweepParams {
 // phases of the block loop, as timed by thread 0 of CTA 0 when DenseSweepParams::prof is set
 enum { kProfDot = 0, kProfDotReduce, kProfGramScan, kProfGramCross, kProfGramMma, kProfGramReduce, kProfBarrier,
        kProfReadback, kProfWalk, kProfAxpy, kProfQuantize, kProfPrologue, kProfWalkIters, kProfWalkSolves, kProfWalkA, kProfGramWait,
-       kProfPhases = 16 };
+       kProfDotRed1, kProfDotRed2, kProfDotRed3, kProfRb1, kProfRb2, kProfPhases = 24 };
 
 struct alignas(16) BlockMeta {
     uint32_t id[kB];
@@ -124,8 +125,6 @@ struct SweepShared {   // fixed-size part; limbs, code buffers, scratch and the 
     uint32_t ns_list[kB];
     uint32_t n_ns;
     uint32_t n_nonskipped_total;
-    uint32_t miss_rowcnt[kWarps][4]; // missing-list entries of warp w for its rows w, w+16, w+32, w+48
-    uint32_t miss_any, miss_overflow;
     uint32_t err;
     alignas(8) uint64_t mbar[2];
 };
@@ -208,7 +207,8 @@ __device__ __forceinline__ void gram_role_pass(const uint32_t *__restrict__ pk, 
     }
 }
 
-// final owner (k-group 0) adds the other k-groups' copies and publishes the needed entries
+// final owner (k-group 0) adds the other k-groups' copies and publishes the needed entries: the two
+// columns (2tig, 2tig+1) a thread holds for a row go out as ONE 64-bit RED (counts are >= 0: no carry)
 template <int ROLE>
 __device__ __forceinline__ void gram_role_publish(const int *__restrict__ scratch, uint32_t nkg, int lane, int (&acc)[5][4],
                                                   int *__restrict__ slotA, uint32_t nb)
@@ -217,11 +217,18 @@ __device__ __forceinline__ void gram_role_publish(const int *__restrict__ scratc
 #pragma unroll
     for (int t = 0; t < 5; ++t)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            int s = acc[t][r];
-            for (uint32_t g = 1; g < nkg; ++g) s += scratch[(((g - 1) * 4 + ROLE) * 20 + t * 4 + r) * 32 + lane];
-            const uint32_t row = 16 * gram_role_mi(ROLE, t) + gid + 8 * (r >> 1), col = 8 * gram_role_nj(ROLE, t) + 2 * tig + (r & 1);
-            if (row < col && col < nb && s != 0) atomicAdd(slotA + row * kB + col, s);
+        for (int rr = 0; rr < 2; ++rr) {
+            int s0 = acc[t][2 * rr], s1 = acc[t][2 * rr + 1];
+            for (uint32_t g = 1; g < nkg; ++g) {
+                s0 += scratch[(((g - 1) * 4 + ROLE) * 20 + t * 4 + 2 * rr) * 32 + lane];
+                s1 += scratch[(((g - 1) * 4 + ROLE) * 20 + t * 4 + 2 * rr + 1) * 32 + lane];
+            }
+            const uint32_t row = 16 * gram_role_mi(ROLE, t) + gid + 8 * rr, col = 8 * gram_role_nj(ROLE, t) + 2 * tig;
+            if (!(row < col)) s0 = 0;                       // keep the lower triangle (both-missing counts) clean
+            if (!(row < col + 1) || col + 1 >= nb) s1 = 0;
+            if (col >= nb) s0 = 0;
+            const unsigned long long v = (unsigned long long)(unsigned)s0 | ((unsigned long long)(unsigned)s1 << 32);
+            if (v) atomicAdd(reinterpret_cast<unsigned long long *>(slotA + row * kB + col), v);
         }
 }
 
@@ -279,7 +286,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     const uint32_t B = p.B, K = p.K;
     const uint32_t NP = SL / 64;                     // 64-individual k-step pairs per slice
     const uint32_t NI = SL / 4;                      // register items (4 individuals each) per slice
-    const uint32_t CB = SL / 4;                      // bytes per (marker, CTA) row in HBM
+    const uint32_t PWT = PW + kTail;                 // words per (marker, CTA) row in HBM: codes + missing list
+    const uint32_t CB = PWT * 4;                     // bytes per row = one TMA bulk copy
     const double NM1 = double(p.n_total - 1), Nt = double(p.n_total);
     const uint32_t nBlocks = (p.n_order + B - 1) / B;
     const uint32_t slice0 = cta * SL;
@@ -307,12 +315,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     }
     fill_group_consts(sh.gc, p.nG, K, NM1, p.sigmaE, p.pi, p.sigmaG, p.cva);
     for (int i = tid; i < kMaxGK; i += kThreads) { sh.v_s[i] = 0; sh.betasq_s[i] = 0.0; }
-    if (tid < kWarps * 4) sh.miss_rowcnt[tid >> 2][tid & 3] = 0;
     for (uint32_t i = tid; i < 2 * kB * RS; i += kThreads) pkbuf[i] = 0;
     if (tid == 0) {
         mbar_init(&sh.mbar[0], 1); mbar_init(&sh.mbar[1], 1);
         mbar_fence_init();
-        sh.n_nonskipped_total = 0; sh.n_ns = 0; sh.err = 0; sh.miss_any = 0; sh.miss_overflow = 0;
+        sh.n_nonskipped_total = 0; sh.n_ns = 0; sh.err = 0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -340,12 +347,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 if (r < nb) {
                     const uint32_t id = p.order[b * B + r];
                     sh.ids[b & 1][r] = id;
-                    bulk_g2s(dst + size_t(r) * RS, p.codes + (size_t(id) * p.nCTA + cta) * PW, CB, bar);
+                    bulk_g2s(dst + size_t(r) * RS, p.codes + (size_t(id) * p.nCTA + cta) * PWT, CB, bar);
                 }
             }
         } else if (nb < B && warp >= 2) {
-            for (uint32_t i = (warp - 2) * 32 + lane; i < (B - nb) * PW; i += (kWarps - 2) * 32)
-                dst[size_t(nb + i / PW) * RS + i % PW] = 0;
+            for (uint32_t i = (warp - 2) * 32 + lane; i < (B - nb) * PWT; i += (kWarps - 2) * 32)
+                dst[size_t(nb + i / PWT) * RS + i % PWT] = 0;
         }
     };
     if (nBlocks > 0) prefetch(0);
@@ -407,47 +414,46 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     quantize();
 
     // ---- missing-genotype side pass --------------------------------------------------------------
-    // Each warp lists the missing entries (slice-local individual ids) of its rows into its private
-    // segment of the list: no atomics, deterministic.  all_rows: warp w scans rows w, w+16, w+32, w+48;
-    // else every warp scans its share of the words of the single row m_one (a row with more missing
-    // genotypes than a segment holds is handled that way, one row at a time).
-    auto scan_missing = [&](const uint32_t *pk, uint32_t nb, bool all_rows, uint32_t m_one) {
+    // Every code row carries its missing list (count + first 15 slice-local ids) in its tail.  A warp
+    // visits the missing entries of a row in chunks copied to its private scratch segment: one chunk from
+    // the tail when the count fits, else by scanning the row 16 words (<= 256 entries) at a time.
+    auto for_missing_chunks = [&](const uint32_t *row, auto &&fn) {
         uint32_t *seg = miss_list + warp * kMissSeg;
-        uint32_t cnt = 0;
-        const uint32_t chunk = (PW + kWarps - 1) / kWarps;
-        for (int r = 0; r < 4; ++r) {
-            const uint32_t m = all_rows ? uint32_t(warp + 16 * r) : m_one;
-            uint32_t c_r = 0;
-            if (m < nb && (all_rows || r == 0)) {
-                const uint32_t *row = pk + size_t(m) * RS;
-                const uint32_t w_lo = all_rows ? 0u : warp * chunk, w_hi = all_rows ? PW : min(PW, w_lo + chunk);
-                for (uint32_t w0 = w_lo; w0 < w_hi; w0 += 32) {
-                    const uint32_t w = w0 + lane;
-                    const uint32_t x = (w < w_hi) ? row[w] : 0u;
-                    uint32_t mm = x & (x >> 1) & 0x55555555u;
-                    const uint32_t n = __popc(mm);
-                    unsigned bal = __ballot_sync(0xffffffffu, n != 0);
-                    while (bal) {
-                        const int l = __ffs(bal) - 1;
-                        bal &= bal - 1;
-                        const uint32_t nl = __shfl_sync(0xffffffffu, n, l);
-                        if (lane == l) {
-                            uint32_t pos = cnt;
-                            while (mm) {
-                                const int bit = __ffs(mm) - 1;
-                                mm &= mm - 1;
-                                if (pos < (uint32_t)kMissSeg) seg[pos] = 16 * w + (bit >> 1);
-                                ++pos;
-                            }
-                        }
-                        cnt += nl; c_r += nl;
+        const uint16_t *tail = reinterpret_cast<const uint16_t *>(row + PW);
+        const uint32_t cnt = tail[0];
+        if (cnt == 0) return;
+        if (cnt <= 15) {
+            if (uint32_t(lane) < cnt) seg[lane] = tail[1 + lane];
+            __syncwarp();
+            fn(seg, cnt);
+            __syncwarp();
+            return;
+        }
+        for (uint32_t w0 = 0; w0 < PW; w0 += 16) {
+            const uint32_t w = w0 + lane;
+            const uint32_t x = (lane < 16 && w < PW) ? row[w] : 0u;
+            uint32_t mm = x & (x >> 1) & 0x55555555u;
+            const uint32_t n = __popc(mm);
+            unsigned bal = __ballot_sync(0xffffffffu, n != 0);
+            uint32_t tot = 0;
+            while (bal) {
+                const int l = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const uint32_t nl = __shfl_sync(0xffffffffu, n, l);
+                if (lane == l) {
+                    uint32_t pos = tot;
+                    while (mm) {
+                        const int bit = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        seg[pos++] = 16 * w + (bit >> 1);
                     }
                 }
+                tot += nl;
             }
-            if (lane == 0) sh.miss_rowcnt[warp][r] = c_r;
+            __syncwarp();
+            if (tot) fn(seg, tot);
+            __syncwarp();
         }
-        if (lane == 0 && cnt) { sh.miss_any = 1; if (cnt > (uint32_t)kMissSeg) sh.miss_overflow = 1; }
-        __syncwarp();
     };
     // cross counts of this warp's listed entries of row m with every other marker of the block, straight
     // into the global slot: YT[m][a] += g_a(i) (a present), Wlow[m][a] += 1 (a < m, a missing too)
@@ -467,10 +473,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             }
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 2; ++h) {                  // neighbouring lanes share one 64-bit RED (counts are >= 0: no carry)
             const uint32_t a = lane + 32 * h;
-            if (y[h]) atomicAdd(slot + kSlotY + m * kB + a, y[h]);
-            if (wv[h]) atomicAdd(slot + kSlotA + m * kB + a, wv[h]);
+            const unsigned long long yy = (unsigned long long)(unsigned)y[h] | ((unsigned long long)(unsigned)__shfl_down_sync(0xffffffffu, y[h], 1) << 32);
+            const unsigned long long ww = (unsigned long long)(unsigned)wv[h] | ((unsigned long long)(unsigned)__shfl_down_sync(0xffffffffu, wv[h], 1) << 32);
+            if (!(lane & 1)) {
+                if (yy) atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotY + m * kB + a), yy);
+                if (ww) atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotA + m * kB + a), ww);
+            }
         }
     };
     // sum of q over this warp's listed entries of row m -> global slot (exact, order independent)
@@ -498,41 +508,28 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         }
     };
 
-    // Gram pass of block b: missing scan + cross counts + the 64x64 integer Gram, published into slot b%4
+    // Gram pass of block b: cross counts of the missing entries + the 64x64 integer Gram, published into slot b%4
     auto gram_pass = [&](uint32_t b) {
         const uint32_t nb = min(B, p.n_order - b * B);
         const uint32_t *pk = pkbuf + size_t(b & 1) * kB * RS;
         int *slot = p.slots + size_t(b % kSlots) * kSlotInts;
         mbar_wait(&sh.mbar[b & 1], (b >> 1) & 1);
-        if (tid == 0) { sh.miss_any = 0; sh.miss_overflow = 0; }
-        __syncthreads();
         PHASE(kProfGramWait);
-        scan_missing(pk, nb, true, 0);
-        __syncthreads();
-        PHASE(kProfGramScan);
-        const bool any_missing = sh.miss_any != 0, overflow = sh.miss_overflow != 0;
-        if (any_missing && tid == 0) atomicAdd(slot + kSlotFlag, 1);
         const bool want_gram = !p.async_mode && nb > 1;
-        if (any_missing && want_gram) {
-            if (!overflow) {
-                uint32_t off = 0;
-                for (int r = 0; r < 4; ++r) {
-                    const uint32_t n = sh.miss_rowcnt[warp][r];
-                    if (n) cross_missing(pk, slot, nb, warp + 16 * r, miss_list + warp * kMissSeg + off, n);
-                    off += n;
+        {
+            bool any = false;
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t m = warp + 16 * r;
+                if (m < nb) {
+                    const uint32_t *row = pk + size_t(m) * RS;
+                    any |= reinterpret_cast<const uint16_t *>(row + PW)[0] != 0;
+                    if (want_gram)
+                        for_missing_chunks(row, [&](const uint32_t *ent, uint32_t n) { cross_missing(pk, slot, nb, m, ent, n); });
                 }
-            } else {                                   // too many for the list: one row at a time
-                for (uint32_t m = 0; m < nb; ++m) {
-                    __syncthreads();
-                    scan_missing(pk, nb, false, m);
-                    const uint32_t n = min(sh.miss_rowcnt[warp][0], (uint32_t)kMissSeg);
-                    if (n) cross_missing(pk, slot, nb, m, miss_list + warp * kMissSeg, n);
-                }
-                __syncthreads();
-                if (tid == 0) sh.miss_overflow = 1;      // tells the dot pass to rescan as well
             }
-            PHASE(kProfGramCross);
+            if (any && lane == 0) atomicAdd(slot + kSlotFlag, 1);
         }
+        PHASE(kProfGramCross);
         if (want_gram) {
             const uint32_t role = warp & 3, kg = warp >> 2, nkg = kWarps / 4;
             int acc[5][4];
@@ -605,42 +602,37 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         __syncthreads();
         PHASE(kProfDot);
         {
-            // one output per thread: tile mi = tid/128, register r, lane l
-            int s = 0;
-            const int o = tid;      // (mi*4 + r)*32 + lane
+            // two outputs per thread of the first 8 warps: tile mi, row half rr, lane l5 -> limbs (2tig, 2tig+1) of one
+            // marker, published as ONE signed 64-bit RED (even limb + odd limb * 2^32)
+            if (tid < 256) {
+                const int l5 = tid & 31, rr = (tid >> 5) & 1, mi = tid >> 6;
+                const int o = (mi * 4 + 2 * rr) * 32 + l5;
+                int s0 = 0, s1 = 0;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) s += scratch[w * 512 + o];
-            const int l5 = o & 31, r = (o >> 5) & 3, mi = o >> 7;
-            const uint32_t m = 16 * mi + (l5 >> 2) + 8 * (r >> 1), limb = 2 * (l5 & 3) + (r & 1);
-            if (s != 0 && m < nb) atomicAdd(slot + kSlotDots + m * kLimbs + limb, s);
-            if (warp == 0) {                      // lane 2w+h holds part h of warp w's sum of q
+                for (int w = 0; w < kWarps; ++w) { s0 += scratch[w * 512 + o]; s1 += scratch[w * 512 + o + 32]; }
+                const uint32_t m = 16 * mi + (l5 >> 2) + 8 * rr;
+                const long long v = (long long)s0 + ((long long)s1 << 32);
+                if (v != 0 && m < nb)
+                    atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotDots) + m * 4 + (l5 & 3), (unsigned long long)v);
+            }
+            PHASE(kProfDotRed1);
+            if (warp == 8) {                      // lane 2w+h holds part h of warp w's sum of q
                 unsigned long long v = sh.wq[lane >> 1][lane & 1];
 #pragma unroll
                 for (int o2 = 2; o2 < 32; o2 <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
                 if (lane < 2) atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotEps) + lane, v);
             }
-            // sum of q over the missing individuals of every marker (list built by this block's Gram pass)
-            if (sh.miss_any) {
-                if (!sh.miss_overflow) {
-                    uint32_t off = 0;
-                    for (int r2 = 0; r2 < 4; ++r2) {
-                        const uint32_t n = sh.miss_rowcnt[warp][r2];
-                        if (n) missing_q_sum(slot, warp + 16 * r2, miss_list + warp * kMissSeg + off, n);
-                        off += n;
-                    }
-                } else {                               // list overflowed: rescan, one row at a time
-                    for (uint32_t m2 = 0; m2 < nb; ++m2) {
-                        __syncthreads();
-                        scan_missing(pk, nb, false, m2);
-                        const uint32_t n = min(sh.miss_rowcnt[warp][0], (uint32_t)kMissSeg);
-                        if (n) missing_q_sum(slot, m2, miss_list + warp * kMissSeg, n);
-                    }
-                    __syncthreads();
-                    if (tid == 0) { sh.miss_any = 1; sh.miss_overflow = 1; }
-                }
+            // sum of q over the missing individuals of this warp's rows (exact: the rows' lists are in their tails)
+            for (int r2 = 0; r2 < 4; ++r2) {
+                const uint32_t m2 = warp + 16 * r2;
+                if (m2 < nb)
+                    for_missing_chunks(pk + size_t(m2) * RS, [&](const uint32_t *ent, uint32_t n) { missing_q_sum(slot, m2, ent, n); });
             }
         }
 
+        PHASE(kProfDotRed2);
+        __syncthreads();
+        PHASE(kProfDotRed3);
         // ---- 2. the one grid-wide exchange per block: arrive ... ------------------------------------
         grid_arrive(p.bar);
         PHASE(kProfDotReduce);
@@ -666,7 +658,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             int4 d_lo = make_int4(0, 0, 0, 0), d_hi = d_lo;
             long long sm_hi = 0, sm_lo = 0, e_hi = 0, e_lo = 0;
             if (uint32_t(tid) < nb) {
-                const int4 *dp = reinterpret_cast<const int4 *>(slot + kSlotDots + tid * kLimbs);
+                const int4 *dp = reinterpret_cast<const int4 *>(slot + kSlotDots + tid * kLimbs);      // 4 x int64
                 d_lo = __ldcg(dp); d_hi = __ldcg(dp + 1);
                 if (has_missing) {
                     const long long *sp = reinterpret_cast<const long long *>(slot + kSlotSm) + 2 * tid;
@@ -677,12 +669,26 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t) { const int i = tid + t * kThreads; if (i < n4) dst[i] = va[t]; }
+            PHASE(kProfRb1);
             if (uint32_t(tid) < nb) {
                 cp_async_wait_all();
                 derive_block_meta(meta, tid);
                 const double eps_sum_total = (double(e_hi) * 4294967296.0 + double(e_lo)) * inv_scale;
-                const long long tlo = (long long)d_lo.x + ((long long)d_lo.y << 8) + ((long long)d_lo.z << 16) + ((long long)d_lo.w << 24);
-                const long long thi = (long long)d_hi.x + ((long long)d_hi.y << 8) + ((long long)d_hi.z << 16) + ((long long)d_hi.w << 24);
+                // unpack the limb sums: each int64 holds (even limb) + (odd limb) * 2^32, both signed
+                long long S[8];
+                {
+                    const long long pk64[4] = {(long long)(((unsigned long long)(unsigned)d_lo.y << 32) | (unsigned)d_lo.x),
+                                               (long long)(((unsigned long long)(unsigned)d_lo.w << 32) | (unsigned)d_lo.z),
+                                               (long long)(((unsigned long long)(unsigned)d_hi.y << 32) | (unsigned)d_hi.x),
+                                               (long long)(((unsigned long long)(unsigned)d_hi.w << 32) | (unsigned)d_hi.z)};
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const long long ev = (long long)(int)(unsigned)(pk64[q4] & 0xffffffffLL);
+                        S[2 * q4] = ev; S[2 * q4 + 1] = (pk64[q4] - ev) >> 32;
+                    }
+                }
+                const long long tlo = S[0] + (S[1] << 8) + (S[2] << 16) + (S[3] << 24);
+                const long long thi = S[4] + (S[5] << 8) + (S[6] << 16) + (S[7] << 24);
                 const double dprime = (double(thi) * 4294967296.0 + double(tlo)) * inv_scale;    // sum_i g'_i eps_i
                 const double smd = (double(sm_hi) * 4294967296.0 + double(sm_lo)) * inv_scale;
                 const double *L = meta.lut[tid];
@@ -690,6 +696,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 sh.d0[tid] = L[0] * eps_sum_total + meta.sj[tid] * (dprime - 3.0 * smd) + (L[3] - L[0]) * smd;
             }
         }
+        PHASE(kProfRb2);
         // recycle the slot of block b-1 (every CTA has read it before arriving at this block's barrier)
         if (cta == b % p.nCTA) {
             int4 *z = reinterpret_cast<int4 *>(p.slots + size_t((b + kSlots - 1) % kSlots) * kSlotInts);
@@ -854,13 +861,25 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 const uint32_t item = tid + it * kThreads;
                 if (item < NI) {
                     const uint32_t w = item >> 2, c2 = 2 * (item & 3u);
-                    for (uint32_t q = 0; q < n_ns; ++q) {
+                    uint32_t q = 0;
+                    for (; q + 1 < n_ns; q += 2) {          // two markers per step: independent loads, same order of adds
+                        const uint32_t m0 = sh.ns_list[q], m1 = sh.ns_list[q + 1];
+                        const double dB0 = sh.dbeta[m0], dB1 = sh.dbeta[m1];
+                        const uint32_t r0 = (pk[size_t(m0) * RS + w] >> c2) & kM3, r1 = (pk[size_t(m1) * RS + w] >> c2) & kM3;
+                        const double *L0 = meta.lut[m0], *L1 = meta.lut[m1];
+                        double x0[4], x1[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) { x0[t] = L0[(r0 >> (8 * t)) & 3u]; x1[t] = L1[(r1 >> (8 * t)) & 3u]; }
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) { e[it][t] += dB0 * x0[t]; e[it][t] += dB1 * x1[t]; }   // eps += (beta_old-beta) * x
+                    }
+                    if (q < n_ns) {
                         const uint32_t m = sh.ns_list[q];
                         const double dB = sh.dbeta[m];
                         const uint32_t r = (pk[size_t(m) * RS + w] >> c2) & kM3;
                         const double *L = meta.lut[m];
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) e[it][t] += dB * L[(r >> (8 * t)) & 3u];   // eps += (beta_old-beta) * x
+                        for (int t = 0; t < 4; ++t) e[it][t] += dB * L[(r >> (8 * t)) & 3u];
                     }
                 }
             }
