@@ -261,11 +261,12 @@ class Engine:
         return int(self.lib.brr_gpu_launch_count(self._h))
 
     PROFILE_PHASES = ["dot", "dot_reduce", "gram_scan", "gram_cross", "gram_mma", "gram_reduce", "barrier_wait", "readback",
-                      "walk", "axpy", "quantize", "prologue", "walk_iters", "walk_solves", "walk_a", "gram_wait"]
+                      "walk", "axpy", "quantize", "prologue", "walk_iters", "walk_solves", "walk_a", "gram_wait",
+                      "dotred1", "dotred2", "dotred3", "rb1", "rb2", "spare0", "spare1", "spare2"]
 
     def profile_cycles(self, reset=True):
         """Phase cycle counters of the dense sweep kernel (needs BRR_GPU_PROFILE=1 at construction)."""
-        a = np.zeros(16, dtype=np.uint64)
+        a = np.zeros(24, dtype=np.uint64)
         self._check(self.lib.brr_gpu_profile_cycles(self._h, _ptr(a), int(reset)))
         return dict(zip(self.PROFILE_PHASES, (int(x) for x in a)))
 

@@ -653,24 +653,17 @@ extern "C" int brr_gpu_info(brr_gpu_ctx *c, uint32_t *n_ctas, uint32_t *slice_in
 
 extern "C" uint64_t brr_gpu_launch_count(brr_gpu_ctx *c) { return c ? c->launches : 0; }
 
-extern "C" int brr_gpu_profile_cycles(brr_gpu_ctx *c, uint64_t *cycles16, int reset)
+extern "C" int brr_gpu_profile_cycles(brr_gpu_ctx *c, uint64_t *cycles24, int reset)
 {
     CHECK_CTX(c);
-    if (!cycles16) return fail(BRR_GPU_EINVAL, "null output");
-    if (c->prof && getenv("BRR_GPU_PROFILE_FINE")) {      // developer aid: the 8 extra fine-grained counters
-        uint64_t fine[8];
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        CUDA_TRY(cudaMemcpy(fine, c->prof + 16, sizeof(fine), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[brr_gpu fine] dotred1=%llu dotred2=%llu dotred3=%llu rb1=%llu rb2=%llu\n", (unsigned long long)fine[0],
-                (unsigned long long)fine[1], (unsigned long long)fine[2], (unsigned long long)fine[3], (unsigned long long)fine[4]);
-        if (reset) CUDA_TRY(cudaMemset(c->prof + 16, 0, sizeof(fine)));
-    }
+    if (!cycles24) return fail(BRR_GPU_EINVAL, "null output");
     if (!c->prof) return fail(BRR_GPU_ESTATE, "phase profiling is off: set BRR_GPU_PROFILE=1 before brr_gpu_create");
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaMemcpy(cycles16, c->prof, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost));
-    if (reset) CUDA_TRY(cudaMemset(c->prof, 0, sizeof(uint64_t) * 16));
+    CUDA_TRY(cudaMemcpy(cycles24, c->prof, sizeof(uint64_t) * 24, cudaMemcpyDeviceToHost));
+    if (reset) CUDA_TRY(cudaMemset(c->prof, 0, sizeof(uint64_t) * 24));
     return 0;
 }
+
 extern "C" void *brr_gpu_stream(brr_gpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 #include "ragged_host.inl"

@@ -41,21 +41,24 @@ namespace brr {
 constexpr int kB = 64;                 // markers per block = tile structure of the MMA passes
 constexpr int kLimbs = 8;
 constexpr uint32_t kM3 = 0x03030303u;
-constexpr int kMissSeg = 256;          // entries of a warp's missing-list scratch segment
+constexpr int kMissSeg = 256 + 4;      // entries of a warp's missing-list scratch segment (16 words x 16 + sentinels)
 constexpr uint32_t kTail = 8;          // tail words of a code row: 16 x uint16 missing list (store_kernels.cuh)
 constexpr int kMissCap = kMissSeg * kWarps;
 constexpr int kMaxSL = 4096;           // individuals per CTA (2 register items of 4 per thread)
 constexpr int kScratchInts = 8192;     // 32 KB shared scratch
 constexpr int kHeadroomBits = 6;       // |eps| may grow 64x inside a sweep before the fixed point overflows
 
-// rotating global slot (int32 units)
+// rotating global slot (int32 units).  Everything that ALL CTAs add into between two barriers sits on its
+// own 128-byte line: RED throughput is per L2 line/slice, and 148 CTAs hammering 16 lines was measured to
+// cost ~4k cycles per block on the critical path (profiles/).
+constexpr int kLine = 32;              // ints per 128-byte line
 constexpr int kSlotA = 0;              // [64][64]: upper (j<k) = sum g'_j g'_k ; lower [k][j] = # both missing
 constexpr int kSlotY = 4096;           // [64][64]: YT[b][a] = sum over {i: b missing, a present} of g_a
-constexpr int kSlotDots = 8192;        // [64][4] int64: limb sums packed in pairs (even limb + odd limb * 2^32)
-constexpr int kSlotSm = 8704;          // [64][2] int64: sum of q over missing individuals (hi, lo parts)
-constexpr int kSlotEps = 8960;         // [2] int64: sum of q over all individuals (hi, lo parts)
-constexpr int kSlotFlag = 8964;        // != 0: some slice of the block has missing genotypes
-constexpr int kSlotInts = 8968;
+constexpr int kSlotDots = 8192;        // [64][4] int64, one per line: limb sums in pairs (even limb + odd limb * 2^32)
+constexpr int kSlotSm = kSlotDots + 256 * kLine;   // [64][2] int64, one per line: sum of q over missing individuals (hi, lo)
+constexpr int kSlotEps = kSlotSm + 128 * kLine;    // [2] int64, one per line: sum of q over all individuals (hi, lo)
+constexpr int kSlotFlag = kSlotEps + 2 * kLine;    // != 0: some slice of the block has missing genotypes
+constexpr int kSlotInts = kSlotFlag + kLine;
 constexpr int kSlots = 4;
 
 struct DenseSweepParams {
@@ -89,6 +92,8 @@ struct DenseSweepParams {
     unsigned *out_counts;    // [0]=non-skipped markers, [1]=blocks, [2]=error flags
     unsigned long long *prof; // optional [kProfPhases]: SM cycles of CTA 0 per phase (nullptr = off)
 };
+
+
 
 // phases of the block loop, as timed by thread 0 of CTA 0 when DenseSweepParams::prof is set
 enum { kProfDot = 0, kProfDotReduce, kProfGramScan, kProfGramCross, kProfGramMma, kProfGramReduce, kProfBarrier,
@@ -126,6 +131,7 @@ struct SweepShared {   // fixed-size part; limbs, code buffers, scratch and the 
     uint32_t n_ns;
     uint32_t n_nonskipped_total;
     uint32_t err;
+    unsigned long long prof[kProfPhases];   // phase cycle counters of this CTA (flushed by CTA 0 at the end)
     alignas(8) uint64_t mbar[2];
 };
 
@@ -248,8 +254,9 @@ __device__ __forceinline__ void derive_block_meta(BlockMeta &m, int k)
 {
     const double l0 = m.lut[k][0], l2 = m.lut[k][2], l3 = m.lut[k][3];
     const double s = 0.5 * (l2 - l0);          // value table is affine in the allele count
-    const double cc = -l0 / s;
-    m.sj[k] = s; m.cj[k] = cc; m.ej[k] = l3 / s + cc;
+    const double inv_s = 1.0 / s;
+    const double cc = -l0 * inv_s;
+    m.sj[k] = s; m.cj[k] = cc; m.ej[k] = l3 * inv_s + cc;
     m.sumg[k] = double(m.cnt[k][1]) + 2.0 * double(m.cnt[k][2]);
     m.nmiss[k] = double(m.cnt[k][3]);
 }
@@ -294,8 +301,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     unsigned bar_gen = 0;
     const bool prof_on = (p.prof != nullptr) && cta == 0 && tid == 0;
     long long t_prev = prof_on ? clock64() : 0;
+    if (prof_on) for (int i = 0; i < kProfPhases; ++i) sh.prof[i] = 0;
     auto PHASE = [&](int ph) {          // charge the cycles since the previous mark to phase `ph`
-        if (prof_on) { const long long t = clock64(); p.prof[ph] += (unsigned long long)(t - t_prev); t_prev = t; }
+        if (prof_on) { const long long t = clock64(); sh.prof[ph] += (unsigned long long)(t - t_prev); t_prev = clock64(); }
     };
 
     // ---- prologue -----------------------------------------------------------------------------
@@ -423,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         const uint32_t cnt = tail[0];
         if (cnt == 0) return;
         if (cnt <= 15) {
-            if (uint32_t(lane) < cnt) seg[lane] = tail[1 + lane];
+            if (lane < 20) seg[lane] = (uint32_t(lane) < cnt) ? uint32_t(tail[1 + lane]) : 0xffffffffu;   // + sentinels
             __syncwarp();
             fn(seg, cnt);
             __syncwarp();
@@ -450,6 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 }
                 tot += nl;
             }
+            if (lane < 4) seg[tot + lane] = 0xffffffffu;          // sentinels (tot <= 256 - 4 is not guaranteed: see kMissSeg)
             __syncwarp();
             if (tot) fn(seg, tot);
             __syncwarp();
@@ -459,16 +468,25 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     // into the global slot: YT[m][a] += g_a(i) (a present), Wlow[m][a] += 1 (a < m, a missing too)
     auto cross_missing = [&](const uint32_t *pk, int *slot, uint32_t nb, uint32_t m, const uint32_t *ent, uint32_t n) {
         int y[2] = {0, 0}, wv[2] = {0, 0};
-        for (uint32_t en = 0; en < n; en += 2) {
-            const uint32_t i0 = ent[en], i1 = (en + 1 < n) ? ent[en + 1] : 0xffffffffu;
+        for (uint32_t en = 0; en < n; en += 4) {       // four entries per step (the list is padded with sentinels)
+            const uint4 i4 = *reinterpret_cast<const uint4 *>(ent + en);
+            const uint32_t ii[4] = {i4.x, i4.y, i4.z, i4.w};
+            uint32_t cw[2][4];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint32_t a = lane + 32 * h;
-                if (a < nb && a != m) {
-                    const uint32_t c0 = (pk[size_t(a) * RS + (i0 >> 4)] >> (2 * (i0 & 15u))) & 3u;
-                    const uint32_t c1 = (i1 != 0xffffffffu) ? (pk[size_t(a) * RS + (i1 >> 4)] >> (2 * (i1 & 15u))) & 3u : 0u;
-                    y[h] += (c0 == 3u ? 0 : int(c0)) + (c1 == 3u ? 0 : int(c1));
-                    if (a < m) wv[h] += int(c0 == 3u) + int(c1 == 3u);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    cw[h][q] = (a < nb && a != m && ii[q] != 0xffffffffu) ? pk[size_t(a) * RS + (ii[q] >> 4)] : 0u;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t a = lane + 32 * h;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t c = (cw[h][q] >> (2 * (ii[q] & 15u))) & 3u;
+                    y[h] += (c == 3u) ? 0 : int(c);
+                    wv[h] += (c == 3u && a < m) ? 1 : 0;
                 }
             }
         }
@@ -503,8 +521,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             slo += __shfl_xor_sync(0xffffffffu, slo, o);
         }
         if (lane == 0 && n) {
-            unsigned long long *g = reinterpret_cast<unsigned long long *>(slot + kSlotSm) + 2 * m;
-            atomicAdd(g, (unsigned long long)shi); atomicAdd(g + 1, slo);
+            atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotSm + (2 * m) * kLine), (unsigned long long)shi);
+            atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotSm + (2 * m + 1) * kLine), slo);
         }
     };
 
@@ -613,20 +631,54 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 const uint32_t m = 16 * mi + (l5 >> 2) + 8 * rr;
                 const long long v = (long long)s0 + ((long long)s1 << 32);
                 if (v != 0 && m < nb)
-                    atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotDots) + m * 4 + (l5 & 3), (unsigned long long)v);
+                    atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotDots + (m * 4 + (l5 & 3)) * kLine), (unsigned long long)v);
             }
             PHASE(kProfDotRed1);
             if (warp == 8) {                      // lane 2w+h holds part h of warp w's sum of q
                 unsigned long long v = sh.wq[lane >> 1][lane & 1];
 #pragma unroll
                 for (int o2 = 2; o2 < 32; o2 <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
-                if (lane < 2) atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotEps) + lane, v);
+                if (lane < 2) atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotEps + lane * kLine), v);
             }
-            // sum of q over the missing individuals of this warp's rows (exact: the rows' lists are in their tails)
-            for (int r2 = 0; r2 < 4; ++r2) {
-                const uint32_t m2 = warp + 16 * r2;
-                if (m2 < nb)
-                    for_missing_chunks(pk + size_t(m2) * RS, [&](const uint32_t *ent, uint32_t n) { missing_q_sum(slot, m2, ent, n); });
+            // sum of q over the missing individuals of this warp's rows (exact: the rows' lists are in their tails).
+            // Fast path: 8 lanes per row read the first 8 entries straight from the tail; longer rows go the general way.
+            {
+                const uint32_t r2 = lane >> 3, e8 = lane & 7, m2 = warp + 16 * r2;
+                uint32_t cnt = 0;
+                long long qh = 0; unsigned long long ql = 0;
+                if (m2 < nb) {
+                    const uint16_t *tail = reinterpret_cast<const uint16_t *>(pk + size_t(m2) * RS + PW);
+                    cnt = tail[0];
+                    if (cnt <= 8 && e8 < cnt) {
+                        const uint32_t i = tail[1 + e8];
+                        const uint32_t w = i >> 4, c = i & 3u, t = (i >> 2) & 3u;
+                        const uint32_t *lw = reinterpret_cast<const uint32_t *>(limbs) + c;
+                        unsigned long long uq = 0;
+#pragma unroll
+                        for (int l = 0; l < kLimbs; ++l)
+                            uq |= (unsigned long long)((lw[(size_t(l) * RS + w) * 4] >> (8 * t)) & 0xffu) << (8 * l);
+                        const long long q = (long long)((uq ^ 0x8080808080808080ULL) - 0x8080808080808080ULL);
+                        qh = q >> 32; ql = (unsigned long long)(q & 0xffffffffLL);
+                    }
+                }
+                const unsigned any = __ballot_sync(0xffffffffu, cnt != 0);
+                if (any) {
+#pragma unroll
+                    for (int o2 = 1; o2 < 8; o2 <<= 1) {
+                        qh += __shfl_xor_sync(0xffffffffu, qh, o2);
+                        ql += __shfl_xor_sync(0xffffffffu, ql, o2);
+                    }
+                    if (e8 == 0 && cnt != 0 && cnt <= 8) {
+                        atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotSm + (2 * m2) * kLine), (unsigned long long)qh);
+                        atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotSm + (2 * m2 + 1) * kLine), ql);
+                    }
+                    const unsigned big = __ballot_sync(0xffffffffu, cnt > 8);
+                    for (int r3 = 0; r3 < 4; ++r3)
+                        if (big & (1u << (8 * r3))) {
+                            const uint32_t m3 = warp + 16 * r3;
+                            for_missing_chunks(pk + size_t(m3) * RS, [&](const uint32_t *ent, uint32_t n) { missing_q_sum(slot, m3, ent, n); });
+                        }
+                }
             }
         }
 
@@ -646,27 +698,27 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         PHASE(kProfBarrier);
 
         // ---- 5. read the reduced block back (all loads in flight at once) ----------------------------------
-        const bool has_missing = __ldcg(slot + kSlotFlag) != 0;
         const bool want_gram = !p.async_mode && nb > 1;
+        const int flag = __ldcg(slot + kSlotFlag);
+        bool has_missing;
         {
             const int4 *src = reinterpret_cast<const int4 *>(slot + kSlotA);
             int4 *dst = reinterpret_cast<int4 *>(scratch);
-            const int n4 = want_gram ? (has_missing ? 2048 : 1024) : 0;          // A, then YT
+            const int n4 = want_gram ? 2048 : 0;          // A, then YT (all zero when nothing is missing)
             int4 va[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) { const int i = tid + t * kThreads; if (i < n4) va[t] = __ldcg(src + i); }
-            int4 d_lo = make_int4(0, 0, 0, 0), d_hi = d_lo;
+            long long dq[4] = {0, 0, 0, 0};
             long long sm_hi = 0, sm_lo = 0, e_hi = 0, e_lo = 0;
             if (uint32_t(tid) < nb) {
-                const int4 *dp = reinterpret_cast<const int4 *>(slot + kSlotDots + tid * kLimbs);      // 4 x int64
-                d_lo = __ldcg(dp); d_hi = __ldcg(dp + 1);
-                if (has_missing) {
-                    const long long *sp = reinterpret_cast<const long long *>(slot + kSlotSm) + 2 * tid;
-                    sm_hi = __ldcg(sp); sm_lo = __ldcg(sp + 1);
-                }
-                const long long *eq = reinterpret_cast<const long long *>(slot + kSlotEps);
-                e_hi = __ldcg(eq); e_lo = __ldcg(eq + 1);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) dq[q4] = __ldcg(reinterpret_cast<const long long *>(slot + kSlotDots + (tid * 4 + q4) * kLine));
+                sm_hi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * tid) * kLine));
+                sm_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * tid + 1) * kLine));
+                e_hi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps));
+                e_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps + kLine));
             }
+            has_missing = flag != 0;
 #pragma unroll
             for (int t = 0; t < 4; ++t) { const int i = tid + t * kThreads; if (i < n4) dst[i] = va[t]; }
             PHASE(kProfRb1);
@@ -676,16 +728,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 const double eps_sum_total = (double(e_hi) * 4294967296.0 + double(e_lo)) * inv_scale;
                 // unpack the limb sums: each int64 holds (even limb) + (odd limb) * 2^32, both signed
                 long long S[8];
-                {
-                    const long long pk64[4] = {(long long)(((unsigned long long)(unsigned)d_lo.y << 32) | (unsigned)d_lo.x),
-                                               (long long)(((unsigned long long)(unsigned)d_lo.w << 32) | (unsigned)d_lo.z),
-                                               (long long)(((unsigned long long)(unsigned)d_hi.y << 32) | (unsigned)d_hi.x),
-                                               (long long)(((unsigned long long)(unsigned)d_hi.w << 32) | (unsigned)d_hi.z)};
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const long long ev = (long long)(int)(unsigned)(pk64[q4] & 0xffffffffLL);
-                        S[2 * q4] = ev; S[2 * q4 + 1] = (pk64[q4] - ev) >> 32;
-                    }
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const long long ev = (long long)(int)(unsigned)(dq[q4] & 0xffffffffLL);
+                    S[2 * q4] = ev; S[2 * q4 + 1] = (dq[q4] - ev) >> 32;
                 }
                 const long long tlo = S[0] + (S[1] << 8) + (S[2] << 16) + (S[3] << 24);
                 const long long thi = S[4] + (S[5] << 8) + (S[6] << 16) + (S[7] << 24);
@@ -773,7 +819,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 asm volatile("bar.sync 2, 64;" ::: "memory");
                 const unsigned nsm0 = sh.w_nsm[0], nsm1 = sh.w_nsm[1];
                 if ((nsm0 | nsm1) == 0) break;
-                if (prof_on) { p.prof[kProfWalkIters] += 1; p.prof[kProfWalkSolves] += __popc(nsm0) + __popc(nsm1); }
+                if (prof_on) { sh.prof[kProfWalkIters] += 1; sh.prof[kProfWalkSolves] += __popc(nsm0) + __popc(nsm1); }
                 double corr = 0.0;
                 if (warp == 0) {
                     // (b) triangular solve over the non-skipped markers, in block order
@@ -937,6 +983,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             if (lane == 0) {
                 p.out_scalars[0] = s; p.out_scalars[1] = q;
                 p.out_counts[0] = sh.n_nonskipped_total; p.out_counts[1] = nBlocks;
+                if (p.prof) for (int i = 0; i < kProfPhases; ++i) p.prof[i] += sh.prof[i];
             }
         }
         for (uint32_t i = tid; i < p.nG * K; i += kThreads) p.v[i] = double(sh.v_s[i]);

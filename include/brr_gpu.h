@@ -201,10 +201,11 @@ int brr_gpu_info(brr_gpu_ctx *ctx, uint32_t *n_ctas, uint32_t *slice_inds, uint3
                  uint64_t *genotype_bytes);
 uint64_t brr_gpu_launch_count(brr_gpu_ctx *ctx);
 /* Phase breakdown of the dense sweep kernel (SM cycles of CTA 0, accumulated over sweeps), available when
- * the environment has BRR_GPU_PROFILE=1 at brr_gpu_create: 16 counters in the order dot, dot-reduce,
- * gram-scan, gram-cross, gram-mma, gram-reduce, barrier wait, readback, walk, axpy, quantize, prologue,
- * walk iterations, walk solve steps (counts), walk first round, wait for the code rows.  reset != 0 clears them. */
-int brr_gpu_profile_cycles(brr_gpu_ctx *ctx, uint64_t *cycles16, int reset);
+ * the environment has BRR_GPU_PROFILE=1 at brr_gpu_create: 24 counters in the order dot, dot-reduce,
+ * gram-scan (unused), gram-cross, gram-mma, gram-reduce, barrier wait, readback, walk, axpy, quantize, prologue,
+ * walk iterations, walk solve steps (counts), walk first round, wait for the code rows, then 5 sub-phases
+ * (dot-reduce 1-3, readback 1-2) and 3 spare.  reset != 0 clears them. */
+int brr_gpu_profile_cycles(brr_gpu_ctx *ctx, uint64_t *cycles24, int reset);
 
 #ifdef __cplusplus
 }

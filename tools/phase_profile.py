@@ -32,7 +32,7 @@ for s in range(sweeps):
     tot = sum(v_ for k, v_ in pc.items() if k not in ("walk_iters", "walk_solves"))
     print("sweep %d: %.3f ms, %.2f us/block, nonskipped %.2f%%, walk iters/block %.2f, solves/block %.2f" % (
         s, out.kernel_ms, 1e3 * out.kernel_ms / nb, 100.0 * out.n_nonskipped / M, pc["walk_iters"] / nb, pc["walk_solves"] / nb))
-    print("   cycles/block: " + "  ".join("%s=%d" % (k, pc[k] // nb) for k in e.PROFILE_PHASES[:11] + ["walk_a", "gram_wait"]) + "  | prologue=%d total/block=%d" % (pc["prologue"], tot // nb))
+    print("   cycles/block: " + "  ".join("%s=%d" % (k, pc[k] // nb) for k in e.PROFILE_PHASES[:11] + ["walk_a", "gram_wait", "dotred1", "dotred2", "dotred3", "rb1", "rb2"]) + "  | prologue=%d total/block=%d" % (pc["prologue"], tot // nb))
     m0 = v[0, 1:].sum()
     pi = rng.dirichlet(v[0] + 1.0)[None, :]
     sigmaG = np.array([max(1e-6, (bs[0] * 1.0 + 1e-8) / max(1.0, m0))])
