@@ -19,7 +19,7 @@ SYMBOLS = [
     "brr_gpu_get_dense_lut", "brr_gpu_upload_ragged", "brr_gpu_upload_ragged_from_bed", "brr_gpu_get_ragged_stats",
     "brr_gpu_set_model", "brr_gpu_set_state", "brr_gpu_get_state", "brr_gpu_eps_add_scalar", "brr_gpu_eps_reduce",
     "brr_gpu_sweep", "brr_gpu_sweep_stage", "brr_gpu_sweep_run", "brr_gpu_sweep_fetch", "brr_gpu_compute_num",
-    "brr_gpu_apply_delta", "brr_gpu_ipc_export", "brr_gpu_ipc_attach", "brr_gpu_block_stats", "brr_gpu_block_finish",
+    "brr_gpu_apply_delta", "brr_gpu_ipc_export", "brr_gpu_ipc_attach", "brr_gpu_attach_local",
     "brr_gpu_num_blocks", "brr_gpu_stream", "brr_gpu_synth_dense", "brr_gpu_synth_bed_host", "brr_gpu_info",
     "brr_gpu_launch_count", "brr_gpu_profile_cycles",
 ]
@@ -78,8 +78,7 @@ def load_library():
     lib.brr_gpu_apply_delta.argtypes = [vp, u32, dbl, dbl, C.POINTER(dbl)]
     lib.brr_gpu_ipc_export.argtypes = [vp, vp]
     lib.brr_gpu_ipc_attach.argtypes = [vp, vp]
-    lib.brr_gpu_block_stats.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u32), C.POINTER(vp), C.POINTER(u32)]
-    lib.brr_gpu_block_finish.argtypes = [vp, u32]
+    lib.brr_gpu_attach_local.argtypes = [C.POINTER(vp), C.c_int]
     lib.brr_gpu_num_blocks.argtypes = [vp]
     lib.brr_gpu_num_blocks.restype = u32
     lib.brr_gpu_stream.argtypes = [vp]
@@ -251,6 +250,12 @@ class Engine:
     def ipc_attach(self, handles):
         blob = b"".join(handles)
         self._check(self.lib.brr_gpu_ipc_attach(self._h, blob))
+
+    @staticmethod
+    def attach_local(engines):
+        """Wire several engines of this process (rank i = engines[i]) for the in-kernel exchange."""
+        arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+        engines[0]._check(engines[0].lib.brr_gpu_attach_local(arr, len(engines)))
 
     def info(self):
         a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()

@@ -74,6 +74,14 @@ struct brr_gpu_ctx {
     double *v = nullptr, *betasq = nullptr, *out_scalars = nullptr;
     unsigned *out_counts = nullptr;
     unsigned long long *prof = nullptr;     // phase cycle counters (BRR_GPU_PROFILE=1)
+    // multi-GPU exchange (world > 1)
+    int *xchg = nullptr;                    // this rank's exchange buffer (mailboxes + flags), cudaMalloc'd, IPC-exported
+    int **peer_ptrs_dev = nullptr;          // device array [world] of every rank's exchange buffer
+    std::vector<void *> peer_opened;        // IPC mappings to close
+    unsigned *bar2 = nullptr;
+    unsigned long long round_base = 0;      // exchange rounds completed so far (identical on all ranks)
+    bool attached = false;
+    uint32_t xchg_ctas = 1;
     // pinned host mirrors for the small outputs
     double *h_small = nullptr;   // [kMaxGK + kMaxGK + 2 + 2*1024]
     unsigned *h_counts = nullptr;
@@ -110,6 +118,9 @@ extern "C" void brr_gpu_destroy(brr_gpu_ctx *c)
                     c->red_partial, c->slots, c->v, c->betasq, c->out_scalars, c->out_counts, c->prof,
                     c->rag.idx16, c->rag.cta_base, c->rag.stats, c->rag.seg};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *q : c->peer_opened) cudaIpcCloseMemHandle(q);
+    if (c->xchg) cudaFree(c->xchg);
+    if (c->peer_ptrs_dev) cudaFree(c->peer_ptrs_dev);
     if (c->h_small) cudaFreeHost(c->h_small);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -203,6 +214,14 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
         TRY_OR_DESTROY(dev_alloc(&c->slots, slot_ints));
         c->absmax = reinterpret_cast<unsigned long long *>(c->slots + size_t(kSlots) * kSlotInts);
         c->bar = reinterpret_cast<unsigned *>(c->slots + size_t(kSlots) * kSlotInts + 2);
+        c->bar2 = c->bar + 1;
+        if (cfg->world > 1) {
+            TRY_OR_DESTROY(dev_alloc(&c->xchg, xchg_total_ints(cfg->world)));
+            CUDA_OR_DESTROY(cudaMemset(c->xchg, 0, sizeof(int) * xchg_total_ints(cfg->world)));
+            const int hdr = (int)c->nCTA;       // peers read this at attach time to agree on the number of exchange CTAs
+            CUDA_OR_DESTROY(cudaMemcpy(c->xchg + xchg_total_ints(cfg->world) - 8, &hdr, sizeof(int), cudaMemcpyHostToDevice));
+            TRY_OR_DESTROY(dev_alloc(&c->peer_ptrs_dev, (size_t)cfg->world));
+        }
     } else {
         TRY_OR_DESTROY(dev_alloc(&c->bar, 4));
         c->slots = reinterpret_cast<int *>(c->bar);      // single owner pointer for destroy
@@ -475,6 +494,10 @@ static int launch_dense(brr_gpu_ctx *c)
     p.slots = c->slots; p.absmax = c->absmax; p.bar = c->bar; p.cta_red = c->cta_red;
     p.v = c->v; p.betasq = c->betasq; p.out_scalars = c->out_scalars; p.out_counts = c->out_counts;
     p.prof = c->prof;
+    p.world = c->cfg.world; p.rank = c->cfg.rank; p.peer_xchg = c->peer_ptrs_dev; p.bar2 = c->bar2; p.round_base = c->round_base; p.xchg_ctas = c->xchg_ctas;
+    if (c->cfg.world > 1 && !c->attached)
+        return fail(BRR_GPU_ESTATE, "world=%d but brr_gpu_ipc_attach has not been called: the shards cannot exchange their partial sums", c->cfg.world);
+    c->round_base += uint64_t((c->n_order + p.B - 1) / p.B) + 1;      // one round per block + the prologue round
     CUDA_TRY(cudaMemsetAsync(c->slots, 0, sizeof(int) * (size_t(kSlots) * kSlotInts + 8), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->out_counts, 0, sizeof(unsigned) * 4, c->stream));
     void *args[] = {&p};

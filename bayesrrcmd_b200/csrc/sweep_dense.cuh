@@ -91,7 +91,21 @@ struct DenseSweepParams {
     double *out_scalars;     // [0]=sum eps, [1]=||eps||^2
     unsigned *out_counts;    // [0]=non-skipped markers, [1]=blocks, [2]=error flags
     unsigned long long *prof; // optional [kProfPhases]: SM cycles of CTA 0 per phase (nullptr = off)
+    // multi-GPU exchange over NVLink peer memory (world > 1): see the "cross-GPU exchange" section of the kernel
+    int world, rank;
+    int *const *peer_xchg;   // [world] device pointers to every rank's exchange buffer (own entry = local buffer)
+    unsigned *bar2;          // local counter: exchange CTAs that have merged the peers' contributions (zero at launch)
+    unsigned long long round_base;   // exchange rounds completed before this launch (identical on all ranks)
+    uint32_t xchg_ctas;      // CTAs sharing the exchange work: min(kXchgCtas, smallest grid of any rank)
 };
+
+// exchange buffer of a rank (int32 units): mailbox[src][rot] of kMsgInts, then flags[src][kXchgCtas] (uint64 round ids)
+constexpr int kXchgCtas = 8;           // CTAs that push / merge a share of the block's counts
+constexpr int kXchgRot = 4;
+constexpr int kMsgA = 0, kMsgY = 4096, kMsgDots = 8192, kMsgSm = 8192 + 512, kMsgEps = kMsgSm + 256, kMsgFlag = kMsgEps + 4,
+              kMsgAbs = kMsgFlag + 2, kMsgInts = kMsgAbs + 2;     // = 8968 + 2
+__host__ __device__ inline size_t xchg_mailbox_ints(int world) { return size_t(world) * kXchgRot * kMsgInts; }
+__host__ __device__ inline size_t xchg_total_ints(int world) { return xchg_mailbox_ints(world) + size_t(world) * kXchgCtas * 2 + 8; }
 
 
 
@@ -161,6 +175,25 @@ __device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, 
 __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// slot index of message element i of the small (line-strided) part
+__device__ __forceinline__ int slot_index_of_msg(int i)
+{
+    if (i < kMsgSm) { const int j = i - kMsgDots; return kSlotDots + (j >> 1) * kLine + (j & 1); }
+    if (i < kMsgEps) { const int j = i - kMsgSm; return kSlotSm + (j >> 1) * kLine + (j & 1); }
+    if (i < kMsgFlag) { const int j = i - kMsgEps; return kSlotEps + (j >> 1) * kLine + (j & 1); }
+    return kSlotFlag + (i - kMsgFlag);
 }
 
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory"); }
@@ -366,8 +399,96 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     if (nBlocks > 0) prefetch(0);
     if (nBlocks > 1) prefetch(1);
 
+    // ---- cross-GPU exchange (world > 1) -----------------------------------------------------------------
+    // Individuals are sharded over the GPUs; a block's integer counts must be summed over all of them before
+    // the walk.  After the LOCAL grid barrier of a round, the first kXchgCtas CTAs each take a share of the
+    // slot: they store it into their mailbox on every peer (plain 16-byte stores over NVLink), publish a
+    // round id (st.release.sys) in the peer's flag array, wait for the peers' flags, add the peers' shares
+    // into the local slot, and arrive on a second local counter that releases all CTAs.  Sums are integers:
+    // the result does not depend on the arrival order or on the number of GPUs.
+    unsigned xround = 0;                                    // rounds done in this launch
+    auto cross_gpu_exchange = [&](int *slot, bool abs_round) {
+        ++xround;
+        if (p.world <= 1) return;
+        const unsigned long long rid = p.round_base + xround;
+        const int rot = int(rid % kXchgRot);
+        const uint32_t E = p.xchg_ctas;
+        if (cta < E) {
+            int *mine = p.peer_xchg[p.rank];
+            // my share: an int4 range of A|Y; CTA 0 also takes the small line-strided part (or, in the
+            // prologue round, the two ints of max|eps|)
+            const int per = (2048 + int(E) - 1) / int(E);
+            const int lo4 = abs_round ? 0 : int(cta) * per, hi4 = abs_round ? 0 : min(2048, lo4 + per);
+            const int s_lo = abs_round ? kMsgAbs : kMsgDots, s_hi = (cta != 0) ? s_lo : (abs_round ? kMsgInts : kMsgAbs);
+            const int *abs_i = reinterpret_cast<const int *>(p.absmax);
+            // 1. push
+            for (int i4 = lo4 + tid; i4 < hi4; i4 += kThreads) {
+                const int4 v = __ldcg(reinterpret_cast<const int4 *>(slot) + i4);
+                for (int pr = 0; pr < p.world; ++pr)
+                    if (pr != p.rank) reinterpret_cast<int4 *>(p.peer_xchg[pr] + (size_t(p.rank) * kXchgRot + rot) * kMsgInts)[i4] = v;
+            }
+            for (int i = s_lo + tid; i < s_hi; i += kThreads) {
+                const int v = abs_round ? __ldcg(abs_i + (i - kMsgAbs)) : __ldcg(slot + slot_index_of_msg(i));
+                for (int pr = 0; pr < p.world; ++pr)
+                    if (pr != p.rank) (p.peer_xchg[pr] + (size_t(p.rank) * kXchgRot + rot) * kMsgInts)[i] = v;
+            }
+            __threadfence_system();
+            __syncthreads();
+            // 2. publish my round id on every peer, wait for theirs
+            if (tid < p.world && tid != p.rank) {
+                unsigned long long *pf = reinterpret_cast<unsigned long long *>(p.peer_xchg[tid] + xchg_mailbox_ints(p.world)) + size_t(p.rank) * kXchgCtas + cta;
+                st_release_sys_u64(pf, rid);
+                const unsigned long long *lf = reinterpret_cast<const unsigned long long *>(mine + xchg_mailbox_ints(p.world)) + size_t(tid) * kXchgCtas + cta;
+                const long long t0 = clock64();
+                while (ld_acquire_sys_u64(lf) < rid) {
+                    if ((sh.err & 2u) || clock64() - t0 > 6000000000LL) { sh.err |= 2u; break; }   // ~3 s: a peer is gone; fail, do not hang
+                }
+            }
+            __syncthreads();
+            // 3. merge the peers' shares into the local slot (integers: any order gives the same sums)
+            for (int i4 = lo4 + tid; i4 < hi4; i4 += kThreads) {
+                int4 v = __ldcg(reinterpret_cast<const int4 *>(slot) + i4);
+                for (int pr = 0; pr < p.world; ++pr)
+                    if (pr != p.rank) {
+                        const int4 o = __ldcg(reinterpret_cast<const int4 *>(mine + (size_t(pr) * kXchgRot + rot) * kMsgInts) + i4);
+                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                    }
+                reinterpret_cast<int4 *>(slot)[i4] = v;
+            }
+            // the small part holds 64-bit sums as (lo, hi) int pairs: the even thread of each pair does the work
+            for (int i = s_lo + 2 * tid; i < s_hi; i += 2 * kThreads) {
+                const bool pair64 = abs_round || i < kMsgFlag;
+                unsigned long long v;
+                if (abs_round) v = __ldcg(reinterpret_cast<const unsigned long long *>(abs_i + (i - kMsgAbs)));
+                else if (pair64) v = __ldcg(reinterpret_cast<const unsigned long long *>(slot + slot_index_of_msg(i)));
+                else v = (unsigned long long)(unsigned)__ldcg(slot + slot_index_of_msg(i));      // the missing flag (+ pad)
+                for (int pr = 0; pr < p.world; ++pr)
+                    if (pr != p.rank) {
+                        const unsigned long long o = __ldcg(reinterpret_cast<const unsigned long long *>(mine + (size_t(pr) * kXchgRot + rot) * kMsgInts + i));
+                        if (abs_round) v = v > o ? v : o;          // bits of non-negative doubles order like integers
+                        else if (pair64) v += o;
+                        else v = (unsigned long long)(unsigned)(int(unsigned(v)) + int(unsigned(o)));
+                    }
+                if (abs_round) *reinterpret_cast<unsigned long long *>(const_cast<int *>(abs_i) + (i - kMsgAbs)) = v;
+                else if (pair64) *reinterpret_cast<unsigned long long *>(slot + slot_index_of_msg(i)) = v;
+                else slot[slot_index_of_msg(i)] = int(unsigned(v));
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) red_release_add(p.bar2, 1u);
+        }
+        if (tid == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire(p.bar2) < xround * E) {
+                if (clock64() - t0 > 8000000000LL) { sh.err |= 2u; break; }
+            }
+        }
+        __syncthreads();
+    };
+
     grid_arrive(p.bar);
     grid_wait(p.bar, (++bar_gen) * p.nCTA);
+    cross_gpu_exchange(nullptr, true);                   // max |eps| over all GPUs
     {   // common fixed-point scale: |q| <= 2^(62 - headroom) at the start of the sweep
         const double a = __longlong_as_double((long long)__ldcg(p.absmax));
         int ex = 0;
@@ -695,6 +816,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
 
         // ---- 4. wait -----------------------------------------------------------------------------------
         grid_wait(p.bar, (++bar_gen) * p.nCTA);
+        cross_gpu_exchange(slot, false);
         PHASE(kProfBarrier);
 
         // ---- 5. read the reduced block back (all loads in flight at once) ----------------------------------

@@ -172,15 +172,17 @@ int brr_gpu_apply_delta(brr_gpu_ctx *ctx, uint32_t marker, double beta_old, doub
 #define BRR_GPU_IPC_HANDLE_BYTES 64
 /* Export this context's exchange mailbox; gather the handles of all ranks (any transport), then
  * attach.  After attach, brr_gpu_sweep on every rank (called collectively, same arguments except
- * the shard-local ones) exchanges the per-block partial dots and Gram counts inside the kernel by
- * peer stores + flags; every rank then performs the identical scalar sampling. */
+ * the shard-local ones) exchanges the per-block integer dot / Gram counts inside the kernel by
+ * peer stores + flags over NVLink; every rank then performs the identical scalar sampling, so beta,
+ * components and acum are replicated and eps stays sharded.  The sums are integers: the chain is
+ * bit-identical for any number of ranks.  A rank that stops participating makes the others fail
+ * with BRR_GPU_ESTATE after a few seconds instead of hanging. */
 int brr_gpu_ipc_export(brr_gpu_ctx *ctx, void *handle_out);
 int brr_gpu_ipc_attach(brr_gpu_ctx *ctx, const void *handles_all_ranks);
-/* Baseline exchange through an external allreduce (e.g. NCCL): run the statistics phase of block
- * `b`, hand back DEVICE pointers to the buffer to be sum-allreduced, then finish the block. */
-int brr_gpu_block_stats(brr_gpu_ctx *ctx, uint32_t block, void **dbl_dev, uint32_t *n_dbl, void **int_dev,
-                        uint32_t *n_int);
-int brr_gpu_block_finish(brr_gpu_ctx *ctx, uint32_t block);
+/* The same wiring for several contexts living in ONE process (rank i = ctxs[i], world = n): raw peer
+ * pointers instead of IPC handles.  With both contexts on one device this also serves as a single-GPU test
+ * of the exchange protocol (the two kernels must then be co-resident: keep n_inds small). */
+int brr_gpu_attach_local(brr_gpu_ctx **ctxs, int n);
 uint32_t brr_gpu_num_blocks(brr_gpu_ctx *ctx);
 /* The context's CUDA stream (cudaStream_t), so the external allreduce can be ordered on it. */
 void *brr_gpu_stream(brr_gpu_ctx *ctx);

@@ -179,3 +179,68 @@ def test_synthetic_generator_matches_its_host_twin():
     e.set_state(eps=eps); e2.set_state(eps=eps)
     for j in (0, 17, 63):
         assert e.compute_num(j, 0.1) == e2.compute_num(j, 0.1)
+
+
+def _shard_bounds(N, world):
+    per = ((N + world - 1) // world + 63) // 64 * 64
+    return [(min(N, r * per), min(N, (r + 1) * per)) for r in range(world)]
+
+
+def _shard_bed(bed, lo, hi):
+    """Rows lo:hi of a PLINK payload (lo is a multiple of 4)."""
+    assert lo % 4 == 0
+    return np.ascontiguousarray(bed[:, lo // 4:(hi + 3) // 4])
+
+
+@pytest.mark.parametrize("world,N,M,p_miss,block", [(2, 3000, 150, 0.01, 64), (3, 5000, 100, 0.0, 16)])
+def test_sharded_individuals_exchange_on_one_device(world, N, M, p_miss, block):
+    """The in-kernel cross-shard exchange (the multi-GPU path) with all shards on ONE device: the kernels of
+    the shards run concurrently on their own streams and exchange through 'peer' pointers that happen to be
+    local.  The chain must be BIT-identical to the unsharded one (the cross-shard sums are integers)."""
+    O.build()
+    pr = _random_problem(N + M + world, N, M, p_miss)
+    rng = pr["rng"]
+    ref = Engine(N, M, pr["K"], 1, block_markers=block)
+    ref.upload_bed(pr["bed"]); ref.finalize(); ref.set_model(pr["S"])
+    bounds = _shard_bounds(N, world)
+    shards = []
+    for r, (lo, hi) in enumerate(bounds):
+        e = Engine(hi - lo, M, pr["K"], 1, block_markers=block, n_inds_total=N, rank=r, world=world)
+        e.upload_bed(_shard_bed(pr["bed"], lo, hi))
+        shards.append(e)
+    counts = sum(e.counts().astype(np.int64) for e in shards).astype(np.uint32)
+    assert (counts == ref.counts()).all()
+    for e in shards:
+        e.finalize(counts); e.set_model(pr["S"])
+    Engine.attach_local(shards)
+    beta = np.where(rng.random(M) < 0.3, rng.normal(size=M) * 0.05, 0.0)
+    ref.set_state(eps=pr["eps"], beta=beta, comp=(beta != 0).astype(float), acum=np.zeros(M))
+    for e, (lo, hi) in zip(shards, bounds):
+        e.set_state(eps=pr["eps"][lo:hi], beta=beta, comp=(beta != 0).astype(float), acum=np.zeros(M))
+    for sweep_i in range(3):
+        order = rng.permutation(M).astype(np.uint32)
+        rand_uz = np.c_[rng.random(M), rng.normal(size=M)]
+        v0, bs0, out0 = ref.sweep(order, rand_uz, pr["pi"], pr["sigmaG"], pr["sigmaE"])
+        for e in shards:
+            e.sweep_stage(order, rand_uz, pr["pi"], pr["sigmaG"], pr["sigmaE"])
+        for e in shards:
+            e.sweep_run()                      # asynchronous: all shards must be in flight together
+        res = [e.sweep_fetch() for e in shards]
+        eps0, b0, c0, a0 = ref.get_state()
+        eps_sh = np.concatenate([e.get_state()[0] for e in shards])
+        assert np.array_equal(eps_sh, eps0)
+        for e, (v, bs, out) in zip(shards, res):
+            _, b, c, a = e.get_state()
+            assert np.array_equal(b, b0) and np.array_equal(c, c0) and np.array_equal(a, a0)
+            assert np.array_equal(v, v0) and np.array_equal(bs, bs0)
+            assert out.n_nonskipped == out0.n_nonskipped
+        assert abs(sum(o.eps_sqnorm for _, _, o in res) - out0.eps_sqnorm) <= 1e-9 * out0.eps_sqnorm
+
+
+def test_world_gt_1_requires_attach():
+    from bayesrrcmd_b200 import BrrGpuError
+    pr = _random_problem(5, 640, 20, 0.0)
+    e = Engine(320, 20, 4, 1, n_inds_total=640, rank=0, world=2)
+    e.upload_bed(_shard_bed(pr["bed"], 0, 320)); e.finalize(); e.set_model(pr["S"])
+    with pytest.raises(BrrGpuError, match="attach"):
+        e.sweep(np.arange(20, dtype=np.uint32), np.zeros((20, 2)), pr["pi"], pr["sigmaG"], 0.5)
