@@ -265,9 +265,12 @@ class Engine:
     def launch_count(self):
         return int(self.lib.brr_gpu_launch_count(self._h))
 
-    PROFILE_PHASES = ["dot", "dot_reduce", "gram_scan", "gram_cross", "gram_mma", "gram_reduce", "barrier_wait", "readback",
-                      "walk", "axpy", "quantize", "prologue", "walk_iters", "walk_solves", "walk_a", "gram_wait",
-                      "dotred1", "dotred2", "dotred3", "rb1", "rb2", "spare0", "spare1", "spare2"]
+    PROFILE_PHASES = ["wait", "xchg", "readback", "sample", "join", "lazy_cross", "lazy_mma", "lazy_barrier", "lazy_readback",
+                      "solve", "finalize", "axpy", "quantize", "redo_dot", "publish", "prologue",
+                      "walk_iters", "walk_solves", "lazy_rounds", "lazy_rows", "blocks_updated",
+                      "worker_wait", "worker_dot", "spare"]
+    PROFILE_COUNTERS = ("walk_iters", "walk_solves", "lazy_rounds", "lazy_rows", "blocks_updated")
+    PROFILE_OVERLAPPED = ("worker_wait", "worker_dot")     # timed on a dot-pass warp, concurrent with the walker phases
 
     def profile_cycles(self, reset=True):
         """Phase cycle counters of the dense sweep kernel (needs BRR_GPU_PROFILE=1 at construction)."""

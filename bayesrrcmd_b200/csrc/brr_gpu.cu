@@ -79,7 +79,7 @@ struct brr_gpu_ctx {
     int **peer_ptrs_dev = nullptr;          // device array [world] of every rank's exchange buffer
     std::vector<void *> peer_opened;        // IPC mappings to close
     unsigned *bar2 = nullptr;
-    unsigned long long round_base = 0;      // exchange rounds completed so far (identical on all ranks)
+    unsigned long long *round_ctr = nullptr; // device: exchange rounds completed so far (identical on all ranks)
     bool attached = false;
     uint32_t xchg_ctas = 1;
     // pinned host mirrors for the small outputs
@@ -115,7 +115,7 @@ extern "C" void brr_gpu_destroy(brr_gpu_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->codes, c->lut, c->counts_local, c->counts_global, c->group, c->cva, c->eps, c->beta, c->comp,
                     c->acum, c->order, c->rand_uz, c->pi, c->sigmaG, c->part_dot, c->cta_red,
-                    c->red_partial, c->slots, c->v, c->betasq, c->out_scalars, c->out_counts, c->prof,
+                    c->red_partial, c->slots, c->v, c->betasq, c->out_scalars, c->out_counts, c->prof, c->round_ctr,
                     c->rag.idx16, c->rag.cta_base, c->rag.stats, c->rag.seg};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *q : c->peer_opened) cudaIpcCloseMemHandle(q);
@@ -221,6 +221,8 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
             const int hdr = (int)c->nCTA;       // peers read this at attach time to agree on the number of exchange CTAs
             CUDA_OR_DESTROY(cudaMemcpy(c->xchg + xchg_total_ints(cfg->world) - 8, &hdr, sizeof(int), cudaMemcpyHostToDevice));
             TRY_OR_DESTROY(dev_alloc(&c->peer_ptrs_dev, (size_t)cfg->world));
+            TRY_OR_DESTROY(dev_alloc(&c->round_ctr, 1));
+            CUDA_OR_DESTROY(cudaMemset(c->round_ctr, 0, sizeof(unsigned long long)));
         }
     } else {
         TRY_OR_DESTROY(dev_alloc(&c->bar, 4));
@@ -494,10 +496,9 @@ static int launch_dense(brr_gpu_ctx *c)
     p.slots = c->slots; p.absmax = c->absmax; p.bar = c->bar; p.cta_red = c->cta_red;
     p.v = c->v; p.betasq = c->betasq; p.out_scalars = c->out_scalars; p.out_counts = c->out_counts;
     p.prof = c->prof;
-    p.world = c->cfg.world; p.rank = c->cfg.rank; p.peer_xchg = c->peer_ptrs_dev; p.bar2 = c->bar2; p.round_base = c->round_base; p.xchg_ctas = c->xchg_ctas;
+    p.world = c->cfg.world; p.rank = c->cfg.rank; p.peer_xchg = c->peer_ptrs_dev; p.bar2 = c->bar2; p.round_ctr = c->round_ctr; p.xchg_ctas = c->xchg_ctas;
     if (c->cfg.world > 1 && !c->attached)
         return fail(BRR_GPU_ESTATE, "world=%d but brr_gpu_ipc_attach has not been called: the shards cannot exchange their partial sums", c->cfg.world);
-    c->round_base += uint64_t((c->n_order + p.B - 1) / p.B) + 1;      // one round per block + the prologue round
     CUDA_TRY(cudaMemsetAsync(c->slots, 0, sizeof(int) * (size_t(kSlots) * kSlotInts + 8), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->out_counts, 0, sizeof(unsigned) * 4, c->stream));
     void *args[] = {&p};

@@ -1,4 +1,4 @@
-// Persistent cooperative Gibbs-sweep kernel, dense 2-bit layout (sm_100a), version 2.
+// Persistent cooperative Gibbs-sweep kernel, dense 2-bit layout (sm_100a), version 3.
 //
 // One launch = one AnalysisGraph::exec (reference src/sequential.cpp:10-27 driving
 // src/BayesRBase.cpp:287-392 over all markers of the sweep, in the given order).
@@ -14,18 +14,22 @@
 //   * All O(N) arithmetic runs on the tensor cores as INTEGER matrix products (mma.sync m16n8k32,
 //     u8 x u8 / u8 x s8 -> s32): a register-only 2-bit -> int8 expansion ((w >> 2c) & 0x03030303) feeds
 //       - the DOT pass:   64 markers x 8 limbs,   S[m][l] = sum_i g_mi * limb_l(q_i)
-//       - the GRAM pass:  64 x 64 marker pairs,   GG[j][k] = sum_i g_ji * g_ki   (upper triangle)
+//       - the GRAM rows:  u x 64 marker pairs,    GG[j][k] = sum_i g_ji * g_ki, ONLY for the rows j of
+//         markers that change the residual (not skipUpdate, src/BayesRBase.cpp:372) -- computed on demand.
 //     Both are exact, so the per-CTA partial results are combined over CTAs (and GPUs) with integer
 //     reductions (RED.ADD) into a small rotating global slot: the result is bit-identical for every
 //     slicing of the individuals and needs no ordered floating-point reduction.
-//   * One grid-wide barrier per block.  The Gram pass of block b+1 runs between the arrival at the
-//     barrier of block b and the wait on it, so its cost hides the barrier latency.
-//   * After the barrier every CTA redundantly reconstructs the 64 dots x_j . eps and one warp walks the
-//     block (two half-blocks of 32 lanes): lane k samples marker k with
+//   * One grid-wide barrier per block, and its latency is hidden: warps 0-1 (the "walkers") wait for the
+//     barrier of block b, read the reduced dots back and sample the 64 markers, while warps 2-15 already
+//     run the dot pass of block b+1 against the current residual -- speculating that block b leaves the
+//     residual untouched (true for most blocks once the chain has left burn-in).  If block b does update
+//     the residual, the speculative partial sums are dropped and the dot pass is repeated after the update.
+//   * The walk: lane k samples marker k with
 //         num_k = x_k.eps_blockstart - sum_{j<k updated} (beta_j,new - beta_j,old) x_j.x_k + beta_old,k (N-1),
 //     which is exactly the dot against the residual the one-by-one loop would have seen.  Lanes
-//     speculate that no earlier marker of the block changes eps; each marker that does (not
-//     skipUpdate, src/BayesRBase.cpp:372) triggers one more SIMT round for the lanes behind it.
+//     speculate that no earlier marker of the block changes eps; the markers that do get their Gram rows
+//     computed (one more grid-wide round, only then), a triangular solve fixes the betas, and the lanes
+//     behind re-sample until every component is confirmed.
 //   * Finally every thread applies eps += (beta_old - beta_new) x_j for the block's updated markers to
 //     its registers (codes are still resident in shared memory) and re-quantises its limbs.
 //   Missing genotypes (code 3) enter the integer products as the value 3 and are corrected exactly by a
@@ -45,20 +49,21 @@ constexpr int kMissSeg = 256 + 4;      // entries of a warp's missing-list scrat
 constexpr uint32_t kTail = 8;          // tail words of a code row: 16 x uint16 missing list (store_kernels.cuh)
 constexpr int kMissCap = kMissSeg * kWarps;
 constexpr int kMaxSL = 4096;           // individuals per CTA (2 register items of 4 per thread)
-constexpr int kScratchInts = 8192;     // 32 KB shared scratch
+constexpr int kScratchInts = 8192;     // 32 KB shared scratch: dot partials of 16 warps, or the 64x64 Gram rows (doubles)
 constexpr int kHeadroomBits = 6;       // |eps| may grow 64x inside a sweep before the fixed point overflows
+constexpr int kWalkWarps = 2;          // warps 0,1: barrier wait, read-back, sampling
+constexpr int kDotWarps = kWarps - kWalkWarps;   // warps 2..15: speculative dot pass of the next block
 
 // rotating global slot (int32 units).  Everything that ALL CTAs add into between two barriers sits on its
-// own 128-byte line: RED throughput is per L2 line/slice, and 148 CTAs hammering 16 lines was measured to
-// cost ~4k cycles per block on the critical path (profiles/).
+// own 128-byte line: RED throughput is per L2 line/slice, and 148 CTAs hammering a few lines was measured to
+// cost thousands of cycles per block on the critical path (profiles/).
 constexpr int kLine = 32;              // ints per 128-byte line
-constexpr int kSlotA = 0;              // [64][64]: upper (j<k) = sum g'_j g'_k ; lower [k][j] = # both missing
-constexpr int kSlotY = 4096;           // [64][64]: YT[b][a] = sum over {i: b missing, a present} of g_a
-constexpr int kSlotDots = 8192;        // [64][4] int64, one per line: limb sums in pairs (even limb + odd limb * 2^32)
+constexpr int kSlotDots = 0;           // [64][4] int64, one per line: limb sums in pairs (even limb + odd limb * 2^32)
 constexpr int kSlotSm = kSlotDots + 256 * kLine;   // [64][2] int64, one per line: sum of q over missing individuals (hi, lo)
 constexpr int kSlotEps = kSlotSm + 128 * kLine;    // [2] int64, one per line: sum of q over all individuals (hi, lo)
-constexpr int kSlotFlag = kSlotEps + 2 * kLine;    // != 0: some slice of the block has missing genotypes
-constexpr int kSlotInts = kSlotFlag + kLine;
+constexpr int kSlotLazy = kSlotEps + 2 * kLine;    // [64 row slots][64 columns], one line each, first 16 bytes:
+                                                   //   u64 #0 = a | cw << 32,  u64 #1 = cy | cz << 32   (see GramCounts)
+constexpr int kSlotInts = kSlotLazy + kB * kB * kLine;
 constexpr int kSlots = 4;
 
 struct DenseSweepParams {
@@ -89,30 +94,35 @@ struct DenseSweepParams {
     double *v;               // [nG][K]
     double *betasq;          // [nG]
     double *out_scalars;     // [0]=sum eps, [1]=||eps||^2
-    unsigned *out_counts;    // [0]=non-skipped markers, [1]=blocks, [2]=error flags
+    unsigned *out_counts;    // [0]=non-skipped markers, [1]=blocks, [2]=error flags, [3]=grid-wide rounds
     unsigned long long *prof; // optional [kProfPhases]: SM cycles of CTA 0 per phase (nullptr = off)
     // multi-GPU exchange over NVLink peer memory (world > 1): see the "cross-GPU exchange" section of the kernel
     int world, rank;
     int *const *peer_xchg;   // [world] device pointers to every rank's exchange buffer (own entry = local buffer)
     unsigned *bar2;          // local counter: exchange CTAs that have merged the peers' contributions (zero at launch)
-    unsigned long long round_base;   // exchange rounds completed before this launch (identical on all ranks)
-    uint32_t xchg_ctas;      // CTAs sharing the exchange work: min(kXchgCtas, smallest grid of any rank)
+    unsigned long long *round_ctr;   // exchange rounds completed by earlier launches (persistent; identical on all ranks)
+    uint32_t xchg_ctas;      // CTAs sharing the exchange work of a Gram round: min(kXchgCtas, smallest grid of any rank)
 };
 
-// exchange buffer of a rank (int32 units): mailbox[src][rot] of kMsgInts, then flags[src][kXchgCtas] (uint64 round ids)
-constexpr int kXchgCtas = 8;           // CTAs that push / merge a share of the block's counts
+// exchange buffer of a rank (uint64 units): mailbox[src][rot] of kMsgU64, then flags[src][kXchgCtas] (round ids)
+constexpr int kXchgCtas = 8;           // CTAs that push / merge a share of a Gram round's counts
 constexpr int kXchgRot = 4;
-constexpr int kMsgA = 0, kMsgY = 4096, kMsgDots = 8192, kMsgSm = 8192 + 512, kMsgEps = kMsgSm + 256, kMsgFlag = kMsgEps + 4,
-              kMsgAbs = kMsgFlag + 2, kMsgInts = kMsgAbs + 2;     // = 8968 + 2
-__host__ __device__ inline size_t xchg_mailbox_ints(int world) { return size_t(world) * kXchgRot * kMsgInts; }
+constexpr int kMsgLazy = 0;                        // [64 row slots][64 columns][2]
+constexpr int kMsgDots = kMsgLazy + 2 * kB * kB;   // [64][4]
+constexpr int kMsgSm = kMsgDots + 4 * kB;          // [64][2]
+constexpr int kMsgEps = kMsgSm + 2 * kB;           // [2]
+constexpr int kMsgAbs = kMsgEps + 2;               // [1]
+constexpr int kMsgU64 = kMsgAbs + 2;
+__host__ __device__ inline size_t xchg_mailbox_ints(int world) { return size_t(world) * kXchgRot * kMsgU64 * 2; }
 __host__ __device__ inline size_t xchg_total_ints(int world) { return xchg_mailbox_ints(world) + size_t(world) * kXchgCtas * 2 + 8; }
+enum { kXAbs = 0, kXMain = 1, kXLazy = 2 };
 
-
-
-// phases of the block loop, as timed by thread 0 of CTA 0 when DenseSweepParams::prof is set
-enum { kProfDot = 0, kProfDotReduce, kProfGramScan, kProfGramCross, kProfGramMma, kProfGramReduce, kProfBarrier,
-       kProfReadback, kProfWalk, kProfAxpy, kProfQuantize, kProfPrologue, kProfWalkIters, kProfWalkSolves, kProfWalkA, kProfGramWait,
-       kProfDotRed1, kProfDotRed2, kProfDotRed3, kProfRb1, kProfRb2, kProfPhases = 24 };
+// phases of the block loop, as timed by thread 0 of CTA 0 (a walker) when DenseSweepParams::prof is set;
+// kProfWorker* are timed by the first lane of warp 2 (a dot-pass warp) and overlap the walker's phases
+enum { kProfWait = 0, kProfXchg, kProfReadback, kProfSample, kProfJoin, kProfLazyCross, kProfLazyMma, kProfLazyBarrier,
+       kProfLazyReadback, kProfSolve, kProfFinalize, kProfAxpy, kProfQuantize, kProfRedoDot, kProfPublish, kProfPrologue,
+       kProfWalkIters, kProfWalkSolves, kProfLazyRounds, kProfLazyRows, kProfBlocksUpdated, kProfWorkerWait, kProfWorkerDot,
+       kProfSpare, kProfPhases = 24 };
 
 struct alignas(16) BlockMeta {
     uint32_t id[kB];
@@ -128,18 +138,20 @@ struct alignas(16) BlockMeta {
 
 struct SweepShared {   // fixed-size part; limbs, code buffers, scratch and the missing list follow (dynamic)
     GroupConsts gc;
-    BlockMeta meta;
+    BlockMeta meta[2];               // per code buffer
     double d0[kB];
     double dbeta[kB];
     double w_corr[kB];               // walk: corrections of the second half-block, betasq partials of warp 1
     int w_comp[kB];                  // walk: tentative components
     uint32_t w_nsm[2], w_chg[2], w_cnt[2], w_cnt2[2];
     uint32_t ids[2][kB];             // marker ids of the blocks in the two code buffers
+    uint32_t lz_rows[kB];            // markers (block-local) of the Gram rows being computed in this round
+    uint32_t rowslot[kB];            // Gram row slot of a marker (valid for the rows computed so far)
+    uint32_t lz_hist[kSlots];        // row slots used by the block that last used each global slot
     double warp_tmp[kWarps];
     double betasq_s[kMaxGK];
     int v_s[kMaxGK];
     unsigned long long wq[kWarps][2]; // per-warp sums of q over the slice, (hi, lo) parts
-    double eps_sum_total;
     double scale, inv_scale;
     uint32_t ns_list[kB];
     uint32_t n_ns;
@@ -187,89 +199,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// slot index of message element i of the small (line-strided) part
-__device__ __forceinline__ int slot_index_of_msg(int i)
-{
-    if (i < kMsgSm) { const int j = i - kMsgDots; return kSlotDots + (j >> 1) * kLine + (j & 1); }
-    if (i < kMsgEps) { const int j = i - kMsgSm; return kSlotSm + (j >> 1) * kLine + (j & 1); }
-    if (i < kMsgFlag) { const int j = i - kMsgEps; return kSlotEps + (j >> 1) * kLine + (j & 1); }
-    return kSlotFlag + (i - kMsgFlag);
-}
+__device__ __forceinline__ void walker_sync() { asm volatile("bar.sync 2, 64;" ::: "memory"); }   // warps 0,1
 
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// Gram pass: which 16x8 output tiles a warp role computes.  Tile (mi, nj) covers row markers
-// 16mi..16mi+15 and column markers 8nj..8nj+7; only tiles with some row < column are needed.
-__host__ __device__ constexpr int gram_role_mi(int role, int t)
-{
-    constexpr int tab[4][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 1, 1}, {1, 1, 1, 1, 2}, {2, 2, 2, 3, 3}};
-    return tab[role][t];
-}
-__host__ __device__ constexpr int gram_role_nj(int role, int t)
-{
-    constexpr int tab[4][5] = {{0, 1, 2, 3, 4}, {5, 6, 7, 6, 7}, {2, 3, 4, 5, 4}, {5, 6, 7, 6, 7}};
-    return tab[role][t];
-}
-
-// one warp, one role, its share of the 64-individual k-step pairs: acc[t] += tile t
-template <int ROLE>
-__device__ __forceinline__ void gram_role_pass(const uint32_t *__restrict__ pk, uint32_t RS, uint32_t NP, uint32_t kg,
-                                               uint32_t nkg, int lane, int (&acc)[5][4])
-{
-    const uint32_t gid = lane >> 2, tig = lane & 3;
-    for (uint32_t p = kg; p < NP; p += nkg) {
-        const uint32_t wo = 4 * p + tig;
-        uint32_t wa[4][2];      // A words of the m-tiles this role touches (rows gid, gid+8)
-        uint32_t wb[8];         // B words of the n-tiles this role touches (column gid)
-#pragma unroll
-        for (int t = 0; t < 5; ++t) {
-            const int mi = gram_role_mi(ROLE, t), nj = gram_role_nj(ROLE, t);
-            bool first_m = true, first_n = true;
-#pragma unroll
-            for (int s = 0; s < t; ++s) { if (gram_role_mi(ROLE, s) == mi) first_m = false; if (gram_role_nj(ROLE, s) == nj) first_n = false; }
-            if (first_m) {
-                wa[mi][0] = pk[(16 * mi + gid) * RS + wo];
-                wa[mi][1] = pk[(16 * mi + gid + 8) * RS + wo];
-            }
-            if (first_n) wb[nj] = pk[(8 * nj + gid) * RS + wo];
-        }
-#pragma unroll
-        for (int t = 0; t < 5; ++t) {
-            const int mi = gram_role_mi(ROLE, t), nj = gram_role_nj(ROLE, t);
-            const uint32_t w0 = wa[mi][0], w1 = wa[mi][1], wc = wb[nj];
-            mma_u8u8(acc[t], w0 & kM3, w1 & kM3, (w0 >> 2) & kM3, (w1 >> 2) & kM3, wc & kM3, (wc >> 2) & kM3);
-            mma_u8u8(acc[t], (w0 >> 4) & kM3, (w1 >> 4) & kM3, (w0 >> 6) & kM3, (w1 >> 6) & kM3, (wc >> 4) & kM3, (wc >> 6) & kM3);
-        }
-    }
-}
-
-// final owner (k-group 0) adds the other k-groups' copies and publishes the needed entries: the two
-// columns (2tig, 2tig+1) a thread holds for a row go out as ONE 64-bit RED (counts are >= 0: no carry)
-template <int ROLE>
-__device__ __forceinline__ void gram_role_publish(const int *__restrict__ scratch, uint32_t nkg, int lane, int (&acc)[5][4],
-                                                  int *__restrict__ slotA, uint32_t nb)
-{
-    const uint32_t gid = lane >> 2, tig = lane & 3;
-#pragma unroll
-    for (int t = 0; t < 5; ++t)
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            int s0 = acc[t][2 * rr], s1 = acc[t][2 * rr + 1];
-            for (uint32_t g = 1; g < nkg; ++g) {
-                s0 += scratch[(((g - 1) * 4 + ROLE) * 20 + t * 4 + 2 * rr) * 32 + lane];
-                s1 += scratch[(((g - 1) * 4 + ROLE) * 20 + t * 4 + 2 * rr + 1) * 32 + lane];
-            }
-            const uint32_t row = 16 * gram_role_mi(ROLE, t) + gid + 8 * rr, col = 8 * gram_role_nj(ROLE, t) + 2 * tig;
-            if (!(row < col)) s0 = 0;                       // keep the lower triangle (both-missing counts) clean
-            if (!(row < col + 1) || col + 1 >= nb) s1 = 0;
-            if (col >= nb) s0 = 0;
-            const unsigned long long v = (unsigned long long)(unsigned)s0 | ((unsigned long long)(unsigned)s1 << 32);
-            if (v) atomicAdd(reinterpret_cast<unsigned long long *>(slotA + row * kB + col), v);
-        }
-}
 
 // per-marker inputs of a block: asynchronous gather into shared memory (thread k = marker k of the block) ...
 __device__ __forceinline__ void gather_block_meta(const DenseSweepParams &p, BlockMeta &m, uint32_t id, int k)
@@ -294,15 +229,12 @@ __device__ __forceinline__ void derive_block_meta(BlockMeta &m, int k)
     m.nmiss[k] = double(m.cnt[k][3]);
 }
 
-// x_j . x_k for j < k from the reduced integer counts (A, Y in shared memory)
-__device__ __forceinline__ double gram_entry(const BlockMeta &m, const int *__restrict__ A, const int *__restrict__ Y,
-                                             bool has_missing, int j, int k, double Nt)
+// x_j . x_k from the reduced integer counts of the pair (j = the Gram row, k = the column):
+//   a  = sum_i g'_j g'_k with missing genotypes entering as the value 3
+//   cw = #{i: both missing},  cy = sum over {i: k missing, j present} of g_j,  cz = sum over {i: j missing, k present} of g_k
+__device__ __forceinline__ double gram_entry(const BlockMeta &m, int j, int k, double a, double cw, double cy, double cz, double Nt)
 {
-    double a = double(A[j * kB + k]), cy = 0.0, cz = 0.0, cw = 0.0;
-    if (has_missing) {
-        cw = double(A[k * kB + j]); cy = double(Y[k * kB + j]); cz = double(Y[j * kB + k]);     // Y is stored transposed
-        a = a - 3.0 * cy - 3.0 * cz - 9.0 * cw;
-    }
+    a = a - 3.0 * cy - 3.0 * cz - 9.0 * cw;                  // sum over both present of g_j g_k
     const double cj = m.cj[j], ck = m.cj[k], ej = m.ej[j], ek = m.ej[k];
     double t = a - ck * m.sumg[j] - cj * m.sumg[k] + Nt * cj * ck;
     t += ek * cy + ej * cz - cj * ek * m.nmiss[k] - ck * ej * m.nmiss[j] + ej * ek * cw;
@@ -331,12 +263,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     const double NM1 = double(p.n_total - 1), Nt = double(p.n_total);
     const uint32_t nBlocks = (p.n_order + B - 1) / B;
     const uint32_t slice0 = cta * SL;
-    unsigned bar_gen = 0;
+    unsigned bar_gen = 0;                            // grid-wide rounds so far (identical in every thread of the grid)
     const bool prof_on = (p.prof != nullptr) && cta == 0 && tid == 0;
-    long long t_prev = prof_on ? clock64() : 0;
+    const bool prof_w = (p.prof != nullptr) && cta == 0 && tid == 32 * kWalkWarps;
+    long long t_prev = (prof_on || prof_w) ? clock64() : 0;
     if (prof_on) for (int i = 0; i < kProfPhases; ++i) sh.prof[i] = 0;
     auto PHASE = [&](int ph) {          // charge the cycles since the previous mark to phase `ph`
         if (prof_on) { const long long t = clock64(); sh.prof[ph] += (unsigned long long)(t - t_prev); t_prev = clock64(); }
+    };
+    auto PHASE_W = [&](int ph, bool charge) {   // the same for the worker probe
+        if (prof_w) { const long long t = clock64(); if (charge) sh.prof[ph] += (unsigned long long)(t - t_prev); t_prev = clock64(); }
     };
 
     // ---- prologue -----------------------------------------------------------------------------
@@ -357,10 +293,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     fill_group_consts(sh.gc, p.nG, K, NM1, p.sigmaE, p.pi, p.sigmaG, p.cva);
     for (int i = tid; i < kMaxGK; i += kThreads) { sh.v_s[i] = 0; sh.betasq_s[i] = 0.0; }
     for (uint32_t i = tid; i < 2 * kB * RS; i += kThreads) pkbuf[i] = 0;
+    if (tid < kB) sh.rowslot[tid] = 0;
     if (tid == 0) {
         mbar_init(&sh.mbar[0], 1); mbar_init(&sh.mbar[1], 1);
         mbar_fence_init();
         sh.n_nonskipped_total = 0; sh.n_ns = 0; sh.err = 0;
+        for (int s = 0; s < kSlots; ++s) sh.lz_hist[s] = 0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -400,95 +338,86 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     if (nBlocks > 1) prefetch(1);
 
     // ---- cross-GPU exchange (world > 1) -----------------------------------------------------------------
-    // Individuals are sharded over the GPUs; a block's integer counts must be summed over all of them before
-    // the walk.  After the LOCAL grid barrier of a round, the first kXchgCtas CTAs each take a share of the
-    // slot: they store it into their mailbox on every peer (plain 16-byte stores over NVLink), publish a
-    // round id (st.release.sys) in the peer's flag array, wait for the peers' flags, add the peers' shares
-    // into the local slot, and arrive on a second local counter that releases all CTAs.  Sums are integers:
-    // the result does not depend on the arrival order or on the number of GPUs.
-    unsigned xround = 0;                                    // rounds done in this launch
-    auto cross_gpu_exchange = [&](int *slot, bool abs_round) {
-        ++xround;
+    // Individuals are sharded over the GPUs; the integer sums of a grid-wide round must be summed over all of
+    // them before they are used.  After the LOCAL grid barrier of a round, the exchange CTAs (CTA 0 for the
+    // small per-block message; the first xchg_ctas CTAs share the Gram rows of a lazy round) store their part
+    // into their mailbox on every peer (plain stores over NVLink), publish a round id (st.release.sys) in the
+    // peer's flag array, wait for the peers' flags, add the peers' parts into the local slot, and arrive on a
+    // second local counter that releases everybody.  Sums are integers: the result does not depend on the
+    // arrival order or on the number of GPUs.  `t`/`nthr`/`sync` name the thread group that runs the round
+    // (the 64 walker threads for the per-block message, the whole CTA otherwise).
+    const unsigned long long round_base = (p.world > 1) ? *p.round_ctr : 0ULL;
+    unsigned xround = 0;                                    // exchange rounds done in this launch
+    unsigned bar2_target = 0;
+    auto xchg = [&](int kind, int *slot, uint32_t r0, uint32_t nrows, int t, int nthr, auto &&sync) {
         if (p.world <= 1) return;
-        const unsigned long long rid = p.round_base + xround;
+        ++xround;
+        const unsigned long long rid = round_base + xround;
         const int rot = int(rid % kXchgRot);
-        const uint32_t E = p.xchg_ctas;
+        const uint32_t E = (kind == kXLazy) ? p.xchg_ctas : 1u;
+        bar2_target += E;
         if (cta < E) {
-            int *mine = p.peer_xchg[p.rank];
-            // my share: an int4 range of A|Y; CTA 0 also takes the small line-strided part (or, in the
-            // prologue round, the two ints of max|eps|)
-            const int per = (2048 + int(E) - 1) / int(E);
-            const int lo4 = abs_round ? 0 : int(cta) * per, hi4 = abs_round ? 0 : min(2048, lo4 + per);
-            const int s_lo = abs_round ? kMsgAbs : kMsgDots, s_hi = (cta != 0) ? s_lo : (abs_round ? kMsgInts : kMsgAbs);
-            const int *abs_i = reinterpret_cast<const int *>(p.absmax);
+            unsigned long long *mine = reinterpret_cast<unsigned long long *>(p.peer_xchg[p.rank]);
+            uint32_t lo, hi;                                // my range of message elements (uint64 units)
+            if (kind == kXAbs) { lo = kMsgAbs; hi = kMsgAbs + 1; }
+            else if (kind == kXMain) { lo = kMsgDots; hi = kMsgAbs; }
+            else { const uint32_t tot = nrows * 2 * kB, per = (tot + E - 1) / E; lo = min(tot, cta * per); hi = min(tot, lo + per); }
+            auto local_ptr = [&](uint32_t i) -> unsigned long long * {
+                if (i < uint32_t(kMsgDots)) return reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0) * kB + (i >> 1)) * kLine) + (i & 1u);
+                if (i < uint32_t(kMsgSm)) return reinterpret_cast<unsigned long long *>(slot + kSlotDots + (i - kMsgDots) * kLine);
+                if (i < uint32_t(kMsgEps)) return reinterpret_cast<unsigned long long *>(slot + kSlotSm + (i - kMsgSm) * kLine);
+                if (i < uint32_t(kMsgAbs)) return reinterpret_cast<unsigned long long *>(slot + kSlotEps + (i - kMsgEps) * kLine);
+                return p.absmax;
+            };
             // 1. push
-            for (int i4 = lo4 + tid; i4 < hi4; i4 += kThreads) {
-                const int4 v = __ldcg(reinterpret_cast<const int4 *>(slot) + i4);
+            for (uint32_t i = lo + t; i < hi; i += nthr) {
+                const unsigned long long v = __ldcg(local_ptr(i));
                 for (int pr = 0; pr < p.world; ++pr)
-                    if (pr != p.rank) reinterpret_cast<int4 *>(p.peer_xchg[pr] + (size_t(p.rank) * kXchgRot + rot) * kMsgInts)[i4] = v;
-            }
-            for (int i = s_lo + tid; i < s_hi; i += kThreads) {
-                const int v = abs_round ? __ldcg(abs_i + (i - kMsgAbs)) : __ldcg(slot + slot_index_of_msg(i));
-                for (int pr = 0; pr < p.world; ++pr)
-                    if (pr != p.rank) (p.peer_xchg[pr] + (size_t(p.rank) * kXchgRot + rot) * kMsgInts)[i] = v;
+                    if (pr != p.rank) reinterpret_cast<unsigned long long *>(p.peer_xchg[pr])[(size_t(p.rank) * kXchgRot + rot) * kMsgU64 + i] = v;
             }
             __threadfence_system();
-            __syncthreads();
+            sync();
             // 2. publish my round id on every peer, wait for theirs
-            if (tid < p.world && tid != p.rank) {
-                unsigned long long *pf = reinterpret_cast<unsigned long long *>(p.peer_xchg[tid] + xchg_mailbox_ints(p.world)) + size_t(p.rank) * kXchgCtas + cta;
+            if (t < p.world && t != p.rank) {
+                unsigned long long *pf = reinterpret_cast<unsigned long long *>(p.peer_xchg[t] + xchg_mailbox_ints(p.world)) + size_t(p.rank) * kXchgCtas + cta;
                 st_release_sys_u64(pf, rid);
-                const unsigned long long *lf = reinterpret_cast<const unsigned long long *>(mine + xchg_mailbox_ints(p.world)) + size_t(tid) * kXchgCtas + cta;
+                const unsigned long long *lf = reinterpret_cast<const unsigned long long *>(p.peer_xchg[p.rank] + xchg_mailbox_ints(p.world)) + size_t(t) * kXchgCtas + cta;
                 const long long t0 = clock64();
                 while (ld_acquire_sys_u64(lf) < rid) {
                     if ((sh.err & 2u) || clock64() - t0 > 6000000000LL) { sh.err |= 2u; break; }   // ~3 s: a peer is gone; fail, do not hang
                 }
             }
-            __syncthreads();
-            // 3. merge the peers' shares into the local slot (integers: any order gives the same sums)
-            for (int i4 = lo4 + tid; i4 < hi4; i4 += kThreads) {
-                int4 v = __ldcg(reinterpret_cast<const int4 *>(slot) + i4);
+            sync();
+            // 3. merge the peers' parts into the local slot (integers: any order gives the same sums)
+            for (uint32_t i = lo + t; i < hi; i += nthr) {
+                unsigned long long *lp = local_ptr(i);
+                unsigned long long v = __ldcg(lp);
                 for (int pr = 0; pr < p.world; ++pr)
                     if (pr != p.rank) {
-                        const int4 o = __ldcg(reinterpret_cast<const int4 *>(mine + (size_t(pr) * kXchgRot + rot) * kMsgInts) + i4);
-                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                        const unsigned long long o = __ldcg(mine + (size_t(pr) * kXchgRot + rot) * kMsgU64 + i);
+                        if (kind == kXAbs) v = v > o ? v : o;          // bits of non-negative doubles order like integers
+                        else v += o;
                     }
-                reinterpret_cast<int4 *>(slot)[i4] = v;
-            }
-            // the small part holds 64-bit sums as (lo, hi) int pairs: the even thread of each pair does the work
-            for (int i = s_lo + 2 * tid; i < s_hi; i += 2 * kThreads) {
-                const bool pair64 = abs_round || i < kMsgFlag;
-                unsigned long long v;
-                if (abs_round) v = __ldcg(reinterpret_cast<const unsigned long long *>(abs_i + (i - kMsgAbs)));
-                else if (pair64) v = __ldcg(reinterpret_cast<const unsigned long long *>(slot + slot_index_of_msg(i)));
-                else v = (unsigned long long)(unsigned)__ldcg(slot + slot_index_of_msg(i));      // the missing flag (+ pad)
-                for (int pr = 0; pr < p.world; ++pr)
-                    if (pr != p.rank) {
-                        const unsigned long long o = __ldcg(reinterpret_cast<const unsigned long long *>(mine + (size_t(pr) * kXchgRot + rot) * kMsgInts + i));
-                        if (abs_round) v = v > o ? v : o;          // bits of non-negative doubles order like integers
-                        else if (pair64) v += o;
-                        else v = (unsigned long long)(unsigned)(int(unsigned(v)) + int(unsigned(o)));
-                    }
-                if (abs_round) *reinterpret_cast<unsigned long long *>(const_cast<int *>(abs_i) + (i - kMsgAbs)) = v;
-                else if (pair64) *reinterpret_cast<unsigned long long *>(slot + slot_index_of_msg(i)) = v;
-                else slot[slot_index_of_msg(i)] = int(unsigned(v));
+                *lp = v;
             }
             __threadfence();
-            __syncthreads();
-            if (tid == 0) red_release_add(p.bar2, 1u);
+            sync();
+            if (t == 0) red_release_add(p.bar2, 1u);
         }
-        if (tid == 0) {
+        if (t == 0) {
             const long long t0 = clock64();
-            while (ld_acquire(p.bar2) < xround * E) {
+            while (ld_acquire(p.bar2) < bar2_target) {
                 if (clock64() - t0 > 8000000000LL) { sh.err |= 2u; break; }
             }
         }
-        __syncthreads();
+        sync();
     };
+    auto cta_sync = [&]() { __syncthreads(); };
+    auto wlk_sync = [&]() { walker_sync(); };
 
     grid_arrive(p.bar);
     grid_wait(p.bar, (++bar_gen) * p.nCTA);
-    cross_gpu_exchange(nullptr, true);                   // max |eps| over all GPUs
+    xchg(kXAbs, nullptr, 0, 0, tid, kThreads, cta_sync);   // max |eps| over all GPUs
     {   // common fixed-point scale: |q| <= 2^(62 - headroom) at the start of the sweep
         const double a = __longlong_as_double((long long)__ldcg(p.absmax));
         int ex = 0;
@@ -579,47 +508,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 }
                 tot += nl;
             }
-            if (lane < 4) seg[tot + lane] = 0xffffffffu;          // sentinels (tot <= 256 - 4 is not guaranteed: see kMissSeg)
+            if (lane < 4) seg[tot + lane] = 0xffffffffu;          // sentinels (kMissSeg leaves room for them)
             __syncwarp();
             if (tot) fn(seg, tot);
             __syncwarp();
-        }
-    };
-    // cross counts of this warp's listed entries of row m with every other marker of the block, straight
-    // into the global slot: YT[m][a] += g_a(i) (a present), Wlow[m][a] += 1 (a < m, a missing too)
-    auto cross_missing = [&](const uint32_t *pk, int *slot, uint32_t nb, uint32_t m, const uint32_t *ent, uint32_t n) {
-        int y[2] = {0, 0}, wv[2] = {0, 0};
-        for (uint32_t en = 0; en < n; en += 4) {       // four entries per step (the list is padded with sentinels)
-            const uint4 i4 = *reinterpret_cast<const uint4 *>(ent + en);
-            const uint32_t ii[4] = {i4.x, i4.y, i4.z, i4.w};
-            uint32_t cw[2][4];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t a = lane + 32 * h;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    cw[h][q] = (a < nb && a != m && ii[q] != 0xffffffffu) ? pk[size_t(a) * RS + (ii[q] >> 4)] : 0u;
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t a = lane + 32 * h;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t c = (cw[h][q] >> (2 * (ii[q] & 15u))) & 3u;
-                    y[h] += (c == 3u) ? 0 : int(c);
-                    wv[h] += (c == 3u && a < m) ? 1 : 0;
-                }
-            }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {                  // neighbouring lanes share one 64-bit RED (counts are >= 0: no carry)
-            const uint32_t a = lane + 32 * h;
-            const unsigned long long yy = (unsigned long long)(unsigned)y[h] | ((unsigned long long)(unsigned)__shfl_down_sync(0xffffffffu, y[h], 1) << 32);
-            const unsigned long long ww = (unsigned long long)(unsigned)wv[h] | ((unsigned long long)(unsigned)__shfl_down_sync(0xffffffffu, wv[h], 1) << 32);
-            if (!(lane & 1)) {
-                if (yy) atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotY + m * kB + a), yy);
-                if (ww) atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotA + m * kB + a), ww);
-            }
         }
     };
     // sum of q over this warp's listed entries of row m -> global slot (exact, order independent)
@@ -647,206 +539,273 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         }
     };
 
-    // Gram pass of block b: cross counts of the missing entries + the 64x64 integer Gram, published into slot b%4
-    auto gram_pass = [&](uint32_t b) {
-        const uint32_t nb = min(B, p.n_order - b * B);
-        const uint32_t *pk = pkbuf + size_t(b & 1) * kB * RS;
-        int *slot = p.slots + size_t(b % kSlots) * kSlotInts;
-        mbar_wait(&sh.mbar[b & 1], (b >> 1) & 1);
-        PHASE(kProfGramWait);
-        const bool want_gram = !p.async_mode && nb > 1;
+    // ---- dot pass of one block: S[m][l] = sum_i g'_mi * limb_l(q_i) ---------------------------------------------
+    // Warp `wi` of `nw` takes the 64-individual k-step pairs wi, wi + nw, ...; its 64 x 8 partial sums go to
+    // region wi of the scratch (16 registers x 32 lanes).
+    auto dot_partial = [&](const uint32_t *pk, uint32_t nb, uint32_t wi, uint32_t nw) {
+        int acc[4][4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) { acc[mi][0] = 0; acc[mi][1] = 0; acc[mi][2] = 0; acc[mi][3] = 0; }
+        for (uint32_t pr = wi; pr < NP; pr += nw) {
+            const uint32_t wo = 4 * pr + tig;
+            const uint4 L = limbs[size_t(gid) * RS + wo];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                if (16u * mi < nb) {
+                    const uint32_t w0 = pk[(16 * mi + gid) * RS + wo], w1 = pk[(16 * mi + gid + 8) * RS + wo];
+                    mma_u8s8(acc[mi], w0 & kM3, w1 & kM3, (w0 >> 2) & kM3, (w1 >> 2) & kM3, L.x, L.y);
+                    mma_u8s8(acc[mi], (w0 >> 4) & kM3, (w1 >> 4) & kM3, (w0 >> 6) & kM3, (w1 >> 6) & kM3, L.z, L.w);
+                }
+            }
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) scratch[(wi * 16 + mi * 4 + r) * 32 + lane] = acc[mi][r];
+    };
+    // Combine the `nw` partial regions of block bn's dot pass and publish them (with the slice's sum of q and the
+    // sums over the missing individuals) into the block's global slot; then arrive at the block's grid barrier.
+    // All threads call; the scratch writes of dot_partial must be visible (a __syncthreads in between).
+    auto publish_dots = [&](uint32_t bn, uint32_t nw) {
+        const uint32_t nbn = min(B, p.n_order - bn * B);
+        const uint32_t *pkn = pkbuf + size_t(bn & 1) * kB * RS;
+        int *slotn = p.slots + size_t(bn % kSlots) * kSlotInts;
+        // two outputs per thread of the first 8 warps: tile mi, row half rr, lane l5 -> limbs (2tig, 2tig+1) of one
+        // marker, published as ONE signed 64-bit RED (even limb + odd limb * 2^32)
+        if (tid < 256) {
+            const int l5 = tid & 31, rr = (tid >> 5) & 1, mi = tid >> 6;
+            const int o = (mi * 4 + 2 * rr) * 32 + l5;
+            int s0 = 0, s1 = 0;
+            for (uint32_t w = 0; w < nw; ++w) { s0 += scratch[w * 512 + o]; s1 += scratch[w * 512 + o + 32]; }
+            const uint32_t m = 16 * mi + (l5 >> 2) + 8 * rr;
+            const long long v = (long long)s0 + ((long long)s1 << 32);
+            if (v != 0 && m < nbn)
+                atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotDots + (m * 4 + (l5 & 3)) * kLine), (unsigned long long)v);
+        }
+        if (warp == 8) {                      // lane 2w+h holds part h of warp w's sum of q
+            unsigned long long v = sh.wq[lane >> 1][lane & 1];
+#pragma unroll
+            for (int o2 = 2; o2 < 32; o2 <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+            if (lane < 2) atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotEps + lane * kLine), v);
+        }
+        // sum of q over the missing individuals of this warp's rows (exact: the rows' lists are in their tails).
+        // Fast path: 8 lanes per row read the first 8 entries straight from the tail; longer rows go the general way.
         {
-            bool any = false;
-            for (int r = 0; r < 4; ++r) {
-                const uint32_t m = warp + 16 * r;
-                if (m < nb) {
-                    const uint32_t *row = pk + size_t(m) * RS;
-                    any |= reinterpret_cast<const uint16_t *>(row + PW)[0] != 0;
-                    if (want_gram)
-                        for_missing_chunks(row, [&](const uint32_t *ent, uint32_t n) { cross_missing(pk, slot, nb, m, ent, n); });
+            const uint32_t r2 = lane >> 3, e8 = lane & 7, m2 = warp + 16 * r2;
+            uint32_t cnt = 0;
+            long long qh = 0; unsigned long long ql = 0;
+            if (m2 < nbn) {
+                const uint16_t *tail = reinterpret_cast<const uint16_t *>(pkn + size_t(m2) * RS + PW);
+                cnt = tail[0];
+                if (cnt <= 8 && e8 < cnt) {
+                    const uint32_t i = tail[1 + e8];
+                    const uint32_t w = i >> 4, c = i & 3u, t = (i >> 2) & 3u;
+                    const uint32_t *lw = reinterpret_cast<const uint32_t *>(limbs) + c;
+                    unsigned long long uq = 0;
+#pragma unroll
+                    for (int l = 0; l < kLimbs; ++l)
+                        uq |= (unsigned long long)((lw[(size_t(l) * RS + w) * 4] >> (8 * t)) & 0xffu) << (8 * l);
+                    const long long q = (long long)((uq ^ 0x8080808080808080ULL) - 0x8080808080808080ULL);
+                    qh = q >> 32; ql = (unsigned long long)(q & 0xffffffffLL);
                 }
             }
-            if (any && lane == 0) atomicAdd(slot + kSlotFlag, 1);
-        }
-        PHASE(kProfGramCross);
-        if (want_gram) {
-            const uint32_t role = warp & 3, kg = warp >> 2, nkg = kWarps / 4;
-            int acc[5][4];
+            const unsigned any = __ballot_sync(0xffffffffu, cnt != 0);
+            if (any) {
 #pragma unroll
-            for (int t = 0; t < 5; ++t) { acc[t][0] = 0; acc[t][1] = 0; acc[t][2] = 0; acc[t][3] = 0; }
-            switch (role) {
-            case 0: gram_role_pass<0>(pk, RS, NP, kg, nkg, lane, acc); break;
-            case 1: gram_role_pass<1>(pk, RS, NP, kg, nkg, lane, acc); break;
-            case 2: gram_role_pass<2>(pk, RS, NP, kg, nkg, lane, acc); break;
-            default: gram_role_pass<3>(pk, RS, NP, kg, nkg, lane, acc); break;
-            }
-            if (kg > 0) {
-                int *dst = scratch + ((kg - 1) * 4 + role) * 20 * 32;
-#pragma unroll
-                for (int t = 0; t < 5; ++t)
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) dst[(t * 4 + r) * 32 + lane] = acc[t][r];
-            }
-            __syncthreads();
-            PHASE(kProfGramMma);
-            if (kg == 0) {
-                switch (role) {
-                case 0: gram_role_publish<0>(scratch, nkg, lane, acc, slot + kSlotA, nb); break;
-                case 1: gram_role_publish<1>(scratch, nkg, lane, acc, slot + kSlotA, nb); break;
-                case 2: gram_role_publish<2>(scratch, nkg, lane, acc, slot + kSlotA, nb); break;
-                default: gram_role_publish<3>(scratch, nkg, lane, acc, slot + kSlotA, nb); break;
+                for (int o2 = 1; o2 < 8; o2 <<= 1) {
+                    qh += __shfl_xor_sync(0xffffffffu, qh, o2);
+                    ql += __shfl_xor_sync(0xffffffffu, ql, o2);
                 }
+                if (e8 == 0 && cnt != 0 && cnt <= 8) {
+                    atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotSm + (2 * m2) * kLine), (unsigned long long)qh);
+                    atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotSm + (2 * m2 + 1) * kLine), ql);
+                }
+                const unsigned big = __ballot_sync(0xffffffffu, cnt > 8);
+                for (int r3 = 0; r3 < 4; ++r3)
+                    if (big & (1u << (8 * r3))) {
+                        const uint32_t m3 = warp + 16 * r3;
+                        for_missing_chunks(pkn + size_t(m3) * RS, [&](const uint32_t *ent, uint32_t n) { missing_q_sum(slotn, m3, ent, n); });
+                    }
             }
-            __syncthreads();
-            PHASE(kProfGramReduce);
         }
+        grid_arrive(p.bar);
     };
 
+    // ---- Gram rows on demand ------------------------------------------------------------------------------------
+    // One grid-wide round: the integer pair counts of the rows of the markers in (need0, need1) (bit masks over the
+    // two half-blocks) against all 64 columns of the block, reduced over CTAs / GPUs, standardised into x_j.x_k and
+    // stored as doubles in row slots r0, r0+1, ... of the scratch.  Every CTA calls with identical arguments.
+    auto lazy_round = [&](const uint32_t *pk, int *slot, const BlockMeta &meta, uint32_t nb, uint32_t need0, uint32_t need1, uint32_t r0) {
+        const uint32_t n0 = __popc(need0), nnew = n0 + __popc(need1);
+        if (tid < kB) {
+            const bool hi = tid >= 32;
+            const uint32_t msk = hi ? need1 : need0, bit = 1u << (tid & 31);
+            if (msk & bit) {
+                const uint32_t pos = (hi ? n0 : 0u) + __popc(msk & (bit - 1u));
+                sh.lz_rows[pos] = tid; sh.rowslot[tid] = r0 + pos;
+            }
+        }
+        __syncthreads();
+        // (1) missing-genotype cross counts.  (i) the missing list of each new row j against every column a:
+        //     cz[j][a] += g_a(i) (a present), cw[j][a] += 1 (a missing too); lanes = columns
+        for (uint32_t idx = warp; idx < nnew; idx += kWarps) {
+            const uint32_t j = sh.lz_rows[idx];
+            for_missing_chunks(pk + size_t(j) * RS, [&](const uint32_t *ent, uint32_t n) {
+                int z[2] = {0, 0}, wv[2] = {0, 0};
+                for (uint32_t en = 0; en < n; en += 4) {       // four entries per step (the list is padded with sentinels)
+                    const uint4 i4 = *reinterpret_cast<const uint4 *>(ent + en);
+                    const uint32_t ii[4] = {i4.x, i4.y, i4.z, i4.w};
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t a = lane + 32 * h;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t cwd = (a < nb && a != j && ii[q] != 0xffffffffu) ? pk[size_t(a) * RS + (ii[q] >> 4)] : 0u;
+                            const uint32_t c = (cwd >> (2 * (ii[q] & 15u))) & 3u;
+                            z[h] += (c == 3u) ? 0 : int(c);
+                            wv[h] += (c == 3u) ? 1 : 0;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t a = lane + 32 * h;
+                    unsigned long long *ln = reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0 + idx) * kB + a) * kLine);
+                    if (wv[h]) atomicAdd(ln, (unsigned long long)(unsigned)wv[h] << 32);
+                    if (z[h]) atomicAdd(ln + 1, (unsigned long long)(unsigned)z[h] << 32);
+                }
+            });
+        }
+        //     (ii) the missing list of every column k against each new row j: cy[j][k] += g_j(i) (j present); lanes = entries
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t k = warp + 16 * r;
+            if (k < nb)
+                for_missing_chunks(pk + size_t(k) * RS, [&](const uint32_t *ent, uint32_t n) {
+                    for (uint32_t idx = 0; idx < nnew; ++idx) {
+                        const uint32_t j = sh.lz_rows[idx];
+                        if (j == k) continue;
+                        int s = 0;
+                        for (uint32_t en = lane; en < n; en += 32) {
+                            const uint32_t i = ent[en];
+                            const uint32_t c = (pk[size_t(j) * RS + (i >> 4)] >> (2 * (i & 15u))) & 3u;
+                            s += (c == 3u) ? 0 : int(c);
+                        }
+                        s = __reduce_add_sync(0xffffffffu, s);
+                        if (lane == 0 && s)
+                            atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0 + idx) * kB + k) * kLine) + 1, (unsigned long long)(unsigned)s);
+                    }
+                });
+        }
+        __syncthreads();                       // the warps' missing-list segments are free: reused below
+        PHASE(kProfLazyCross);
+        // (2) integer products: warp = (column tile nt, k-half kh); 16 new rows per pass
+        {
+            const uint32_t nt = warp & 7u, kh = warp >> 3;
+            int *sc2 = reinterpret_cast<int *>(miss_list);
+            for (uint32_t mt = 0; mt * 16 < nnew; ++mt) {
+                const uint32_t ia = mt * 16 + gid, ib = ia + 8;
+                const bool va = ia < nnew, vb = ib < nnew;
+                const uint32_t ra = va ? sh.lz_rows[ia] : 0u, rb = vb ? sh.lz_rows[ib] : 0u;
+                int acc[4] = {0, 0, 0, 0};
+                for (uint32_t pr = kh; pr < NP; pr += 2) {
+                    const uint32_t wo = 4 * pr + tig;
+                    const uint32_t w0 = va ? pk[size_t(ra) * RS + wo] : 0u, w1 = vb ? pk[size_t(rb) * RS + wo] : 0u;
+                    const uint32_t wc = pk[size_t(8 * nt + gid) * RS + wo];
+                    mma_u8u8(acc, w0 & kM3, w1 & kM3, (w0 >> 2) & kM3, (w1 >> 2) & kM3, wc & kM3, (wc >> 2) & kM3);
+                    mma_u8u8(acc, (w0 >> 4) & kM3, (w1 >> 4) & kM3, (w0 >> 6) & kM3, (w1 >> 6) & kM3, (wc >> 4) & kM3, (wc >> 6) & kM3);
+                }
+                if (kh == 1) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) sc2[(nt * 4 + r) * 32 + lane] = acc[r];
+                }
+                __syncthreads();
+                if (kh == 0) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[r] += sc2[(nt * 4 + r) * 32 + lane];
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const bool valid = rr ? vb : va;
+                        const uint32_t rowm = rr ? rb : ra, rs = r0 + (rr ? ib : ia);
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc) {
+                            const uint32_t col = 8 * nt + 2 * tig + cc;
+                            const int val = acc[2 * rr + cc];
+                            if (valid && col < nb && col != rowm && val)
+                                atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(rs) * kB + col) * kLine), (unsigned long long)(unsigned)val);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        PHASE(kProfLazyMma);
+        // (3) the grid-wide round
+        grid_arrive(p.bar);
+        grid_wait(p.bar, (++bar_gen) * p.nCTA);
+        xchg(kXLazy, slot, r0, nnew, tid, kThreads, cta_sync);
+        PHASE(kProfLazyBarrier);
+        // (4) read back and standardise into x_j . x_k
+        double *G = reinterpret_cast<double *>(scratch);
+        for (uint32_t en = tid; en < nnew * kB; en += kThreads) {
+            const uint32_t idx = en >> 6, k = en & 63u, j = sh.lz_rows[idx];
+            const int4 v = __ldcg(reinterpret_cast<const int4 *>(slot + kSlotLazy + (size_t(r0 + idx) * kB + k) * kLine));
+            double g = 0.0;
+            if (k != j && k < nb)
+                g = gram_entry(meta, int(j), int(k), double(unsigned(v.x)), double(unsigned(v.y)), double(unsigned(v.z)), double(unsigned(v.w)), Nt);
+            G[(r0 + idx) * kB + k] = g;
+        }
+        __syncthreads();
+        if (prof_on) { sh.prof[kProfLazyRounds] += 1; sh.prof[kProfLazyRows] += nnew; }
+        PHASE(kProfLazyReadback);
+    };
+
+    // ---- first block: its dot pass runs on all warps --------------------------------------------------------------
     if (nBlocks > 0) {
-        if (uint32_t(tid) < min(B, p.n_order)) gather_block_meta(p, sh.meta, sh.ids[0][tid], tid);
-        gram_pass(0);
+        const uint32_t nb0 = min(B, p.n_order);
+        if (uint32_t(tid) < nb0) gather_block_meta(p, sh.meta[0], sh.ids[0][tid], tid);
+        mbar_wait(&sh.mbar[0], 0);
+        dot_partial(pkbuf, nb0, warp, kWarps);
+        cp_async_wait_all();
+        __syncthreads();
+        publish_dots(0, kWarps);
     }
-    __syncthreads();
     PHASE(kProfPrologue);
+    PHASE_W(0, false);
 
     for (uint32_t b = 0; b < nBlocks; ++b) {
         const uint32_t nb = min(B, p.n_order - b * B);
         const uint32_t buf = b & 1;
         const uint32_t *pk = pkbuf + size_t(buf) * kB * RS;
         int *slot = p.slots + size_t(b % kSlots) * kSlotInts;
-        BlockMeta &meta = sh.meta;
+        BlockMeta &meta = sh.meta[buf];
+        const bool have_next = b + 1 < nBlocks;
+        const uint32_t nb_next = have_next ? min(B, p.n_order - (b + 1) * B) : 0u;
+        const uint32_t *pk_next = pkbuf + size_t(buf ^ 1u) * kB * RS;
+        ++bar_gen;                                              // the round publish_dots(b) arrived at
 
-        // ---- 1. dot pass: S[m][l] = sum_i g'_mi * limb_l(q_i); warp = k-group ------------------------
-        {
-            int acc[4][4];
+        // ---- A. walkers: wait for the block's round, read it back, sample.  Workers: dot pass of block b+1 ------
+        const bool walker = warp < kWalkWarps;
+        const int wk = tid;                                   // marker of a walker thread
+        const bool act = walker && uint32_t(wk) < nb;
+        double bo = 0.0, uu = 2.0, zz = 0.0, base = 0.0; int gg = 0;
+        double bo1 = 0.0, zz1 = 0.0, base1 = 0.0; int gg1 = 0; bool act1 = false;    // warp 0: marker 32+lane
+        double corr_used = 0.0;
+        Draw dr; dr.beta_new = 0.0; dr.acum0 = 0.0; dr.comp = -1;
+        if (walker) {
+            if (tid == 0) { while (ld_acquire(p.bar) < bar_gen * p.nCTA) { } }
+            walker_sync();
+            PHASE(kProfWait);
+            xchg(kXMain, slot, 0, 0, tid, 32 * kWalkWarps, wlk_sync);
+            PHASE(kProfXchg);
+            if (act) {
+                long long dq[4];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) { acc[mi][0] = 0; acc[mi][1] = 0; acc[mi][2] = 0; acc[mi][3] = 0; }
-            for (uint32_t pr = warp; pr < NP; pr += kWarps) {
-                const uint32_t wo = 4 * pr + tig;
-                const uint4 L = limbs[size_t(gid) * RS + wo];
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi) {
-                    if (16u * mi < nb) {
-                        const uint32_t w0 = pk[(16 * mi + gid) * RS + wo], w1 = pk[(16 * mi + gid + 8) * RS + wo];
-                        mma_u8s8(acc[mi], w0 & kM3, w1 & kM3, (w0 >> 2) & kM3, (w1 >> 2) & kM3, L.x, L.y);
-                        mma_u8s8(acc[mi], (w0 >> 4) & kM3, (w1 >> 4) & kM3, (w0 >> 6) & kM3, (w1 >> 6) & kM3, L.z, L.w);
-                    }
-                }
-            }
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) scratch[(warp * 16 + mi * 4 + r) * 32 + lane] = acc[mi][r];
-        }
-        __syncthreads();
-        PHASE(kProfDot);
-        {
-            // two outputs per thread of the first 8 warps: tile mi, row half rr, lane l5 -> limbs (2tig, 2tig+1) of one
-            // marker, published as ONE signed 64-bit RED (even limb + odd limb * 2^32)
-            if (tid < 256) {
-                const int l5 = tid & 31, rr = (tid >> 5) & 1, mi = tid >> 6;
-                const int o = (mi * 4 + 2 * rr) * 32 + l5;
-                int s0 = 0, s1 = 0;
-#pragma unroll
-                for (int w = 0; w < kWarps; ++w) { s0 += scratch[w * 512 + o]; s1 += scratch[w * 512 + o + 32]; }
-                const uint32_t m = 16 * mi + (l5 >> 2) + 8 * rr;
-                const long long v = (long long)s0 + ((long long)s1 << 32);
-                if (v != 0 && m < nb)
-                    atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotDots + (m * 4 + (l5 & 3)) * kLine), (unsigned long long)v);
-            }
-            PHASE(kProfDotRed1);
-            if (warp == 8) {                      // lane 2w+h holds part h of warp w's sum of q
-                unsigned long long v = sh.wq[lane >> 1][lane & 1];
-#pragma unroll
-                for (int o2 = 2; o2 < 32; o2 <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
-                if (lane < 2) atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotEps + lane * kLine), v);
-            }
-            // sum of q over the missing individuals of this warp's rows (exact: the rows' lists are in their tails).
-            // Fast path: 8 lanes per row read the first 8 entries straight from the tail; longer rows go the general way.
-            {
-                const uint32_t r2 = lane >> 3, e8 = lane & 7, m2 = warp + 16 * r2;
-                uint32_t cnt = 0;
-                long long qh = 0; unsigned long long ql = 0;
-                if (m2 < nb) {
-                    const uint16_t *tail = reinterpret_cast<const uint16_t *>(pk + size_t(m2) * RS + PW);
-                    cnt = tail[0];
-                    if (cnt <= 8 && e8 < cnt) {
-                        const uint32_t i = tail[1 + e8];
-                        const uint32_t w = i >> 4, c = i & 3u, t = (i >> 2) & 3u;
-                        const uint32_t *lw = reinterpret_cast<const uint32_t *>(limbs) + c;
-                        unsigned long long uq = 0;
-#pragma unroll
-                        for (int l = 0; l < kLimbs; ++l)
-                            uq |= (unsigned long long)((lw[(size_t(l) * RS + w) * 4] >> (8 * t)) & 0xffu) << (8 * l);
-                        const long long q = (long long)((uq ^ 0x8080808080808080ULL) - 0x8080808080808080ULL);
-                        qh = q >> 32; ql = (unsigned long long)(q & 0xffffffffLL);
-                    }
-                }
-                const unsigned any = __ballot_sync(0xffffffffu, cnt != 0);
-                if (any) {
-#pragma unroll
-                    for (int o2 = 1; o2 < 8; o2 <<= 1) {
-                        qh += __shfl_xor_sync(0xffffffffu, qh, o2);
-                        ql += __shfl_xor_sync(0xffffffffu, ql, o2);
-                    }
-                    if (e8 == 0 && cnt != 0 && cnt <= 8) {
-                        atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotSm + (2 * m2) * kLine), (unsigned long long)qh);
-                        atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotSm + (2 * m2 + 1) * kLine), ql);
-                    }
-                    const unsigned big = __ballot_sync(0xffffffffu, cnt > 8);
-                    for (int r3 = 0; r3 < 4; ++r3)
-                        if (big & (1u << (8 * r3))) {
-                            const uint32_t m3 = warp + 16 * r3;
-                            for_missing_chunks(pk + size_t(m3) * RS, [&](const uint32_t *ent, uint32_t n) { missing_q_sum(slot, m3, ent, n); });
-                        }
-                }
-            }
-        }
-
-        PHASE(kProfDotRed2);
-        __syncthreads();
-        PHASE(kProfDotRed3);
-        // ---- 2. the one grid-wide exchange per block: arrive ... ------------------------------------
-        grid_arrive(p.bar);
-        PHASE(kProfDotReduce);
-
-        // ---- 3. ... and hide its latency behind the Gram pass of the next block ----------------------
-        if (b > 0 && uint32_t(tid) < nb) gather_block_meta(p, meta, sh.ids[buf][tid], tid);   // meta of block b-1 is dead
-        if (b + 1 < nBlocks) gram_pass(b + 1);
-
-        // ---- 4. wait -----------------------------------------------------------------------------------
-        grid_wait(p.bar, (++bar_gen) * p.nCTA);
-        cross_gpu_exchange(slot, false);
-        PHASE(kProfBarrier);
-
-        // ---- 5. read the reduced block back (all loads in flight at once) ----------------------------------
-        const bool want_gram = !p.async_mode && nb > 1;
-        const int flag = __ldcg(slot + kSlotFlag);
-        bool has_missing;
-        {
-            const int4 *src = reinterpret_cast<const int4 *>(slot + kSlotA);
-            int4 *dst = reinterpret_cast<int4 *>(scratch);
-            const int n4 = want_gram ? 2048 : 0;          // A, then YT (all zero when nothing is missing)
-            int4 va[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) { const int i = tid + t * kThreads; if (i < n4) va[t] = __ldcg(src + i); }
-            long long dq[4] = {0, 0, 0, 0};
-            long long sm_hi = 0, sm_lo = 0, e_hi = 0, e_lo = 0;
-            if (uint32_t(tid) < nb) {
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) dq[q4] = __ldcg(reinterpret_cast<const long long *>(slot + kSlotDots + (tid * 4 + q4) * kLine));
-                sm_hi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * tid) * kLine));
-                sm_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * tid + 1) * kLine));
-                e_hi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps));
-                e_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps + kLine));
-            }
-            has_missing = flag != 0;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) { const int i = tid + t * kThreads; if (i < n4) dst[i] = va[t]; }
-            PHASE(kProfRb1);
-            if (uint32_t(tid) < nb) {
-                cp_async_wait_all();
-                derive_block_meta(meta, tid);
+                for (int q4 = 0; q4 < 4; ++q4) dq[q4] = __ldcg(reinterpret_cast<const long long *>(slot + kSlotDots + (wk * 4 + q4) * kLine));
+                const long long sm_hi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * wk) * kLine));
+                const long long sm_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * wk + 1) * kLine));
+                const long long e_hi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps));
+                const long long e_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps + kLine));
+                derive_block_meta(meta, wk);
                 const double eps_sum_total = (double(e_hi) * 4294967296.0 + double(e_lo)) * inv_scale;
                 // unpack the limb sums: each int64 holds (even limb) + (odd limb) * 2^32, both signed
                 long long S[8];
@@ -859,37 +818,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 const long long thi = S[4] + (S[5] << 8) + (S[6] << 16) + (S[7] << 24);
                 const double dprime = (double(thi) * 4294967296.0 + double(tlo)) * inv_scale;    // sum_i g'_i eps_i
                 const double smd = (double(sm_hi) * 4294967296.0 + double(sm_lo)) * inv_scale;
-                const double *L = meta.lut[tid];
+                const double *L = meta.lut[wk];
                 // x.eps = L0 sum(eps) + s (S1 + 2 S2) + (L3 - L0) Smissing ; the products saw missing as 3
-                sh.d0[tid] = L[0] * eps_sum_total + meta.sj[tid] * (dprime - 3.0 * smd) + (L[3] - L[0]) * smd;
+                sh.d0[wk] = L[0] * eps_sum_total + meta.sj[wk] * (dprime - 3.0 * smd) + (L[3] - L[0]) * smd;
+                sh.rowslot[wk] = 0;
             }
-        }
-        PHASE(kProfRb2);
-        // recycle the slot of block b-1 (every CTA has read it before arriving at this block's barrier)
-        if (cta == b % p.nCTA) {
-            int4 *z = reinterpret_cast<int4 *>(p.slots + size_t((b + kSlots - 1) % kSlots) * kSlotInts);
-            for (int i = tid; i < kSlotInts / 4; i += kThreads) z[i] = make_int4(0, 0, 0, 0);
-        }
-        __syncthreads();
-        PHASE(kProfReadback);
-
-        // ---- 6. the walk: one warp, lane l owns markers l and l+32 of the block ----------------------------
-        // The one-by-one loop is reproduced exactly in three steps that iterate to a fixed point:
-        //   (a) every marker is sampled against its current dot (speculating no earlier marker changes eps);
-        //   (b) with the components fixed, the non-skipped markers (src/BayesRBase.cpp:372) are solved in
-        //       order: beta_j from its corrected dot, then the dots of all later markers are corrected by
-        //       (beta_old_j - beta_j) x_j.x_k.  This is a triangular solve with O(1) flops per step -- no exp;
-        //   (c) every marker whose dot moved is sampled again; if all components (hence all betas, bit for
-        //       bit) are confirmed, the state equals the sequential chain's, else (b) restarts with the new ones.
-        // Two warps: thread k < 64 samples marker k of the block; warp 0 runs the solve for both halves.
-        const bool walker = warp < 2;
-        const int wk = tid;                                   // marker of a walker thread
-        const bool act = walker && uint32_t(wk) < nb;
-        double bo = 0.0, uu = 2.0, zz = 0.0, base = 0.0; int gg = 0;
-        double bo1 = 0.0, zz1 = 0.0, base1 = 0.0; int gg1 = 0; bool act1 = false;    // warp 0: marker 32+lane
-        Draw dr; dr.beta_new = 0.0; dr.acum0 = 0.0; dr.comp = -1;
-        if (walker) {
-            // (a) on warps 0 and 1 ...
+            walker_sync();
+            PHASE(kProfReadback);
+            // (a) every marker is sampled against its dot at the start of the block
             if (act) {
                 bo = meta.beta_old[wk]; uu = meta.uz[wk][0]; zz = meta.uz[wk][1]; gg = meta.grp[wk];
                 base = sh.d0[wk] + bo * NM1;
@@ -900,51 +836,49 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             }
             dr.beta_new = bo;
             if (act) dr = sample_marker_k(sh.gc, gg, K, base, p.sigmaE, bo, uu, zz);
-        } else if (want_gram) {
-            // ... while warps 2..15 turn the integer counts into the standardised Gram x_j.x_k (doubles, in place).
-            // Pairs are visited along diagonals k - j = d so that both A[j][k] and the transposed reads are
-            // bank-conflict free.
-            const int *As = scratch, *Ys = scratch + 4096;
-            constexpr int kStd = kThreads - 64;
-            constexpr int kPer = (32 * kB + kStd - 1) / kStd;
-            double gv[kPer];
-#pragma unroll
-            for (int t = 0; t < kPer; ++t) {
-                const int idx = (tid - 64) + t * kStd;
-                const int dd = (idx >> 6) + 1, x = idx & 63;
-                const bool lo = x < 64 - dd;
-                const int d = lo ? dd : 64 - dd, j = lo ? x : x - (64 - dd), k = j + d;
-                const bool ok = idx < 32 * kB && !(dd == 32 && !lo) && uint32_t(k) < nb;
-                gv[t] = ok ? gram_entry(meta, As, Ys, has_missing, j, k, Nt) : 0.0;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(kStd) : "memory");
-            double *G = reinterpret_cast<double *>(scratch);
-#pragma unroll
-            for (int t = 0; t < kPer; ++t) {
-                const int idx = (tid - 64) + t * kStd;
-                const int dd = (idx >> 6) + 1, x = idx & 63;
-                const bool lo = x < 64 - dd;
-                const int d = lo ? dd : 64 - dd, j = lo ? x : x - (64 - dd), k = j + d;
-                const bool ok = idx < 32 * kB && !(dd == 32 && !lo) && uint32_t(k) < nb;
-                if (ok) G[j * kB + k] = gv[t];
+            const unsigned nsm = __ballot_sync(0xffffffffu, act && !(bo == 0.0 && dr.beta_new == 0.0));
+            if (lane == 0) sh.w_nsm[warp] = nsm;
+            sh.w_comp[wk] = dr.comp;
+            PHASE(kProfSample);
+        } else {
+            if (have_next) {
+                const int k2 = tid - 32 * kWalkWarps;
+                if (uint32_t(k2) < nb_next) gather_block_meta(p, sh.meta[buf ^ 1u], sh.ids[buf ^ 1u][k2], k2);
+                mbar_wait(&sh.mbar[buf ^ 1u], ((b + 1) >> 1) & 1u);
+                PHASE_W(kProfWorkerWait, true);
+                dot_partial(pk_next, nb_next, warp - kWalkWarps, kDotWarps);
+                cp_async_wait_all();
+                PHASE_W(kProfWorkerDot, true);
             }
         }
         __syncthreads();
-        PHASE(kProfWalkA);
-        if (walker) {
-            const double *G = reinterpret_cast<const double *>(scratch);
-            double corr_used = 0.0;
-            for (int iter = 0; iter < 2 * kB && !p.async_mode; ++iter) {
-                const unsigned nsm = __ballot_sync(0xffffffffu, act && !(bo == 0.0 && dr.beta_new == 0.0));
-                if (lane == 0) sh.w_nsm[warp] = nsm;
-                sh.w_comp[wk] = dr.comp;
-                asm volatile("bar.sync 2, 64;" ::: "memory");
+        PHASE(kProfJoin);
+        PHASE_W(0, false);
+
+        // ---- B. the walk -----------------------------------------------------------------------------------------------
+        // The one-by-one loop is reproduced exactly by iterating to a fixed point:
+        //   (a) [done above] every marker is sampled against its current dot (speculating no earlier marker changes eps);
+        //   (b) the non-skipped markers (src/BayesRBase.cpp:372) get their Gram rows (one grid-wide round, only for rows
+        //       not yet known) and are solved in order: beta_j from its corrected dot, then the dots of all later markers
+        //       are corrected by (beta_old_j - beta_j) x_j.x_k.  A triangular solve with O(1) flops per step -- no exp;
+        //   (c) every marker whose dot moved is sampled again; if all components (hence all betas, bit for bit) are
+        //       confirmed, the state equals the sequential chain's, else (b) restarts with the new ones.
+        // Thread k < 64 samples marker k of the block; warp 0 runs the solve for both halves.
+        uint32_t have0 = 0, have1 = 0, lz_used = 0;             // Gram rows known so far (identical in every CTA)
+        if (!p.async_mode) {
+            for (int iter = 0; iter < 2 * kB; ++iter) {
                 const unsigned nsm0 = sh.w_nsm[0], nsm1 = sh.w_nsm[1];
                 if ((nsm0 | nsm1) == 0) break;
                 if (prof_on) { sh.prof[kProfWalkIters] += 1; sh.prof[kProfWalkSolves] += __popc(nsm0) + __popc(nsm1); }
+                uint32_t need0 = nsm0 & ~have0, need1 = nsm1 & ~have1;
+                if (nb - 1 < 32) need0 &= ~(1u << (nb - 1)); else need1 &= ~(1u << (nb - 33));   // the last marker corrects nobody
+                if (need0 | need1) {
+                    lazy_round(pk, slot, meta, nb, need0, need1, lz_used);
+                    have0 |= need0; have1 |= need1; lz_used += __popc(need0) + __popc(need1);
+                }
                 double corr = 0.0;
                 if (warp == 0) {
-                    // (b) triangular solve over the non-skipped markers, in block order
+                    const double *G = reinterpret_cast<const double *>(scratch);
                     const int comp1 = sh.w_comp[32 + lane];
                     double c0 = 0.0, c1 = 0.0;
                     unsigned m = nsm0;
@@ -954,8 +888,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                         const double mine = bo - beta_given_comp(sh.gc, gg, K, dr.comp, base + c0, bo, zz);
                         const double dB = __shfl_sync(0xffffffffu, mine, jl);          // eps += dB * x_j
                         if (dB != 0.0) {
-                            if (act && lane > jl) c0 += dB * G[jl * kB + lane];
-                            if (act1) c1 += dB * G[jl * kB + 32 + lane];
+                            const double *Gr = G + size_t(sh.rowslot[jl]) * kB;
+                            if (act && lane > jl) c0 += dB * Gr[lane];
+                            if (act1) c1 += dB * Gr[32 + lane];
                         }
                     }
                     m = nsm1;
@@ -964,26 +899,34 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                         m &= m - 1;
                         const double mine = bo1 - beta_given_comp(sh.gc, gg1, K, comp1, base1 + c1, bo1, zz1);
                         const double dB = __shfl_sync(0xffffffffu, mine, jl);
-                        if (dB != 0.0 && act1 && lane > jl) c1 += dB * G[(32 + jl) * kB + 32 + lane];
+                        if (dB != 0.0 && act1 && lane > jl) c1 += dB * (G + size_t(sh.rowslot[32 + jl]) * kB)[32 + lane];
                     }
                     corr = c0;
                     sh.w_corr[32 + lane] = c1;
                 }
-                asm volatile("bar.sync 2, 64;" ::: "memory");
-                if (warp == 1) corr = sh.w_corr[wk];
-                // (c) re-sample where the dot moved; confirm the components
-                bool changed = false;
-                if (act && corr != corr_used) {
-                    const Draw nd = sample_marker_k(sh.gc, gg, K, base + corr, p.sigmaE, bo, uu, zz);
-                    changed = nd.comp != dr.comp;
-                    dr = nd;
-                    corr_used = corr;
+                __syncthreads();
+                PHASE(kProfSolve);
+                if (walker) {
+                    if (warp == 1) corr = sh.w_corr[wk];
+                    // (c) re-sample where the dot moved; confirm the components
+                    bool changed = false;
+                    if (act && corr != corr_used) {
+                        const Draw nd = sample_marker_k(sh.gc, gg, K, base + corr, p.sigmaE, bo, uu, zz);
+                        changed = nd.comp != dr.comp;
+                        dr = nd;
+                        corr_used = corr;
+                    }
+                    const unsigned chg = __ballot_sync(0xffffffffu, changed);
+                    const unsigned nsm = __ballot_sync(0xffffffffu, act && !(bo == 0.0 && dr.beta_new == 0.0));
+                    if (lane == 0) { sh.w_chg[warp] = chg; sh.w_nsm[warp] = nsm; }
+                    sh.w_comp[wk] = dr.comp;
                 }
-                const unsigned chg = __ballot_sync(0xffffffffu, changed);
-                if (lane == 0) sh.w_chg[warp] = chg;
-                asm volatile("bar.sync 2, 64;" ::: "memory");
+                __syncthreads();
+                PHASE(kProfSample);
                 if ((sh.w_chg[0] | sh.w_chg[1]) == 0) break;
             }
+        }
+        if (walker) {
             const double dB = act ? (bo - dr.beta_new) : 0.0;
             const bool upd = act && dB != 0.0;
             const bool nonskip = act && !(bo == 0.0 && dr.beta_new == 0.0);
@@ -1008,20 +951,23 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                         const double sgi = warp_sum(b2);
                         if (lane == 0) { if (warp == 0) sh.d0[gi] = sgi; else sh.w_corr[gi] = sgi; }
                     }
-                    asm volatile("bar.sync 2, 64;" ::: "memory");
+                    walker_sync();
                     if (uint32_t(tid) < ng) sh.betasq_s[g0 + tid] += sh.d0[tid] + sh.w_corr[tid];
-                    asm volatile("bar.sync 2, 64;" ::: "memory");
+                    walker_sync();
                 }
             }
-            asm volatile("bar.sync 2, 64;" ::: "memory");
+            walker_sync();
             const uint32_t off = warp ? sh.w_cnt[0] : 0u;
             if (upd) sh.ns_list[off + __popc(um & ((1u << lane) - 1u))] = wk;
-            if (tid == 0) { sh.n_ns = sh.w_cnt[0] + sh.w_cnt[1]; sh.n_nonskipped_total += sh.w_cnt2[0] + sh.w_cnt2[1]; }
+            if (tid == 0) {
+                sh.n_ns = sh.w_cnt[0] + sh.w_cnt[1]; sh.n_nonskipped_total += sh.w_cnt2[0] + sh.w_cnt2[1];
+                sh.lz_hist[b % kSlots] = lz_used;
+            }
         }
         __syncthreads();
-        PHASE(kProfWalk);
+        PHASE(kProfFinalize);
 
-        // ---- 7. residual update in registers, re-quantise --------------------------------------------------
+        // ---- C. residual update in registers, re-quantise --------------------------------------------------
         const uint32_t n_ns = sh.n_ns;
         if (n_ns) {
 #pragma unroll
@@ -1063,12 +1009,35 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 }
             }
             quantize();
+            if (prof_on) sh.prof[kProfBlocksUpdated] += 1;
+            __syncthreads();
+            PHASE(kProfQuantize);
         }
-        __syncthreads();
-        PHASE(kProfQuantize);
 
-        // ---- 8. this buffer is free: prefetch block b+2 into it ------------------------------------------
+        // ---- D. the round of block b+1 ---------------------------------------------------------------------------
+        // recycle the slot of block b-1 (every CTA finished reading it before it arrived at block b's round)
+        if (b > 0 && cta == b % p.nCTA) {
+            int *old = p.slots + size_t((b - 1) % kSlots) * kSlotInts;
+            for (int i = tid; i < 256 + 128 + 2; i += kThreads) *reinterpret_cast<unsigned long long *>(old + i * kLine) = 0ULL;
+            const uint32_t used = sh.lz_hist[(b - 1) % kSlots];
+            for (uint32_t i = tid; i < used * kB; i += kThreads) *reinterpret_cast<int4 *>(old + kSlotLazy + size_t(i) * kLine) = make_int4(0, 0, 0, 0);
+        }
+        if (have_next) {
+            mbar_wait(&sh.mbar[buf ^ 1u], ((b + 1) >> 1) & 1u);   // the walkers have not observed the rows of block b+1 yet
+            if (n_ns || lz_used) {              // the residual (or the scratch holding the speculative sums) changed: redo
+                dot_partial(pk_next, nb_next, warp, kWarps);
+                __syncthreads();
+                PHASE(kProfRedoDot);
+                publish_dots(b + 1, kWarps);
+            } else {
+                publish_dots(b + 1, kDotWarps);
+            }
+        }
+        // block b's buffer is free: prefetch block b+2 into it
         if (b + 2 < nBlocks) prefetch(b + 2);
+        __syncthreads();            // the ids / zero rows written by prefetch are read by the dot warps right away
+        PHASE(kProfPublish);
+        PHASE_W(0, false);
     }
 
     // ---- epilogue: eps back to HBM, sweep scalars ------------------------------------------------
@@ -1104,10 +1073,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             s = warp_sum(s); q = warp_sum(q);
             if (lane == 0) {
                 p.out_scalars[0] = s; p.out_scalars[1] = q;
-                p.out_counts[0] = sh.n_nonskipped_total; p.out_counts[1] = nBlocks;
-                if (p.prof) for (int i = 0; i < kProfPhases; ++i) p.prof[i] += sh.prof[i];
+                p.out_counts[0] = sh.n_nonskipped_total; p.out_counts[1] = nBlocks; p.out_counts[3] = bar_gen;
+                if (p.world > 1) *p.round_ctr = round_base + xround;
             }
         }
+        __syncthreads();
+        if (p.prof && tid == 0) for (int i = 0; i < kProfPhases; ++i) p.prof[i] += sh.prof[i];
         for (uint32_t i = tid; i < p.nG * K; i += kThreads) p.v[i] = double(sh.v_s[i]);
         for (uint32_t i = tid; i < p.nG; i += kThreads) p.betasq[i] = sh.betasq_s[i];
     }

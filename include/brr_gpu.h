@@ -203,10 +203,12 @@ int brr_gpu_info(brr_gpu_ctx *ctx, uint32_t *n_ctas, uint32_t *slice_inds, uint3
                  uint64_t *genotype_bytes);
 uint64_t brr_gpu_launch_count(brr_gpu_ctx *ctx);
 /* Phase breakdown of the dense sweep kernel (SM cycles of CTA 0, accumulated over sweeps), available when
- * the environment has BRR_GPU_PROFILE=1 at brr_gpu_create: 24 counters in the order dot, dot-reduce,
- * gram-scan (unused), gram-cross, gram-mma, gram-reduce, barrier wait, readback, walk, axpy, quantize, prologue,
- * walk iterations, walk solve steps (counts), walk first round, wait for the code rows, then 5 sub-phases
- * (dot-reduce 1-3, readback 1-2) and 3 spare.  reset != 0 clears them. */
+ * the environment has BRR_GPU_PROFILE=1 at brr_gpu_create: 24 counters in the order wait (grid barrier),
+ * cross-GPU exchange, read-back, sampling, join (walkers waiting for the dot warps), Gram-row cross counts,
+ * Gram-row products, Gram-row barrier, Gram-row read-back, triangular solve, finalize, axpy, quantize,
+ * repeated dot pass, publish, prologue; then 5 counts (walk iterations, solve steps, Gram rounds, Gram rows,
+ * blocks that updated the residual); then the dot warps' wait for the code rows and their dot pass (these two
+ * overlap the walker phases); 1 spare.  reset != 0 clears them. */
 int brr_gpu_profile_cycles(brr_gpu_ctx *ctx, uint64_t *cycles24, int reset);
 
 #ifdef __cplusplus

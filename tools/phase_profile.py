@@ -29,10 +29,14 @@ for s in range(sweeps):
     v, bs, out = e.sweep(order, rand_uz, pi, sigmaG, sigmaE)
     pc = e.profile_cycles(reset=True)
     nb = max(1, out.n_blocks)
-    tot = sum(v_ for k, v_ in pc.items() if k not in ("walk_iters", "walk_solves"))
-    print("sweep %d: %.3f ms, %.2f us/block, nonskipped %.2f%%, walk iters/block %.2f, solves/block %.2f" % (
-        s, out.kernel_ms, 1e3 * out.kernel_ms / nb, 100.0 * out.n_nonskipped / M, pc["walk_iters"] / nb, pc["walk_solves"] / nb))
-    print("   cycles/block: " + "  ".join("%s=%d" % (k, pc[k] // nb) for k in e.PROFILE_PHASES[:11] + ["walk_a", "gram_wait", "dotred1", "dotred2", "dotred3", "rb1", "rb2"]) + "  | prologue=%d total/block=%d" % (pc["prologue"], tot // nb))
+    skip = set(e.PROFILE_COUNTERS) | set(e.PROFILE_OVERLAPPED) | {"spare", "prologue"}
+    tot = sum(v_ for k, v_ in pc.items() if k not in skip)
+    print("sweep %d: %.3f ms, %.2f us/block, nonskipped %.3f%%, blocks updated %.1f%%, walk iters/block %.2f, solves/block %.2f, gram rounds/block %.3f, gram rows/block %.3f" % (
+        s, out.kernel_ms, 1e3 * out.kernel_ms / nb, 100.0 * out.n_nonskipped / M, 100.0 * pc["blocks_updated"] / nb,
+        pc["walk_iters"] / nb, pc["walk_solves"] / nb, pc["lazy_rounds"] / nb, pc["lazy_rows"] / nb))
+    print("   walker cycles/block: " + "  ".join("%s=%d" % (k, pc[k] // nb) for k in e.PROFILE_PHASES if k not in skip)
+          + "  | total/block=%d  prologue=%d" % (tot // nb, pc["prologue"]))
+    print("   dot warps (overlapped) cycles/block: " + "  ".join("%s=%d" % (k, pc[k] // nb) for k in e.PROFILE_OVERLAPPED))
     m0 = v[0, 1:].sum()
     pi = rng.dirichlet(v[0] + 1.0)[None, :]
     sigmaG = np.array([max(1e-6, (bs[0] * 1.0 + 1e-8) / max(1.0, m0))])
