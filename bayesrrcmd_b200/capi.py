@@ -265,16 +265,17 @@ class Engine:
     def launch_count(self):
         return int(self.lib.brr_gpu_launch_count(self._h))
 
-    PROFILE_PHASES = ["wait", "xchg", "readback", "sample", "join", "lazy_cross", "lazy_mma", "lazy_barrier", "lazy_readback",
-                      "solve", "finalize", "axpy", "quantize", "redo_dot", "publish", "prologue",
-                      "walk_iters", "walk_solves", "lazy_rounds", "lazy_rows", "blocks_updated",
-                      "worker_wait", "worker_dot", "spare"]
-    PROFILE_COUNTERS = ("walk_iters", "walk_solves", "lazy_rounds", "lazy_rows", "blocks_updated")
+    PROFILE_PHASES = ["wait", "xchg", "readback", "sample", "join", "publish", "lazy_cross", "lazy_mma", "lazy_barrier",
+                      "lazy_readback", "solve", "resample", "finalize", "carry", "axpy", "quantize", "tail", "prologue",
+                      "walk_iters", "lazy_rounds", "lazy_rows", "blocks_updated", "worker_wait", "worker_dot",
+                      "pub_reduce", "pub_missing", "pub_arrive", "lz_loop", "lz_red", "pub_pre", "lz_c0", "lz_c1", "lz_c2",
+                      "spare0", "spare1", "spare2", "spare3"]
+    PROFILE_COUNTERS = ("walk_iters", "lazy_rounds", "lazy_rows", "blocks_updated")
     PROFILE_OVERLAPPED = ("worker_wait", "worker_dot")     # timed on a dot-pass warp, concurrent with the walker phases
 
     def profile_cycles(self, reset=True):
         """Phase cycle counters of the dense sweep kernel (needs BRR_GPU_PROFILE=1 at construction)."""
-        a = np.zeros(24, dtype=np.uint64)
+        a = np.zeros(40, dtype=np.uint64)
         self._check(self.lib.brr_gpu_profile_cycles(self._h, _ptr(a), int(reset)))
         return dict(zip(self.PROFILE_PHASES, (int(x) for x in a)))
 

@@ -257,8 +257,8 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
     TRY_OR_DESTROY(dev_alloc(&c->out_counts, 4));
     if (const char *e = getenv("BRR_GPU_PROFILE")) {
         if (e[0] == '1') {
-            TRY_OR_DESTROY(dev_alloc(&c->prof, 24));
-            CUDA_OR_DESTROY(cudaMemset(c->prof, 0, sizeof(unsigned long long) * 24));
+            TRY_OR_DESTROY(dev_alloc(&c->prof, kProfPhases));
+            CUDA_OR_DESTROY(cudaMemset(c->prof, 0, sizeof(unsigned long long) * kProfPhases));
         }
     }
     CUDA_OR_DESTROY(cudaMallocHost(reinterpret_cast<void **>(&c->h_small), sizeof(double) * (2 * kMaxGK + 8 + 2 * kRedBlocks)));
@@ -677,14 +677,14 @@ extern "C" int brr_gpu_info(brr_gpu_ctx *c, uint32_t *n_ctas, uint32_t *slice_in
 
 extern "C" uint64_t brr_gpu_launch_count(brr_gpu_ctx *c) { return c ? c->launches : 0; }
 
-extern "C" int brr_gpu_profile_cycles(brr_gpu_ctx *c, uint64_t *cycles24, int reset)
+extern "C" int brr_gpu_profile_cycles(brr_gpu_ctx *c, uint64_t *cycles40, int reset)
 {
     CHECK_CTX(c);
-    if (!cycles24) return fail(BRR_GPU_EINVAL, "null output");
+    if (!cycles40) return fail(BRR_GPU_EINVAL, "null output");
     if (!c->prof) return fail(BRR_GPU_ESTATE, "phase profiling is off: set BRR_GPU_PROFILE=1 before brr_gpu_create");
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaMemcpy(cycles24, c->prof, sizeof(uint64_t) * 24, cudaMemcpyDeviceToHost));
-    if (reset) CUDA_TRY(cudaMemset(c->prof, 0, sizeof(uint64_t) * 24));
+    CUDA_TRY(cudaMemcpy(cycles40, c->prof, sizeof(uint64_t) * kProfPhases, cudaMemcpyDeviceToHost));
+    if (reset) CUDA_TRY(cudaMemset(c->prof, 0, sizeof(uint64_t) * kProfPhases));
     return 0;
 }
 

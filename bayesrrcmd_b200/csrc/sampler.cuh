@@ -50,21 +50,21 @@ struct Draw {
     int comp;       // chosen component, -1 = walk fell through (nothing assigned, :346-366)
 };
 
-// src/BayesRBase.cpp:325-366.  KT > 0: compile-time component count (arrays stay in registers).
-template <int KT>
-__device__ __forceinline__ Draw sample_marker_t(const GroupConsts &gc, int g, int Krt, double num, double sigmaE,
-                                                double beta_old, double u, double z)
+// src/BayesRBase.cpp:325-366, the literal restatement (up to K*K exponentials).  This is the rarely taken general path
+// (K > 5, or a |logL| difference beyond the reference's 700 guard): one out-of-line copy, loops not unrolled, so that it
+// costs no instruction-cache space on the walkers' critical path.
+__device__ __noinline__ Draw sample_marker_general(const GroupConsts &gc, int g, int K, double num, double sigmaE,
+                                                   double beta_old, double u, double z)
 {
-    const int K = KT > 0 ? KT : Krt;
     const double *logPi = gc.logPi + g * K;
     const double *invDenom = gc.invDenom + g * K;
     const double *sdev = gc.sdev + g * K;
     const double *halfLog = gc.halfLog + g * K;
-    double logL[KT > 0 ? KT : kMaxK], muk[KT > 0 ? KT : kMaxK];
+    double logL[kMaxK], muk[kMaxK];
     muk[0] = 0.0;
     logL[0] = logPi[0];
     bool big = false;
-#pragma unroll
+#pragma unroll 1
     for (int k = 1; k < K; ++k) {
         muk[k] = num * invDenom[k];                                         // :325 (same muk as the fast path and the walk's solve)
         logL[k] = logPi[k] - halfLog[k] + 0.5 * (muk[k] * num) / sigmaE;   // :331-333
@@ -73,7 +73,7 @@ __device__ __forceinline__ Draw sample_marker_t(const GroupConsts &gc, int g, in
     double acum = 0.0;
     if (!big) {
         double s = 0.0;
-#pragma unroll
+#pragma unroll 1
         for (int l = 0; l < K; ++l) s += exp(logL[l] - logL[0]);
         acum = 1.0 / s;                                                     // :338
     }
@@ -81,7 +81,7 @@ __device__ __forceinline__ Draw sample_marker_t(const GroupConsts &gc, int g, in
     d.acum0 = acum;
     d.beta_new = beta_old;
     d.comp = -1;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < K; ++k) {
         if (u <= acum) {                                                    // :347
             d.beta_new = (k == 0) ? 0.0 : __fma_rn(z, sdev[k], muk[k]);     // :350-352
@@ -90,11 +90,11 @@ __device__ __forceinline__ Draw sample_marker_t(const GroupConsts &gc, int g, in
         }
         if (k + 1 == K) break;     // reference reads logL[K] out of bounds; result unused
         bool b2 = false;
-#pragma unroll
+#pragma unroll 1
         for (int l = 1; l < K; ++l) b2 |= fabs(logL[l] - logL[k + 1]) > 700.0;   // :360
         if (!b2) {
             double s = 0.0;
-#pragma unroll
+#pragma unroll 1
             for (int l = 0; l < K; ++l) s += exp(logL[l] - logL[k + 1]);
             acum += 1.0 / s;                                                // :363
         }
@@ -105,7 +105,7 @@ __device__ __forceinline__ Draw sample_marker_t(const GroupConsts &gc, int g, in
 __device__ inline Draw sample_marker(const GroupConsts &gc, int g, int K, double num, double sigmaE,
                                      double beta_old, double u, double z)
 {
-    return sample_marker_t<0>(gc, g, K, num, sigmaE, beta_old, u, z);
+    return sample_marker_general(gc, g, K, num, sigmaE, beta_old, u, z);
 }
 
 // The same draw with K exponentials instead of up to K*K: when no |logL_a - logL_b| can exceed the
@@ -136,7 +136,7 @@ __device__ __forceinline__ Draw sample_marker_fast_t(const GroupConsts &gc, int 
         logL[k] = logPi[k] - halfLog[k] + (muk[k] * num) * hise;           // :331-333
         mx = fmax(mx, logL[k]); mn = fmin(mn, logL[k]);
     }
-    if (!(mx - mn <= 700.0)) return sample_marker_t<KT>(gc, g, Krt, num, sigmaE, beta_old, u, z);
+    if (!(mx - mn <= 700.0)) return sample_marker_general(gc, g, Krt, num, sigmaE, beta_old, u, z);
     double s = 1.0;                                                          // exp(logL[0] - logL[0])
     ex[0] = 1.0;
 #pragma unroll
@@ -162,8 +162,8 @@ __device__ __forceinline__ Draw sample_marker_fast_t(const GroupConsts &gc, int 
     return d;
 }
 
-// dispatch on the common component counts so that muk/logL live in registers
-__device__ __forceinline__ Draw sample_marker_k(const GroupConsts &gc, int g, int K, double num, double sigmaE,
+// dispatch on the common component counts so that muk/logL live in registers; ONE out-of-line copy for all call sites
+__device__ __noinline__ Draw sample_marker_k(const GroupConsts &gc, int g, int K, double num, double sigmaE,
                                                 double beta_old, double u, double z)
 {
     switch (K) {
@@ -171,7 +171,7 @@ __device__ __forceinline__ Draw sample_marker_k(const GroupConsts &gc, int g, in
     case 3: return sample_marker_fast_t<3>(gc, g, K, num, sigmaE, beta_old, u, z);
     case 4: return sample_marker_fast_t<4>(gc, g, K, num, sigmaE, beta_old, u, z);
     case 5: return sample_marker_fast_t<5>(gc, g, K, num, sigmaE, beta_old, u, z);
-    default: return sample_marker_t<0>(gc, g, K, num, sigmaE, beta_old, u, z);
+    default: return sample_marker_general(gc, g, K, num, sigmaE, beta_old, u, z);
     }
 }
 

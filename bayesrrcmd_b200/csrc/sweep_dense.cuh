@@ -52,19 +52,23 @@ constexpr int kMaxSL = 4096;           // individuals per CTA (2 register items 
 constexpr int kScratchInts = 8192;     // 32 KB shared scratch: dot partials of 16 warps, or the 64x64 Gram rows (doubles)
 constexpr int kHeadroomBits = 6;       // |eps| may grow 64x inside a sweep before the fixed point overflows
 constexpr int kWalkWarps = 2;          // warps 0,1: barrier wait, read-back, sampling
-constexpr int kDotWarps = kWarps - kWalkWarps;   // warps 2..15: speculative dot pass of the next block
+constexpr int kDotWarps = kWarps - kWalkWarps;   // warps 2..15: dot pass of the next block, TMA issue
+constexpr int kTmaLanes = 5;           // rows each dot warp requests per block (14 x 5 >= 64).  One warp issuing all 64 bulk
+                                       // copies takes ~3400 cycles (measured, tools/latency_bench2.cu); spread like this ~700.
 
 // rotating global slot (int32 units).  Everything that ALL CTAs add into between two barriers sits on its
 // own 128-byte line: RED throughput is per L2 line/slice, and 148 CTAs hammering a few lines was measured to
 // cost thousands of cycles per block on the critical path (profiles/).
 constexpr int kLine = 32;              // ints per 128-byte line
+constexpr int kCols = 2 * kB;          // columns of a Gram row: the 64 markers of the block, then the 64 of the next block
 constexpr int kSlotDots = 0;           // [64][4] int64, one per line: limb sums in pairs (even limb + odd limb * 2^32)
 constexpr int kSlotSm = kSlotDots + 256 * kLine;   // [64][2] int64, one per line: sum of q over missing individuals (hi, lo)
 constexpr int kSlotEps = kSlotSm + 128 * kLine;    // [2] int64, one per line: sum of q over all individuals (hi, lo)
-constexpr int kSlotLazy = kSlotEps + 2 * kLine;    // [64 row slots][64 columns], one line each, first 16 bytes:
-                                                   //   u64 #0 = a | cw << 32,  u64 #1 = cy | cz << 32   (see GramCounts)
-constexpr int kSlotInts = kSlotLazy + kB * kB * kLine;
-constexpr int kSlots = 4;
+constexpr int kSlotMainLines = 256 + 128 + 2;
+constexpr int kSlotLazy = kSlotEps + 2 * kLine;    // [64 row slots][128 columns], one line each, first 16 bytes:
+                                                   //   u64 #0 = a | cw << 32,  u64 #1 = cy | cz << 32   (see gram_entry)
+constexpr int kSlotInts = kSlotLazy + kB * kCols * kLine;
+constexpr int kSlots = 4;              // blocks b-2 (being recycled), b-1 (still read by slow CTAs), b, b+1 (being published)
 
 struct DenseSweepParams {
     // geometry
@@ -107,8 +111,8 @@ struct DenseSweepParams {
 // exchange buffer of a rank (uint64 units): mailbox[src][rot] of kMsgU64, then flags[src][kXchgCtas] (round ids)
 constexpr int kXchgCtas = 8;           // CTAs that push / merge a share of a Gram round's counts
 constexpr int kXchgRot = 4;
-constexpr int kMsgLazy = 0;                        // [64 row slots][64 columns][2]
-constexpr int kMsgDots = kMsgLazy + 2 * kB * kB;   // [64][4]
+constexpr int kMsgLazy = 0;                        // [64 row slots][128 columns][2]
+constexpr int kMsgDots = kMsgLazy + 2 * kB * kCols; // [64][4]
 constexpr int kMsgSm = kMsgDots + 4 * kB;          // [64][2]
 constexpr int kMsgEps = kMsgSm + 2 * kB;           // [2]
 constexpr int kMsgAbs = kMsgEps + 2;               // [1]
@@ -119,10 +123,12 @@ enum { kXAbs = 0, kXMain = 1, kXLazy = 2 };
 
 // phases of the block loop, as timed by thread 0 of CTA 0 (a walker) when DenseSweepParams::prof is set;
 // kProfWorker* are timed by the first lane of warp 2 (a dot-pass warp) and overlap the walker's phases
-enum { kProfWait = 0, kProfXchg, kProfReadback, kProfSample, kProfJoin, kProfLazyCross, kProfLazyMma, kProfLazyBarrier,
-       kProfLazyReadback, kProfSolve, kProfFinalize, kProfAxpy, kProfQuantize, kProfRedoDot, kProfPublish, kProfPrologue,
-       kProfWalkIters, kProfWalkSolves, kProfLazyRounds, kProfLazyRows, kProfBlocksUpdated, kProfWorkerWait, kProfWorkerDot,
-       kProfSpare, kProfPhases = 24 };
+enum { kProfWait = 0, kProfXchg, kProfReadback, kProfSample, kProfJoin, kProfPublish, kProfLazyCross, kProfLazyMma, kProfLazyBarrier,
+       kProfLazyReadback, kProfSolve, kProfResample, kProfFinalize, kProfCarry, kProfAxpy, kProfQuantize, kProfTail, kProfPrologue,
+       kProfWalkIters, kProfLazyRounds, kProfLazyRows, kProfBlocksUpdated, kProfWorkerWait, kProfWorkerDot,
+       // finer marks inside publish and the Gram-row products (already contained in kProfPublish / kProfLazyMma)
+       kProfPubReduce, kProfPubMissing, kProfPubArrive, kProfLzLoop, kProfLzRed, kProfPubPre, kProfLzC0, kProfLzC1, kProfLzC2,
+       kProfPhases = 40 };
 
 struct alignas(16) BlockMeta {
     uint32_t id[kB];
@@ -136,17 +142,27 @@ struct alignas(16) BlockMeta {
     double sumg[kB], nmiss[kB];      // global n1 + 2 n2, global missing count
 };
 
+struct BlockResult {                 // what the walk leaves for one block; CTA 0 flushes it to HBM off the critical path
+    uint32_t id[kB];
+    int32_t grp[kB];
+    int comp[kB];
+    double beta[kB], acum[kB];
+    uint32_t n;
+};
+
 struct SweepShared {   // fixed-size part; limbs, code buffers, scratch and the missing list follow (dynamic)
     GroupConsts gc;
     BlockMeta meta[2];               // per code buffer
+    BlockResult fin[2];              // by block parity: written by the walk of block b, flushed two passes later
     double d0[kB];
     double dbeta[kB];
-    double w_corr[kB];               // walk: corrections of the second half-block, betasq partials of warp 1
+    double carry[kB];                // correction of the NEXT block's dots by this block's residual updates
+    double w_corr[kB];               // walk: corrections of the second half-block
     int w_comp[kB];                  // walk: tentative components
     uint32_t w_nsm[2], w_chg[2], w_cnt[2], w_cnt2[2];
-    uint32_t ids[2][kB];             // marker ids of the blocks in the two code buffers
     uint32_t lz_rows[kB];            // markers (block-local) of the Gram rows being computed in this round
     uint32_t rowslot[kB];            // Gram row slot of a marker (valid for the rows computed so far)
+    uint32_t slotrow[kB];            // marker of a Gram row slot
     uint32_t lz_hist[kSlots];        // row slots used by the block that last used each global slot
     double warp_tmp[kWarps];
     double betasq_s[kMaxGK];
@@ -199,6 +215,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __noinline__ void prof_mark(unsigned long long *slot_cycles, long long *t_prev, bool charge)
+{
+    const long long t = clock64();
+    if (charge) *slot_cycles += (unsigned long long)(t - *t_prev);
+    *t_prev = clock64();
+}
 __device__ __forceinline__ void walker_sync() { asm volatile("bar.sync 2, 64;" ::: "memory"); }   // warps 0,1
 
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory"); }
@@ -229,16 +251,18 @@ __device__ __forceinline__ void derive_block_meta(BlockMeta &m, int k)
     m.nmiss[k] = double(m.cnt[k][3]);
 }
 
-// x_j . x_k from the reduced integer counts of the pair (j = the Gram row, k = the column):
+// x_j . x_k from the reduced integer counts of the pair (j = the Gram row, a marker of block `mj`; k = the column, a
+// marker of block `mk` -- the same block or the next one):
 //   a  = sum_i g'_j g'_k with missing genotypes entering as the value 3
 //   cw = #{i: both missing},  cy = sum over {i: k missing, j present} of g_j,  cz = sum over {i: j missing, k present} of g_k
-__device__ __forceinline__ double gram_entry(const BlockMeta &m, int j, int k, double a, double cw, double cy, double cz, double Nt)
+__device__ __forceinline__ double gram_entry(const BlockMeta &mj, int j, const BlockMeta &mk, int k, double a, double cw, double cy,
+                                             double cz, double Nt)
 {
     a = a - 3.0 * cy - 3.0 * cz - 9.0 * cw;                  // sum over both present of g_j g_k
-    const double cj = m.cj[j], ck = m.cj[k], ej = m.ej[j], ek = m.ej[k];
-    double t = a - ck * m.sumg[j] - cj * m.sumg[k] + Nt * cj * ck;
-    t += ek * cy + ej * cz - cj * ek * m.nmiss[k] - ck * ej * m.nmiss[j] + ej * ek * cw;
-    return m.sj[j] * m.sj[k] * t;
+    const double cj = mj.cj[j], ck = mk.cj[k], ej = mj.ej[j], ek = mk.ej[k];
+    double t = a - ck * mj.sumg[j] - cj * mk.sumg[k] + Nt * cj * ck;
+    t += ek * cy + ej * cz - cj * ek * mk.nmiss[k] - ck * ej * mj.nmiss[j] + ej * ek * cw;
+    return mj.sj[j] * mk.sj[k] * t;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSweepParams p)
@@ -269,10 +293,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     long long t_prev = (prof_on || prof_w) ? clock64() : 0;
     if (prof_on) for (int i = 0; i < kProfPhases; ++i) sh.prof[i] = 0;
     auto PHASE = [&](int ph) {          // charge the cycles since the previous mark to phase `ph`
-        if (prof_on) { const long long t = clock64(); sh.prof[ph] += (unsigned long long)(t - t_prev); t_prev = clock64(); }
+        if (prof_on) prof_mark(&sh.prof[ph], &t_prev, true);
     };
     auto PHASE_W = [&](int ph, bool charge) {   // the same for the worker probe
-        if (prof_w) { const long long t = clock64(); if (charge) sh.prof[ph] += (unsigned long long)(t - t_prev); t_prev = clock64(); }
+        if (prof_w) prof_mark(&sh.prof[ph], &t_prev, charge);
     };
 
     // ---- prologue -----------------------------------------------------------------------------
@@ -293,11 +317,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     fill_group_consts(sh.gc, p.nG, K, NM1, p.sigmaE, p.pi, p.sigmaG, p.cva);
     for (int i = tid; i < kMaxGK; i += kThreads) { sh.v_s[i] = 0; sh.betasq_s[i] = 0.0; }
     for (uint32_t i = tid; i < 2 * kB * RS; i += kThreads) pkbuf[i] = 0;
-    if (tid < kB) sh.rowslot[tid] = 0;
+    if (tid < kB) { sh.rowslot[tid] = 0; sh.slotrow[tid] = 0; sh.carry[tid] = 0.0; }
     if (tid == 0) {
         mbar_init(&sh.mbar[0], 1); mbar_init(&sh.mbar[1], 1);
         mbar_fence_init();
-        sh.n_nonskipped_total = 0; sh.n_ns = 0; sh.err = 0;
+        sh.n_nonskipped_total = 0; sh.n_ns = 0; sh.err = 0; sh.fin[0].n = 0; sh.fin[1].n = 0;
         for (int s = 0; s < kSlots; ++s) sh.lz_hist[s] = 0;
     }
 #pragma unroll
@@ -310,32 +334,38 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         atomicMax(p.absmax, (unsigned long long)__double_as_longlong(a));
     }
 
-    // TMA prefetch of one block of code rows (issued by warp 1, two rows per lane); rows past the
-    // block's markers are zero-filled so that the fixed 64-row tile structure sees g = 0 there.
+    // TMA prefetch of one block of code rows: every dot warp requests kTmaLanes rows, from marker ids its lanes loaded
+    // earlier (order_ids: the latency of that load is off the critical path).  Nobody waits for the issue: the consumers
+    // of the rows wait on the buffer's mbarrier.  Rows past the block's markers (last block only) are zero-filled so
+    // that the fixed 64-row tile structure sees g = 0 there; the caller then syncs the CTA.
+    uint32_t pf_id = 0u;
+    const uint32_t pf_row = (warp >= kWalkWarps && lane < kTmaLanes) ? uint32_t(warp - kWalkWarps) * kTmaLanes + lane : 0xffffffffu;
+    auto order_ids = [&](uint32_t b) {
+        if (pf_row < B && b < nBlocks) {
+            const uint32_t pos = b * B + pf_row;
+            pf_id = pos < p.n_order ? p.order[pos] : 0u;
+        }
+    };
     auto prefetch = [&](uint32_t b) {
         const uint32_t nb = min(B, p.n_order - b * B);
         uint32_t *dst = pkbuf + size_t(b & 1) * kB * RS;
-        if (warp == 1) {
-            uint64_t *bar = &sh.mbar[b & 1];
+        uint64_t *bar = &sh.mbar[b & 1];
+        if (warp == kWalkWarps) {                     // the first dot warp arms the barrier before anybody's bytes can land
             fence_proxy_async();
             if (lane == 0) mbar_arrive_expect_tx(bar, nb * CB);
-            __syncwarp();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t r = lane + 32 * h;
-                if (r < nb) {
-                    const uint32_t id = p.order[b * B + r];
-                    sh.ids[b & 1][r] = id;
-                    bulk_g2s(dst + size_t(r) * RS, p.codes + (size_t(id) * p.nCTA + cta) * PWT, CB, bar);
-                }
+        }
+        if (warp >= kWalkWarps) {
+            asm volatile("bar.sync 3, %0;" ::"n"(32 * kDotWarps) : "memory");
+            if (pf_row < nb) {
+                fence_proxy_async();
+                bulk_g2s(dst + size_t(pf_row) * RS, p.codes + (size_t(pf_id) * p.nCTA + cta) * PWT, CB, bar);
             }
-        } else if (nb < B && warp >= 2) {
-            for (uint32_t i = (warp - 2) * 32 + lane; i < (B - nb) * PWT; i += (kWarps - 2) * 32)
-                dst[size_t(nb + i / PWT) * RS + i % PWT] = 0;
+            if (nb < B)
+                for (uint32_t i = (warp - kWalkWarps) * 32 + lane; i < (B - nb) * PWT; i += kDotWarps * 32)
+                    dst[size_t(nb + i / PWT) * RS + i % PWT] = 0;
         }
     };
-    if (nBlocks > 0) prefetch(0);
-    if (nBlocks > 1) prefetch(1);
+    if (nBlocks > 0) { order_ids(0); prefetch(0); }      // block 1 follows from the (virtual) first pass of the block loop
 
     // ---- cross-GPU exchange (world > 1) -----------------------------------------------------------------
     // Individuals are sharded over the GPUs; the integer sums of a grid-wide round must be summed over all of
@@ -361,9 +391,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             uint32_t lo, hi;                                // my range of message elements (uint64 units)
             if (kind == kXAbs) { lo = kMsgAbs; hi = kMsgAbs + 1; }
             else if (kind == kXMain) { lo = kMsgDots; hi = kMsgAbs; }
-            else { const uint32_t tot = nrows * 2 * kB, per = (tot + E - 1) / E; lo = min(tot, cta * per); hi = min(tot, lo + per); }
+            else { const uint32_t tot = nrows * 2 * kCols, per = (tot + E - 1) / E; lo = min(tot, cta * per); hi = min(tot, lo + per); }
             auto local_ptr = [&](uint32_t i) -> unsigned long long * {
-                if (i < uint32_t(kMsgDots)) return reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0) * kB + (i >> 1)) * kLine) + (i & 1u);
+                if (i < uint32_t(kMsgDots)) return reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0) * kCols + (i >> 1)) * kLine) + (i & 1u);
                 if (i < uint32_t(kMsgSm)) return reinterpret_cast<unsigned long long *>(slot + kSlotDots + (i - kMsgDots) * kLine);
                 if (i < uint32_t(kMsgEps)) return reinterpret_cast<unsigned long long *>(slot + kSlotSm + (i - kMsgSm) * kLine);
                 if (i < uint32_t(kMsgAbs)) return reinterpret_cast<unsigned long long *>(slot + kSlotEps + (i - kMsgEps) * kLine);
@@ -540,18 +570,26 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     };
 
     // ---- dot pass of one block: S[m][l] = sum_i g'_mi * limb_l(q_i) ---------------------------------------------
-    // Warp `wi` of `nw` takes the 64-individual k-step pairs wi, wi + nw, ...; its 64 x 8 partial sums go to
-    // region wi of the scratch (16 registers x 32 lanes).
-    auto dot_partial = [&](const uint32_t *pk, uint32_t nb, uint32_t wi, uint32_t nw) {
+    // Work items = (marker tile mi, 64-individual k-step pair pr); dot warp `wi` takes, for every tile, the pairs
+    // first(mi), first(mi) + 14, ... where first rotates with mi so that the remainder pairs spread evenly over the
+    // warps (the pass is bound by the integer pipe that expands the 2-bit codes: balance is what matters).  The four
+    // tiles of one round are independent MMA chains with their loads in flight together.  The warp's 64 x 8 partial
+    // sums go to region wi of the scratch (16 registers x 32 lanes).
+    auto dot_partial = [&](const uint32_t *pk, uint32_t nb, uint32_t wi) {
         int acc[4][4];
+        uint32_t first[4];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) { acc[mi][0] = 0; acc[mi][1] = 0; acc[mi][2] = 0; acc[mi][3] = 0; }
-        for (uint32_t pr = wi; pr < NP; pr += nw) {
-            const uint32_t wo = 4 * pr + tig;
-            const uint4 L = limbs[size_t(gid) * RS + wo];
+        for (int mi = 0; mi < 4; ++mi) {
+            acc[mi][0] = 0; acc[mi][1] = 0; acc[mi][2] = 0; acc[mi][3] = 0;
+            first[mi] = (wi + uint32_t(kDotWarps) - uint32_t((4 * mi) % kDotWarps)) % uint32_t(kDotWarps);
+        }
+        for (uint32_t it = 0; it * kDotWarps < NP; ++it) {
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
-                if (16u * mi < nb) {
+                const uint32_t pr = first[mi] + it * kDotWarps;
+                if (16u * mi < nb && pr < NP) {
+                    const uint32_t wo = 4 * pr + tig;
+                    const uint4 L = limbs[size_t(gid) * RS + wo];
                     const uint32_t w0 = pk[(16 * mi + gid) * RS + wo], w1 = pk[(16 * mi + gid + 8) * RS + wo];
                     mma_u8s8(acc[mi], w0 & kM3, w1 & kM3, (w0 >> 2) & kM3, (w1 >> 2) & kM3, L.x, L.y);
                     mma_u8s8(acc[mi], (w0 >> 4) & kM3, (w1 >> 4) & kM3, (w0 >> 6) & kM3, (w1 >> 6) & kM3, L.z, L.w);
@@ -563,10 +601,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
 #pragma unroll
             for (int r = 0; r < 4; ++r) scratch[(wi * 16 + mi * 4 + r) * 32 + lane] = acc[mi][r];
     };
-    // Combine the `nw` partial regions of block bn's dot pass and publish them (with the slice's sum of q and the
+    // Combine the partial regions of block bn's dot pass and publish them (with the slice's sum of q and the
     // sums over the missing individuals) into the block's global slot; then arrive at the block's grid barrier.
     // All threads call; the scratch writes of dot_partial must be visible (a __syncthreads in between).
-    auto publish_dots = [&](uint32_t bn, uint32_t nw) {
+    auto publish_dots = [&](uint32_t bn) {
         const uint32_t nbn = min(B, p.n_order - bn * B);
         const uint32_t *pkn = pkbuf + size_t(bn & 1) * kB * RS;
         int *slotn = p.slots + size_t(bn % kSlots) * kSlotInts;
@@ -576,12 +614,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             const int l5 = tid & 31, rr = (tid >> 5) & 1, mi = tid >> 6;
             const int o = (mi * 4 + 2 * rr) * 32 + l5;
             int s0 = 0, s1 = 0;
-            for (uint32_t w = 0; w < nw; ++w) { s0 += scratch[w * 512 + o]; s1 += scratch[w * 512 + o + 32]; }
+#pragma unroll
+            for (int w = 0; w < kDotWarps; ++w) { s0 += scratch[w * 512 + o]; s1 += scratch[w * 512 + o + 32]; }
             const uint32_t m = 16 * mi + (l5 >> 2) + 8 * rr;
             const long long v = (long long)s0 + ((long long)s1 << 32);
             if (v != 0 && m < nbn)
                 atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotDots + (m * 4 + (l5 & 3)) * kLine), (unsigned long long)v);
         }
+        PHASE(kProfPubReduce);
         if (warp == 8) {                      // lane 2w+h holds part h of warp w's sum of q
             unsigned long long v = sh.wq[lane >> 1][lane & 1];
 #pragma unroll
@@ -628,114 +668,173 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                     }
             }
         }
+        PHASE(kProfPubMissing);
         grid_arrive(p.bar);
+        PHASE(kProfPubArrive);
     };
 
     // ---- Gram rows on demand ------------------------------------------------------------------------------------
     // One grid-wide round: the integer pair counts of the rows of the markers in (need0, need1) (bit masks over the
-    // two half-blocks) against all 64 columns of the block, reduced over CTAs / GPUs, standardised into x_j.x_k and
-    // stored as doubles in row slots r0, r0+1, ... of the scratch.  Every CTA calls with identical arguments.
-    auto lazy_round = [&](const uint32_t *pk, int *slot, const BlockMeta &meta, uint32_t nb, uint32_t need0, uint32_t need1, uint32_t r0) {
+    // two half-blocks of block b) against 128 columns -- the 64 markers of block b and the 64 of block b+1 (whose
+    // dots were taken against the residual BEFORE block b's updates and are corrected through these rows) -- reduced
+    // over CTAs / GPUs.  The block-b half is standardised into x_j.x_k and stored as doubles in row slots r0, r0+1, ...
+    // of the scratch; the block-(b+1) half stays in the global slot for the carry pass.  Every CTA calls with
+    // identical arguments.  nbx = markers of block b+1 (0 = there is none).
+    auto lazy_round = [&](const uint32_t *pk, const uint32_t *pkx, int *slot, const BlockMeta &meta, uint32_t nb, uint32_t nbx,
+                          uint32_t need0, uint32_t need1, uint32_t r0) {
         const uint32_t n0 = __popc(need0), nnew = n0 + __popc(need1);
         if (tid < kB) {
             const bool hi = tid >= 32;
             const uint32_t msk = hi ? need1 : need0, bit = 1u << (tid & 31);
             if (msk & bit) {
                 const uint32_t pos = (hi ? n0 : 0u) + __popc(msk & (bit - 1u));
-                sh.lz_rows[pos] = tid; sh.rowslot[tid] = r0 + pos;
+                sh.lz_rows[pos] = tid; sh.rowslot[tid] = r0 + pos; sh.slotrow[r0 + pos] = tid;
             }
         }
         __syncthreads();
-        // (1) missing-genotype cross counts.  (i) the missing list of each new row j against every column a:
-        //     cz[j][a] += g_a(i) (a present), cw[j][a] += 1 (a missing too); lanes = columns
+        PHASE(kProfLzC0);
+        // (1) missing-genotype cross counts: one warp per new row j, lanes = columns a (4 per lane).
+        //     From the row's own list:   cz[j][a] += g_a(i) (a present), cw[j][a] += 1 (a missing too), i in missing(j);
+        //     from each column's list:   cy[j][a] += g_j(i) (j present), i in missing(a) -- read straight from the column
+        //     row's tail (<= 15 entries); the rare longer lists are rescanned by the whole warp.
         for (uint32_t idx = warp; idx < nnew; idx += kWarps) {
             const uint32_t j = sh.lz_rows[idx];
-            for_missing_chunks(pk + size_t(j) * RS, [&](const uint32_t *ent, uint32_t n) {
-                int z[2] = {0, 0}, wv[2] = {0, 0};
+            const uint32_t *rowj = pk + size_t(j) * RS;
+            int z[4] = {0, 0, 0, 0}, wv[4] = {0, 0, 0, 0}, y[4] = {0, 0, 0, 0};
+            for_missing_chunks(rowj, [&](const uint32_t *ent, uint32_t n) {
                 for (uint32_t en = 0; en < n; en += 4) {       // four entries per step (the list is padded with sentinels)
                     const uint4 i4 = *reinterpret_cast<const uint4 *>(ent + en);
                     const uint32_t ii[4] = {i4.x, i4.y, i4.z, i4.w};
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    for (int h = 0; h < 4; ++h) {
                         const uint32_t a = lane + 32 * h;
+                        const bool okc = (h < 2) ? (a < nb && a != j) : (a - kB < nbx);
+                        const uint32_t *rowp = (h < 2) ? pk + size_t(a) * RS : pkx + size_t(a - kB) * RS;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const uint32_t cwd = (a < nb && a != j && ii[q] != 0xffffffffu) ? pk[size_t(a) * RS + (ii[q] >> 4)] : 0u;
+                            const uint32_t cwd = (okc && ii[q] != 0xffffffffu) ? rowp[ii[q] >> 4] : 0u;
                             const uint32_t c = (cwd >> (2 * (ii[q] & 15u))) & 3u;
                             z[h] += (c == 3u) ? 0 : int(c);
                             wv[h] += (c == 3u) ? 1 : 0;
                         }
                     }
                 }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t a = lane + 32 * h;
-                    unsigned long long *ln = reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0 + idx) * kB + a) * kLine);
-                    if (wv[h]) atomicAdd(ln, (unsigned long long)(unsigned)wv[h] << 32);
-                    if (z[h]) atomicAdd(ln + 1, (unsigned long long)(unsigned)z[h] << 32);
-                }
             });
-        }
-        //     (ii) the missing list of every column k against each new row j: cy[j][k] += g_j(i) (j present); lanes = entries
-        for (int r = 0; r < 4; ++r) {
-            const uint32_t k = warp + 16 * r;
-            if (k < nb)
-                for_missing_chunks(pk + size_t(k) * RS, [&](const uint32_t *ent, uint32_t n) {
-                    for (uint32_t idx = 0; idx < nnew; ++idx) {
-                        const uint32_t j = sh.lz_rows[idx];
-                        if (j == k) continue;
-                        int s = 0;
+            PHASE(kProfLzC1);
+            // the lists of the lane's four columns, walked together (four independent load chains per step)
+            uint32_t cnt4[4], cmax = 0;
+            const uint16_t *tl4[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const uint32_t a = lane + 32 * h;
+                const bool okc = (h < 2) ? (a < nb && a != j) : (a - kB < nbx);
+                tl4[h] = reinterpret_cast<const uint16_t *>(((h < 2) ? pk + size_t(a) * RS : pkx + size_t(a - kB) * RS) + PW);
+                cnt4[h] = okc ? uint32_t(tl4[h][0]) : 0u;
+                cmax = max(cmax, cnt4[h] <= 15u ? cnt4[h] : 0u);
+            }
+            cmax = __reduce_max_sync(0xffffffffu, cmax);
+            for (uint32_t en = 0; en < cmax; ++en) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const bool on = en < cnt4[h] && cnt4[h] <= 15u;
+                    const uint32_t i = on ? uint32_t(tl4[h][1 + en]) : 0u;
+                    const uint32_t c = on ? ((rowj[i >> 4] >> (2 * (i & 15u))) & 3u) : 0u;
+                    y[h] += (c == 3u) ? 0 : int(c);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const uint32_t a = lane + 32 * h;
+                const uint32_t cnt = cnt4[h];
+                unsigned ovf = __ballot_sync(0xffffffffu, cnt > 15u);
+                while (ovf) {                                      // a column with a long list: all lanes scan it
+                    const uint32_t al = __ffs(ovf) - 1;
+                    ovf &= ovf - 1;
+                    const uint32_t a2 = al + 32 * h;
+                    const uint32_t *rowa = (h < 2) ? pk + size_t(a2) * RS : pkx + size_t(a2 - kB) * RS;
+                    int s = 0;
+                    for_missing_chunks(rowa, [&](const uint32_t *ent, uint32_t n) {
                         for (uint32_t en = lane; en < n; en += 32) {
                             const uint32_t i = ent[en];
-                            const uint32_t c = (pk[size_t(j) * RS + (i >> 4)] >> (2 * (i & 15u))) & 3u;
+                            const uint32_t c = (rowj[i >> 4] >> (2 * (i & 15u))) & 3u;
                             s += (c == 3u) ? 0 : int(c);
                         }
-                        s = __reduce_add_sync(0xffffffffu, s);
-                        if (lane == 0 && s)
-                            atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0 + idx) * kB + k) * kLine) + 1, (unsigned long long)(unsigned)s);
-                    }
-                });
+                    });
+                    s = __reduce_add_sync(0xffffffffu, s);
+                    if (lane == al) y[h] += s;
+                }
+                unsigned long long *ln = reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0 + idx) * kCols + a) * kLine);
+                if (wv[h]) atomicAdd(ln, (unsigned long long)(unsigned)wv[h] << 32);
+                if (y[h] | z[h]) atomicAdd(ln + 1, (unsigned long long)(unsigned)y[h] | ((unsigned long long)(unsigned)z[h] << 32));
+            }
         }
+        PHASE(kProfLzC2);
         __syncthreads();                       // the warps' missing-list segments are free: reused below
         PHASE(kProfLazyCross);
-        // (2) integer products: warp = (column tile nt, k-half kh); 16 new rows per pass
+        // (2) integer products, shaped like the dot pass: A = 16 column markers (tile mt of the 128 columns), B = 8 new
+        //     rows (a group) in place of the 8 limbs.  warp = (column tile mt, k-half kh); two groups per pass, and the
+        //     two MMAs of a k-step pair feed separate accumulators so that a warp always has >= 2 independent chains.
         {
-            const uint32_t nt = warp & 7u, kh = warp >> 3;
+            const uint32_t mt = warp & 7u, kh = warp >> 3;
+            const uint32_t first_row = need0 ? uint32_t(__ffs(need0) - 1) : 32u + uint32_t(__ffs(need1) - 1);   // its own column and all before it are not needed
+            const bool mt_ok = (mt < 4) ? (16 * mt < nb && 16 * mt + 15 > first_row) : (16 * (mt - 4) < nbx);
+            const uint32_t *pa = (mt < 4) ? pk + size_t(16 * mt) * RS : pkx + size_t(16 * (mt - 4)) * RS;
             int *sc2 = reinterpret_cast<int *>(miss_list);
-            for (uint32_t mt = 0; mt * 16 < nnew; ++mt) {
-                const uint32_t ia = mt * 16 + gid, ib = ia + 8;
-                const bool va = ia < nnew, vb = ib < nnew;
-                const uint32_t ra = va ? sh.lz_rows[ia] : 0u, rb = vb ? sh.lz_rows[ib] : 0u;
-                int acc[4] = {0, 0, 0, 0};
-                for (uint32_t pr = kh; pr < NP; pr += 2) {
-                    const uint32_t wo = 4 * pr + tig;
-                    const uint32_t w0 = va ? pk[size_t(ra) * RS + wo] : 0u, w1 = vb ? pk[size_t(rb) * RS + wo] : 0u;
-                    const uint32_t wc = pk[size_t(8 * nt + gid) * RS + wo];
-                    mma_u8u8(acc, w0 & kM3, w1 & kM3, (w0 >> 2) & kM3, (w1 >> 2) & kM3, wc & kM3, (wc >> 2) & kM3);
-                    mma_u8u8(acc, (w0 >> 4) & kM3, (w1 >> 4) & kM3, (w0 >> 6) & kM3, (w1 >> 6) & kM3, (wc >> 4) & kM3, (wc >> 6) & kM3);
-                }
-                if (kh == 1) {
+            for (uint32_t g0 = 0; g0 * 8 < nnew; g0 += 2) {
+                const uint32_t i0 = g0 * 8 + gid, i1 = i0 + 8;
+                const bool v0 = i0 < nnew, v1 = i1 < nnew;
+                const uint32_t u0 = v0 ? sh.lz_rows[i0] : 0u, u1 = v1 ? sh.lz_rows[i1] : 0u;
+                const bool two = (g0 + 1) * 8 < nnew;
+                int acc[2][2][4];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) sc2[(nt * 4 + r) * 32 + lane] = acc[r];
-                }
-                __syncthreads();
-                if (kh == 0) {
+                for (int g = 0; g < 2; ++g)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) acc[r] += sc2[(nt * 4 + r) * 32 + lane];
-#pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) {
-                        const bool valid = rr ? vb : va;
-                        const uint32_t rowm = rr ? rb : ra, rs = r0 + (rr ? ib : ia);
-#pragma unroll
-                        for (int cc = 0; cc < 2; ++cc) {
-                            const uint32_t col = 8 * nt + 2 * tig + cc;
-                            const int val = acc[2 * rr + cc];
-                            if (valid && col < nb && col != rowm && val)
-                                atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(rs) * kB + col) * kLine), (unsigned long long)(unsigned)val);
+                    for (int c = 0; c < 2; ++c) { acc[g][c][0] = 0; acc[g][c][1] = 0; acc[g][c][2] = 0; acc[g][c][3] = 0; }
+                if (mt_ok) {
+                    for (uint32_t pr = kh; pr < NP; pr += 2) {
+                        const uint32_t wo = 4 * pr + tig;
+                        const uint32_t w0 = pa[size_t(gid) * RS + wo], w1 = pa[size_t(gid + 8) * RS + wo];
+                        const uint32_t b0 = v0 ? pk[size_t(u0) * RS + wo] : 0u;
+                        mma_u8u8(acc[0][0], w0 & kM3, w1 & kM3, (w0 >> 2) & kM3, (w1 >> 2) & kM3, b0 & kM3, (b0 >> 2) & kM3);
+                        mma_u8u8(acc[0][1], (w0 >> 4) & kM3, (w1 >> 4) & kM3, (w0 >> 6) & kM3, (w1 >> 6) & kM3, (b0 >> 4) & kM3, (b0 >> 6) & kM3);
+                        if (two) {
+                            const uint32_t b1 = v1 ? pk[size_t(u1) * RS + wo] : 0u;
+                            mma_u8u8(acc[1][0], w0 & kM3, w1 & kM3, (w0 >> 2) & kM3, (w1 >> 2) & kM3, b1 & kM3, (b1 >> 2) & kM3);
+                            mma_u8u8(acc[1][1], (w0 >> 4) & kM3, (w1 >> 4) & kM3, (w0 >> 6) & kM3, (w1 >> 6) & kM3, (b1 >> 4) & kM3, (b1 >> 6) & kM3);
                         }
                     }
                 }
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[g][0][r] += acc[g][1][r];
+                PHASE(kProfLzLoop);
+                if (kh == 1) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) sc2[((mt * 2 + g) * 4 + r) * 32 + lane] = acc[g][0][r];
+                }
                 __syncthreads();
+                if (kh == 0 && mt_ok) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int val = acc[g][0][r] + sc2[((mt * 2 + g) * 4 + r) * 32 + lane];
+                            const uint32_t col = 16 * mt + gid + 8 * (r >> 1);                     // 0..127
+                            const uint32_t ui = (g0 + g) * 8 + 2 * tig + (r & 1);                   // index of the new row
+                            if (ui < nnew && val) {
+                                const uint32_t rowm = sh.lz_rows[ui];
+                                const bool okc = (col < uint32_t(kB)) ? (col < nb && col != rowm) : (col - kB < nbx);
+                                if (okc)
+                                    atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0 + ui) * kCols + col) * kLine),
+                                              (unsigned long long)(unsigned)val);
+                            }
+                        }
+                }
+                __syncthreads();
+                PHASE(kProfLzRed);
             }
         }
         PHASE(kProfLazyMma);
@@ -744,44 +843,93 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         grid_wait(p.bar, (++bar_gen) * p.nCTA);
         xchg(kXLazy, slot, r0, nnew, tid, kThreads, cta_sync);
         PHASE(kProfLazyBarrier);
-        // (4) read back and standardise into x_j . x_k
+        // (4) read back the block-b half and standardise it into x_j . x_k (all loads of a thread in flight at once)
         double *G = reinterpret_cast<double *>(scratch);
-        for (uint32_t en = tid; en < nnew * kB; en += kThreads) {
-            const uint32_t idx = en >> 6, k = en & 63u, j = sh.lz_rows[idx];
-            const int4 v = __ldcg(reinterpret_cast<const int4 *>(slot + kSlotLazy + (size_t(r0 + idx) * kB + k) * kLine));
-            double g = 0.0;
-            if (k != j && k < nb)
-                g = gram_entry(meta, int(j), int(k), double(unsigned(v.x)), double(unsigned(v.y)), double(unsigned(v.z)), double(unsigned(v.w)), Nt);
-            G[(r0 + idx) * kB + k] = g;
+        const uint32_t tot = nnew * kB;
+        for (uint32_t base = 0; base < tot; base += 4 * kThreads) {
+            int4 v[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint32_t en = base + tid + t * kThreads;
+                if (en < tot) v[t] = __ldcg(reinterpret_cast<const int4 *>(slot + kSlotLazy + (size_t(r0 + (en >> 6)) * kCols + (en & 63u)) * kLine));
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint32_t en = base + tid + t * kThreads;
+                if (en < tot) {
+                    const uint32_t idx = en >> 6, k = en & 63u, j = sh.lz_rows[idx];
+                    double g = 0.0;
+                    if (k != j && k < nb)
+                        g = gram_entry(meta, int(j), meta, int(k), double(unsigned(v[t].x)), double(unsigned(v[t].y)), double(unsigned(v[t].z)),
+                                       double(unsigned(v[t].w)), Nt);
+                    G[(r0 + idx) * kB + k] = g;
+                }
+            }
         }
         __syncthreads();
         if (prof_on) { sh.prof[kProfLazyRounds] += 1; sh.prof[kProfLazyRows] += nnew; }
         PHASE(kProfLazyReadback);
     };
 
-    // ---- first block: its dot pass runs on all warps --------------------------------------------------------------
-    if (nBlocks > 0) {
-        const uint32_t nb0 = min(B, p.n_order);
-        if (uint32_t(tid) < nb0) gather_block_meta(p, sh.meta[0], sh.ids[0][tid], tid);
-        mbar_wait(&sh.mbar[0], 0);
-        dot_partial(pkbuf, nb0, warp, kWarps);
-        cp_async_wait_all();
-        __syncthreads();
-        publish_dots(0, kWarps);
+    // CTA 0 only, one warp: the previous block's results go to HBM (src/BayesRBase.cpp:341, :350-356 / :492-493) and into
+    // the sweep's counts (:355 / :511) and sums of squares (:353 / :522, fixed summation order) -- off the critical path.
+    auto flush_results = [&](BlockResult &fin) {
+        const uint32_t n = fin.n;
+        double b2[2]; int gk[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t k = lane + 32 * h;
+            b2[h] = 0.0; gk[h] = -1;
+            if (k < n) {
+                const uint32_t id = fin.id[k];
+                const int comp = fin.comp[k];
+                if (!p.async_mode) p.acum[id] = fin.acum[k];
+                if (comp >= 0) {
+                    const double bn = fin.beta[k];
+                    p.beta[id] = bn;
+                    p.comp[id] = double(comp);
+                    atomicAdd(&sh.v_s[fin.grp[k] * K + comp], 1);
+                    if (comp > 0) { b2[h] = bn * bn; gk[h] = fin.grp[k]; }
+                }
+            }
+        }
+        unsigned pend0 = __ballot_sync(0xffffffffu, gk[0] >= 0), pend1 = __ballot_sync(0xffffffffu, gk[1] >= 0);
+        while (pend0 | pend1) {                    // one pass per group that gained a non-zero effect in this block
+            const int g = pend0 ? __shfl_sync(0xffffffffu, gk[0], __ffs(pend0) - 1) : __shfl_sync(0xffffffffu, gk[1], __ffs(pend1) - 1);
+            const double s0 = warp_sum(gk[0] == g ? b2[0] : 0.0), s1 = warp_sum(gk[1] == g ? b2[1] : 0.0);
+            if (lane == 0) sh.betasq_s[g] += s0 + s1;
+            pend0 &= ~__ballot_sync(0xffffffffu, gk[0] == g);
+            pend1 &= ~__ballot_sync(0xffffffffu, gk[1] == g);
+        }
+        __syncwarp();
+        if (lane == 0) fin.n = 0;
+    };
+    constexpr int kFlushWarp = kWarps - 2;             // a dot warp of CTA 0
+
+    // ---- the block loop.  Pass bb works on block bb while the dot warps run ahead on block bb+1; the first pass
+    // (bb = -1) is a virtual empty block that only starts block 0, so that every piece of the pipeline exists once.
+    unsigned gen_wait = 0;                                      // the grid-wide round that carries the current block's dots
+    uint32_t gid_next = 0u;                                     // threads 64..127: marker id of their row of the next block to gather
+    {
+        const int k2 = tid - 32 * kWalkWarps;
+        if (uint32_t(k2) < min(B, p.n_order)) gid_next = p.order[k2];
     }
     PHASE(kProfPrologue);
     PHASE_W(0, false);
 
-    for (uint32_t b = 0; b < nBlocks; ++b) {
-        const uint32_t nb = min(B, p.n_order - b * B);
-        const uint32_t buf = b & 1;
+    for (int bb = -1; bb < int(nBlocks); ++bb) {
+        const bool real = bb >= 0;
+        const uint32_t b = real ? uint32_t(bb) : 0u;
+        const uint32_t nb = real ? min(B, p.n_order - b * B) : 0u;
+        const uint32_t buf = uint32_t(bb) & 1u;
         const uint32_t *pk = pkbuf + size_t(buf) * kB * RS;
         int *slot = p.slots + size_t(b % kSlots) * kSlotInts;
         BlockMeta &meta = sh.meta[buf];
-        const bool have_next = b + 1 < nBlocks;
-        const uint32_t nb_next = have_next ? min(B, p.n_order - (b + 1) * B) : 0u;
+        BlockMeta &meta_next = sh.meta[buf ^ 1u];
+        const uint32_t bn = uint32_t(bb + 1);                   // the block the dot warps work on
+        const bool have_next = bn < nBlocks;
+        const uint32_t nb_next = have_next ? min(B, p.n_order - bn * B) : 0u;
         const uint32_t *pk_next = pkbuf + size_t(buf ^ 1u) * kB * RS;
-        ++bar_gen;                                              // the round publish_dots(b) arrived at
 
         // ---- A. walkers: wait for the block's round, read it back, sample.  Workers: dot pass of block b+1 ------
         const bool walker = warp < kWalkWarps;
@@ -790,9 +938,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         double bo = 0.0, uu = 2.0, zz = 0.0, base = 0.0; int gg = 0;
         double bo1 = 0.0, zz1 = 0.0, base1 = 0.0; int gg1 = 0; bool act1 = false;    // warp 0: marker 32+lane
         double corr_used = 0.0;
+        uint32_t my_id = 0u;
         Draw dr; dr.beta_new = 0.0; dr.acum0 = 0.0; dr.comp = -1;
-        if (walker) {
-            if (tid == 0) { while (ld_acquire(p.bar) < bar_gen * p.nCTA) { } }
+        if (walker && !real) {
+            if (lane == 0) sh.w_nsm[warp] = 0u;
+        } else if (walker) {
+            if (tid == 0) { while (ld_acquire(p.bar) < gen_wait * p.nCTA) { } }
             walker_sync();
             PHASE(kProfWait);
             xchg(kXMain, slot, 0, 0, tid, 32 * kWalkWarps, wlk_sync);
@@ -805,7 +956,6 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 const long long sm_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * wk + 1) * kLine));
                 const long long e_hi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps));
                 const long long e_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps + kLine));
-                derive_block_meta(meta, wk);
                 const double eps_sum_total = (double(e_hi) * 4294967296.0 + double(e_lo)) * inv_scale;
                 // unpack the limb sums: each int64 holds (even limb) + (odd limb) * 2^32, both signed
                 long long S[8];
@@ -819,15 +969,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 const double dprime = (double(thi) * 4294967296.0 + double(tlo)) * inv_scale;    // sum_i g'_i eps_i
                 const double smd = (double(sm_hi) * 4294967296.0 + double(sm_lo)) * inv_scale;
                 const double *L = meta.lut[wk];
-                // x.eps = L0 sum(eps) + s (S1 + 2 S2) + (L3 - L0) Smissing ; the products saw missing as 3
-                sh.d0[wk] = L[0] * eps_sum_total + meta.sj[wk] * (dprime - 3.0 * smd) + (L[3] - L[0]) * smd;
-                sh.rowslot[wk] = 0;
+                // x.eps = L0 sum(eps) + s (S1 + 2 S2) + (L3 - L0) Smissing ; the products saw missing as 3.  The sums were
+                // taken before the previous block's residual updates: its carry completes them.
+                sh.d0[wk] = (L[0] * eps_sum_total + meta.sj[wk] * (dprime - 3.0 * smd) + (L[3] - L[0]) * smd) + sh.carry[wk];
+                sh.carry[wk] = 0.0;
             }
             walker_sync();
             PHASE(kProfReadback);
             // (a) every marker is sampled against its dot at the start of the block
             if (act) {
-                bo = meta.beta_old[wk]; uu = meta.uz[wk][0]; zz = meta.uz[wk][1]; gg = meta.grp[wk];
+                bo = meta.beta_old[wk]; uu = meta.uz[wk][0]; zz = meta.uz[wk][1]; gg = meta.grp[wk]; my_id = meta.id[wk];
                 base = sh.d0[wk] + bo * NM1;
             }
             if (warp == 0 && uint32_t(32 + lane) < nb) {
@@ -841,21 +992,49 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             sh.w_comp[wk] = dr.comp;
             PHASE(kProfSample);
         } else {
+            order_ids(bn + 1);
+            if (cta == 0 && warp == kFlushWarp && sh.fin[buf].n) flush_results(sh.fin[buf]);
             if (have_next) {
                 const int k2 = tid - 32 * kWalkWarps;
-                if (uint32_t(k2) < nb_next) gather_block_meta(p, sh.meta[buf ^ 1u], sh.ids[buf ^ 1u][k2], k2);
-                mbar_wait(&sh.mbar[buf ^ 1u], ((b + 1) >> 1) & 1u);
+                const uint32_t my_gid = gid_next;
+                if (uint32_t(k2) < uint32_t(kB)) {                 // the id for the NEXT pass's gather: its latency hides behind this pass
+                    const uint32_t pos = (bn + 1) * B + k2;
+                    gid_next = (uint32_t(k2) < B && pos < p.n_order) ? p.order[pos] : 0u;
+                }
+                if (uint32_t(k2) < nb_next) gather_block_meta(p, meta_next, my_gid, k2);
+                mbar_wait(&sh.mbar[buf ^ 1u], (bn >> 1) & 1u);
                 PHASE_W(kProfWorkerWait, true);
-                dot_partial(pk_next, nb_next, warp - kWalkWarps, kDotWarps);
+                dot_partial(pk_next, nb_next, warp - kWalkWarps);
                 cp_async_wait_all();
+                if (uint32_t(k2) < nb_next) derive_block_meta(meta_next, k2);
                 PHASE_W(kProfWorkerDot, true);
             }
         }
         __syncthreads();
         PHASE(kProfJoin);
-        PHASE_W(0, false);
 
-        // ---- B. the walk -----------------------------------------------------------------------------------------------
+        // ---- B. the round of block b+1 goes out NOW: its latency hides behind the rest of block b -----------------
+        // recycle the slot of block b-2 first (every CTA finished with it before it arrived at block b's round, and
+        // nobody adds into it again before passing block b+1's round)
+        if (bb >= 2 && cta == b % p.nCTA) {
+            int *old = p.slots + size_t((b - 2) % kSlots) * kSlotInts;
+            for (int i = tid; i < kSlotMainLines; i += kThreads) *reinterpret_cast<unsigned long long *>(old + i * kLine) = 0ULL;
+            const uint32_t used = sh.lz_hist[(b - 2) % kSlots];
+            for (uint32_t i = tid; i < used * kCols; i += kThreads) *reinterpret_cast<int4 *>(old + kSlotLazy + size_t(i) * kLine) = make_int4(0, 0, 0, 0);
+        }
+        // a block that leaves the residual untouched needs its rows no more: request block b+2 into its buffer already
+        const bool quiet = (sh.w_nsm[0] | sh.w_nsm[1]) == 0u;
+        const bool pf_early = quiet && bn + 1 < nBlocks;
+        if (pf_early) prefetch(bn + 1);
+        PHASE(kProfPubPre);
+        if (have_next) {
+            mbar_wait(&sh.mbar[buf ^ 1u], (bn >> 1) & 1u);   // the walkers have not observed the rows of block b+1 yet
+            publish_dots(bn);
+            gen_wait = ++bar_gen;
+        }
+        PHASE(kProfPublish);
+
+        // ---- C. the walk -----------------------------------------------------------------------------------------------
         // The one-by-one loop is reproduced exactly by iterating to a fixed point:
         //   (a) [done above] every marker is sampled against its current dot (speculating no earlier marker changes eps);
         //   (b) the non-skipped markers (src/BayesRBase.cpp:372) get their Gram rows (one grid-wide round, only for rows
@@ -864,111 +1043,140 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         //   (c) every marker whose dot moved is sampled again; if all components (hence all betas, bit for bit) are
         //       confirmed, the state equals the sequential chain's, else (b) restarts with the new ones.
         // Thread k < 64 samples marker k of the block; warp 0 runs the solve for both halves.
+        // Asynchronous mode: no in-block correction; the rows are only needed for the next block's carry.
         uint32_t have0 = 0, have1 = 0, lz_used = 0;             // Gram rows known so far (identical in every CTA)
-        if (!p.async_mode) {
-            for (int iter = 0; iter < 2 * kB; ++iter) {
-                const unsigned nsm0 = sh.w_nsm[0], nsm1 = sh.w_nsm[1];
-                if ((nsm0 | nsm1) == 0) break;
-                if (prof_on) { sh.prof[kProfWalkIters] += 1; sh.prof[kProfWalkSolves] += __popc(nsm0) + __popc(nsm1); }
-                uint32_t need0 = nsm0 & ~have0, need1 = nsm1 & ~have1;
-                if (nb - 1 < 32) need0 &= ~(1u << (nb - 1)); else need1 &= ~(1u << (nb - 33));   // the last marker corrects nobody
-                if (need0 | need1) {
-                    lazy_round(pk, slot, meta, nb, need0, need1, lz_used);
-                    have0 |= need0; have1 |= need1; lz_used += __popc(need0) + __popc(need1);
-                }
-                double corr = 0.0;
-                if (warp == 0) {
-                    const double *G = reinterpret_cast<const double *>(scratch);
-                    const int comp1 = sh.w_comp[32 + lane];
-                    double c0 = 0.0, c1 = 0.0;
-                    unsigned m = nsm0;
-                    while (m) {
-                        const int jl = __ffs(m) - 1;
-                        m &= m - 1;
-                        const double mine = bo - beta_given_comp(sh.gc, gg, K, dr.comp, base + c0, bo, zz);
-                        const double dB = __shfl_sync(0xffffffffu, mine, jl);          // eps += dB * x_j
-                        if (dB != 0.0) {
-                            const double *Gr = G + size_t(sh.rowslot[jl]) * kB;
-                            if (act && lane > jl) c0 += dB * Gr[lane];
-                            if (act1) c1 += dB * Gr[32 + lane];
-                        }
-                    }
-                    m = nsm1;
-                    while (m) {
-                        const int jl = __ffs(m) - 1;
-                        m &= m - 1;
-                        const double mine = bo1 - beta_given_comp(sh.gc, gg1, K, comp1, base1 + c1, bo1, zz1);
-                        const double dB = __shfl_sync(0xffffffffu, mine, jl);
-                        if (dB != 0.0 && act1 && lane > jl) c1 += dB * (G + size_t(sh.rowslot[32 + jl]) * kB)[32 + lane];
-                    }
-                    corr = c0;
-                    sh.w_corr[32 + lane] = c1;
-                }
-                __syncthreads();
-                PHASE(kProfSolve);
-                if (walker) {
-                    if (warp == 1) corr = sh.w_corr[wk];
-                    // (c) re-sample where the dot moved; confirm the components
-                    bool changed = false;
-                    if (act && corr != corr_used) {
-                        const Draw nd = sample_marker_k(sh.gc, gg, K, base + corr, p.sigmaE, bo, uu, zz);
-                        changed = nd.comp != dr.comp;
-                        dr = nd;
-                        corr_used = corr;
-                    }
-                    const unsigned chg = __ballot_sync(0xffffffffu, changed);
-                    const unsigned nsm = __ballot_sync(0xffffffffu, act && !(bo == 0.0 && dr.beta_new == 0.0));
-                    if (lane == 0) { sh.w_chg[warp] = chg; sh.w_nsm[warp] = nsm; }
-                    sh.w_comp[wk] = dr.comp;
-                }
-                __syncthreads();
-                PHASE(kProfSample);
-                if ((sh.w_chg[0] | sh.w_chg[1]) == 0) break;
+        // A quiet block (nothing sampled away from zero) ends here for the dot warps: they go straight to the dot pass of
+        // block b+2 while the walkers file the results and wait for block b+1's round; no CTA-wide barrier in between.
+        for (int iter = 0; iter < 2 * kB && !quiet; ++iter) {
+            const unsigned nsm0 = sh.w_nsm[0], nsm1 = sh.w_nsm[1];
+            if ((nsm0 | nsm1) == 0) break;
+            if (prof_on) sh.prof[kProfWalkIters] += 1;
+            uint32_t need0 = nsm0 & ~have0, need1 = nsm1 & ~have1;
+            if (!have_next) {                                    // the last marker of the sweep corrects nobody
+                if (nb - 1 < 32) need0 &= ~(1u << (nb - 1)); else need1 &= ~(1u << (nb - 33));
+                if (p.async_mode) { need0 = 0; need1 = 0; }
             }
+            if (need0 | need1) {
+                lazy_round(pk, pk_next, slot, meta, nb, nb_next, need0, need1, lz_used);
+                have0 |= need0; have1 |= need1; lz_used += __popc(need0) + __popc(need1);
+            }
+            if (p.async_mode) break;
+            double corr = 0.0;
+            if (warp == 0) {
+                const double *G = reinterpret_cast<const double *>(scratch);
+                const int comp1 = sh.w_comp[32 + lane];
+                double c0 = 0.0, c1 = 0.0;
+                unsigned m = nsm0;
+                while (m) {
+                    const int jl = __ffs(m) - 1;
+                    m &= m - 1;
+                    const double mine = bo - beta_given_comp(sh.gc, gg, K, dr.comp, base + c0, bo, zz);
+                    const double dB = __shfl_sync(0xffffffffu, mine, jl);          // eps += dB * x_j
+                    if (dB != 0.0) {
+                        const double *Gr = G + size_t(sh.rowslot[jl]) * kB;
+                        if (act && lane > jl) c0 += dB * Gr[lane];
+                        if (act1) c1 += dB * Gr[32 + lane];
+                    }
+                }
+                m = nsm1;
+                while (m) {
+                    const int jl = __ffs(m) - 1;
+                    m &= m - 1;
+                    const double mine = bo1 - beta_given_comp(sh.gc, gg1, K, comp1, base1 + c1, bo1, zz1);
+                    const double dB = __shfl_sync(0xffffffffu, mine, jl);
+                    if (dB != 0.0 && act1 && lane > jl) c1 += dB * (G + size_t(sh.rowslot[32 + jl]) * kB)[32 + lane];
+                }
+                corr = c0;
+                sh.w_corr[32 + lane] = c1;
+            }
+            __syncthreads();
+            PHASE(kProfSolve);
+            if (walker) {
+                if (warp == 1) corr = sh.w_corr[wk];
+                // (c) re-sample where the dot moved; confirm the components
+                bool changed = false;
+                if (act && corr != corr_used) {
+                    const Draw nd = sample_marker_k(sh.gc, gg, K, base + corr, p.sigmaE, bo, uu, zz);
+                    changed = nd.comp != dr.comp;
+                    dr = nd;
+                    corr_used = corr;
+                }
+                const unsigned chg = __ballot_sync(0xffffffffu, changed);
+                const unsigned nsm = __ballot_sync(0xffffffffu, act && !(bo == 0.0 && dr.beta_new == 0.0));
+                if (lane == 0) { sh.w_chg[warp] = chg; sh.w_nsm[warp] = nsm; }
+                sh.w_comp[wk] = dr.comp;
+            }
+            __syncthreads();
+            PHASE(kProfResample);
+            if ((sh.w_chg[0] | sh.w_chg[1]) == 0) break;
         }
         if (walker) {
             const double dB = act ? (bo - dr.beta_new) : 0.0;
             const bool upd = act && dB != 0.0;
             const bool nonskip = act && !(bo == 0.0 && dr.beta_new == 0.0);
-            if (act) sh.dbeta[wk] = dB;
-            const unsigned um = __ballot_sync(0xffffffffu, upd);
-            const unsigned nsk = __ballot_sync(0xffffffffu, nonskip);
-            if (lane == 0) { sh.w_cnt[warp] = __popc(um); sh.w_cnt2[warp] = __popc(nsk); }
-            if (cta == 0 && act) {
-                const uint32_t id = meta.id[wk];
-                if (!p.async_mode) p.acum[id] = dr.acum0;                      // src/BayesRBase.cpp:341
-                if (dr.comp >= 0) {
-                    p.beta[id] = dr.beta_new;                                  // :350-352 / :492
-                    p.comp[id] = double(dr.comp);                              // :356 / :493
-                    atomicAdd(&sh.v_s[gg * K + dr.comp], 1);                   // :355 / :511
-                }
+            BlockResult &fin = sh.fin[buf];
+            if (act) {
+                sh.dbeta[wk] = dB;
+                fin.id[wk] = my_id; fin.grp[wk] = gg; fin.comp[wk] = dr.comp;
+                fin.beta[wk] = dr.beta_new; fin.acum[wk] = dr.acum0;
             }
-            if (cta == 0) {                                                    // :353 / :522, fixed summation order
-                for (uint32_t g0 = 0; g0 < p.nG; g0 += kB) {
-                    const uint32_t ng = min((uint32_t)kB, p.nG - g0);
-                    for (uint32_t gi = 0; gi < ng; ++gi) {
-                        const double b2 = (act && gg == int(g0 + gi) && dr.comp > 0) ? dr.beta_new * dr.beta_new : 0.0;
-                        const double sgi = warp_sum(b2);
-                        if (lane == 0) { if (warp == 0) sh.d0[gi] = sgi; else sh.w_corr[gi] = sgi; }
-                    }
-                    walker_sync();
-                    if (uint32_t(tid) < ng) sh.betasq_s[g0 + tid] += sh.d0[tid] + sh.w_corr[tid];
-                    walker_sync();
+            if (quiet) {
+                if (tid == 0) { if (real) sh.lz_hist[b % kSlots] = 0u; fin.n = nb; }
+            } else {
+                const unsigned um = __ballot_sync(0xffffffffu, upd);
+                const unsigned nsk = __ballot_sync(0xffffffffu, nonskip);
+                if (lane == 0) { sh.w_cnt[warp] = __popc(um); sh.w_cnt2[warp] = __popc(nsk); }
+                walker_sync();
+                const uint32_t off = warp ? sh.w_cnt[0] : 0u;
+                if (upd) sh.ns_list[off + __popc(um & ((1u << lane) - 1u))] = wk;
+                if (tid == 0) {
+                    sh.n_ns = sh.w_cnt[0] + sh.w_cnt[1]; sh.n_nonskipped_total += sh.w_cnt2[0] + sh.w_cnt2[1];
+                    if (real) sh.lz_hist[b % kSlots] = lz_used;
+                    fin.n = nb;
                 }
-            }
-            walker_sync();
-            const uint32_t off = warp ? sh.w_cnt[0] : 0u;
-            if (upd) sh.ns_list[off + __popc(um & ((1u << lane) - 1u))] = wk;
-            if (tid == 0) {
-                sh.n_ns = sh.w_cnt[0] + sh.w_cnt[1]; sh.n_nonskipped_total += sh.w_cnt2[0] + sh.w_cnt2[1];
-                sh.lz_hist[b % kSlots] = lz_used;
             }
         }
-        __syncthreads();
+        if (!quiet) __syncthreads();
         PHASE(kProfFinalize);
 
-        // ---- C. residual update in registers, re-quantise --------------------------------------------------
-        const uint32_t n_ns = sh.n_ns;
+        // ---- D. carry: the dots of block b+1 were taken before this block's updates -------------------------------
+        // carry_k = sum over the updated markers j (in row-slot order) of (beta_old_j - beta_j) x_j . x_k, from the block-(b+1)
+        // half of the Gram rows (still in the global slot).  512 threads = 64 columns x 8 row groups, fixed-order sums:
+        // every CTA computes bit-identical values.
+        const uint32_t n_ns = quiet ? 0u : sh.n_ns;
+        if (n_ns && lz_used && have_next) {
+            const uint32_t kc = tid & 63u, rg = tid >> 6;
+            int4 v[kB / 8];
+#pragma unroll
+            for (int t = 0; t < kB / 8; ++t) {
+                const uint32_t r = rg + 8 * t;
+                if (r < lz_used) v[t] = __ldcg(reinterpret_cast<const int4 *>(slot + kSlotLazy + (size_t(r) * kCols + kB + kc) * kLine));
+            }
+            double acc = 0.0;
+#pragma unroll
+            for (int t = 0; t < kB / 8; ++t) {
+                const uint32_t r = rg + 8 * t;
+                if (r < lz_used && kc < nb_next) {
+                    const uint32_t j = sh.slotrow[r];
+                    const double dB = sh.dbeta[j];
+                    if (dB != 0.0)
+                        acc += dB * gram_entry(meta, int(j), meta_next, int(kc), double(unsigned(v[t].x)), double(unsigned(v[t].y)),
+                                               double(unsigned(v[t].z)), double(unsigned(v[t].w)), Nt);
+                }
+            }
+            double *part = reinterpret_cast<double *>(miss_list);
+            part[rg * kB + kc] = acc;
+            __syncthreads();
+            if (tid < kB) {
+                double s = 0.0;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) s += part[g * kB + tid];
+                sh.carry[tid] = s;
+            }
+            PHASE(kProfCarry);
+        }
+
+        // ---- E. residual update in registers, re-quantise --------------------------------------------------
         if (n_ns) {
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
@@ -1014,30 +1222,19 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             PHASE(kProfQuantize);
         }
 
-        // ---- D. the round of block b+1 ---------------------------------------------------------------------------
-        // recycle the slot of block b-1 (every CTA finished reading it before it arrived at block b's round)
-        if (b > 0 && cta == b % p.nCTA) {
-            int *old = p.slots + size_t((b - 1) % kSlots) * kSlotInts;
-            for (int i = tid; i < 256 + 128 + 2; i += kThreads) *reinterpret_cast<unsigned long long *>(old + i * kLine) = 0ULL;
-            const uint32_t used = sh.lz_hist[(b - 1) % kSlots];
-            for (uint32_t i = tid; i < used * kB; i += kThreads) *reinterpret_cast<int4 *>(old + kSlotLazy + size_t(i) * kLine) = make_int4(0, 0, 0, 0);
+        // ---- F. block b's buffer is free: prefetch block b+2 into it ----------------------------------------------
+        if (!pf_early && bn + 1 < nBlocks) {
+            prefetch(bn + 1);
+            if (p.n_order - (bn + 1) * B < B) __syncthreads();      // zero rows of a partial last block: visible before its dot pass
         }
-        if (have_next) {
-            mbar_wait(&sh.mbar[buf ^ 1u], ((b + 1) >> 1) & 1u);   // the walkers have not observed the rows of block b+1 yet
-            if (n_ns || lz_used) {              // the residual (or the scratch holding the speculative sums) changed: redo
-                dot_partial(pk_next, nb_next, warp, kWarps);
-                __syncthreads();
-                PHASE(kProfRedoDot);
-                publish_dots(b + 1, kWarps);
-            } else {
-                publish_dots(b + 1, kDotWarps);
-            }
-        }
-        // block b's buffer is free: prefetch block b+2 into it
-        if (b + 2 < nBlocks) prefetch(b + 2);
-        __syncthreads();            // the ids / zero rows written by prefetch are read by the dot warps right away
-        PHASE(kProfPublish);
+        PHASE(kProfTail);
         PHASE_W(0, false);
+    }
+    __syncthreads();
+    if (cta == 0 && warp == kFlushWarp) {                       // the last two blocks, in block order
+        const uint32_t older = nBlocks & 1u;                    // parity of block nBlocks-2
+        if (sh.fin[older].n) flush_results(sh.fin[older]);
+        if (sh.fin[older ^ 1u].n) flush_results(sh.fin[older ^ 1u]);
     }
 
     // ---- epilogue: eps back to HBM, sweep scalars ------------------------------------------------

@@ -245,6 +245,9 @@ def main():
     for _ in range(a.warmup):
         one_sweep(False)
     launches0 = eng.launch_count()
+    profiling = os.environ.get("BRR_GPU_PROFILE") == "1"
+    if profiling:
+        eng.profile_cycles(reset=True)
     if rank == 0:
         sampler = ClockSampler(local_rank); sampler.start()
     for _ in range(a.steps):
@@ -253,6 +256,15 @@ def main():
     if sampler:
         sampler.stop_flag = True; sampler.join(timeout=2)
 
+    if profiling and rank == 0:           # phase breakdown of the timed sweeps (cycles of CTA 0 per block) -> stderr
+        pc = eng.profile_cycles(reset=True)
+        nblk = max(1, int(np.sum(blocks)))
+        skip = set(eng.PROFILE_COUNTERS) | set(eng.PROFILE_OVERLAPPED) | {"prologue"}
+        sys.stderr.write("phase cycles/block over %d timed sweeps (%d blocks): " % (a.steps, nblk)
+                         + "  ".join("%s=%d" % (k, pc[k] // nblk) for k in eng.PROFILE_PHASES if k not in skip)
+                         + "  | total=%d" % (sum(pc[k] for k in eng.PROFILE_PHASES if k not in skip) // nblk)
+                         + "  | overlapped: " + "  ".join("%s=%d" % (k, pc[k] // nblk) for k in eng.PROFILE_OVERLAPPED)
+                         + "  | per block: " + "  ".join("%s=%.3f" % (k, pc[k] / nblk) for k in eng.PROFILE_COUNTERS) + "\n")
     ksum = sum(kernel_ms) / 1e3; esum = sum(e2e_s)
     if world > 1:
         t = torch.tensor([ksum, esum], dtype=torch.float64, device="cuda")

@@ -203,13 +203,14 @@ int brr_gpu_info(brr_gpu_ctx *ctx, uint32_t *n_ctas, uint32_t *slice_inds, uint3
                  uint64_t *genotype_bytes);
 uint64_t brr_gpu_launch_count(brr_gpu_ctx *ctx);
 /* Phase breakdown of the dense sweep kernel (SM cycles of CTA 0, accumulated over sweeps), available when
- * the environment has BRR_GPU_PROFILE=1 at brr_gpu_create: 24 counters in the order wait (grid barrier),
- * cross-GPU exchange, read-back, sampling, join (walkers waiting for the dot warps), Gram-row cross counts,
- * Gram-row products, Gram-row barrier, Gram-row read-back, triangular solve, finalize, axpy, quantize,
- * repeated dot pass, publish, prologue; then 5 counts (walk iterations, solve steps, Gram rounds, Gram rows,
- * blocks that updated the residual); then the dot warps' wait for the code rows and their dot pass (these two
- * overlap the walker phases); 1 spare.  reset != 0 clears them. */
-int brr_gpu_profile_cycles(brr_gpu_ctx *ctx, uint64_t *cycles24, int reset);
+ * the environment has BRR_GPU_PROFILE=1 at brr_gpu_create: 40 counters in the order wait (grid barrier),
+ * cross-GPU exchange, read-back, sampling, join (walkers waiting for the dot warps), publish (next block's
+ * round), Gram-row cross counts, Gram-row products, Gram-row barrier, Gram-row read-back, triangular solve,
+ * re-sampling, finalize, carry, axpy, quantize, tail (prefetch), prologue; then 4 counts (walk iterations,
+ * Gram rounds, Gram rows, blocks that updated the residual); then the dot warps' wait for the code rows and
+ * their dot pass (these two overlap the walker phases); then finer marks inside publish (reduce, missing sums,
+ * arrive, preamble) and the Gram-row round (loop, reduction, three marks of the cross counts), and 4 spare.  reset != 0 clears them. */
+int brr_gpu_profile_cycles(brr_gpu_ctx *ctx, uint64_t *cycles40, int reset);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,7 @@ tail -5 gpurun_out/${TAG}_pytest.log
 if ! grep -q " passed" gpurun_out/${TAG}_pytest.log || grep -q "failed\|Timeout" gpurun_out/${TAG}_pytest.log; then echo "TESTS NOT GREEN: stopping"; exit 1; fi
 timeout 120 python tools/phase_profile.py 20000 8 > gpurun_out/${TAG}_phase.txt 2>&1; tail -9 gpurun_out/${TAG}_phase.txt
 BRR_BENCH_N=62500 timeout 120 python tools/phase_profile.py 20000 8 > gpurun_out/${TAG}_phase_n62500.txt 2>&1; tail -3 gpurun_out/${TAG}_phase_n62500.txt
+BRR_GPU_PROFILE=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/${TAG}_bench_prof.json 2> gpurun_out/${TAG}_bench_prof.err; grep -h "phase cycles" gpurun_out/${TAG}_bench_prof.err; python -c "import json;d=json.load(open('gpurun_out/${TAG}_bench_prof.json'));print('profiled bench: %.4f s/sweep' % d['s_per_sweep'])"
 if [ "$2" != "quick" ]; then
   timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
 fi

@@ -29,11 +29,11 @@ for s in range(sweeps):
     v, bs, out = e.sweep(order, rand_uz, pi, sigmaG, sigmaE)
     pc = e.profile_cycles(reset=True)
     nb = max(1, out.n_blocks)
-    skip = set(e.PROFILE_COUNTERS) | set(e.PROFILE_OVERLAPPED) | {"spare", "prologue"}
+    skip = set(e.PROFILE_COUNTERS) | set(e.PROFILE_OVERLAPPED) | {"prologue"}
     tot = sum(v_ for k, v_ in pc.items() if k not in skip)
-    print("sweep %d: %.3f ms, %.2f us/block, nonskipped %.3f%%, blocks updated %.1f%%, walk iters/block %.2f, solves/block %.2f, gram rounds/block %.3f, gram rows/block %.3f" % (
+    print("sweep %d: %.3f ms, %.2f us/block, nonskipped %.3f%%, blocks updated %.1f%%, walk iters/block %.2f, gram rounds/block %.3f, gram rows/block %.3f" % (
         s, out.kernel_ms, 1e3 * out.kernel_ms / nb, 100.0 * out.n_nonskipped / M, 100.0 * pc["blocks_updated"] / nb,
-        pc["walk_iters"] / nb, pc["walk_solves"] / nb, pc["lazy_rounds"] / nb, pc["lazy_rows"] / nb))
+        pc["walk_iters"] / nb, pc["lazy_rounds"] / nb, pc["lazy_rows"] / nb))
     print("   walker cycles/block: " + "  ".join("%s=%d" % (k, pc[k] // nb) for k in e.PROFILE_PHASES if k not in skip)
           + "  | total/block=%d  prologue=%d" % (tot // nb, pc["prologue"]))
     print("   dot warps (overlapped) cycles/block: " + "  ".join("%s=%d" % (k, pc[k] // nb) for k in e.PROFILE_OVERLAPPED))
