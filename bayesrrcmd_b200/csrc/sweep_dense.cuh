@@ -45,6 +45,11 @@ namespace brr {
 constexpr int kB = 64;                 // markers per block = tile structure of the MMA passes
 constexpr int kLimbs = 8;
 constexpr uint32_t kM3 = 0x03030303u;
+// The four 2-bit codes of a byte, left IN PLACE (no shifts): class c of a code word is (w & kCls[c]) = 4^c * code.  An MMA whose
+// A (and B) fragments all come from one class yields 4^c (16^c) times the wanted sum; one accumulator per class, recombined by exact
+// shifts at the end.  This halves the integer work of expanding the codes, which is what bounds the MMA passes (the integer pipe
+// issues one warp instruction per 2 cycles per sub-partition: tools/microbench.cu).
+constexpr uint32_t kC0 = 0x03030303u, kC1 = 0x0C0C0C0Cu, kC2 = 0x30303030u, kC3 = 0xC0C0C0C0u;
 constexpr int kMissSeg = 256 + 4;      // entries of a warp's missing-list scratch segment (16 words x 16 + sentinels)
 constexpr uint32_t kTail = 8;          // tail words of a code row: 16 x uint16 missing list (store_kernels.cuh)
 constexpr int kMissCap = kMissSeg * kWarps;
@@ -544,9 +549,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             __syncwarp();
         }
     };
-    // sum of q over this warp's listed entries of row m -> global slot (exact, order independent)
-    auto missing_q_sum = [&](int *slot, uint32_t m, const uint32_t *ent, uint32_t n) {
-        long long shi = 0; unsigned long long slo = 0;
+    // sum of q over this warp's listed entries (lane partials, exact: integers)
+    auto missing_q_sum = [&](const uint32_t *ent, uint32_t n, long long &shi, unsigned long long &slo) {
         for (uint32_t en = lane; en < n; en += 32) {
             const uint32_t i = ent[en];
             const uint32_t w = i >> 4, c = i & 3u, t = (i >> 2) & 3u;
@@ -558,80 +562,71 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             const long long q = (long long)((uq ^ 0x8080808080808080ULL) - 0x8080808080808080ULL);
             shi += q >> 32; slo += (unsigned long long)(q & 0xffffffffLL);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            shi += __shfl_xor_sync(0xffffffffu, shi, o);
-            slo += __shfl_xor_sync(0xffffffffu, slo, o);
-        }
-        if (lane == 0 && n) {
-            atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotSm + (2 * m) * kLine), (unsigned long long)shi);
-            atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotSm + (2 * m + 1) * kLine), slo);
-        }
     };
+    // Between a dot pass and the publish of its block the head of the scratch holds the block's sums: the 64 x 8 limb sums
+    // (512 ints) and 64 x 2 sums of q over the rows' missing individuals; behind them the dot warps' partial regions.
+    // Critical-path code runs on one or two warps at ~10 cycles per instruction (measured), so everything that can be is
+    // done by the 14 dot warps right after their pass instead of in the publish.
+    int *dot_acc = scratch;
+    unsigned long long *msum = reinterpret_cast<unsigned long long *>(scratch + 512);
+    int *dot_part = scratch + 1024;                  // [kDotWarps][512]
 
     // ---- dot pass of one block: S[m][l] = sum_i g'_mi * limb_l(q_i) ---------------------------------------------
-    // Work items = (marker tile mi, 64-individual k-step pair pr); dot warp `wi` takes, for every tile, the pairs
-    // first(mi), first(mi) + 14, ... where first rotates with mi so that the remainder pairs spread evenly over the
-    // warps (the pass is bound by the integer pipe that expands the 2-bit codes: balance is what matters).  The four
-    // tiles of one round are independent MMA chains with their loads in flight together.  The warp's 64 x 8 partial
-    // sums go to region wi of the scratch (16 registers x 32 lanes).
+    // Work items = (marker tile mi, word pair wp): a word pair is two 64-individual k-steps; dot warp `wi` takes the word
+    // pairs wi, wi + 14, ... of every tile.  One item = four MMAs, one per code class (kC0..kC3), each fed by the class-c
+    // bytes of the lane's two code words of both rows (A) and the class-c limb bytes of the same individuals (B): four
+    // independent chains, 16 LOP3 and no shift per item.  The warp's 64 x 8 partial sums go to its region of the scratch.
     auto dot_partial = [&](const uint32_t *pk, uint32_t nb, uint32_t wi) {
-        int acc[4][4];
-        uint32_t first[4];
+        const uint32_t NW2 = (NP + 1) / 2;
+        const uint32_t lo = gid * RS + tig;
+        const uint4 *limp = limbs + lo;
+#pragma unroll 1
+        for (uint32_t mi = 0; mi < 4; ++mi) {
+            int acc[4][4];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-            acc[mi][0] = 0; acc[mi][1] = 0; acc[mi][2] = 0; acc[mi][3] = 0;
-            first[mi] = (wi + uint32_t(kDotWarps) - uint32_t((4 * mi) % kDotWarps)) % uint32_t(kDotWarps);
-        }
-        for (uint32_t it = 0; it * kDotWarps < NP; ++it) {
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi) {
-                const uint32_t pr = first[mi] + it * kDotWarps;
-                if (16u * mi < nb && pr < NP) {
-                    const uint32_t wo = 4 * pr + tig;
-                    const uint4 L = limbs[size_t(gid) * RS + wo];
-                    const uint32_t w0 = pk[(16 * mi + gid) * RS + wo], w1 = pk[(16 * mi + gid + 8) * RS + wo];
-                    mma_u8s8(acc[mi], w0 & kM3, w1 & kM3, (w0 >> 2) & kM3, (w1 >> 2) & kM3, L.x, L.y);
-                    mma_u8s8(acc[mi], (w0 >> 4) & kM3, (w1 >> 4) & kM3, (w0 >> 6) & kM3, (w1 >> 6) & kM3, L.z, L.w);
+            for (int c = 0; c < 4; ++c) { acc[c][0] = 0; acc[c][1] = 0; acc[c][2] = 0; acc[c][3] = 0; }
+            if (16u * mi < nb) {
+                const uint32_t *r0p = pk + size_t(16 * mi) * RS + lo, *r1p = r0p + 8 * RS;
+                for (uint32_t wp = wi; wp < NW2; wp += kDotWarps) {
+                    const uint32_t oA = 8 * wp, oB = oA + 4;
+                    const bool hasB = 2 * wp + 1 < NP;
+                    const uint4 LA = limp[oA];
+                    const uint32_t a0 = r0p[oA], a1 = r1p[oA];
+                    uint4 LB = make_uint4(0u, 0u, 0u, 0u);
+                    uint32_t b0 = 0u, b1 = 0u;
+                    if (hasB) { LB = limp[oB]; b0 = r0p[oB]; b1 = r1p[oB]; }
+                    mma_u8s8(acc[0], a0 & kC0, a1 & kC0, b0 & kC0, b1 & kC0, LA.x, LB.x);
+                    mma_u8s8(acc[1], a0 & kC1, a1 & kC1, b0 & kC1, b1 & kC1, LA.y, LB.y);
+                    mma_u8s8(acc[2], a0 & kC2, a1 & kC2, b0 & kC2, b1 & kC2, LA.z, LB.z);
+                    mma_u8s8(acc[3], a0 & kC3, a1 & kC3, b0 & kC3, b1 & kC3, LA.w, LB.w);
                 }
             }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                dot_part[wi * 512 + (mi * 4 + r) * 32 + lane] = acc[0][r] + (acc[1][r] >> 2) + (acc[2][r] >> 4) + (acc[3][r] >> 6);
         }
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) scratch[(wi * 16 + mi * 4 + r) * 32 + lane] = acc[mi][r];
     };
-    // Combine the partial regions of block bn's dot pass and publish them (with the slice's sum of q and the
-    // sums over the missing individuals) into the block's global slot; then arrive at the block's grid barrier.
-    // All threads call; the scratch writes of dot_partial must be visible (a __syncthreads in between).
-    auto publish_dots = [&](uint32_t bn) {
-        const uint32_t nbn = min(B, p.n_order - bn * B);
-        const uint32_t *pkn = pkbuf + size_t(bn & 1) * kB * RS;
-        int *slotn = p.slots + size_t(bn % kSlots) * kSlotInts;
-        // two outputs per thread of the first 8 warps: tile mi, row half rr, lane l5 -> limbs (2tig, 2tig+1) of one
-        // marker, published as ONE signed 64-bit RED (even limb + odd limb * 2^32)
-        if (tid < 256) {
-            const int l5 = tid & 31, rr = (tid >> 5) & 1, mi = tid >> 6;
-            const int o = (mi * 4 + 2 * rr) * 32 + l5;
-            int s0 = 0, s1 = 0;
+    // ... and, once all dot warps have stored theirs (a barrier among them), the sums over the warps
+    auto dot_combine = [&](uint32_t wi) {
+        asm volatile("bar.sync 3, %0;" ::"n"(32 * kDotWarps) : "memory");
+        const uint32_t o = wi * 32 + lane;               // 448 threads, 512 outputs
 #pragma unroll
-            for (int w = 0; w < kDotWarps; ++w) { s0 += scratch[w * 512 + o]; s1 += scratch[w * 512 + o + 32]; }
-            const uint32_t m = 16 * mi + (l5 >> 2) + 8 * rr;
-            const long long v = (long long)s0 + ((long long)s1 << 32);
-            if (v != 0 && m < nbn)
-                atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotDots + (m * 4 + (l5 & 3)) * kLine), (unsigned long long)v);
-        }
-        PHASE(kProfPubReduce);
-        if (warp == 8) {                      // lane 2w+h holds part h of warp w's sum of q
-            unsigned long long v = sh.wq[lane >> 1][lane & 1];
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t oo = o + h * 32 * kDotWarps;
+            if (oo < 512) {
+                int sacc = 0;
 #pragma unroll
-            for (int o2 = 2; o2 < 32; o2 <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
-            if (lane < 2) atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotEps + lane * kLine), v);
+                for (int w = 0; w < kDotWarps; ++w) sacc += dot_part[w * 512 + oo];
+                dot_acc[oo] = sacc;
+            }
         }
-        // sum of q over the missing individuals of this warp's rows (exact: the rows' lists are in their tails).
-        // Fast path: 8 lanes per row read the first 8 entries straight from the tail; longer rows go the general way.
-        {
-            const uint32_t r2 = lane >> 3, e8 = lane & 7, m2 = warp + 16 * r2;
+    };
+    // sums of q over the missing individuals of the block's rows (exact: the rows' lists are in their tails): dot warp wi
+    // takes rows 4wi..4wi+3 (+56), 8 lanes per row reading up to 8 entries straight from the tail; longer lists go the
+    // general way.  Every row < nb gets its pair written.
+    auto missing_sums = [&](const uint32_t *pkn, uint32_t nbn, uint32_t wi) {
+        for (uint32_t m0 = 0; m0 < nbn; m0 += 4 * kDotWarps) {
+            const uint32_t r2 = lane >> 3, e8 = lane & 7, m2 = m0 + 4 * wi + r2;
             uint32_t cnt = 0;
             long long qh = 0; unsigned long long ql = 0;
             if (m2 < nbn) {
@@ -649,26 +644,54 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                     qh = q >> 32; ql = (unsigned long long)(q & 0xffffffffLL);
                 }
             }
-            const unsigned any = __ballot_sync(0xffffffffu, cnt != 0);
-            if (any) {
 #pragma unroll
-                for (int o2 = 1; o2 < 8; o2 <<= 1) {
-                    qh += __shfl_xor_sync(0xffffffffu, qh, o2);
-                    ql += __shfl_xor_sync(0xffffffffu, ql, o2);
-                }
-                if (e8 == 0 && cnt != 0 && cnt <= 8) {
-                    atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotSm + (2 * m2) * kLine), (unsigned long long)qh);
-                    atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotSm + (2 * m2 + 1) * kLine), ql);
-                }
-                const unsigned big = __ballot_sync(0xffffffffu, cnt > 8);
-                for (int r3 = 0; r3 < 4; ++r3)
-                    if (big & (1u << (8 * r3))) {
-                        const uint32_t m3 = warp + 16 * r3;
-                        for_missing_chunks(pkn + size_t(m3) * RS, [&](const uint32_t *ent, uint32_t n) { missing_q_sum(slotn, m3, ent, n); });
-                    }
+            for (int o2 = 1; o2 < 8; o2 <<= 1) {
+                qh += __shfl_xor_sync(0xffffffffu, qh, o2);
+                ql += __shfl_xor_sync(0xffffffffu, ql, o2);
             }
+            if (e8 == 0 && m2 < nbn && cnt <= 8) { msum[2 * m2] = (unsigned long long)qh; msum[2 * m2 + 1] = ql; }
+            const unsigned big = __ballot_sync(0xffffffffu, cnt > 8);
+            for (int r3 = 0; r3 < 4; ++r3)
+                if (big & (1u << (8 * r3))) {
+                    const uint32_t m3 = m0 + 4 * wi + r3;
+                    long long shi = 0; unsigned long long slo = 0;
+                    for_missing_chunks(pkn + size_t(m3) * RS, [&](const uint32_t *ent, uint32_t n) { missing_q_sum(ent, n, shi, slo); });
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        shi += __shfl_xor_sync(0xffffffffu, shi, o);
+                        slo += __shfl_xor_sync(0xffffffffu, slo, o);
+                    }
+                    if (lane == 0) { msum[2 * m3] = (unsigned long long)shi; msum[2 * m3 + 1] = slo; }
+                }
         }
-        PHASE(kProfPubMissing);
+    };
+    // Publish block bn's sums (limb sums, sums over the missing individuals, the slice's sum of q) into the block's global
+    // slot and arrive at the block's grid barrier.  All threads call, after a __syncthreads that follows the dot pass.
+    auto publish_dots = [&](uint32_t bn) {
+        const uint32_t nbn = min(B, p.n_order - bn * B);
+        int *slotn = p.slots + size_t(bn % kSlots) * kSlotInts;
+        if (tid < 256) {
+            // tile mi, row half rr, lane l5 -> limbs (2tig, 2tig+1) of one marker, as ONE signed 64-bit RED (even limb + odd limb * 2^32)
+            const int l5 = tid & 31, rr = (tid >> 5) & 1, mi = tid >> 6;
+            const int o = (mi * 4 + 2 * rr) * 32 + l5;
+            const int s0 = dot_acc[o], s1 = dot_acc[o + 32];
+            const uint32_t m = 16 * mi + (l5 >> 2) + 8 * rr;
+            const long long v = (long long)s0 + ((long long)s1 << 32);
+            if (v != 0 && m < nbn)
+                atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotDots + (m * 4 + (l5 & 3)) * kLine), (unsigned long long)v);
+        } else if (tid < 256 + 2 * kB) {
+            const uint32_t i = tid - 256;                 // (marker, hi/lo part)
+            if ((i >> 1) < nbn) {
+                const unsigned long long v = msum[i];
+                if (v) atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotSm + i * kLine), v);
+            }
+        } else if (warp == 12) {              // lane 2w+h holds part h of warp w's sum of q
+            unsigned long long v = sh.wq[lane >> 1][lane & 1];
+#pragma unroll
+            for (int o2 = 2; o2 < 32; o2 <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+            if (lane < 2) atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotEps + lane * kLine), v);
+        }
+        PHASE(kProfPubReduce);
         grid_arrive(p.bar);
         PHASE(kProfPubArrive);
     };
@@ -693,145 +716,131 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         }
         __syncthreads();
         PHASE(kProfLzC0);
-        // (1) missing-genotype cross counts: one warp per new row j, lanes = columns a (4 per lane).
-        //     From the row's own list:   cz[j][a] += g_a(i) (a present), cw[j][a] += 1 (a missing too), i in missing(j);
-        //     from each column's list:   cy[j][a] += g_j(i) (j present), i in missing(a) -- read straight from the column
-        //     row's tail (<= 15 entries); the rare longer lists are rescanned by the whole warp.
-        for (uint32_t idx = warp; idx < nnew; idx += kWarps) {
-            const uint32_t j = sh.lz_rows[idx];
-            const uint32_t *rowj = pk + size_t(j) * RS;
-            int z[4] = {0, 0, 0, 0}, wv[4] = {0, 0, 0, 0}, y[4] = {0, 0, 0, 0};
-            for_missing_chunks(rowj, [&](const uint32_t *ent, uint32_t n) {
-                for (uint32_t en = 0; en < n; en += 4) {       // four entries per step (the list is padded with sentinels)
-                    const uint4 i4 = *reinterpret_cast<const uint4 *>(ent + en);
-                    const uint32_t ii[4] = {i4.x, i4.y, i4.z, i4.w};
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const uint32_t a = lane + 32 * h;
-                        const bool okc = (h < 2) ? (a < nb && a != j) : (a - kB < nbx);
-                        const uint32_t *rowp = (h < 2) ? pk + size_t(a) * RS : pkx + size_t(a - kB) * RS;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint32_t cwd = (okc && ii[q] != 0xffffffffu) ? rowp[ii[q] >> 4] : 0u;
-                            const uint32_t c = (cwd >> (2 * (ii[q] & 15u))) & 3u;
-                            z[h] += (c == 3u) ? 0 : int(c);
-                            wv[h] += (c == 3u) ? 1 : 0;
-                        }
+        // (1) missing-genotype cross counts, all warps: warp w takes the columns a = 8w..8w+7, lane = (column, row subset);
+        //     a lane handles the pairs (row idx0 + s4, column a):
+        //       from the row's list:     cz += g_a(i) (a present), cw += 1 (a missing too),  i in missing(j)
+        //       from the column's list:  cy += g_j(i) (j present),                           i in missing(a)
+        //     both read straight from the rows' tails (<= 15 entries); pairs with a longer list are redone by the whole warp.
+        {
+            const uint32_t a = 8 * warp + (lane >> 2), s4 = lane & 3u;
+            const bool okcol = (a < uint32_t(kB)) ? (a < nb) : (a - kB < nbx);
+            const uint32_t *rowa = (a < uint32_t(kB)) ? pk + size_t(a) * RS : pkx + size_t(a - kB) * RS;
+            const uint16_t *tla = reinterpret_cast<const uint16_t *>(rowa + PW);
+            const uint32_t cnta = okcol ? uint32_t(tla[0]) : 0u;
+            for (uint32_t idx0 = 0; idx0 < nnew; idx0 += 4) {
+                const uint32_t idx = idx0 + s4;
+                const bool on = okcol && idx < nnew;
+                const uint32_t j = on ? sh.lz_rows[idx] : 0u;
+                const bool pair = on && a != j;                            // a >= 64 never equals a row marker
+                const uint32_t *rowj = pk + size_t(j) * RS;
+                const uint16_t *tlj = reinterpret_cast<const uint16_t *>(rowj + PW);
+                const uint32_t cntj = pair ? uint32_t(tlj[0]) : 0u;
+                const bool slow = pair && (cntj > 15u || cnta > 15u);
+                int z = 0, wv = 0, y = 0;
+                if (pair && !slow) {
+                    for (uint32_t en = 0; en < cntj; ++en) {
+                        const uint32_t i = tlj[1 + en];
+                        const uint32_t c = (rowa[i >> 4] >> (2 * (i & 15u))) & 3u;
+                        z += (c == 3u) ? 0 : int(c);
+                        wv += (c == 3u) ? 1 : 0;
+                    }
+                    for (uint32_t en = 0; en < cnta; ++en) {
+                        const uint32_t i = tla[1 + en];
+                        const uint32_t c = (rowj[i >> 4] >> (2 * (i & 15u))) & 3u;
+                        y += (c == 3u) ? 0 : int(c);
                     }
                 }
-            });
-            PHASE(kProfLzC1);
-            // the lists of the lane's four columns, walked together (four independent load chains per step)
-            uint32_t cnt4[4], cmax = 0;
-            const uint16_t *tl4[4];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                const uint32_t a = lane + 32 * h;
-                const bool okc = (h < 2) ? (a < nb && a != j) : (a - kB < nbx);
-                tl4[h] = reinterpret_cast<const uint16_t *>(((h < 2) ? pk + size_t(a) * RS : pkx + size_t(a - kB) * RS) + PW);
-                cnt4[h] = okc ? uint32_t(tl4[h][0]) : 0u;
-                cmax = max(cmax, cnt4[h] <= 15u ? cnt4[h] : 0u);
-            }
-            cmax = __reduce_max_sync(0xffffffffu, cmax);
-            for (uint32_t en = 0; en < cmax; ++en) {
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const bool on = en < cnt4[h] && cnt4[h] <= 15u;
-                    const uint32_t i = on ? uint32_t(tl4[h][1 + en]) : 0u;
-                    const uint32_t c = on ? ((rowj[i >> 4] >> (2 * (i & 15u))) & 3u) : 0u;
-                    y[h] += (c == 3u) ? 0 : int(c);
-                }
-            }
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                const uint32_t a = lane + 32 * h;
-                const uint32_t cnt = cnt4[h];
-                unsigned ovf = __ballot_sync(0xffffffffu, cnt > 15u);
-                while (ovf) {                                      // a column with a long list: all lanes scan it
-                    const uint32_t al = __ffs(ovf) - 1;
-                    ovf &= ovf - 1;
-                    const uint32_t a2 = al + 32 * h;
-                    const uint32_t *rowa = (h < 2) ? pk + size_t(a2) * RS : pkx + size_t(a2 - kB) * RS;
-                    int s = 0;
-                    for_missing_chunks(rowa, [&](const uint32_t *ent, uint32_t n) {
+                unsigned slow_m = __ballot_sync(0xffffffffu, slow);
+                while (slow_m) {
+                    const int l = __ffs(slow_m) - 1;
+                    slow_m &= slow_m - 1;
+                    const uint32_t a2 = __shfl_sync(0xffffffffu, a, l), j2 = __shfl_sync(0xffffffffu, j, l);
+                    const uint32_t *ra = (a2 < uint32_t(kB)) ? pk + size_t(a2) * RS : pkx + size_t(a2 - kB) * RS;
+                    const uint32_t *rj = pk + size_t(j2) * RS;
+                    int zz = 0, ww = 0, yy = 0;
+                    for_missing_chunks(rj, [&](const uint32_t *ent, uint32_t n) {
                         for (uint32_t en = lane; en < n; en += 32) {
                             const uint32_t i = ent[en];
-                            const uint32_t c = (rowj[i >> 4] >> (2 * (i & 15u))) & 3u;
-                            s += (c == 3u) ? 0 : int(c);
+                            const uint32_t c = (ra[i >> 4] >> (2 * (i & 15u))) & 3u;
+                            zz += (c == 3u) ? 0 : int(c);
+                            ww += (c == 3u) ? 1 : 0;
                         }
                     });
-                    s = __reduce_add_sync(0xffffffffu, s);
-                    if (lane == al) y[h] += s;
+                    for_missing_chunks(ra, [&](const uint32_t *ent, uint32_t n) {
+                        for (uint32_t en = lane; en < n; en += 32) {
+                            const uint32_t i = ent[en];
+                            const uint32_t c = (rj[i >> 4] >> (2 * (i & 15u))) & 3u;
+                            yy += (c == 3u) ? 0 : int(c);
+                        }
+                    });
+                    zz = __reduce_add_sync(0xffffffffu, zz); ww = __reduce_add_sync(0xffffffffu, ww); yy = __reduce_add_sync(0xffffffffu, yy);
+                    if (lane == l) { z = zz; wv = ww; y = yy; }
                 }
-                unsigned long long *ln = reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0 + idx) * kCols + a) * kLine);
-                if (wv[h]) atomicAdd(ln, (unsigned long long)(unsigned)wv[h] << 32);
-                if (y[h] | z[h]) atomicAdd(ln + 1, (unsigned long long)(unsigned)y[h] | ((unsigned long long)(unsigned)z[h] << 32));
+                if (pair) {
+                    unsigned long long *ln = reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0 + idx) * kCols + a) * kLine);
+                    if (wv) atomicAdd(ln, (unsigned long long)(unsigned)wv << 32);
+                    if (y | z) atomicAdd(ln + 1, (unsigned long long)(unsigned)y | ((unsigned long long)(unsigned)z << 32));
+                }
             }
         }
         PHASE(kProfLzC2);
         __syncthreads();                       // the warps' missing-list segments are free: reused below
         PHASE(kProfLazyCross);
         // (2) integer products, shaped like the dot pass: A = 16 column markers (tile mt of the 128 columns), B = 8 new
-        //     rows (a group) in place of the 8 limbs.  warp = (column tile mt, k-half kh); two groups per pass, and the
-        //     two MMAs of a k-step pair feed separate accumulators so that a warp always has >= 2 independent chains.
+        //     rows (a group) in place of the 8 limbs.  warp = (column tile mt, half kh of the word pairs); one group per
+        //     pass; per word pair four MMAs, one per code class, fed by in-place class bytes of both operands (16^c scaling).
         {
             const uint32_t mt = warp & 7u, kh = warp >> 3;
+            const uint32_t NW2 = (NP + 1) / 2;
             const uint32_t first_row = need0 ? uint32_t(__ffs(need0) - 1) : 32u + uint32_t(__ffs(need1) - 1);   // its own column and all before it are not needed
             const bool mt_ok = (mt < 4) ? (16 * mt < nb && 16 * mt + 15 > first_row) : (16 * (mt - 4) < nbx);
-            const uint32_t *pa = (mt < 4) ? pk + size_t(16 * mt) * RS : pkx + size_t(16 * (mt - 4)) * RS;
+            const uint32_t *c0p = ((mt < 4) ? pk + size_t(16 * mt) * RS : pkx + size_t(16 * (mt - 4)) * RS) + gid * RS + tig;
+            const uint32_t *c1p = c0p + 8 * RS;
             int *sc2 = reinterpret_cast<int *>(miss_list);
-            for (uint32_t g0 = 0; g0 * 8 < nnew; g0 += 2) {
-                const uint32_t i0 = g0 * 8 + gid, i1 = i0 + 8;
-                const bool v0 = i0 < nnew, v1 = i1 < nnew;
-                const uint32_t u0 = v0 ? sh.lz_rows[i0] : 0u, u1 = v1 ? sh.lz_rows[i1] : 0u;
-                const bool two = (g0 + 1) * 8 < nnew;
-                int acc[2][2][4];
+            for (uint32_t g0 = 0; g0 * 8 < nnew; ++g0) {
+                const uint32_t i0 = g0 * 8 + gid;
+                const bool v0 = i0 < nnew;
+                const uint32_t *u0p = pk + size_t(v0 ? sh.lz_rows[i0] : 0u) * RS + tig;
+                int acc[4][4];
 #pragma unroll
-                for (int g = 0; g < 2; ++g)
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) { acc[g][c][0] = 0; acc[g][c][1] = 0; acc[g][c][2] = 0; acc[g][c][3] = 0; }
+                for (int c = 0; c < 4; ++c) { acc[c][0] = 0; acc[c][1] = 0; acc[c][2] = 0; acc[c][3] = 0; }
                 if (mt_ok) {
-                    for (uint32_t pr = kh; pr < NP; pr += 2) {
-                        const uint32_t wo = 4 * pr + tig;
-                        const uint32_t w0 = pa[size_t(gid) * RS + wo], w1 = pa[size_t(gid + 8) * RS + wo];
-                        const uint32_t b0 = v0 ? pk[size_t(u0) * RS + wo] : 0u;
-                        mma_u8u8(acc[0][0], w0 & kM3, w1 & kM3, (w0 >> 2) & kM3, (w1 >> 2) & kM3, b0 & kM3, (b0 >> 2) & kM3);
-                        mma_u8u8(acc[0][1], (w0 >> 4) & kM3, (w1 >> 4) & kM3, (w0 >> 6) & kM3, (w1 >> 6) & kM3, (b0 >> 4) & kM3, (b0 >> 6) & kM3);
-                        if (two) {
-                            const uint32_t b1 = v1 ? pk[size_t(u1) * RS + wo] : 0u;
-                            mma_u8u8(acc[1][0], w0 & kM3, w1 & kM3, (w0 >> 2) & kM3, (w1 >> 2) & kM3, b1 & kM3, (b1 >> 2) & kM3);
-                            mma_u8u8(acc[1][1], (w0 >> 4) & kM3, (w1 >> 4) & kM3, (w0 >> 6) & kM3, (w1 >> 6) & kM3, (b1 >> 4) & kM3, (b1 >> 6) & kM3);
-                        }
+                    for (uint32_t wp = kh; wp < NW2; wp += 2) {
+                        const uint32_t oA = 8 * wp, oB = oA + 4;
+                        const bool hasB = 2 * wp + 1 < NP;
+                        const uint32_t a0 = c0p[oA], a1 = c1p[oA];
+                        const uint32_t uA = v0 ? u0p[oA] : 0u;
+                        uint32_t b0 = 0u, b1 = 0u, uB = 0u;
+                        if (hasB) { b0 = c0p[oB]; b1 = c1p[oB]; uB = v0 ? u0p[oB] : 0u; }
+                        mma_u8u8(acc[0], a0 & kC0, a1 & kC0, b0 & kC0, b1 & kC0, uA & kC0, uB & kC0);
+                        mma_u8u8(acc[1], a0 & kC1, a1 & kC1, b0 & kC1, b1 & kC1, uA & kC1, uB & kC1);
+                        mma_u8u8(acc[2], a0 & kC2, a1 & kC2, b0 & kC2, b1 & kC2, uA & kC2, uB & kC2);
+                        mma_u8u8(acc[3], a0 & kC3, a1 & kC3, b0 & kC3, b1 & kC3, uA & kC3, uB & kC3);
                     }
                 }
+                int val[4];
 #pragma unroll
-                for (int g = 0; g < 2; ++g)
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) acc[g][0][r] += acc[g][1][r];
+                for (int r = 0; r < 4; ++r) val[r] = acc[0][r] + (acc[1][r] >> 4) + (acc[2][r] >> 8) + (acc[3][r] >> 12);
                 PHASE(kProfLzLoop);
                 if (kh == 1) {
 #pragma unroll
-                    for (int g = 0; g < 2; ++g)
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) sc2[((mt * 2 + g) * 4 + r) * 32 + lane] = acc[g][0][r];
+                    for (int r = 0; r < 4; ++r) sc2[(mt * 4 + r) * 32 + lane] = val[r];
                 }
                 __syncthreads();
                 if (kh == 0 && mt_ok) {
 #pragma unroll
-                    for (int g = 0; g < 2; ++g)
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const int val = acc[g][0][r] + sc2[((mt * 2 + g) * 4 + r) * 32 + lane];
-                            const uint32_t col = 16 * mt + gid + 8 * (r >> 1);                     // 0..127
-                            const uint32_t ui = (g0 + g) * 8 + 2 * tig + (r & 1);                   // index of the new row
-                            if (ui < nnew && val) {
-                                const uint32_t rowm = sh.lz_rows[ui];
-                                const bool okc = (col < uint32_t(kB)) ? (col < nb && col != rowm) : (col - kB < nbx);
-                                if (okc)
-                                    atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0 + ui) * kCols + col) * kLine),
-                                              (unsigned long long)(unsigned)val);
-                            }
+                    for (int r = 0; r < 4; ++r) {
+                        const int v = val[r] + sc2[(mt * 4 + r) * 32 + lane];
+                        const uint32_t col = 16 * mt + gid + 8 * (r >> 1);                     // 0..127
+                        const uint32_t ui = g0 * 8 + 2 * tig + (r & 1);                         // index of the new row
+                        if (ui < nnew && v) {
+                            const uint32_t rowm = sh.lz_rows[ui];
+                            const bool okc = (col < uint32_t(kB)) ? (col < nb && col != rowm) : (col - kB < nbx);
+                            if (okc)
+                                atomicAdd(reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0 + ui) * kCols + col) * kLine),
+                                          (unsigned long long)(unsigned)v);
                         }
+                    }
                 }
                 __syncthreads();
                 PHASE(kProfLzRed);
@@ -909,6 +918,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     // ---- the block loop.  Pass bb works on block bb while the dot warps run ahead on block bb+1; the first pass
     // (bb = -1) is a virtual empty block that only starts block 0, so that every piece of the pipeline exists once.
     unsigned gen_wait = 0;                                      // the grid-wide round that carries the current block's dots
+    int zero_turn = int(cta);                                   // the next block whose pass recycles a slot on this CTA
+    while (zero_turn < 2) zero_turn += int(p.nCTA);
     uint32_t gid_next = 0u;                                     // threads 64..127: marker id of their row of the next block to gather
     {
         const int k2 = tid - 32 * kWalkWarps;
@@ -1005,6 +1016,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 mbar_wait(&sh.mbar[buf ^ 1u], (bn >> 1) & 1u);
                 PHASE_W(kProfWorkerWait, true);
                 dot_partial(pk_next, nb_next, warp - kWalkWarps);
+                missing_sums(pk_next, nb_next, warp - kWalkWarps);
+                dot_combine(warp - kWalkWarps);
                 cp_async_wait_all();
                 if (uint32_t(k2) < nb_next) derive_block_meta(meta_next, k2);
                 PHASE_W(kProfWorkerDot, true);
@@ -1016,7 +1029,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         // ---- B. the round of block b+1 goes out NOW: its latency hides behind the rest of block b -----------------
         // recycle the slot of block b-2 first (every CTA finished with it before it arrived at block b's round, and
         // nobody adds into it again before passing block b+1's round)
-        if (bb >= 2 && cta == b % p.nCTA) {
+        if (bb == zero_turn) {                                   // block b with b >= 2 and b % nCTA == cta, without a division
+            zero_turn += int(p.nCTA);
             int *old = p.slots + size_t((b - 2) % kSlots) * kSlotInts;
             for (int i = tid; i < kSlotMainLines; i += kThreads) *reinterpret_cast<unsigned long long *>(old + i * kLine) = 0ULL;
             const uint32_t used = sh.lz_hist[(b - 2) % kSlots];
@@ -1028,7 +1042,6 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         if (pf_early) prefetch(bn + 1);
         PHASE(kProfPubPre);
         if (have_next) {
-            mbar_wait(&sh.mbar[buf ^ 1u], (bn >> 1) & 1u);   // the walkers have not observed the rows of block b+1 yet
             publish_dots(bn);
             gen_wait = ++bar_gen;
         }
@@ -1047,6 +1060,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         uint32_t have0 = 0, have1 = 0, lz_used = 0;             // Gram rows known so far (identical in every CTA)
         // A quiet block (nothing sampled away from zero) ends here for the dot warps: they go straight to the dot pass of
         // block b+2 while the walkers file the results and wait for block b+1's round; no CTA-wide barrier in between.
+        if (!quiet && have_next) mbar_wait(&sh.mbar[buf ^ 1u], (bn >> 1) & 1u);   // the walkers have not observed the rows of block b+1 yet
         for (int iter = 0; iter < 2 * kB && !quiet; ++iter) {
             const unsigned nsm0 = sh.w_nsm[0], nsm1 = sh.w_nsm[1];
             if ((nsm0 | nsm1) == 0) break;
@@ -1223,10 +1237,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         }
 
         // ---- F. block b's buffer is free: prefetch block b+2 into it ----------------------------------------------
-        if (!pf_early && bn + 1 < nBlocks) {
-            prefetch(bn + 1);
-            if (p.n_order - (bn + 1) * B < B) __syncthreads();      // zero rows of a partial last block: visible before its dot pass
-        }
+        if (!pf_early && bn + 1 < nBlocks) prefetch(bn + 1);
+        if (!quiet && bn + 1 < nBlocks && p.n_order - (bn + 1) * B < B) __syncthreads();   // zero rows of a partial last block
         PHASE(kProfTail);
         PHASE_W(0, false);
     }
