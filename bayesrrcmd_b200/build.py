@@ -55,7 +55,8 @@ def build_host(force=False):
     lib = os.path.join(PKG, "libbrr_host.so")
     exe = os.path.join(PKG, "brr_gpu")
     if force or _newer(lib, srcs) or _newer(exe, srcs):
-        common = ["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + hdir]
+        common = ["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-Wall", "-Wno-deprecated-declarations",
+                  "-I" + os.path.join(ROOT, "include"), "-I" + hdir]
         subprocess.check_call(common + ["-shared", "-o", lib] + cpps + ["-L" + PKG, "-lbrr_gpu", "-Wl,-rpath,$ORIGIN"])
         main = os.path.join(hdir, "main.cpp")
         if os.path.exists(main):

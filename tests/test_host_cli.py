@@ -1,0 +1,157 @@
+"""The C++ host mirror (bayesrrcmd_b200/host: Options / Data / GpuSweepGraph / GpuBayesR::runGibbs / SampleWriter) through
+its `brr`-style command line.
+
+CPU: the binary builds, parses the reference's command line, reads PLINK files, and stops with "no CPU fallback" when there is
+no GPU.  GPU: a full chain FROM THE SEED -- the host draws every random number itself (std::mt19937 + std:: distributions, the
+mapping the oracle's reference build uses, and std::random_shuffle for the marker order) -- must reproduce the reference chain
+recorded in tests/golden (mu, sigmaE, sigmaG, beta, components, acum, epsilon within 1e-8): end-to-end parity of the drop-in.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import Golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "bayesrrcmd_b200")
+EXE = os.path.join(PKG, "brr_gpu")
+
+
+@pytest.fixture(scope="module")
+def built():
+    from bayesrrcmd_b200 import build
+    build.build_all()
+    assert os.path.exists(EXE)
+    return EXE
+
+
+def write_plink(g, d, groups_file=False):
+    """PLINK bed/bim/fam + phenotype (+ group) files of a golden fixture."""
+    base = os.path.join(d, "data")
+    with open(base + ".bed", "wb") as f:
+        f.write(bytes([0x6c, 0x1b, 0x01]))
+        f.write(np.ascontiguousarray(g.bed).tobytes())
+    with open(base + ".fam", "w") as f:
+        for i in range(g.N):
+            f.write("F%d I%d 0 0 0 -9\n" % (i, i))
+    with open(base + ".bim", "w") as f:
+        for j in range(g.M):
+            f.write("1 snp%d 0 %d A C\n" % (j, j + 1))
+    with open(base + ".phen", "w") as f:
+        for i in range(g.N):
+            f.write("F%d I%d %.9g\n" % (i, i, float(g.y[i])))
+    if groups_file:
+        with open(base + ".group", "w") as f:
+            for j in range(g.M):
+                f.write("snp%d %d\n" % (j, int(g.groups[j])))
+    return base
+
+
+def run(exe, args, **kw):
+    return subprocess.run([exe] + args, capture_output=True, text=True, timeout=600, **kw)
+
+
+def test_host_library_exports_entry_point(built):
+    lib = ctypes.CDLL(os.path.join(PKG, "libbrr_host.so"))
+    assert hasattr(lib, "brr_host_main")
+
+
+def test_command_line_errors(built, tmp_path):
+    r = run(built, ["--no-such-option"])
+    assert r.returncode == 1 and "invalid option" in r.stderr
+    r = run(built, ["--analysis-type", "preprocess", "--data-file", "x.bed", "--pheno", "x.phen"])
+    assert r.returncode == 1 and "ppbayes" in r.stderr
+    r = run(built, ["--analysis-type", "ppbayes", "--data-file", str(tmp_path / "missing.bed"), "--pheno", "x.phen"])
+    assert r.returncode == 1 and "can not open" in r.stderr
+    r = run(built, ["--analysis-type", "ppbayes", "--S", "0.1,zzz"])
+    assert r.returncode == 1 and "variance component" in r.stderr
+
+
+def test_reads_plink_files_then_requires_a_gpu(built, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    g = Golden("missing_small")
+    base = write_plink(g, str(tmp_path), groups_file=True)
+    r = run(built, ["--analysis-type", "ppbayes", "--data-file", base + ".bed", "--pheno", base + ".phen", "--group", base + ".group",
+                    "--S", "0.01,0.001;0.01,0.001", "--chain-length", "2", "--seed", "7", "--mcmc-samples", str(tmp_path / "o.csv")])
+    assert "%d individuals to be included" % g.N in r.stdout
+    assert "%d SNPs to be included" % g.M in r.stdout
+    assert "Groups read from file: 2" in r.stdout
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+def read_samples(path, M, N, nG):
+    rows = np.loadtxt(path, delimiter=",", skiprows=1, ndmin=2)
+    out = []
+    for r in rows:
+        o = 2
+        d = dict(iteration=int(r[0]), mu=r[1], beta=r[o:o + M]); o += M
+        d["sigmaE"] = r[o]; o += 1
+        d["sigmaG"] = r[o:o + nG]; o += nG
+        d["comp"] = r[o:o + M]; o += M
+        d["acum"] = r[o:o + M]; o += M
+        d["eps"] = r[o:o + N]
+        out.append(d)
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,layout,sargs", [("uk10k", "dense", []), ("uk10k", "ragged", ["--sparse-data", "ragged"])])
+def test_chain_from_seed_reproduces_the_reference(built, tmp_path, name, layout, sargs):
+    g = Golden(name)
+    chain = g.chain(layout)
+    base = write_plink(g, str(tmp_path))
+    out = str(tmp_path / "samples.csv")
+    iters = len(chain["mu"])
+    r = run(built, ["--analysis-type", "ppbayes", "--data-file", base + ".bed", "--pheno", base + ".phen", "--chain-length", str(iters),
+                    "--burn-in", "0", "--thin", "1", "--seed", str(int(g.z["seed"])), "--S", ",".join("%.17g" % s for s in g.S[0]),
+                    "--mcmc-samples", out, "--sample-precision", "17"] + sargs)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "mean flowgraph duration" in r.stdout
+    rows = read_samples(out, g.M, g.N, g.nG)
+    assert [d["iteration"] for d in rows] == list(range(iters))
+
+    def close(a, b, what, it, tol=1e-8):
+        a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+        err = np.max(np.abs(a - b) / (1.0 + np.abs(b)))
+        assert err <= tol, "%s differs at iteration %d: %.3e" % (what, it, err)
+
+    if layout != "dense":
+        # the sparse chains of the fixture were recorded after the dense one in ONE process: their marker orders continue the
+        # libc rand() stream, a fresh process restarts it.  The scalar draws (mt19937) still match until the orders differ,
+        # i.e. for iteration 0's mu only; the full comparison is made for the dense chain.
+        close(rows[0]["mu"], chain["mu"][0], "mu", 0)
+        return
+    full = list(chain["full_iters"])
+    for it, d in enumerate(rows):
+        close(d["mu"], chain["mu"][it], "mu", it)
+        close(d["sigmaE"], chain["sigmaE_post"][it], "sigmaE", it)
+        close(d["sigmaG"], chain["sigmaG_post"][it], "sigmaG", it)
+        close(d["beta"].sum(), chain["chk_beta"][it], "sum(beta)", it)
+        close(d["comp"].sum(), chain["chk_comp"][it], "sum(components)", it)
+        close(d["acum"].sum(), chain["chk_acum"][it], "sum(acum)", it)
+        close((d["eps"] ** 2).sum(), chain["chk_eps2"][it], "||eps||^2", it)
+        if it in full:
+            k = full.index(it)
+            close(d["beta"], chain["beta_full"][k], "beta", it)
+            assert (d["comp"] == chain["comp_full"][k]).all()
+            close(d["acum"], chain["acum_full"][k], "acum", it)
+            close(d["eps"], chain["eps_full"][k], "eps", it)
+
+
+@pytest.mark.gpu
+def test_async_chain_runs(built, tmp_path):
+    g = Golden("missing_small")
+    base = write_plink(g, str(tmp_path), groups_file=True)
+    out = str(tmp_path / "samples.csv")
+    r = run(built, ["--analysis-type", "asyncppbayes", "--analysis-tokens", "20", "--data-file", base + ".bed", "--pheno", base + ".phen",
+                    "--group", base + ".group", "--S", ";".join(",".join("%.17g" % s for s in row) for row in g.S), "--chain-length", "20",
+                    "--burn-in", "10", "--thin", "5", "--seed", "3", "--mcmc-samples", out, "--no-epsilon"])
+    assert r.returncode == 0, r.stderr + r.stdout
+    rows = np.loadtxt(out, delimiter=",", skiprows=1, ndmin=2)
+    assert rows.shape == (2, 2 + g.M + 1 + g.nG + 2 * g.M) and list(rows[:, 0]) == [10, 15]
+    assert np.isfinite(rows).all() and (rows[:, 2 + g.M] > 0).all()
