@@ -155,23 +155,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
 
-    # ---- shard individuals over ranks (multiples of 64 rows so plane chunks stay aligned) -----------
-    per = ((N + world - 1) // world + 63) // 64 * 64
-    lo = min(N, rank * per); hi = min(N, lo + per)
+    # ---- shard individuals over ranks (bayesrrcmd_b200/sharding.py) -------------------------------------------
+    from bayesrrcmd_b200.sharding import ShardGroup, shard_bounds
+    grp = ShardGroup(rank, world)
+    lo, hi = shard_bounds(N, world)[rank]
     n_loc = hi - lo
     eng = Engine(n_loc, M, 4, 1, layout="dense", device=local_rank, block_markers=a.block, n_inds_total=N,
                  rank=rank, world=world)
     info = eng.info()
     t0 = time.time()
     eng.synth_dense(SEED, MAF_LO, MAF_HI, False, P_MISSING, ind_offset=lo)
-    counts = eng.counts()
+    counts = grp.allreduce_counts(eng.counts())
     if world > 1:
-        ct = torch.from_numpy(counts.astype(np.int64)).cuda()
-        dist.all_reduce(ct)
-        counts = ct.cpu().numpy().astype(np.uint32)
-        handles = [None] * world
-        dist.all_gather_object(handles, eng.ipc_export())
-        eng.ipc_attach(handles)
+        eng.ipc_attach(grp.gather(eng.ipc_export()))
     eng.finalize(counts)
     eng.set_model(S_CVA)
     gen_s = time.time() - t0
@@ -184,26 +180,10 @@ def main():
     eng.set_state(eps=noise[lo:hi], beta=np.zeros(M), comp=np.zeros(M), acum=np.zeros(M))
     for j, b in zip(causal, bcausal):
         eng.apply_delta(int(j), float(b), 0.0)            # eps += b * x_j
-    y = eng.get_state(beta=False, comp=False, acum=False)[0].astype(np.float32).astype(np.float64)   # VectorXf y
-    s1 = np.array([y.sum(), 0.0])
-    if world > 1:
-        t = torch.from_numpy(s1).cuda(); dist.all_reduce(t); s1 = t.cpu().numpy()
-    y = y - s1[0] / N
-    s2 = np.array([(y ** 2).sum()])
-    if world > 1:
-        t = torch.from_numpy(s2).cuda(); dist.all_reduce(t); s2 = t.cpu().numpy()
-    y = y / np.sqrt(s2[0] / (N - 1))
+    y = grp.standardise(eng.get_state(beta=False, comp=False, acum=False)[0], N)
     eng.set_state(eps=y)
-    y_full = y
-    if world > 1:
-        parts = [None] * world
-        dist.all_gather_object(parts, y)
-        y_full = np.concatenate(parts)
-
-    def allsum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t); return float(t.item())
+    y_full = np.concatenate(grp.gather(y))
+    allsum = grp.allsum
 
     # ---- chain state as BayesRBase::init leaves it (reference src/BayesRBase.cpp:39-99) -------------
     K = 4
