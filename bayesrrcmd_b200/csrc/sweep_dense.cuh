@@ -381,15 +381,51 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     // second local counter that releases everybody.  Sums are integers: the result does not depend on the
     // arrival order or on the number of GPUs.  `t`/`nthr`/`sync` name the thread group that runs the round
     // (the 64 walker threads for the per-block message, the whole CTA otherwise).
+    // The per-block message (every block, on the critical path) takes a shorter way: CTA 0 pushes and publishes,
+    // the walkers of EVERY CTA wait for the peers' round ids themselves and add the peers' mailboxes to the local
+    // sums as they read them (peer_sum) -- no merge, no second counter.
     const unsigned long long round_base = (p.world > 1) ? *p.round_ctr : 0ULL;
     unsigned xround = 0;                                    // exchange rounds done in this launch
     unsigned bar2_target = 0;
+    int main_rot = 0;                                       // mailbox rotation of the current per-block round
+    auto peer_sum = [&](long long v, uint32_t msg) -> long long {      // local sum + the peers' parts of message element `msg`
+        if (p.world > 1) {
+            const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(p.peer_xchg[p.rank]);
+            for (int pr = 0; pr < p.world; ++pr)
+                if (pr != p.rank) v += (long long)__ldcg(mine + (size_t(pr) * kXchgRot + main_rot) * kMsgU64 + msg);
+        }
+        return v;
+    };
     auto xchg = [&](int kind, int *slot, uint32_t r0, uint32_t nrows, int t, int nthr, auto &&sync) {
         if (p.world <= 1) return;
         ++xround;
         const unsigned long long rid = round_base + xround;
         const int rot = int(rid % kXchgRot);
         const uint32_t E = (kind == kXLazy) ? p.xchg_ctas : 1u;
+        if (kind == kXMain) {
+            main_rot = rot;
+            if (cta == 0) {
+                for (uint32_t i = kMsgDots + t; i < uint32_t(kMsgAbs); i += nthr) {
+                    const int *lp = i < uint32_t(kMsgSm) ? slot + kSlotDots + (i - kMsgDots) * kLine
+                                  : i < uint32_t(kMsgEps) ? slot + kSlotSm + (i - kMsgSm) * kLine : slot + kSlotEps + (i - kMsgEps) * kLine;
+                    const unsigned long long v = __ldcg(reinterpret_cast<const unsigned long long *>(lp));
+                    for (int pr = 0; pr < p.world; ++pr)
+                        if (pr != p.rank) reinterpret_cast<unsigned long long *>(p.peer_xchg[pr])[(size_t(p.rank) * kXchgRot + rot) * kMsgU64 + i] = v;
+                }
+                sync();                                     // the release below covers the group's stores (as in grid_arrive)
+                if (t < p.world && t != p.rank)
+                    st_release_sys_u64(reinterpret_cast<unsigned long long *>(p.peer_xchg[t] + xchg_mailbox_ints(p.world)) + size_t(p.rank) * kXchgCtas, rid);
+            }
+            if (t < p.world && t != p.rank) {
+                const unsigned long long *lf = reinterpret_cast<const unsigned long long *>(p.peer_xchg[p.rank] + xchg_mailbox_ints(p.world)) + size_t(t) * kXchgCtas;
+                const long long t0 = clock64();
+                while (ld_acquire_sys_u64(lf) < rid) {
+                    if ((sh.err & 2u) || clock64() - t0 > 6000000000LL) { sh.err |= 2u; break; }   // ~3 s: a peer is gone; fail, do not hang
+                }
+            }
+            sync();
+            return;
+        }
         bar2_target += E;
         if (cta < E) {
             unsigned long long *mine = reinterpret_cast<unsigned long long *>(p.peer_xchg[p.rank]);
@@ -962,11 +998,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             if (act) {
                 long long dq[4];
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) dq[q4] = __ldcg(reinterpret_cast<const long long *>(slot + kSlotDots + (wk * 4 + q4) * kLine));
-                const long long sm_hi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * wk) * kLine));
-                const long long sm_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * wk + 1) * kLine));
-                const long long e_hi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps));
-                const long long e_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps + kLine));
+                for (int q4 = 0; q4 < 4; ++q4)
+                    dq[q4] = peer_sum(__ldcg(reinterpret_cast<const long long *>(slot + kSlotDots + (wk * 4 + q4) * kLine)), kMsgDots + wk * 4 + q4);
+                const long long sm_hi = peer_sum(__ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * wk) * kLine)), kMsgSm + 2 * wk);
+                const long long sm_lo = peer_sum(__ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * wk + 1) * kLine)), kMsgSm + 2 * wk + 1);
+                const long long e_hi = peer_sum(__ldcg(reinterpret_cast<const long long *>(slot + kSlotEps)), kMsgEps);
+                const long long e_lo = peer_sum(__ldcg(reinterpret_cast<const long long *>(slot + kSlotEps + kLine)), kMsgEps + 1);
                 const double eps_sum_total = (double(e_hi) * 4294967296.0 + double(e_lo)) * inv_scale;
                 // unpack the limb sums: each int64 holds (even limb) + (odd limb) * 2^32, both signed
                 long long S[8];

@@ -122,6 +122,16 @@ def cpu_reference_leg(n_inds, n_markers, eps_y, steps, warmup=0):
 
 def main():
     a = parse()
+    # The contract is ONE JSON line on stdout: keep everything else (NCCL's version banner, library chatter) away from it by
+    # pointing fd 1 at stderr for the duration of the run and writing the line to the saved descriptor.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+
+    def emit(line):
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
+
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     N, M = a.n_inds, a.n_markers
@@ -135,7 +145,7 @@ def main():
         y = rng.standard_normal(N).astype(np.float32)
         leg = cpu_reference_leg(N, a.cpu_markers, y, a.steps, a.warmup)
         if leg is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"})
             return
         line = {"impl": "reference", "metric": "marker updates/sec (ppbayes Gibbs sweep, dense)", "value": leg["value"],
                 "unit": "marker updates/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
@@ -144,7 +154,7 @@ def main():
                 "config": {"workload": workload, "sample": leg["sample"]},
                 "cpu_baseline": leg,
                 "e2e": {"value": leg["value"], "unit": "marker updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -282,7 +292,7 @@ def main():
         except Exception as ex:      # the checker must never take the product's number down with it
             leg = {"error": repr(ex)}
         line["cpu_baseline"] = leg
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
