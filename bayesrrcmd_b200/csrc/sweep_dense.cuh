@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     // takes rows 4wi..4wi+3 (+56), 8 lanes per row reading up to 8 entries straight from the tail; longer lists go the
     // general way.  Every row < nb gets its pair written.
     auto missing_sums = [&](const uint32_t *pkn, uint32_t nbn, uint32_t wi) {
-        for (uint32_t m0 = 0; m0 < nbn; m0 += 4 * kDotWarps) {
+        for (uint32_t m0 = 0; m0 + 4 * wi < nbn; m0 += 4 * kDotWarps) {      // (the second round has rows for two warps only)
             const uint32_t r2 = lane >> 3, e8 = lane & 7, m2 = m0 + 4 * wi + r2;
             uint32_t cnt = 0;
             long long qh = 0; unsigned long long ql = 0;
@@ -739,8 +739,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     // over CTAs / GPUs.  The block-b half is standardised into x_j.x_k and stored as doubles in row slots r0, r0+1, ...
     // of the scratch; the block-(b+1) half stays in the global slot for the carry pass.  Every CTA calls with
     // identical arguments.  nbx = markers of block b+1 (0 = there is none).
-    auto lazy_round = [&](const uint32_t *pk, const uint32_t *pkx, int *slot, const BlockMeta &meta, uint32_t nb, uint32_t nbx,
-                          uint32_t need0, uint32_t need1, uint32_t r0) {
+    auto lazy_round = [&](const uint32_t *pk, const uint32_t *pkx, int *slot, const BlockMeta &meta, const BlockMeta &metax, uint32_t nb,
+                          uint32_t nbx, uint32_t need0, uint32_t need1, uint32_t r0, bool keep_next) {
         const uint32_t n0 = __popc(need0), nnew = n0 + __popc(need1);
         if (tid < kB) {
             const bool hi = tid >= 32;
@@ -888,26 +888,27 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         grid_wait(p.bar, (++bar_gen) * p.nCTA);
         xchg(kXLazy, slot, r0, nnew, tid, kThreads, cta_sync);
         PHASE(kProfLazyBarrier);
-        // (4) read back the block-b half and standardise it into x_j . x_k (all loads of a thread in flight at once)
+        // (4) read back and standardise into x_j . x_k (all loads of a thread in flight at once): the block-b half into row slot
+        //     r of G; the block-(b+1) half, when the block's rows fit 32 slots (keep_next), into row slot 32 + r -- the carry pass
+        //     then needs no second trip to L2
         double *G = reinterpret_cast<double *>(scratch);
-        const uint32_t tot = nnew * kB;
+        const uint32_t ncol = keep_next ? uint32_t(kCols) : uint32_t(kB), csh = keep_next ? 7u : 6u;
+        const uint32_t tot = nnew * ncol;
         for (uint32_t base = 0; base < tot; base += 4 * kThreads) {
             int4 v[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const uint32_t en = base + tid + t * kThreads;
-                if (en < tot) v[t] = __ldcg(reinterpret_cast<const int4 *>(slot + kSlotLazy + (size_t(r0 + (en >> 6)) * kCols + (en & 63u)) * kLine));
+                if (en < tot) v[t] = __ldcg(reinterpret_cast<const int4 *>(slot + kSlotLazy + (size_t(r0 + (en >> csh)) * kCols + (en & (ncol - 1u))) * kLine));
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const uint32_t en = base + tid + t * kThreads;
                 if (en < tot) {
-                    const uint32_t idx = en >> 6, k = en & 63u, j = sh.lz_rows[idx];
-                    double g = 0.0;
-                    if (k != j && k < nb)
-                        g = gram_entry(meta, int(j), meta, int(k), double(unsigned(v[t].x)), double(unsigned(v[t].y)), double(unsigned(v[t].z)),
-                                       double(unsigned(v[t].w)), Nt);
-                    G[(r0 + idx) * kB + k] = g;
+                    const uint32_t idx = en >> csh, k = en & (ncol - 1u), j = sh.lz_rows[idx];
+                    const double a = double(unsigned(v[t].x)), cw = double(unsigned(v[t].y)), cy = double(unsigned(v[t].z)), cz = double(unsigned(v[t].w));
+                    if (k < uint32_t(kB)) G[(r0 + idx) * kB + k] = (k != j && k < nb) ? gram_entry(meta, int(j), meta, int(k), a, cw, cy, cz, Nt) : 0.0;
+                    else G[(32 + r0 + idx) * kB + (k - kB)] = (k - kB < nbx) ? gram_entry(meta, int(j), metax, int(k - kB), a, cw, cy, cz, Nt) : 0.0;
                 }
             }
         }
@@ -1095,6 +1096,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         // Thread k < 64 samples marker k of the block; warp 0 runs the solve for both halves.
         // Asynchronous mode: no in-block correction; the rows are only needed for the next block's carry.
         uint32_t have0 = 0, have1 = 0, lz_used = 0;             // Gram rows known so far (identical in every CTA)
+        bool g2_ok = true;                                       // all rows so far kept their block-(b+1) half in shared memory
         // A quiet block (nothing sampled away from zero) ends here for the dot warps: they go straight to the dot pass of
         // block b+2 while the walkers file the results and wait for block b+1's round; no CTA-wide barrier in between.
         if (!quiet && have_next) mbar_wait(&sh.mbar[buf ^ 1u], (bn >> 1) & 1u);   // the walkers have not observed the rows of block b+1 yet
@@ -1108,8 +1110,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 if (p.async_mode) { need0 = 0; need1 = 0; }
             }
             if (need0 | need1) {
-                lazy_round(pk, pk_next, slot, meta, nb, nb_next, need0, need1, lz_used);
-                have0 |= need0; have1 |= need1; lz_used += __popc(need0) + __popc(need1);
+                const uint32_t nnew = __popc(need0) + __popc(need1);
+                g2_ok = g2_ok && have_next && lz_used + nnew <= 32u;
+                lazy_round(pk, pk_next, slot, meta, meta_next, nb, nb_next, need0, need1, lz_used, g2_ok);
+                have0 |= need0; have1 |= need1; lz_used += nnew;
             }
             if (p.async_mode) break;
             double corr = 0.0;
@@ -1195,7 +1199,18 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         // half of the Gram rows (still in the global slot).  512 threads = 64 columns x 8 row groups, fixed-order sums:
         // every CTA computes bit-identical values.
         const uint32_t n_ns = quiet ? 0u : sh.n_ns;
-        if (n_ns && lz_used && have_next) {
+        if (n_ns && lz_used && have_next && g2_ok) {
+            if (tid < kB) {                                      // fixed order over the row slots: identical in every CTA
+                const double *G2 = reinterpret_cast<const double *>(scratch) + 32 * kB;
+                double sacc = 0.0;
+                for (uint32_t r = 0; r < lz_used; ++r) {
+                    const double dB = sh.dbeta[sh.slotrow[r]];
+                    if (dB != 0.0) sacc += dB * G2[r * kB + tid];
+                }
+                sh.carry[tid] = sacc;
+            }
+            PHASE(kProfCarry);
+        } else if (n_ns && lz_used && have_next) {
             const uint32_t kc = tid & 63u, rg = tid >> 6;
             int4 v[kB / 8];
 #pragma unroll
