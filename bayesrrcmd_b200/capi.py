@@ -269,9 +269,9 @@ class Engine:
                       "lazy_readback", "solve", "resample", "finalize", "carry", "axpy", "quantize", "tail", "prologue",
                       "walk_iters", "lazy_rounds", "lazy_rows", "blocks_updated", "worker_wait", "worker_dot",
                       "pub_reduce", "pub_missing", "pub_arrive", "lz_loop", "lz_red", "pub_pre", "lz_c0", "lz_c1", "lz_c2",
-                      "spare0", "spare1", "spare2", "spare3"]
+                      "w_dot", "w_missing", "w_combine", "spare3"]
     PROFILE_COUNTERS = ("walk_iters", "lazy_rounds", "lazy_rows", "blocks_updated")
-    PROFILE_OVERLAPPED = ("worker_wait", "worker_dot")     # timed on a dot-pass warp, concurrent with the walker phases
+    PROFILE_OVERLAPPED = ("worker_wait", "worker_dot", "w_dot", "w_missing", "w_combine")     # timed on a dot-pass warp, concurrent with the walker phases
 
     def profile_cycles(self, reset=True):
         """Phase cycle counters of the dense sweep kernel (needs BRR_GPU_PROFILE=1 at construction)."""

@@ -133,7 +133,7 @@ enum { kProfWait = 0, kProfXchg, kProfReadback, kProfSample, kProfJoin, kProfPub
        kProfWalkIters, kProfLazyRounds, kProfLazyRows, kProfBlocksUpdated, kProfWorkerWait, kProfWorkerDot,
        // finer marks inside publish and the Gram-row products (already contained in kProfPublish / kProfLazyMma)
        kProfPubReduce, kProfPubMissing, kProfPubArrive, kProfLzLoop, kProfLzRed, kProfPubPre, kProfLzC0, kProfLzC1, kProfLzC2,
-       kProfPhases = 40 };
+       kProfWDot, kProfWMissing, kProfWCombine, kProfPhases = 40 };
 
 struct alignas(16) BlockMeta {
     uint32_t id[kB];
@@ -1054,8 +1054,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 mbar_wait(&sh.mbar[buf ^ 1u], (bn >> 1) & 1u);
                 PHASE_W(kProfWorkerWait, true);
                 dot_partial(pk_next, nb_next, warp - kWalkWarps);
+                if (prof_w) { const long long t = clock64(); sh.prof[kProfWDot] += (unsigned long long)(t - t_prev); }
                 missing_sums(pk_next, nb_next, warp - kWalkWarps);
+                if (prof_w) { const long long t = clock64(); sh.prof[kProfWMissing] += (unsigned long long)(t - t_prev); }
                 dot_combine(warp - kWalkWarps);
+                if (prof_w) { const long long t = clock64(); sh.prof[kProfWCombine] += (unsigned long long)(t - t_prev); }
                 cp_async_wait_all();
                 if (uint32_t(k2) < nb_next) derive_block_meta(meta_next, k2);
                 PHASE_W(kProfWorkerDot, true);

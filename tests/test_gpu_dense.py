@@ -244,3 +244,57 @@ def test_world_gt_1_requires_attach():
     e.upload_bed(_shard_bed(pr["bed"], 0, 320)); e.finalize(); e.set_model(pr["S"])
     with pytest.raises(BrrGpuError, match="attach"):
         e.sweep(np.arange(20, dtype=np.uint32), np.zeros((20, 2)), pr["pi"], pr["sigmaG"], 0.5)
+
+
+def test_full_size_properties_n500k():
+    """At the bench's individual count (N = 500 000, one GPU; M = 1024 keeps it to seconds) the oracle is too slow to replay, so
+    the sweep is checked through size-independent properties: (1) the residual identity eps_end = eps_start + sum_j (beta_old_j -
+    beta_new_j) x_j, rebuilt marker by marker with the parity hook brr_gpu_apply_delta; (2) the sweep's sum(eps) and ||eps||^2
+    against the fetched residual; (3) the counts: v sums to the markers visited, n_nonskipped matches the beta vectors; (4) the
+    chain is bit-identical when repeated from the same inputs, and for another block size (the integer reductions do not
+    depend on the blocking)."""
+    N, M, K = 500000, 1024, 4
+    rng = np.random.default_rng(123)
+    S = np.array([[0.01, 0.001, 0.0001]])
+    y = rng.standard_normal(N); y = (y - y.mean()) / y.std(ddof=1)
+    pi = np.array([[0.7, 0.1, 0.1, 0.1]]); sigmaG = np.array([0.3]); sigmaE = 0.7
+    sweeps = [(rng.permutation(M).astype(np.uint32), np.c_[rng.random(M), rng.standard_normal(M)]) for _ in range(2)]
+
+    def run(block):
+        e = Engine(N, M, K, 1, block_markers=block)
+        e.synth_dense(7, 0.01, 0.5, False, 0.001)
+        e.finalize(); e.set_model(S)
+        e.set_state(eps=y, beta=np.zeros(M), comp=np.zeros(M), acum=np.zeros(M))
+        hist = []
+        for order, uz in sweeps:
+            b_old = e.get_state(eps=False)[1].copy()
+            v, bs, out = e.sweep(order, uz, pi, sigmaG, sigmaE)
+            eps, b_new, comp, acum = e.get_state()
+            hist.append(dict(b_old=b_old, b_new=b_new.copy(), eps=eps.copy(), comp=comp.copy(), acum=acum.copy(), v=v.copy(), bs=bs.copy(), out=out))
+        return e, hist
+
+    e, hist = run(0)
+    eps_ref = y.copy()
+    for h in hist:
+        out = h["out"]
+        assert h["v"].sum() == M
+        nonskipped = int(((h["b_old"] != 0) | (h["b_new"] != 0)).sum())
+        assert out.n_nonskipped == nonskipped and nonskipped > 0
+        assert (h["v"][0, 1:].sum() == (h["b_new"] != 0).sum())
+        assert abs(out.eps_sqnorm - (h["eps"] ** 2).sum()) <= 1e-11 * (h["eps"] ** 2).sum()
+        assert abs(out.eps_sum - h["eps"].sum()) <= 1e-9 * (1 + abs(h["eps"].sum()))
+        assert abs(h["bs"][0] - (h["b_new"] ** 2).sum()) <= 1e-12 * (1 + (h["b_new"] ** 2).sum())
+        # (1) rebuild the residual with the marker-level hook on the same store
+        e.set_state(eps=eps_ref)
+        for j in np.nonzero(h["b_old"] != h["b_new"])[0]:
+            e.apply_delta(int(j), float(h["b_old"][j]), float(h["b_new"][j]))
+        eps_ref = e.get_state(beta=False, comp=False, acum=False)[0]
+        assert np.max(np.abs(eps_ref - h["eps"])) <= 1e-9
+        e.set_state(eps=h["eps"])
+    _, hist2 = run(0)
+    _, hist3 = run(32)
+    for h, h2, h3 in zip(hist, hist2, hist3):
+        for k in ("b_new", "eps", "comp", "acum", "v", "bs"):
+            assert np.array_equal(h[k], h2[k]), k                       # (4) repeatable bit for bit
+        assert np.array_equal(h["comp"], h3["comp"]) and np.array_equal(h["v"], h3["v"])
+        assert np.max(np.abs(h["b_new"] - h3["b_new"])) <= 1e-10 and np.max(np.abs(h["eps"] - h3["eps"])) <= 1e-9
