@@ -265,6 +265,13 @@ def main():
         return
 
     peak, peak_src = measured_peak()
+    traffic = None                              # DRAM bytes of one full-size launch, from the committed ncu capture (one GPU only)
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if world == 1 and N == 500000 and M == 1000000:
+            traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        pass
     alg_bytes = ((n_loc + 3) // 4) * M                  # ceil(N_shard/4) genotype bytes per marker update
     achieved = alg_bytes / (ksum / a.steps) / 1e9
     line = {
@@ -281,9 +288,9 @@ def main():
                 "s_per_sweep": esum / a.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "sweep_dense_kernel",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "sweep_dense_kernel",
                      "algorithmic_bytes_per_launch": int(alg_bytes),
-                     "note": "dense 2-bit path is co-bounded by fp64 issue rate and per-block exchange latency (DESIGN.md)"},
+                     "note": "traffic = dram bytes of one launch (ncu, profiles/ncu_traffic.json): 1.05x the algorithmic bytes (row tails); the gap to the roofline is per-block latency, not traffic (DESIGN.md 4.1)"},
         "clocks": sampler.summary() if sampler else None,
     }
     if not a.no_cpu_baseline:
