@@ -95,6 +95,11 @@ def _random_problem(seed, N, M, p_miss, nG=1, K=4):
     (70001, 96, 0.001, 1, 4, 16, 0),   # every SM busy
     (3000, 257, 0.01, 2, 4, 16, 20),   # asynchronous, 20 tokens (reference default)
     (3000, 100, 0.0, 1, 2, 4, 0),      # K = 2
+    (2500, 640, 0.3, 3, 4, 64, 0),     # 30% missing: missing lists far beyond the 15 kept in a row's tail (rescans, long-list pairs)
+    (4000, 700, 0.05, 1, 8, 64, 0),    # K = 8 (general sampler), full blocks, carry across blocks
+    (9000, 520, 0.002, 5, 4, 48, 0),   # blocks of 48 (3 marker tiles), 5 groups
+    (3000, 400, 0.01, 2, 4, 64, 64),   # asynchronous with 64 tokens: carry only
+    (1200, 300, 0.6, 1, 3, 64, 0),     # mostly missing genotypes
 ])
 def test_sweep_matches_oracle_on_random_inputs(N, M, p_miss, nG, K, block, tokens):
     O.build()
