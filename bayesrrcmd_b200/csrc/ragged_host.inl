@@ -128,6 +128,7 @@ static int launch_ragged(brr_gpu_ctx *c)
     p.part_dot = c->part_dot; p.bar = c->bar; p.cta_red = c->cta_red;
     p.v = c->v; p.betasq = c->betasq; p.out_scalars = c->out_scalars; p.out_counts = c->out_counts;
     CUDA_TRY(cudaMemsetAsync(c->bar, 0, sizeof(unsigned) * 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->out_counts, 0, sizeof(unsigned) * 4, c->stream));      // [2] = error flags read by sweep_fetch
     void *args[] = {&p};
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
     CUDA_TRY(cudaLaunchCooperativeKernel((const void *)sweep_ragged_kernel, dim3(c->nCTA), dim3(kThreads), args, c->smem_bytes, c->stream));

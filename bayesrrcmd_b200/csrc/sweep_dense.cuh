@@ -541,6 +541,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         for (int w = 0; w < kWarps; ++w) { hi += sh.wq[w][0]; lo += sh.wq[w][1]; }
     };
     quantize();
+    __syncthreads();                 // the limbs are read by other warps right away (found by compute-sanitizer racecheck)
 
     // ---- missing-genotype side pass --------------------------------------------------------------
     // Every code row carries its missing list (count + first 15 slice-local ids) in its tail.  A warp

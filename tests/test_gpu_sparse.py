@@ -118,3 +118,25 @@ def test_upload_lists_directly_and_reject_bad_lists():
     bad = idx.copy(); bad[0], bad[1] = bad[1], bad[0]
     with pytest.raises(BrrGpuError, match="ascending"):
         e.upload_ragged(off, bad)
+
+
+def test_sparse_sweep_after_dense_contexts_were_freed():
+    """The error word of a sweep must be cleared by the launcher, not inherited from recycled device memory (a sparse sweep
+    right after dense contexts were destroyed used to report stale error flags)."""
+    import gc
+    g = Golden("missing_small")
+    chain = g.chain("dense")
+    for _ in range(3):
+        e = Engine(g.N, g.M, g.K, g.nG, layout="dense")
+        e.upload_bed(g.bed); e.finalize(); e.set_model(g.S, g.groups)
+        e.set_state(eps=chain["eps0"], beta=np.zeros(g.M), comp=np.zeros(g.M), acum=np.zeros(g.M))
+        e.sweep(chain["order"][0].astype(np.uint32), chain["rand_uz"][0], chain["pi_in"][0], chain["sigmaG_in"][0], float(chain["sigmaE_in"][0]))
+        del e
+        gc.collect()
+    for layout in ("ragged", "eigen"):
+        e = Engine(g.N, g.M, g.K, g.nG, layout=layout)
+        e.upload_bed(g.bed); e.finalize(); e.set_model(g.S, g.groups)
+        e.set_state(eps=chain["eps0"], beta=np.zeros(g.M), comp=np.zeros(g.M), acum=np.zeros(g.M))
+        v, bs, out = e.sweep(chain["order"][0].astype(np.uint32), chain["rand_uz"][0], chain["pi_in"][0], chain["sigmaG_in"][0],
+                             float(chain["sigmaE_in"][0]), float(chain["eps0"].sum()))
+        assert v.sum() == g.M
