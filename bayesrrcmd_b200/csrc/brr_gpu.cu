@@ -530,7 +530,7 @@ extern "C" int brr_gpu_sweep_fetch(brr_gpu_ctx *c, double *v, double *betasqn, b
     double *h = c->h_small;
     CUDA_TRY(cudaMemcpyAsync(h, c->v, sizeof(double) * nG * K, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(h + kMaxGK, c->betasq, sizeof(double) * nG, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(h + 2 * kMaxGK, c->out_scalars, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(h + 2 * kMaxGK, c->out_scalars, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));   // [0] = sum eps, [1] = ||eps||^2
     CUDA_TRY(cudaMemcpyAsync(c->h_counts, c->out_counts, sizeof(unsigned) * 4, cudaMemcpyDeviceToHost, c->stream));
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(BRR_GPU_ECUDA, "sweep failed: %s", cudaGetErrorString(e));
