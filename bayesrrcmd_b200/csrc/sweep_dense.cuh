@@ -658,11 +658,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             }
         }
     };
-    // sums of q over the missing individuals of the block's rows (exact: the rows' lists are in their tails): dot warp wi
-    // takes rows 4wi..4wi+3 (+56), 8 lanes per row reading up to 8 entries straight from the tail; longer lists go the
-    // general way.  Every row < nb gets its pair written.
-    auto missing_sums = [&](const uint32_t *pkn, uint32_t nbn, uint32_t wi) {
-        for (uint32_t m0 = 0; m0 + 4 * wi < nbn; m0 += 4 * kDotWarps) {      // (the second round has rows for two warps only)
+    // sums of q over the missing individuals of the block's rows (exact: the rows' lists are in their tails): group wi
+    // takes rows 4wi..4wi+3, 8 lanes per row reading up to 8 entries straight from the tail; longer lists go the
+    // general way.  Every row < nb gets its pair written.  16 groups: the 14 dot warps after their dot pass, and the two
+    // walker warps (which have slack) after sampling.
+    auto missing_sums = [&](const uint32_t *pkn, uint32_t nbn, uint32_t wi) {      // wi = row group: 0..13 the dot warps, 14..15 the walkers
+        for (uint32_t m0 = 0; m0 + 4 * wi < nbn; m0 += 4 * kWarps) {
             const uint32_t r2 = lane >> 3, e8 = lane & 7, m2 = m0 + 4 * wi + r2;
             uint32_t cnt = 0;
             long long qh = 0; unsigned long long ql = 0;
@@ -1064,6 +1065,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 if (uint32_t(k2) < nb_next) derive_block_meta(meta_next, k2);
                 PHASE_W(kProfWorkerDot, true);
             }
+        }
+        if (walker && have_next && 4u * (kDotWarps + warp) < nb_next) {   // the walkers' share of the next block's missing sums
+            mbar_wait(&sh.mbar[buf ^ 1u], (bn >> 1) & 1u);
+            missing_sums(pk_next, nb_next, kDotWarps + warp);
         }
         __syncthreads();
         PHASE(kProfJoin);
