@@ -20,7 +20,7 @@ SYMBOLS = [
     "brr_gpu_set_model", "brr_gpu_set_state", "brr_gpu_get_state", "brr_gpu_eps_add_scalar", "brr_gpu_eps_reduce",
     "brr_gpu_sweep", "brr_gpu_sweep_stage", "brr_gpu_sweep_run", "brr_gpu_sweep_fetch", "brr_gpu_compute_num",
     "brr_gpu_apply_delta", "brr_gpu_ipc_export", "brr_gpu_ipc_attach", "brr_gpu_attach_local",
-    "brr_gpu_num_blocks", "brr_gpu_stream", "brr_gpu_synth_dense", "brr_gpu_synth_bed_host", "brr_gpu_info",
+    "brr_gpu_num_blocks", "brr_gpu_stream", "brr_gpu_synth_dense", "brr_gpu_synth_ragged", "brr_gpu_synth_bed_host", "brr_gpu_info",
     "brr_gpu_launch_count", "brr_gpu_profile_cycles",
 ]
 
@@ -84,6 +84,7 @@ def load_library():
     lib.brr_gpu_stream.argtypes = [vp]
     lib.brr_gpu_stream.restype = vp
     lib.brr_gpu_synth_dense.argtypes = [vp, C.c_uint64, dbl, dbl, C.c_int, dbl, u32]
+    lib.brr_gpu_synth_ragged.argtypes = [vp, C.c_uint64, dbl, dbl, C.c_int, dbl, u32]
     lib.brr_gpu_synth_bed_host.argtypes = [C.c_uint64, dbl, dbl, C.c_int, dbl, u32, u32, u32, u32, vp]
     lib.brr_gpu_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64)]
     lib.brr_gpu_launch_count.argtypes = [vp]
@@ -173,6 +174,9 @@ class Engine:
 
     def synth_dense(self, seed, maf_lo=0.01, maf_hi=0.5, log_uniform=False, p_missing=0.001, ind_offset=0):
         self._check(self.lib.brr_gpu_synth_dense(self._h, seed, maf_lo, maf_hi, int(log_uniform), p_missing, ind_offset))
+
+    def synth_ragged(self, seed, maf_lo=0.01, maf_hi=0.5, log_uniform=False, p_missing=0.001, ind_offset=0):
+        self._check(self.lib.brr_gpu_synth_ragged(self._h, seed, maf_lo, maf_hi, int(log_uniform), p_missing, ind_offset))
 
     # model / state
     def set_model(self, cva, groups=None):

@@ -106,6 +106,73 @@ extern "C" int brr_gpu_upload_ragged_from_bed(brr_gpu_ctx *c, const uint8_t *bed
     return ragged_build_store(c, off.data(), idx.data(), nullptr);
 }
 
+// Synthetic sparse workload generated on the device (bench / scale tests): the genotypes of brr_gpu_synth_dense as index lists.
+extern "C" int brr_gpu_synth_ragged(brr_gpu_ctx *c, uint64_t seed, double maf_lo, double maf_hi, int log_uniform, double p_missing,
+                                    uint32_t ind_offset)
+{
+    CHECK_CTX(c);
+    if (!is_sparse_layout(c->cfg.layout)) return fail(BRR_GPU_ESTATE, "context layout is not ragged/eigen");
+    if (!(maf_lo > 0.0 && maf_hi <= 0.5 && maf_lo <= maf_hi) || p_missing < 0.0 || p_missing >= 1.0) return fail(BRR_GPU_EINVAL, "bad maf / missing parameters");
+    const uint32_t M = c->cfg.n_markers, nCTA = c->nCTA, SL = c->SL;
+    std::vector<uint32_t> thr(size_t(M) * 3);
+    synth_thresholds(seed, maf_lo, maf_hi, log_uniform, p_missing, 0, M, thr.data());
+    uint32_t *dthr = nullptr, *dcnt = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&dthr, size_t(M) * 3))) return rc;
+    if ((rc = dev_alloc(&dcnt, size_t(nCTA) * M * 3))) { cudaFree(dthr); return rc; }
+    auto cleanup = [&]() { cudaFree(dthr); cudaFree(dcnt); };
+    cudaError_t e = cudaMemcpyAsync(dthr, thr.data(), sizeof(uint32_t) * 3 * M, cudaMemcpyHostToDevice, c->stream);
+    const dim3 grid(nCTA, std::min<uint32_t>((M + 7) / 8, 2048));
+    if (e == cudaSuccess) {
+        synth_ragged_count_kernel<<<grid, 256, 0, c->stream>>>(seed, dthr, M, c->cfg.n_inds, ind_offset, nCTA, SL, dcnt);
+        ++c->launches;
+        e = cudaGetLastError();
+    }
+    std::vector<uint32_t> cnt(size_t(nCTA) * M * 3);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.data(), dcnt, cnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { cleanup(); return fail(BRR_GPU_ECUDA, "synthetic generation failed: %s", cudaGetErrorString(e)); }
+    // per-slice prefix sums -> seg, per-marker class counts of this shard
+    std::vector<uint32_t> seg(size_t(nCTA) * M * 4), counts(size_t(M) * 4, 0);
+    std::vector<uint64_t> base(nCTA, 0);
+    uint64_t total = 0;
+    for (uint32_t k = 0; k < nCTA; ++k) {
+        uint64_t fill = 0;
+        for (uint32_t j = 0; j < M; ++j) {
+            const uint32_t *n = &cnt[(size_t(k) * M + j) * 3];
+            uint32_t *sg = &seg[(size_t(k) * M + j) * 4];
+            sg[0] = uint32_t(fill); sg[1] = uint32_t(fill + n[0]); sg[2] = uint32_t(fill + n[0] + n[1]); sg[3] = uint32_t(fill + n[0] + n[1] + n[2]);
+            fill += uint64_t(n[0]) + n[1] + n[2];
+            counts[4 * size_t(j) + 1] += n[0]; counts[4 * size_t(j) + 2] += n[1]; counts[4 * size_t(j) + 3] += n[2];
+        }
+        if (fill >= (uint64_t(1) << 32)) { cleanup(); return fail(BRR_GPU_EINVAL, "too many entries in one slice"); }
+        base[k] = total;
+        total = (total + fill + 7) & ~uint64_t(7);
+    }
+    for (uint32_t j = 0; j < M; ++j)
+        counts[4 * size_t(j)] = c->cfg.n_inds - counts[4 * size_t(j) + 1] - counts[4 * size_t(j) + 2] - counts[4 * size_t(j) + 3];
+    RaggedStore &r = c->rag;
+    for (void *q : {(void *)r.idx16, (void *)r.seg, (void *)r.cta_base, (void *)r.stats}) if (q) cudaFree(q);
+    r.idx16 = nullptr; r.seg = nullptr; r.cta_base = nullptr; r.stats = nullptr;
+    if ((rc = dev_alloc(&r.idx16, std::max<uint64_t>(total, 1))) || (rc = dev_alloc(&r.seg, seg.size())) || (rc = dev_alloc(&r.cta_base, nCTA)) ||
+        (rc = dev_alloc(&r.stats, size_t(M) * 4))) { cleanup(); return rc; }
+    e = cudaMemcpyAsync(r.seg, seg.data(), seg.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r.cta_base, base.data(), nCTA * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->counts_local, counts.data(), counts.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        synth_ragged_fill_kernel<<<grid, 256, 0, c->stream>>>(seed, dthr, M, c->cfg.n_inds, ind_offset, nCTA, SL, r.seg, r.cta_base, r.idx16);
+        ++c->launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(BRR_GPU_ECUDA, "synthetic generation failed: %s", cudaGetErrorString(e));
+    r.n_entries = total; r.idx_bytes = std::max<uint64_t>(total, 1) * sizeof(uint16_t);
+    r.stats_given = false;
+    c->uploaded = true; c->finalized = false;
+    return 0;
+}
+
 extern "C" int brr_gpu_get_ragged_stats(brr_gpu_ctx *c, double *stats)
 {
     CHECK_CTX(c);

@@ -81,6 +81,52 @@ __global__ void synth_codes_kernel(uint64_t seed, const uint32_t *__restrict__ t
     }
 }
 
+// ---- synthetic genotypes straight into the ragged / eigen store -----------------------------------------------------
+// The same counter-based genotypes as synth_codes_kernel, as index lists.  Pass 1 counts the ones / twos / missing of
+// every (CTA slice, marker); after a per-slice prefix sum on the host (seg), pass 2 writes the slice-local 16-bit ids in
+// ascending order.  One warp per (slice, marker).
+__global__ void synth_ragged_count_kernel(uint64_t seed, const uint32_t *__restrict__ thr, uint32_t M, uint32_t n_local,
+                                          uint32_t ind_offset, uint32_t nCTA, uint32_t SL, uint32_t *__restrict__ cnt3)
+{
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const uint32_t cta = blockIdx.x;
+    for (uint32_t mk = blockIdx.y * wpb + wib; mk < M; mk += gridDim.y * wpb) {
+        const uint32_t t3[3] = {thr[3 * mk], thr[3 * mk + 1], thr[3 * mk + 2]};
+        uint32_t n1 = 0, n2 = 0, nm = 0;
+        for (uint32_t i = lane; i < SL; i += 32) {
+            const uint32_t gi = cta * SL + i;
+            const uint32_t cls = gi < n_local ? synth_class(seed, mk, ind_offset + gi, t3) : 0u;
+            n1 += cls == 1u; n2 += cls == 2u; nm += cls == 3u;
+        }
+        n1 = __reduce_add_sync(0xffffffffu, n1); n2 = __reduce_add_sync(0xffffffffu, n2); nm = __reduce_add_sync(0xffffffffu, nm);
+        if (lane == 0) { uint32_t *o = cnt3 + (size_t(cta) * M + mk) * 3; o[0] = n1; o[1] = n2; o[2] = nm; }
+    }
+}
+
+__global__ void synth_ragged_fill_kernel(uint64_t seed, const uint32_t *__restrict__ thr, uint32_t M, uint32_t n_local,
+                                         uint32_t ind_offset, uint32_t nCTA, uint32_t SL, const uint32_t *__restrict__ seg,
+                                         const uint64_t *__restrict__ cta_base, uint16_t *__restrict__ idx16)
+{
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const uint32_t cta = blockIdx.x;
+    uint16_t *dst = idx16 + cta_base[cta];
+    for (uint32_t mk = blockIdx.y * wpb + wib; mk < M; mk += gridDim.y * wpb) {
+        const uint32_t t3[3] = {thr[3 * mk], thr[3 * mk + 1], thr[3 * mk + 2]};
+        const uint32_t *sg = seg + (size_t(cta) * M + mk) * 4;
+        uint32_t pos[3] = {sg[0], sg[1], sg[2]};                 // write cursors of the ones / twos / missing lists
+        for (uint32_t i0 = 0; i0 < SL; i0 += 32) {
+            const uint32_t i = i0 + lane, gi = cta * SL + i;
+            const uint32_t cls = (i < SL && gi < n_local) ? synth_class(seed, mk, ind_offset + gi, t3) : 0u;
+#pragma unroll
+            for (uint32_t l = 0; l < 3; ++l) {
+                const unsigned m = __ballot_sync(0xffffffffu, cls == l + 1u);
+                if (cls == l + 1u) dst[pos[l] + __popc(m & ((1u << lane) - 1u))] = uint16_t(i);
+                pos[l] += __popc(m);
+            }
+        }
+    }
+}
+
 // missing lists of the rows [first_row, first_row + n_rows): one warp per row, ordered compaction
 __global__ void build_row_tails_kernel(uint32_t *__restrict__ codes, size_t first_row, size_t n_rows, uint32_t PW)
 {

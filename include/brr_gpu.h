@@ -194,6 +194,9 @@ void *brr_gpu_stream(brr_gpu_ctx *ctx);
  * (seed, marker, GLOBAL individual id) so that shards of one dataset agree. */
 int brr_gpu_synth_dense(brr_gpu_ctx *ctx, uint64_t seed, double maf_lo, double maf_hi, int log_uniform,
                         double p_missing, uint32_t ind_offset);
+/* The same genotypes straight into the ragged / eigen store (index lists built on the device). */
+int brr_gpu_synth_ragged(brr_gpu_ctx *ctx, uint64_t seed, double maf_lo, double maf_hi, int log_uniform,
+                         double p_missing, uint32_t ind_offset);
 /* The same genotypes as a host PLINK payload for markers [first, first+count) (for CPU baselines). */
 int brr_gpu_synth_bed_host(uint64_t seed, double maf_lo, double maf_hi, int log_uniform, double p_missing,
                            uint32_t n_inds, uint32_t ind_offset, uint32_t first, uint32_t count, uint8_t *bed_out);
