@@ -67,7 +67,7 @@ typedef struct {
     uint32_t n_markers;       /* M */
     uint32_t n_components;    /* K = cols(S)+1, 2..16 */
     uint32_t n_groups;        /* >= 1 */
-    uint32_t block_markers;   /* markers sampled per grid-wide exchange (0 = default 16; 1..32).  Any
+    uint32_t block_markers;   /* markers sampled per grid-wide exchange (0 = default: 64 dense, 32 sparse; 1..64 dense, 1..32 sparse).  Any
                                  value gives the SAME chain as the reference's one-by-one loop: later
                                  markers of a block are corrected with the block's Gram matrix. */
     uint32_t max_ctas;        /* 0 = one CTA per SM */

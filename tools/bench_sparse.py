@@ -16,6 +16,7 @@ ap.add_argument("--n-markers", type=int, default=100000)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--layouts", default="ragged,eigen")
+ap.add_argument("--block", type=int, default=0, help="markers per window (0 = engine default 16, max 32)")
 a = ap.parse_args()
 N, M, K = a.n_inds, a.n_markers, 4
 SEED = 20260101
@@ -33,7 +34,7 @@ def inv_scaled_chisq(rng, dof, scale):
 
 for layout in a.layouts.split(","):
     t0 = time.time()
-    e = Engine(N, M, K, 1, layout=layout)
+    e = Engine(N, M, K, 1, layout=layout, block_markers=a.block)
     e.synth_ragged(SEED, 0.001, 0.5, True, 0.001)
     e.finalize(); e.set_model(S)
     setup = time.time() - t0
@@ -77,7 +78,7 @@ for layout in a.layouts.split(","):
             "higher_is_better": True, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "synthetic %s N=%d x M=%d, MAF log-uniform [0.001,0.5], 0.1%% missing" % (layout, N, M),
                        "mean_nonzero_fraction": float(nnz.mean() / N), "index_bytes": int(e.info()["genotype_bytes"]),
-                       "nonskipped_fraction": float(np.mean(nsk)) / M, "grid_rounds_per_sweep": float(np.mean(passes)), "setup_s": setup},
+                       "window_markers": e.info()["block_markers"], "nonskipped_fraction": float(np.mean(nsk)) / M, "grid_rounds_per_sweep": float(np.mean(passes)), "setup_s": setup},
             "e2e": {"value": M * a.steps / sum(e2e), "unit": "marker updates/s"},
             "roofline": {"bound": "hbm", "achieved": alg / (ksum / a.steps) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (ksum / a.steps) / 1e9 / peak, "kernel": "sweep_ragged_kernel", "algorithmic_bytes_per_launch": alg}}
