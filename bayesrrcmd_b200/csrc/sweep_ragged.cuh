@@ -109,9 +109,18 @@ __global__ void ragged_stats_kernel(const uint32_t *__restrict__ counts, uint32_
 __device__ __forceinline__ double seg_gather_sum(const uint16_t *__restrict__ idx, uint32_t a, uint32_t b,
                                                  const double *eps_s, int lane)
 {
-    double s = 0.0;
-    for (uint32_t i = a + lane; i < b; i += 32) s += eps_s[idx[i]];
-    return warp_sum(s);
+    // eight index loads in flight per lane (the lists stream from HBM: memory-level parallelism is what bounds this loop),
+    // four partial sums in a fixed order
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    uint32_t i = a + lane;
+    for (; i + 224 < b; i += 256) {
+        const uint16_t j0 = idx[i], j1 = idx[i + 32], j2 = idx[i + 64], j3 = idx[i + 96], j4 = idx[i + 128], j5 = idx[i + 160],
+                       j6 = idx[i + 192], j7 = idx[i + 224];
+        s0 += eps_s[j0]; s1 += eps_s[j1]; s2 += eps_s[j2]; s3 += eps_s[j3];
+        s0 += eps_s[j4]; s1 += eps_s[j5]; s2 += eps_s[j6]; s3 += eps_s[j7];
+    }
+    for (; i < b; i += 32) s0 += eps_s[idx[i]];
+    return warp_sum((s0 + s1) + (s2 + s3));
 }
 
 __global__ void __launch_bounds__(kThreads, 1) sweep_ragged_kernel(const RaggedSweepParams p)
