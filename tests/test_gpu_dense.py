@@ -303,3 +303,36 @@ def test_full_size_properties_n500k():
             assert np.array_equal(h[k], h2[k]), k                       # (4) repeatable bit for bit
         assert np.array_equal(h["comp"], h3["comp"]) and np.array_equal(h["v"], h3["v"])
         assert np.max(np.abs(h["b_new"] - h3["b_new"])) <= 1e-10 and np.max(np.abs(h["eps"] - h3["eps"])) <= 1e-9
+
+
+def test_replay_reference_chain_at_n500k():
+    """Tier 2 at the bench's individual count: the REFERENCE ITSELF (oracle/_ref, built from the reference's sources) runs two
+    Gibbs sweeps over N = 500 000 individuals x 96 markers of the bench's synthetic data set; the GPU sweep replays each of them
+    from the recorded inputs (residual, betas, order, (u, z), pi, sigmaG, sigmaE) and must land on the reference's betas,
+    components, acum and residual within 1e-8."""
+    import ref_lib as R
+    from bayesrrcmd_b200.capi import synth_bed_host
+    if not R.ref_available():
+        pytest.skip("oracle/_ref is not built")
+    N, M = 500000, 96
+    S = np.array([[0.01, 0.001, 0.0001]])
+    bed = synth_bed_host(20260101, N, 0, M, p_missing=0.001)
+    rng = np.random.default_rng(5)
+    y = rng.standard_normal(N).astype(np.float32)
+    arr, _ = R.run_chain(bed, N, M, y, S, seed=3, iterations=2, layout=0)
+    e = Engine(N, M, 4, 1)
+    e.upload_bed(bed); e.finalize(); e.set_model(S)
+    comp_in = np.zeros(M)
+    for it in range(2):
+        e.set_state(eps=arr["eps_in"][it], beta=arr["beta_in"][it], comp=comp_in, acum=np.zeros(M))
+        v, bs, out = e.sweep(arr["order"][it].astype(np.uint32), arr["rand_uz"][it], arr["pi_in"][it], arr["sigmaG_in"][it],
+                             float(arr["sigmaE_in"][it]))
+        eps, beta, comp, acum = e.get_state()
+        assert np.array_equal(comp, arr["comp_out"][it])
+        assert np.array_equal(v, arr["v_out"][it])
+        for got, ref, what in ((beta, arr["beta_out"][it], "beta"), (acum, arr["acum_out"][it], "acum"), (eps, arr["eps_out"][it], "eps"),
+                               (bs, arr["betasq_out"][it], "betasqnG")):
+            err = np.max(np.abs(got - ref) / (1.0 + np.abs(ref)))
+            assert err <= 1e-8, "%s differs at iteration %d: %.3e" % (what, it, err)
+        assert (arr["beta_out"][it] != 0).sum() > 0
+        comp_in = arr["comp_out"][it]
