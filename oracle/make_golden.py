@@ -154,6 +154,13 @@ def main():
     bed2 = R.read_bed(d + "data.bed", N2, M2)
     y2 = R.read_phen(d + "data.phen", ids)
     cols2 = np.arange(0, M2, 37)
+    # S2 long: 300 iterations of the reference chain on test.gauss, posterior summaries only (tier 3: agreement within Monte Carlo error)
+    arr, _ = R.run_chain(bed2, N2, M2, y2, S, seed=11, iterations=300, layout=0)
+    np.savez_compressed(os.path.join(OUT, "gauss_long.npz"), N=N2, M=M2, S=S, seed=11, iterations=300, burn_in=100, bed_from="gauss", y=y2,
+                        mu=arr["mu"], sigmaE=arr["sigmaE_post"], sigmaG=arr["sigmaG_post"][:, 0], m0=arr["v_out"][:, 0, 1:].sum(axis=1),
+                        beta2=(arr["beta_out"] ** 2).sum(axis=1), beta_mean=arr["beta_out"][100:].mean(axis=0),
+                        pip=(arr["comp_out"][100:] != 0).mean(axis=0).astype(np.float32))
+    del arr
     save("gauss", bed=bed2, y=y2, S=S, N=N2, M=M2, seed=1,
          dense=chain_record(bed2, N2, M2, y2, S, 1, 10, 0),
          tier1=tier1_record(bed2, N2, cols2, standardise(y2), rng))

@@ -155,3 +155,39 @@ def test_async_chain_runs(built, tmp_path):
     rows = np.loadtxt(out, delimiter=",", skiprows=1, ndmin=2)
     assert rows.shape == (2, 2 + g.M + 1 + g.nG + 2 * g.M) and list(rows[:, 0]) == [10, 15]
     assert np.isfinite(rows).all() and (rows[:, 2 + g.M] > 0).all()
+
+
+@pytest.mark.gpu
+def test_posterior_on_test_gauss_agrees_with_the_reference_chain(built, tmp_path):
+    """Tier 3 (BASELINE.json north_star): posterior summaries of a 300-iteration ppbayes chain on test.gauss (burn-in 100) against
+    the reference's own chain from the same seed (tests/golden/gauss_long.npz, made by oracle/make_golden.py).  The chains start
+    identical; floating-point differences may eventually flip a draw, after which they are two samples of the same posterior,
+    so the gate is agreement within Monte Carlo error (a fraction of the posterior sd) -- and it reports how long they stayed
+    identical."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "gauss_long.npz"))
+    g = Golden("gauss")
+    base = write_plink(g, str(tmp_path))
+    out = str(tmp_path / "samples.csv")
+    iters, burn = int(z["iterations"]), int(z["burn_in"])
+    r = run(built, ["--analysis-type", "ppbayes", "--data-file", base + ".bed", "--pheno", base + ".phen", "--chain-length", str(iters),
+                    "--burn-in", "0", "--thin", "1", "--seed", str(int(z["seed"])), "--S", ",".join("%.17g" % s for s in g.S[0]),
+                    "--mcmc-samples", out, "--sample-precision", "12", "--no-epsilon"])
+    assert r.returncode == 0, r.stderr + r.stdout
+    M = g.M
+    cols = [0, 1, 2 + M, 3 + M]                                  # iteration, mu, sigmaE, sigmaG[1]
+    data = np.loadtxt(out, delimiter=",", skiprows=1, usecols=cols, ndmin=2)
+    assert data.shape[0] == iters
+    mu, sigmaE, sigmaG = data[:, 1], data[:, 2], data[:, 3]
+    same = np.abs(sigmaE - z["sigmaE"]) <= 1e-8 * (1 + np.abs(z["sigmaE"]))
+    n_same = iters if same.all() else int(np.argmin(same))
+    print("chains identical (1e-8) for the first %d of %d iterations" % (n_same, iters))
+    assert n_same >= 10
+    for name, got, ref in (("sigmaE", sigmaE, z["sigmaE"]), ("sigmaG", sigmaG, z["sigmaG"]), ("mu", mu, z["mu"])):
+        gm, rm, sd = got[burn:].mean(), ref[burn:].mean(), max(ref[burn:].std(), 1e-12)
+        assert abs(gm - rm) <= 0.5 * sd, "%s: posterior mean %.6g vs reference %.6g (posterior sd %.3g)" % (name, gm, rm, sd)
+    # effect sizes: posterior-mean betas of the last 200 iterations
+    beta = np.loadtxt(out, delimiter=",", skiprows=1 + burn, usecols=range(2, 2 + M), ndmin=2).mean(axis=0)
+    ref = z["beta_mean"]
+    assert abs((beta ** 2).sum() - (ref ** 2).sum()) <= 0.5 * max((ref ** 2).sum(), 1e-12) + 1e-6
+    top = np.argsort(-np.abs(ref))[:20]
+    assert np.corrcoef(beta[top], ref[top])[0, 1] > 0.5 or n_same == iters
