@@ -197,8 +197,8 @@ def _shard_bed(bed, lo, hi):
     return np.ascontiguousarray(bed[:, lo // 4:(hi + 3) // 4])
 
 
-@pytest.mark.parametrize("world,N,M,p_miss,block", [(2, 3000, 150, 0.01, 64), (3, 5000, 100, 0.0, 16)])
-def test_sharded_individuals_exchange_on_one_device(world, N, M, p_miss, block):
+@pytest.mark.parametrize("world,N,M,p_miss,block,tokens", [(2, 3000, 150, 0.01, 64, 0), (3, 5000, 100, 0.0, 16, 0), (2, 4000, 300, 0.02, 64, 20)])
+def test_sharded_individuals_exchange_on_one_device(world, N, M, p_miss, block, tokens):
     """The in-kernel cross-shard exchange (the multi-GPU path) with all shards on ONE device: the kernels of
     the shards run concurrently on their own streams and exchange through 'peer' pointers that happen to be
     local.  The chain must be BIT-identical to the unsharded one (the cross-shard sums are integers)."""
@@ -225,9 +225,9 @@ def test_sharded_individuals_exchange_on_one_device(world, N, M, p_miss, block):
     for sweep_i in range(3):
         order = rng.permutation(M).astype(np.uint32)
         rand_uz = np.c_[rng.random(M), rng.normal(size=M)]
-        v0, bs0, out0 = ref.sweep(order, rand_uz, pr["pi"], pr["sigmaG"], pr["sigmaE"])
+        v0, bs0, out0 = ref.sweep(order, rand_uz, pr["pi"], pr["sigmaG"], pr["sigmaE"], 0.0, tokens)
         for e in shards:
-            e.sweep_stage(order, rand_uz, pr["pi"], pr["sigmaG"], pr["sigmaE"])
+            e.sweep_stage(order, rand_uz, pr["pi"], pr["sigmaG"], pr["sigmaE"], 0.0, tokens)
         for e in shards:
             e.sweep_run()                      # asynchronous: all shards must be in flight together
         res = [e.sweep_fetch() for e in shards]
