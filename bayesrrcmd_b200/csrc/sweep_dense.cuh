@@ -662,8 +662,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     // takes rows 4wi..4wi+3, 8 lanes per row reading up to 8 entries straight from the tail; longer lists go the
     // general way.  Every row < nb gets its pair written.  16 groups: the 14 dot warps after their dot pass, and the two
     // walker warps (which have slack) after sampling.
+    // (with several GPUs the walkers carry the cross-GPU exchange and are the critical chain: the dot warps then take all groups)
+    const uint32_t miss_groups = p.world > 1 ? uint32_t(kDotWarps) : uint32_t(kWarps);
     auto missing_sums = [&](const uint32_t *pkn, uint32_t nbn, uint32_t wi) {      // wi = row group: 0..13 the dot warps, 14..15 the walkers
-        for (uint32_t m0 = 0; m0 + 4 * wi < nbn; m0 += 4 * kWarps) {
+        for (uint32_t m0 = 0; m0 + 4 * wi < nbn; m0 += 4 * miss_groups) {
             const uint32_t r2 = lane >> 3, e8 = lane & 7, m2 = m0 + 4 * wi + r2;
             uint32_t cnt = 0;
             long long qh = 0; unsigned long long ql = 0;
@@ -1066,7 +1068,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 PHASE_W(kProfWorkerDot, true);
             }
         }
-        if (walker && have_next && 4u * (kDotWarps + warp) < nb_next) {   // the walkers' share of the next block's missing sums
+        if (walker && have_next && p.world == 1 && 4u * (kDotWarps + warp) < nb_next) {   // the walkers' share of the next block's missing sums
             mbar_wait(&sh.mbar[buf ^ 1u], (bn >> 1) & 1u);
             missing_sums(pk_next, nb_next, kDotWarps + warp);
         }
