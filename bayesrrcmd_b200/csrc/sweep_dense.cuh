@@ -58,6 +58,7 @@ constexpr int kScratchInts = 8192;     // 32 KB shared scratch: dot partials of 
 constexpr int kHeadroomBits = 6;       // |eps| may grow 64x inside a sweep before the fixed point overflows
 constexpr int kWalkWarps = 2;          // warps 0,1: barrier wait, read-back, sampling
 constexpr int kDotWarps = kWarps - kWalkWarps;   // warps 2..15: dot pass of the next block, TMA issue
+static_assert(kDotWarps == 14, "dot_partial / dot_combine split the four marker tiles over 4+4+3+3 dot warps");
 constexpr int kTmaLanes = 5;           // rows each dot warp requests per block (14 x 5 >= 64).  One warp issuing all 64 bulk
                                        // copies takes ~3400 cycles (measured, tools/latency_bench2.cu); spread like this ~700.
 
@@ -204,6 +205,21 @@ __device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, 
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// shared-memory loads by 32-bit address with an immediate byte offset: the MMA loops keep three address registers and bump them,
+// nothing else (the compiler's own addressing of these loops re-derived the addresses from tid every iteration: ~45 of ~85
+// instructions, and the passes are bound by instruction issue)
+template <int OFF> __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF> __device__ __forceinline__ uint4 lds_v4(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(OFF));
+    return v;
 }
 __device__ __forceinline__ void fence_proxy_async()
 {
@@ -606,44 +622,61 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     // done by the 14 dot warps right after their pass instead of in the publish.
     int *dot_acc = scratch;
     unsigned long long *msum = reinterpret_cast<unsigned long long *>(scratch + 512);
-    int *dot_part = scratch + 1024;                  // [kDotWarps][512]
+    int *dot_part = scratch + 1024;                  // [kDotWarps][128]: a dot warp's partial sums of its tile
 
     // ---- dot pass of one block: S[m][l] = sum_i g'_mi * limb_l(q_i) ---------------------------------------------
-    // Work items = (marker tile mi, word pair wp): a word pair is two 64-individual k-steps; dot warp `wi` takes the word
-    // pairs wi, wi + 14, ... of every tile.  One item = four MMAs, one per code class (kC0..kC3), each fed by the class-c
-    // bytes of the lane's two code words of both rows (A) and the class-c limb bytes of the same individuals (B): four
-    // independent chains, 16 LOP3 and no shift per item.  The warp's 64 x 8 partial sums go to its region of the scratch.
+    // Work items = (marker tile mi, word pair wp): a word pair is two 64-individual k-steps.  Dot warp `wi` works on ONE tile,
+    // mi = wi & 3 (tiles 0,1 have four warps, tiles 2,3 three), and takes every n_t-th word pair of it: one address set-up
+    // and one epilogue per warp and block instead of four (these passes are bound by the per-warp instruction chain, not
+    // by the tensor pipe), and only 3-4 partials per output to combine.  One item = four MMAs, one per code class
+    // (kC0..kC3), each fed by the class-c bytes of the lane's two code words of both rows (A) and the class-c limb bytes of
+    // the same individuals (B): four independent chains, 16 LOP3 and no shift per item.  The operands of the next item are
+    // loaded before the MMAs of the current one are issued (software pipeline by hand: the compiler does not).
     auto dot_partial = [&](const uint32_t *pk, uint32_t nb, uint32_t wi) {
-        const uint32_t NW2 = (NP + 1) / 2;
+        const uint32_t NF = NP / 2;                                        // full word pairs; an odd NP leaves a half pair behind them
+        const uint32_t mi = wi & 3u, r = wi >> 2, n_t = (mi < 2u) ? 4u : 3u;
         const uint32_t lo = gid * RS + tig;
-        const uint4 *limp = limbs + lo;
-#pragma unroll 1
-        for (uint32_t mi = 0; mi < 4; ++mi) {
-            int acc[4][4];
+        int acc[4][4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { acc[c][0] = 0; acc[c][1] = 0; acc[c][2] = 0; acc[c][3] = 0; }
-            if (16u * mi < nb) {
-                const uint32_t *r0p = pk + size_t(16 * mi) * RS + lo, *r1p = r0p + 8 * RS;
-                for (uint32_t wp = wi; wp < NW2; wp += kDotWarps) {
-                    const uint32_t oA = 8 * wp, oB = oA + 4;
-                    const bool hasB = 2 * wp + 1 < NP;
-                    const uint4 LA = limp[oA];
-                    const uint32_t a0 = r0p[oA], a1 = r1p[oA];
-                    uint4 LB = make_uint4(0u, 0u, 0u, 0u);
-                    uint32_t b0 = 0u, b1 = 0u;
-                    if (hasB) { LB = limp[oB]; b0 = r0p[oB]; b1 = r1p[oB]; }
+        for (int c = 0; c < 4; ++c) { acc[c][0] = 0; acc[c][1] = 0; acc[c][2] = 0; acc[c][3] = 0; }
+        if (16u * mi < nb) {
+            uint32_t aR0 = smem_u32(pk + size_t(16 * mi) * RS + lo + 8 * r);       // row gid of the tile, this lane's word of pair r
+            const uint32_t dR1 = 32u * RS;                                         // row gid + 8 (bytes)
+            uint32_t aL = smem_u32(limbs + lo + 8 * r);
+            const uint32_t stepA = 32u * n_t, stepL = 128u * n_t;
+            uint32_t cnt = NF > r ? (mi < 2u ? (NF - r + 3u) >> 2 : (NF - r + 2u) / 3u) : 0u;   // n_t is 3 or 4: no runtime division
+            if (cnt) {
+                uint4 LA = lds_v4<0>(aL), LB = lds_v4<64>(aL);
+                uint32_t a0 = lds_u32<0>(aR0), a1 = lds_u32<0>(aR0 + dR1), b0 = lds_u32<16>(aR0), b1 = lds_u32<16>(aR0 + dR1);
+#pragma unroll 1
+                for (;;) {
+                    const bool more = --cnt != 0u;
+                    if (more) { aR0 += stepA; aL += stepL; }                       // the last item re-loads itself (dropped)
+                    const uint4 LAn = lds_v4<0>(aL), LBn = lds_v4<64>(aL);
+                    const uint32_t a0n = lds_u32<0>(aR0), a1n = lds_u32<0>(aR0 + dR1), b0n = lds_u32<16>(aR0), b1n = lds_u32<16>(aR0 + dR1);
                     mma_u8s8(acc[0], a0 & kC0, a1 & kC0, b0 & kC0, b1 & kC0, LA.x, LB.x);
                     mma_u8s8(acc[1], a0 & kC1, a1 & kC1, b0 & kC1, b1 & kC1, LA.y, LB.y);
                     mma_u8s8(acc[2], a0 & kC2, a1 & kC2, b0 & kC2, b1 & kC2, LA.z, LB.z);
                     mma_u8s8(acc[3], a0 & kC3, a1 & kC3, b0 & kC3, b1 & kC3, LA.w, LB.w);
+                    if (!more) break;
+                    LA = LAn; LB = LBn; a0 = a0n; a1 = a1n; b0 = b0n; b1 = b1n;
                 }
             }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                dot_part[wi * 512 + (mi * 4 + r) * 32 + lane] = acc[0][r] + (acc[1][r] >> 2) + (acc[2][r] >> 4) + (acc[3][r] >> 6);
+            if ((NP & 1u) && (mi < 2u ? (NF & 3u) : NF % 3u) == r) {                                      // the half pair at the end of the slice
+                const uint32_t *r0p = pk + size_t(16 * mi) * RS + lo + 8 * NF;
+                const uint4 LA = limbs[lo + 8 * NF];
+                const uint32_t a0 = r0p[0], a1 = r0p[8 * RS];
+                mma_u8s8(acc[0], a0 & kC0, a1 & kC0, 0u, 0u, LA.x, 0u);
+                mma_u8s8(acc[1], a0 & kC1, a1 & kC1, 0u, 0u, LA.y, 0u);
+                mma_u8s8(acc[2], a0 & kC2, a1 & kC2, 0u, 0u, LA.z, 0u);
+                mma_u8s8(acc[3], a0 & kC3, a1 & kC3, 0u, 0u, LA.w, 0u);
+            }
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            dot_part[wi * 128 + q * 32 + lane] = acc[0][q] + (acc[1][q] >> 2) + (acc[2][q] >> 4) + (acc[3][q] >> 6);
     };
-    // ... and, once all dot warps have stored theirs (a barrier among them), the sums over the warps
+    // ... and, once all dot warps have stored theirs (a barrier among them), the sums over the warps of each tile
     auto dot_combine = [&](uint32_t wi) {
         asm volatile("bar.sync 3, %0;" ::"n"(32 * kDotWarps) : "memory");
         const uint32_t o = wi * 32 + lane;               // 448 threads, 512 outputs
@@ -651,9 +684,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         for (int h = 0; h < 2; ++h) {
             const uint32_t oo = o + h * 32 * kDotWarps;
             if (oo < 512) {
-                int sacc = 0;
-#pragma unroll
-                for (int w = 0; w < kDotWarps; ++w) sacc += dot_part[w * 512 + oo];
+                const uint32_t mi = oo >> 7, e7 = oo & 127u;
+                int sacc = dot_part[mi * 128 + e7] + dot_part[(4 + mi) * 128 + e7] + dot_part[(8 + mi) * 128 + e7];
+                if (mi < 2u) sacc += dot_part[(12 + mi) * 128 + e7];
                 dot_acc[oo] = sacc;
             }
         }
