@@ -691,51 +691,53 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             }
         }
     };
-    // sums of q over the missing individuals of the block's rows (exact: the rows' lists are in their tails): group wi
-    // takes rows 4wi..4wi+3, 8 lanes per row reading up to 8 entries straight from the tail; longer lists go the
-    // general way.  Every row < nb gets its pair written.  16 groups: the 14 dot warps after their dot pass, and the two
-    // walker warps (which have slack) after sampling.
-    // (with several GPUs the walkers carry the cross-GPU exchange and are the critical chain: the dot warps then take all groups)
-    const uint32_t miss_groups = p.world > 1 ? uint32_t(kDotWarps) : uint32_t(kWarps);
-    auto missing_sums = [&](const uint32_t *pkn, uint32_t nbn, uint32_t wi) {      // wi = row group: 0..13 the dot warps, 14..15 the walkers
-        for (uint32_t m0 = 0; m0 + 4 * wi < nbn; m0 += 4 * miss_groups) {
-            const uint32_t r2 = lane >> 3, e8 = lane & 7, m2 = m0 + 4 * wi + r2;
-            uint32_t cnt = 0;
-            long long qh = 0; unsigned long long ql = 0;
-            if (m2 < nbn) {
-                const uint16_t *tail = reinterpret_cast<const uint16_t *>(pkn + size_t(m2) * RS + PW);
-                cnt = tail[0];
-                if (cnt <= 8 && e8 < cnt) {
-                    const uint32_t i = tail[1 + e8];
-                    const uint32_t w = i >> 4, c = i & 3u, t = (i >> 2) & 3u;
-                    const uint32_t *lw = reinterpret_cast<const uint32_t *>(limbs) + c;
-                    unsigned long long uq = 0;
+    // sums of q over the missing individuals of the block's rows (exact: the rows' lists are in their tails): row group rg
+    // takes rows 8rg..8rg+7, 4 lanes per row, lane e4 the entries e4, e4+4, ... of the tail's list (<= 15 entries); longer
+    // lists go the general way.  Every row < nb gets its pair written.  The 8 groups are taken by the 8 dot warps of marker
+    // tiles 0 and 1 (7 dot items each against the 9 of the other six warps) right after their dot pass.
+    auto missing_sums = [&](const uint32_t *pkn, uint32_t nbn, uint32_t rg) {
+        const uint32_t r8 = lane >> 2, e4 = lane & 3u, m2 = 8 * rg + r8;
+        uint32_t cnt = 0;
+        long long qh = 0; unsigned long long ql = 0;
+        if (m2 < nbn) {
+            const uint16_t *tail = reinterpret_cast<const uint16_t *>(pkn + size_t(m2) * RS + PW);
+            cnt = tail[0];
+            if (cnt <= 15u) {
+#pragma unroll 1
+                for (uint32_t en = e4; en < cnt; en += 4) {
+                    const uint32_t i = tail[1 + en];
+                    // limb byte l of individual i: word (l*RS + i/16)*4 + i%4 of the limb array, byte (i/4)%4
+                    const uint8_t *lb = reinterpret_cast<const uint8_t *>(limbs) + ((i >> 4) * 4 + (i & 3u)) * 4 + ((i >> 2) & 3u);
+                    uint32_t ulo = 0, uhi = 0;
 #pragma unroll
-                    for (int l = 0; l < kLimbs; ++l)
-                        uq |= (unsigned long long)((lw[(size_t(l) * RS + w) * 4] >> (8 * t)) & 0xffu) << (8 * l);
-                    const long long q = (long long)((uq ^ 0x8080808080808080ULL) - 0x8080808080808080ULL);
-                    qh = q >> 32; ql = (unsigned long long)(q & 0xffffffffLL);
-                }
-            }
-#pragma unroll
-            for (int o2 = 1; o2 < 8; o2 <<= 1) {
-                qh += __shfl_xor_sync(0xffffffffu, qh, o2);
-                ql += __shfl_xor_sync(0xffffffffu, ql, o2);
-            }
-            if (e8 == 0 && m2 < nbn && cnt <= 8) { msum[2 * m2] = (unsigned long long)qh; msum[2 * m2 + 1] = ql; }
-            const unsigned big = __ballot_sync(0xffffffffu, cnt > 8);
-            for (int r3 = 0; r3 < 4; ++r3)
-                if (big & (1u << (8 * r3))) {
-                    const uint32_t m3 = m0 + 4 * wi + r3;
-                    long long shi = 0; unsigned long long slo = 0;
-                    for_missing_chunks(pkn + size_t(m3) * RS, [&](const uint32_t *ent, uint32_t n) { missing_q_sum(ent, n, shi, slo); });
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        shi += __shfl_xor_sync(0xffffffffu, shi, o);
-                        slo += __shfl_xor_sync(0xffffffffu, slo, o);
+                    for (int l = 0; l < 4; ++l) {
+                        ulo |= uint32_t(lb[size_t(l) * RS * 16]) << (8 * l);
+                        uhi |= uint32_t(lb[size_t(4 + l) * RS * 16]) << (8 * l);
                     }
-                    if (lane == 0) { msum[2 * m3] = (unsigned long long)shi; msum[2 * m3 + 1] = slo; }
+                    const unsigned long long uq = (unsigned long long)ulo | ((unsigned long long)uhi << 32);
+                    const long long q = (long long)((uq ^ 0x8080808080808080ULL) - 0x8080808080808080ULL);
+                    qh += q >> 32; ql += (unsigned long long)(q & 0xffffffffLL);
                 }
+            }
+        }
+#pragma unroll
+        for (int o2 = 1; o2 < 4; o2 <<= 1) {
+            qh += __shfl_xor_sync(0xffffffffu, qh, o2);
+            ql += __shfl_xor_sync(0xffffffffu, ql, o2);
+        }
+        if (e4 == 0 && m2 < nbn && cnt <= 15u) { msum[2 * m2] = (unsigned long long)qh; msum[2 * m2 + 1] = ql; }
+        unsigned big = __ballot_sync(0xffffffffu, cnt > 15u && e4 == 0);
+        while (big) {
+            const uint32_t m3 = 8 * rg + uint32_t(__ffs(big) - 1) / 4u;
+            big &= big - 1;
+            long long shi = 0; unsigned long long slo = 0;
+            for_missing_chunks(pkn + size_t(m3) * RS, [&](const uint32_t *ent, uint32_t n) { missing_q_sum(ent, n, shi, slo); });
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                shi += __shfl_xor_sync(0xffffffffu, shi, o);
+                slo += __shfl_xor_sync(0xffffffffu, slo, o);
+            }
+            if (lane == 0) { msum[2 * m3] = (unsigned long long)shi; msum[2 * m3 + 1] = slo; }
         }
     };
     // Publish block bn's sums (limb sums, sums over the missing individuals, the slice's sum of q) into the block's global
@@ -864,31 +866,46 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         //     pass; per word pair four MMAs, one per code class, fed by in-place class bytes of both operands (16^c scaling).
         {
             const uint32_t mt = warp & 7u, kh = warp >> 3;
-            const uint32_t NW2 = (NP + 1) / 2;
+            const uint32_t NF = NP / 2;                                        // full word pairs (see dot_partial)
             const uint32_t first_row = need0 ? uint32_t(__ffs(need0) - 1) : 32u + uint32_t(__ffs(need1) - 1);   // its own column and all before it are not needed
             const bool mt_ok = (mt < 4) ? (16 * mt < nb && 16 * mt + 15 > first_row) : (16 * (mt - 4) < nbx);
             const uint32_t *c0p = ((mt < 4) ? pk + size_t(16 * mt) * RS : pkx + size_t(16 * (mt - 4)) * RS) + gid * RS + tig;
-            const uint32_t *c1p = c0p + 8 * RS;
+            const uint32_t dC1 = 32u * RS;                                     // row gid + 8 (bytes)
             int *sc2 = reinterpret_cast<int *>(miss_list);
             for (uint32_t g0 = 0; g0 * 8 < nnew; ++g0) {
                 const uint32_t i0 = g0 * 8 + gid;
                 const bool v0 = i0 < nnew;
                 const uint32_t *u0p = pk + size_t(v0 ? sh.lz_rows[i0] : 0u) * RS + tig;
+                const uint32_t m0 = v0 ? kC0 : 0u, m1 = v0 ? kC1 : 0u, m2 = v0 ? kC2 : 0u, m3 = v0 ? kC3 : 0u;   // an empty row slot feeds zeros
                 int acc[4][4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) { acc[c][0] = 0; acc[c][1] = 0; acc[c][2] = 0; acc[c][3] = 0; }
                 if (mt_ok) {
-                    for (uint32_t wp = kh; wp < NW2; wp += 2) {
-                        const uint32_t oA = 8 * wp, oB = oA + 4;
-                        const bool hasB = 2 * wp + 1 < NP;
-                        const uint32_t a0 = c0p[oA], a1 = c1p[oA];
-                        const uint32_t uA = v0 ? u0p[oA] : 0u;
-                        uint32_t b0 = 0u, b1 = 0u, uB = 0u;
-                        if (hasB) { b0 = c0p[oB]; b1 = c1p[oB]; uB = v0 ? u0p[oB] : 0u; }
-                        mma_u8u8(acc[0], a0 & kC0, a1 & kC0, b0 & kC0, b1 & kC0, uA & kC0, uB & kC0);
-                        mma_u8u8(acc[1], a0 & kC1, a1 & kC1, b0 & kC1, b1 & kC1, uA & kC1, uB & kC1);
-                        mma_u8u8(acc[2], a0 & kC2, a1 & kC2, b0 & kC2, b1 & kC2, uA & kC2, uB & kC2);
-                        mma_u8u8(acc[3], a0 & kC3, a1 & kC3, b0 & kC3, b1 & kC3, uA & kC3, uB & kC3);
+                    uint32_t aC = smem_u32(c0p + 8 * kh), aU = smem_u32(u0p + 8 * kh);
+                    uint32_t cnt = NF > kh ? (NF - kh + 1u) >> 1 : 0u;
+                    if (cnt) {
+                        uint32_t a0 = lds_u32<0>(aC), a1 = lds_u32<0>(aC + dC1), b0 = lds_u32<16>(aC), b1 = lds_u32<16>(aC + dC1);
+                        uint32_t uA = lds_u32<0>(aU), uB = lds_u32<16>(aU);
+#pragma unroll 1
+                        for (;;) {
+                            const bool more = --cnt != 0u;
+                            if (more) { aC += 64u; aU += 64u; }                    // the last item re-loads itself (dropped)
+                            const uint32_t a0n = lds_u32<0>(aC), a1n = lds_u32<0>(aC + dC1), b0n = lds_u32<16>(aC), b1n = lds_u32<16>(aC + dC1);
+                            const uint32_t uAn = lds_u32<0>(aU), uBn = lds_u32<16>(aU);
+                            mma_u8u8(acc[0], a0 & kC0, a1 & kC0, b0 & kC0, b1 & kC0, uA & m0, uB & m0);
+                            mma_u8u8(acc[1], a0 & kC1, a1 & kC1, b0 & kC1, b1 & kC1, uA & m1, uB & m1);
+                            mma_u8u8(acc[2], a0 & kC2, a1 & kC2, b0 & kC2, b1 & kC2, uA & m2, uB & m2);
+                            mma_u8u8(acc[3], a0 & kC3, a1 & kC3, b0 & kC3, b1 & kC3, uA & m3, uB & m3);
+                            if (!more) break;
+                            a0 = a0n; a1 = a1n; b0 = b0n; b1 = b1n; uA = uAn; uB = uBn;
+                        }
+                    }
+                    if ((NP & 1u) && (NF & 1u) == kh) {                            // the half pair at the end of the slice
+                        const uint32_t a0 = c0p[8 * NF], a1 = c0p[8 * NF + 8 * RS], uA = u0p[8 * NF];
+                        mma_u8u8(acc[0], a0 & kC0, a1 & kC0, 0u, 0u, uA & m0, 0u);
+                        mma_u8u8(acc[1], a0 & kC1, a1 & kC1, 0u, 0u, uA & m1, 0u);
+                        mma_u8u8(acc[2], a0 & kC2, a1 & kC2, 0u, 0u, uA & m2, 0u);
+                        mma_u8u8(acc[3], a0 & kC3, a1 & kC3, 0u, 0u, uA & m3, 0u);
                     }
                 }
                 int val[4];
@@ -1092,7 +1109,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 PHASE_W(kProfWorkerWait, true);
                 dot_partial(pk_next, nb_next, warp - kWalkWarps);
                 if (prof_w) { const long long t = clock64(); sh.prof[kProfWDot] += (unsigned long long)(t - t_prev); }
-                missing_sums(pk_next, nb_next, warp - kWalkWarps);
+                { const uint32_t wi = warp - kWalkWarps; if ((wi & 3u) < 2u) missing_sums(pk_next, nb_next, (wi >> 2) * 2 + (wi & 1u)); }
                 if (prof_w) { const long long t = clock64(); sh.prof[kProfWMissing] += (unsigned long long)(t - t_prev); }
                 dot_combine(warp - kWalkWarps);
                 if (prof_w) { const long long t = clock64(); sh.prof[kProfWCombine] += (unsigned long long)(t - t_prev); }
@@ -1100,10 +1117,6 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 if (uint32_t(k2) < nb_next) derive_block_meta(meta_next, k2);
                 PHASE_W(kProfWorkerDot, true);
             }
-        }
-        if (walker && have_next && p.world == 1 && 4u * (kDotWarps + warp) < nb_next) {   // the walkers' share of the next block's missing sums
-            mbar_wait(&sh.mbar[buf ^ 1u], (bn >> 1) & 1u);
-            missing_sums(pk_next, nb_next, kDotWarps + warp);
         }
         __syncthreads();
         PHASE(kProfJoin);
