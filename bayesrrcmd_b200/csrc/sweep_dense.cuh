@@ -37,6 +37,7 @@
 //   Asynchronous mode (bounded staleness, src/BayesRBase.cpp:394-523 under src/parallelgraph.cpp):
 //   same pipeline with B = tokens and no Gram correction.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "sampler.cuh"
 
@@ -59,6 +60,7 @@ constexpr int kHeadroomBits = 6;       // |eps| may grow 64x inside a sweep befo
 constexpr int kWalkWarps = 2;          // warps 0,1: barrier wait, read-back, sampling
 constexpr int kDotWarps = kWarps - kWalkWarps;   // warps 2..15: dot pass of the next block, TMA issue
 static_assert(kDotWarps == 14, "dot_partial / dot_combine split the four marker tiles over 4+4+3+3 dot warps");
+constexpr int kMetaWarp0 = kWalkWarps + 10;  // warps 12,13 (dot warps 10,11: 8 dot items, no missing sums) gather and derive the block metadata
 constexpr int kTmaLanes = 5;           // rows each dot warp requests per block (14 x 5 >= 64).  One warp issuing all 64 bulk
                                        // copies takes ~3400 cycles (measured, tools/latency_bench2.cu); spread like this ~700.
 
@@ -67,10 +69,10 @@ constexpr int kTmaLanes = 5;           // rows each dot warp requests per block 
 // cost thousands of cycles per block on the critical path (profiles/).
 constexpr int kLine = 32;              // ints per 128-byte line
 constexpr int kCols = 2 * kB;          // columns of a Gram row: the 64 markers of the block, then the 64 of the next block
-constexpr int kSlotDots = 0;           // [64][4] int64, one per line: limb sums in pairs (even limb + odd limb * 2^32)
-constexpr int kSlotSm = kSlotDots + 256 * kLine;   // [64][2] int64, one per line: sum of q over missing individuals (hi, lo)
+constexpr int kSlotDots = 0;           // [64][2] int64, one per line: the limb sums of a half combined, sum_l S_(4h+l) 2^(8l)
+constexpr int kSlotSm = kSlotDots + 128 * kLine;   // [64][2] int64, one per line: sum of q over missing individuals (hi, lo)
 constexpr int kSlotEps = kSlotSm + 128 * kLine;    // [2] int64, one per line: sum of q over all individuals (hi, lo)
-constexpr int kSlotMainLines = 256 + 128 + 2;
+constexpr int kSlotMainLines = 128 + 128 + 2;
 constexpr int kSlotLazy = kSlotEps + 2 * kLine;    // [64 row slots][128 columns], one line each, first 16 bytes:
                                                    //   u64 #0 = a | cw << 32,  u64 #1 = cy | cz << 32   (see gram_entry)
 constexpr int kSlotInts = kSlotLazy + kB * kCols * kLine;
@@ -118,8 +120,8 @@ struct DenseSweepParams {
 constexpr int kXchgCtas = 8;           // CTAs that push / merge a share of a Gram round's counts
 constexpr int kXchgRot = 4;
 constexpr int kMsgLazy = 0;                        // [64 row slots][128 columns][2]
-constexpr int kMsgDots = kMsgLazy + 2 * kB * kCols; // [64][4]
-constexpr int kMsgSm = kMsgDots + 4 * kB;          // [64][2]
+constexpr int kMsgDots = kMsgLazy + 2 * kB * kCols; // [64][2]
+constexpr int kMsgSm = kMsgDots + 2 * kB;          // [64][2]
 constexpr int kMsgEps = kMsgSm + 2 * kB;           // [2]
 constexpr int kMsgAbs = kMsgEps + 2;               // [1]
 constexpr int kMsgU64 = kMsgAbs + 2;
@@ -745,22 +747,21 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     auto publish_dots = [&](uint32_t bn) {
         const uint32_t nbn = min(B, p.n_order - bn * B);
         int *slotn = p.slots + size_t(bn % kSlots) * kSlotInts;
-        if (tid < 256) {
-            // tile mi, row half rr, lane l5 -> limbs (2tig, 2tig+1) of one marker, as ONE signed 64-bit RED (even limb + odd limb * 2^32)
-            const int l5 = tid & 31, rr = (tid >> 5) & 1, mi = tid >> 6;
-            const int o = (mi * 4 + 2 * rr) * 32 + l5;
-            const int s0 = dot_acc[o], s1 = dot_acc[o + 32];
-            const uint32_t m = 16 * mi + (l5 >> 2) + 8 * rr;
-            const long long v = (long long)s0 + ((long long)s1 << 32);
+        if (tid < 2 * kB) {
+            // (marker m, half h): the four limb sums 4h..4h+3 of the marker combined into sum_l S_l 2^(8l) -- exact, < 2^46 per CTA --
+            // as ONE signed 64-bit RED.  dot_acc holds the MMA C fragments: limb 2 tig + (q & 1) of marker 16 mi + gid + 8 (q >> 1).
+            const uint32_t m = tid >> 1, h = tid & 1u;
+            const int *da = dot_acc + ((m >> 4) * 4 + ((m >> 3) & 1u) * 2) * 32 + (m & 7u) * 4 + 2 * h;
+            const long long v = (long long)da[0] + ((long long)da[32] << 8) + ((long long)da[1] << 16) + ((long long)da[33] << 24);
             if (v != 0 && m < nbn)
-                atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotDots + (m * 4 + (l5 & 3)) * kLine), (unsigned long long)v);
-        } else if (tid < 256 + 2 * kB) {
-            const uint32_t i = tid - 256;                 // (marker, hi/lo part)
+                atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotDots + tid * kLine), (unsigned long long)v);
+        } else if (tid < 4 * kB) {
+            const uint32_t i = tid - 2 * kB;              // (marker, hi/lo part)
             if ((i >> 1) < nbn) {
                 const unsigned long long v = msum[i];
                 if (v) atomicAdd(reinterpret_cast<unsigned long long *>(slotn + kSlotSm + i * kLine), v);
             }
-        } else if (warp == 12) {              // lane 2w+h holds part h of warp w's sum of q
+        } else if (warp == 8) {               // lane 2w+h holds part h of warp w's sum of q
             unsigned long long v = sh.wq[lane >> 1][lane & 1];
 #pragma unroll
             for (int o2 = 2; o2 < 32; o2 <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
@@ -802,61 +803,70 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             const uint32_t *rowa = (a < uint32_t(kB)) ? pk + size_t(a) * RS : pkx + size_t(a - kB) * RS;
             const uint16_t *tla = reinterpret_cast<const uint16_t *>(rowa + PW);
             const uint32_t cnta = okcol ? uint32_t(tla[0]) : 0u;
-            for (uint32_t idx0 = 0; idx0 < nnew; idx0 += 4) {
-                const uint32_t idx = idx0 + s4;
-                const bool on = okcol && idx < nnew;
-                const uint32_t j = on ? sh.lz_rows[idx] : 0u;
-                const bool pair = on && a != j;                            // a >= 64 never equals a row marker
-                const uint32_t *rowj = pk + size_t(j) * RS;
-                const uint16_t *tlj = reinterpret_cast<const uint16_t *>(rowj + PW);
-                const uint32_t cntj = pair ? uint32_t(tlj[0]) : 0u;
-                const bool slow = pair && (cntj > 15u || cnta > 15u);
-                int z = 0, wv = 0, y = 0;
-                if (pair && !slow) {
-                    for (uint32_t en = 0; en < cntj; ++en) {
-                        const uint32_t i = tlj[1 + en];
-                        const uint32_t c = (rowa[i >> 4] >> (2 * (i & 15u))) & 3u;
-                        z += (c == 3u) ? 0 : int(c);
-                        wv += (c == 3u) ? 1 : 0;
-                    }
-                    for (uint32_t en = 0; en < cnta; ++en) {
-                        const uint32_t i = tla[1 + en];
-                        const uint32_t c = (rowj[i >> 4] >> (2 * (i & 15u))) & 3u;
-                        y += (c == 3u) ? 0 : int(c);
-                    }
-                }
-                unsigned slow_m = __ballot_sync(0xffffffffu, slow);
-                while (slow_m) {
-                    const int l = __ffs(slow_m) - 1;
-                    slow_m &= slow_m - 1;
-                    const uint32_t a2 = __shfl_sync(0xffffffffu, a, l), j2 = __shfl_sync(0xffffffffu, j, l);
-                    const uint32_t *ra = (a2 < uint32_t(kB)) ? pk + size_t(a2) * RS : pkx + size_t(a2 - kB) * RS;
-                    const uint32_t *rj = pk + size_t(j2) * RS;
-                    int zz = 0, ww = 0, yy = 0;
-                    for_missing_chunks(rj, [&](const uint32_t *ent, uint32_t n) {
-                        for (uint32_t en = lane; en < n; en += 32) {
-                            const uint32_t i = ent[en];
-                            const uint32_t c = (ra[i >> 4] >> (2 * (i & 15u))) & 3u;
-                            zz += (c == 3u) ? 0 : int(c);
-                            ww += (c == 3u) ? 1 : 0;
+            // the four lanes of a column take R rows at a time, 4/R lanes per (row, column) pair sharing the list entries:
+            // R = 1 for the one or two rows of a typical round (short dependent chains), R = 4 when many rows are new
+            auto cross = [&](auto rc) {
+                constexpr uint32_t R = decltype(rc)::value, ES = 4u / R;
+                const uint32_t rsub = s4 / ES, e0 = s4 % ES;
+                for (uint32_t idx0 = 0; idx0 < nnew; idx0 += R) {
+                    const uint32_t idx = idx0 + rsub;
+                    const bool on = okcol && idx < nnew;
+                    const uint32_t j = on ? sh.lz_rows[idx] : 0u;
+                    const bool pair = on && a != j;                            // a >= 64 never equals a row marker
+                    const uint32_t *rowj = pk + size_t(j) * RS;
+                    const uint16_t *tlj = reinterpret_cast<const uint16_t *>(rowj + PW);
+                    const uint32_t cntj = pair ? uint32_t(tlj[0]) : 0u;
+                    const bool slow = pair && (cntj > 15u || cnta > 15u);
+                    uint32_t zwy = 0;                                          // z | wv << 8 | y << 16 (each <= 2 * 15)
+                    if (pair && !slow) {
+                        for (uint32_t en = e0; en < cntj; en += ES) {
+                            const uint32_t i = tlj[1 + en];
+                            const uint32_t c = (rowa[i >> 4] >> (2 * (i & 15u))) & 3u;
+                            zwy += (c == 3u) ? 0x100u : c;
                         }
-                    });
-                    for_missing_chunks(ra, [&](const uint32_t *ent, uint32_t n) {
-                        for (uint32_t en = lane; en < n; en += 32) {
-                            const uint32_t i = ent[en];
-                            const uint32_t c = (rj[i >> 4] >> (2 * (i & 15u))) & 3u;
-                            yy += (c == 3u) ? 0 : int(c);
+                        for (uint32_t en = e0; en < cnta; en += ES) {
+                            const uint32_t i = tla[1 + en];
+                            const uint32_t c = (rowj[i >> 4] >> (2 * (i & 15u))) & 3u;
+                            zwy += (c == 3u) ? 0u : (c << 16);
                         }
-                    });
-                    zz = __reduce_add_sync(0xffffffffu, zz); ww = __reduce_add_sync(0xffffffffu, ww); yy = __reduce_add_sync(0xffffffffu, yy);
-                    if (lane == l) { z = zz; wv = ww; y = yy; }
+                    }
+#pragma unroll
+                    for (uint32_t o2 = 1; o2 < ES; o2 <<= 1) zwy += __shfl_xor_sync(0xffffffffu, zwy, o2);
+                    int z = int(zwy & 0xffu), wv = int((zwy >> 8) & 0xffu), y = int(zwy >> 16);
+                    unsigned slow_m = __ballot_sync(0xffffffffu, slow && e0 == 0u);
+                    while (slow_m) {
+                        const int l = __ffs(slow_m) - 1;
+                        slow_m &= slow_m - 1;
+                        const uint32_t a2 = __shfl_sync(0xffffffffu, a, l), j2 = __shfl_sync(0xffffffffu, j, l);
+                        const uint32_t *ra = (a2 < uint32_t(kB)) ? pk + size_t(a2) * RS : pkx + size_t(a2 - kB) * RS;
+                        const uint32_t *rj = pk + size_t(j2) * RS;
+                        int zz = 0, ww = 0, yy = 0;
+                        for_missing_chunks(rj, [&](const uint32_t *ent, uint32_t n) {
+                            for (uint32_t en = lane; en < n; en += 32) {
+                                const uint32_t i = ent[en];
+                                const uint32_t c = (ra[i >> 4] >> (2 * (i & 15u))) & 3u;
+                                zz += (c == 3u) ? 0 : int(c);
+                                ww += (c == 3u) ? 1 : 0;
+                            }
+                        });
+                        for_missing_chunks(ra, [&](const uint32_t *ent, uint32_t n) {
+                            for (uint32_t en = lane; en < n; en += 32) {
+                                const uint32_t i = ent[en];
+                                const uint32_t c = (rj[i >> 4] >> (2 * (i & 15u))) & 3u;
+                                yy += (c == 3u) ? 0 : int(c);
+                            }
+                        });
+                        zz = __reduce_add_sync(0xffffffffu, zz); ww = __reduce_add_sync(0xffffffffu, ww); yy = __reduce_add_sync(0xffffffffu, yy);
+                        if (lane == l) { z = zz; wv = ww; y = yy; }
+                    }
+                    if (pair && e0 == 0u) {
+                        unsigned long long *ln = reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0 + idx) * kCols + a) * kLine);
+                        if (wv) atomicAdd(ln, (unsigned long long)(unsigned)wv << 32);
+                        if (y | z) atomicAdd(ln + 1, (unsigned long long)(unsigned)y | ((unsigned long long)(unsigned)z << 32));
+                    }
                 }
-                if (pair) {
-                    unsigned long long *ln = reinterpret_cast<unsigned long long *>(slot + kSlotLazy + (size_t(r0 + idx) * kCols + a) * kLine);
-                    if (wv) atomicAdd(ln, (unsigned long long)(unsigned)wv << 32);
-                    if (y | z) atomicAdd(ln + 1, (unsigned long long)(unsigned)y | ((unsigned long long)(unsigned)z << 32));
-                }
-            }
+            };
+            if (nnew <= 2u) cross(std::integral_constant<uint32_t, 1u>{}); else cross(std::integral_constant<uint32_t, 4u>{});
         }
         PHASE(kProfLzC2);
         __syncthreads();                       // the warps' missing-list segments are free: reused below
@@ -1011,9 +1021,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     unsigned gen_wait = 0;                                      // the grid-wide round that carries the current block's dots
     int zero_turn = int(cta);                                   // the next block whose pass recycles a slot on this CTA
     while (zero_turn < 2) zero_turn += int(p.nCTA);
-    uint32_t gid_next = 0u;                                     // threads 64..127: marker id of their row of the next block to gather
+    uint32_t gid_next = 0u;                                     // threads of warps kMetaWarp0, +1: marker id of their row of the next block to gather
     {
-        const int k2 = tid - 32 * kWalkWarps;
+        const int k2 = tid - 32 * kMetaWarp0;
         if (uint32_t(k2) < min(B, p.n_order)) gid_next = p.order[k2];
     }
     PHASE(kProfPrologue);
@@ -1051,24 +1061,20 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             xchg(kXMain, slot, 0, 0, tid, 32 * kWalkWarps, wlk_sync);
             PHASE(kProfXchg);
             if (act) {
-                long long dq[4];
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4)
-                    dq[q4] = peer_sum(__ldcg(reinterpret_cast<const long long *>(slot + kSlotDots + (wk * 4 + q4) * kLine)), kMsgDots + wk * 4 + q4);
-                const long long sm_hi = peer_sum(__ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * wk) * kLine)), kMsgSm + 2 * wk);
-                const long long sm_lo = peer_sum(__ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * wk + 1) * kLine)), kMsgSm + 2 * wk + 1);
-                const long long e_hi = peer_sum(__ldcg(reinterpret_cast<const long long *>(slot + kSlotEps)), kMsgEps);
-                const long long e_lo = peer_sum(__ldcg(reinterpret_cast<const long long *>(slot + kSlotEps + kLine)), kMsgEps + 1);
-                const double eps_sum_total = (double(e_hi) * 4294967296.0 + double(e_lo)) * inv_scale;
-                // unpack the limb sums: each int64 holds (even limb) + (odd limb) * 2^32, both signed
-                long long S[8];
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const long long ev = (long long)(int)(unsigned)(dq[q4] & 0xffffffffLL);
-                    S[2 * q4] = ev; S[2 * q4 + 1] = (dq[q4] - ev) >> 32;
+                // all six loads in flight at once, then the peers' parts
+                long long tlo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotDots + (2 * wk) * kLine));
+                long long thi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotDots + (2 * wk + 1) * kLine));
+                long long sm_hi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * wk) * kLine));
+                long long sm_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * wk + 1) * kLine));
+                long long e_hi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps));
+                long long e_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps + kLine));
+                if (p.world > 1) {
+                    tlo = peer_sum(tlo, kMsgDots + 2 * wk); thi = peer_sum(thi, kMsgDots + 2 * wk + 1);
+                    sm_hi = peer_sum(sm_hi, kMsgSm + 2 * wk); sm_lo = peer_sum(sm_lo, kMsgSm + 2 * wk + 1);
+                    e_hi = peer_sum(e_hi, kMsgEps); e_lo = peer_sum(e_lo, kMsgEps + 1);
                 }
-                const long long tlo = S[0] + (S[1] << 8) + (S[2] << 16) + (S[3] << 24);
-                const long long thi = S[4] + (S[5] << 8) + (S[6] << 16) + (S[7] << 24);
+                const double eps_sum_total = (double(e_hi) * 4294967296.0 + double(e_lo)) * inv_scale;
+                // tlo = sum_l S_l 2^(8l) over limbs 0..3, thi over limbs 4..7 (combined per CTA before the reduction)
                 const double dprime = (double(thi) * 4294967296.0 + double(tlo)) * inv_scale;    // sum_i g'_i eps_i
                 const double smd = (double(sm_hi) * 4294967296.0 + double(sm_lo)) * inv_scale;
                 const double *L = meta.lut[wk];
@@ -1098,7 +1104,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             order_ids(bn + 1);
             if (cta == 0 && warp == kFlushWarp && sh.fin[buf].n) flush_results(sh.fin[buf]);
             if (have_next) {
-                const int k2 = tid - 32 * kWalkWarps;
+                const int k2 = tid - 32 * kMetaWarp0;
                 const uint32_t my_gid = gid_next;
                 if (uint32_t(k2) < uint32_t(kB)) {                 // the id for the NEXT pass's gather: its latency hides behind this pass
                     const uint32_t pos = (bn + 1) * B + k2;
