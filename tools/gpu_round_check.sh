@@ -13,7 +13,7 @@ if [ "$2" != "quick" ]; then  # full bench also in ncu mode
   timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
 fi
 if [ "$2" == "ncu" ]; then
-  BRR_BENCH_M=8000 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
+  BRR_BENCH_M=8000 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"sweep_dense_kernel|eps_add_reduce_kernel" -c 30 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
   BRR_BENCH_M=64000 timeout 600 ncu --set full --clock-control none --import-source on -k sweep_dense_kernel -s 4 -c 1 -o gpurun_out/${TAG}_sweep -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
   ls -la gpurun_out/${TAG}_*
 fi
