@@ -129,6 +129,13 @@ extern "C" void brr_gpu_destroy(brr_gpu_ctx *c)
     delete c;
 }
 
+// the instantiation of the dense sweep kernel for (several GPUs, phase profiling)
+static const void *dense_sweep_fn(bool multi, bool prof)
+{
+    if (multi) return prof ? (const void *)sweep_dense_kernel<true, true> : (const void *)sweep_dense_kernel<true, false>;
+    return prof ? (const void *)sweep_dense_kernel<false, true> : (const void *)sweep_dense_kernel<false, false>;
+}
+
 static int choose_geometry(brr_gpu_ctx *c)
 {
     const brr_gpu_config &cfg = c->cfg;
@@ -203,9 +210,13 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
                            c->smem_bytes, c->SL, size_t(prop.sharedMemPerBlockOptin));
             brr_gpu_destroy(c); return rc_;
         }
-        CUDA_OR_DESTROY(cudaFuncSetAttribute(sweep_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-        int occ = 0;
-        CUDA_OR_DESTROY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_dense_kernel, kThreads, c->smem_bytes));
+        int occ = 8;
+        for (const void *fn : {dense_sweep_fn(false, false), dense_sweep_fn(false, true), dense_sweep_fn(true, false), dense_sweep_fn(true, true)}) {
+            CUDA_OR_DESTROY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+            int o = 0;
+            CUDA_OR_DESTROY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, kThreads, c->smem_bytes));
+            occ = std::min(occ, o);
+        }
         if (occ < 1 || uint32_t(occ) * c->numSMs < c->nCTA) {
             int rc_ = fail(BRR_GPU_EINVAL, "sweep kernel does not fit: %zu bytes of shared memory per CTA, %u CTAs", c->smem_bytes, c->nCTA);
             brr_gpu_destroy(c); return rc_;
@@ -503,7 +514,7 @@ static int launch_dense(brr_gpu_ctx *c)
     CUDA_TRY(cudaMemsetAsync(c->out_counts, 0, sizeof(unsigned) * 4, c->stream));
     void *args[] = {&p};
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    CUDA_TRY(cudaLaunchCooperativeKernel((const void *)sweep_dense_kernel, dim3(c->nCTA), dim3(kThreads), args,
+    CUDA_TRY(cudaLaunchCooperativeKernel(dense_sweep_fn(c->cfg.world > 1, p.prof != nullptr), dim3(c->nCTA), dim3(kThreads), args,
                                          c->smem_bytes, c->stream));
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     c->launches += 1; c->last_launches = 1;

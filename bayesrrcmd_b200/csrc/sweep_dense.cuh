@@ -126,7 +126,14 @@ constexpr int kMsgEps = kMsgSm + 2 * kB;           // [2]
 constexpr int kMsgAbs = kMsgEps + 2;               // [1]
 constexpr int kMsgU64 = kMsgAbs + 2;
 __host__ __device__ inline size_t xchg_mailbox_ints(int world) { return size_t(world) * kXchgRot * kMsgU64 * 2; }
-__host__ __device__ inline size_t xchg_total_ints(int world) { return xchg_mailbox_ints(world) + size_t(world) * kXchgCtas * 2 + 8; }
+// The per-block message (the 258 reduced 64-bit sums of a block: 128 dot halves, 128 missing sums, 2 residual sums, in slot-line
+// order) travels in "LL" form, as NCCL's low-latency protocol does: each value is one 16-byte cell {lo32 | id << 32, hi32 | id << 32},
+// id = the low 32 bits of the round id, written with ONE vector store.  8-byte stores arrive whole, so a reader that finds the
+// round's id in both halves has the value: no flag, no release fence, no second trip over NVLink.
+constexpr int kMainVals = 4 * kB + 2;
+__host__ __device__ inline size_t xchg_ll_off_ints(int world) { return xchg_mailbox_ints(world) + size_t(world) * kXchgCtas * 2; }
+__host__ __device__ inline size_t xchg_ll_ints(int world) { return size_t(world) * kXchgRot * kMainVals * 4; }
+__host__ __device__ inline size_t xchg_total_ints(int world) { return xchg_ll_off_ints(world) + xchg_ll_ints(world) + 8; }
 enum { kXAbs = 0, kXMain = 1, kXLazy = 2 };
 
 // phases of the block loop, as timed by thread 0 of CTA 0 (a walker) when DenseSweepParams::prof is set;
@@ -238,6 +245,16 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_sys_v2(ulonglong2 *p, unsigned long long a, unsigned long long b)
+{
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ ulonglong2 ld_sys_v2(const ulonglong2 *p)
+{
+    ulonglong2 v;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __noinline__ void prof_mark(unsigned long long *slot_cycles, long long *t_prev, bool charge)
 {
     const long long t = clock64();
@@ -288,8 +305,13 @@ __device__ __forceinline__ double gram_entry(const BlockMeta &mj, int j, const B
     return mj.sj[j] * mk.sj[k] * t;
 }
 
+// MG: several GPUs (world > 1) -- the single-GPU instantiation carries no exchange code at all; PROF: phase cycle counters
+// (BRR_GPU_PROFILE) -- the production instantiations carry no timing calls.  Smaller code and fewer live registers on the
+// walkers' critical path are worth the four instantiations.
+template <bool MG, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSweepParams p)
 {
+    const int world = MG ? p.world : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SweepShared &sh = *reinterpret_cast<SweepShared *>(smem_raw);
     const uint32_t RS = p.RS, PW = p.PW, SL = p.SL;
@@ -311,8 +333,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     const uint32_t nBlocks = (p.n_order + B - 1) / B;
     const uint32_t slice0 = cta * SL;
     unsigned bar_gen = 0;                            // grid-wide rounds so far (identical in every thread of the grid)
-    const bool prof_on = (p.prof != nullptr) && cta == 0 && tid == 0;
-    const bool prof_w = (p.prof != nullptr) && cta == 0 && tid == 32 * kWalkWarps;
+    const bool prof_on = PROF && (p.prof != nullptr) && cta == 0 && tid == 0;
+    const bool prof_w = PROF && (p.prof != nullptr) && cta == 0 && tid == 32 * kWalkWarps;
     long long t_prev = (prof_on || prof_w) ? clock64() : 0;
     if (prof_on) for (int i = 0; i < kProfPhases; ++i) sh.prof[i] = 0;
     auto PHASE = [&](int ph) {          // charge the cycles since the previous mark to phase `ph`
@@ -402,46 +424,41 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     // The per-block message (every block, on the critical path) takes a shorter way: CTA 0 pushes and publishes,
     // the walkers of EVERY CTA wait for the peers' round ids themselves and add the peers' mailboxes to the local
     // sums as they read them (peer_sum) -- no merge, no second counter.
-    const unsigned long long round_base = (p.world > 1) ? *p.round_ctr : 0ULL;
+    const unsigned long long round_base = (world > 1) ? *p.round_ctr : 0ULL;
     unsigned xround = 0;                                    // exchange rounds done in this launch
     unsigned bar2_target = 0;
     int main_rot = 0;                                       // mailbox rotation of the current per-block round
-    auto peer_sum = [&](long long v, uint32_t msg) -> long long {      // local sum + the peers' parts of message element `msg`
-        if (p.world > 1) {
-            const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(p.peer_xchg[p.rank]);
-            for (int pr = 0; pr < p.world; ++pr)
-                if (pr != p.rank) v += (long long)__ldcg(mine + (size_t(pr) * kXchgRot + main_rot) * kMsgU64 + msg);
-        }
-        return v;
-    };
+    unsigned mcount = 0;                                    // per-block rounds done in this launch (their mailbox rotation)
+    uint32_t main_id = 0u;                                  // LL id of the current per-block round
     auto xchg = [&](int kind, int *slot, uint32_t r0, uint32_t nrows, int t, int nthr, auto &&sync) {
-        if (p.world <= 1) return;
+        if (world <= 1) return;
         ++xround;
         const unsigned long long rid = round_base + xround;
         const int rot = int(rid % kXchgRot);
         const uint32_t E = (kind == kXLazy) ? p.xchg_ctas : 1u;
         if (kind == kXMain) {
-            main_rot = rot;
+            // CTA 0 pushes the block's reduced sums to every peer as LL cells; the walkers of EVERY CTA then poll the cells they
+            // need in their own mailbox while they read the local sums back (peer_cells below): no flag, no fence, no merge
+            main_rot = int(mcount++ % kXchgRot);
+            main_id = uint32_t(rid);
             if (cta == 0) {
-                for (uint32_t i = kMsgDots + t; i < uint32_t(kMsgAbs); i += nthr) {
-                    const int *lp = i < uint32_t(kMsgSm) ? slot + kSlotDots + (i - kMsgDots) * kLine
-                                  : i < uint32_t(kMsgEps) ? slot + kSlotSm + (i - kMsgSm) * kLine : slot + kSlotEps + (i - kMsgEps) * kLine;
-                    const unsigned long long v = __ldcg(reinterpret_cast<const unsigned long long *>(lp));
-                    for (int pr = 0; pr < p.world; ++pr)
-                        if (pr != p.rank) reinterpret_cast<unsigned long long *>(p.peer_xchg[pr])[(size_t(p.rank) * kXchgRot + rot) * kMsgU64 + i] = v;
+                unsigned long long v[(kMainVals + 32 * kWalkWarps - 1) / (32 * kWalkWarps)];
+#pragma unroll
+                for (int k = 0; k < int(sizeof(v) / sizeof(v[0])); ++k) {
+                    const uint32_t i = t + k * nthr;
+                    if (i < uint32_t(kMainVals)) v[k] = __ldcg(reinterpret_cast<const unsigned long long *>(slot + kSlotDots + i * kLine));
                 }
-                sync();                                     // the release below covers the group's stores (as in grid_arrive)
-                if (t < p.world && t != p.rank)
-                    st_release_sys_u64(reinterpret_cast<unsigned long long *>(p.peer_xchg[t] + xchg_mailbox_ints(p.world)) + size_t(p.rank) * kXchgCtas, rid);
-            }
-            if (t < p.world && t != p.rank) {
-                const unsigned long long *lf = reinterpret_cast<const unsigned long long *>(p.peer_xchg[p.rank] + xchg_mailbox_ints(p.world)) + size_t(t) * kXchgCtas;
-                const long long t0 = clock64();
-                while (ld_acquire_sys_u64(lf) < rid) {
-                    if ((sh.err & 2u) || clock64() - t0 > 6000000000LL) { sh.err |= 2u; break; }   // ~3 s: a peer is gone; fail, do not hang
+                const unsigned long long idh = (unsigned long long)main_id << 32;
+#pragma unroll
+                for (int k = 0; k < int(sizeof(v) / sizeof(v[0])); ++k) {
+                    const uint32_t i = t + k * nthr;
+                    if (i < uint32_t(kMainVals))
+                        for (int pr = 0; pr < world; ++pr)
+                            if (pr != p.rank)
+                                st_sys_v2(reinterpret_cast<ulonglong2 *>(p.peer_xchg[pr] + xchg_ll_off_ints(world)) + (size_t(p.rank) * kXchgRot + main_rot) * kMainVals + i,
+                                          (v[k] & 0xffffffffULL) | idh, (v[k] >> 32) | idh);
                 }
             }
-            sync();
             return;
         }
         bar2_target += E;
@@ -461,16 +478,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             // 1. push
             for (uint32_t i = lo + t; i < hi; i += nthr) {
                 const unsigned long long v = __ldcg(local_ptr(i));
-                for (int pr = 0; pr < p.world; ++pr)
+                for (int pr = 0; pr < world; ++pr)
                     if (pr != p.rank) reinterpret_cast<unsigned long long *>(p.peer_xchg[pr])[(size_t(p.rank) * kXchgRot + rot) * kMsgU64 + i] = v;
             }
             __threadfence_system();
             sync();
             // 2. publish my round id on every peer, wait for theirs
-            if (t < p.world && t != p.rank) {
-                unsigned long long *pf = reinterpret_cast<unsigned long long *>(p.peer_xchg[t] + xchg_mailbox_ints(p.world)) + size_t(p.rank) * kXchgCtas + cta;
+            if (t < world && t != p.rank) {
+                unsigned long long *pf = reinterpret_cast<unsigned long long *>(p.peer_xchg[t] + xchg_mailbox_ints(world)) + size_t(p.rank) * kXchgCtas + cta;
                 st_release_sys_u64(pf, rid);
-                const unsigned long long *lf = reinterpret_cast<const unsigned long long *>(p.peer_xchg[p.rank] + xchg_mailbox_ints(p.world)) + size_t(t) * kXchgCtas + cta;
+                const unsigned long long *lf = reinterpret_cast<const unsigned long long *>(p.peer_xchg[p.rank] + xchg_mailbox_ints(world)) + size_t(t) * kXchgCtas + cta;
                 const long long t0 = clock64();
                 while (ld_acquire_sys_u64(lf) < rid) {
                     if ((sh.err & 2u) || clock64() - t0 > 6000000000LL) { sh.err |= 2u; break; }   // ~3 s: a peer is gone; fail, do not hang
@@ -481,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             for (uint32_t i = lo + t; i < hi; i += nthr) {
                 unsigned long long *lp = local_ptr(i);
                 unsigned long long v = __ldcg(lp);
-                for (int pr = 0; pr < p.world; ++pr)
+                for (int pr = 0; pr < world; ++pr)
                     if (pr != p.rank) {
                         const unsigned long long o = __ldcg(mine + (size_t(pr) * kXchgRot + rot) * kMsgU64 + i);
                         if (kind == kXAbs) v = v > o ? v : o;          // bits of non-negative doubles order like integers
@@ -1068,10 +1085,24 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 long long sm_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * wk + 1) * kLine));
                 long long e_hi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps));
                 long long e_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps + kLine));
-                if (p.world > 1) {
-                    tlo = peer_sum(tlo, kMsgDots + 2 * wk); thi = peer_sum(thi, kMsgDots + 2 * wk + 1);
-                    sm_hi = peer_sum(sm_hi, kMsgSm + 2 * wk); sm_lo = peer_sum(sm_lo, kMsgSm + 2 * wk + 1);
-                    e_hi = peer_sum(e_hi, kMsgEps); e_lo = peer_sum(e_lo, kMsgEps + 1);
+                for (int pr = 0; pr < world; ++pr) {              // + the peers' sums, as their LL cells arrive
+                    if (pr == p.rank) continue;
+                    const ulonglong2 *cell = reinterpret_cast<const ulonglong2 *>(p.peer_xchg[p.rank] + xchg_ll_off_ints(world)) + (size_t(pr) * kXchgRot + main_rot) * kMainVals;
+                    const uint32_t ci[6] = {2u * wk, 2u * wk + 1u, 2u * kB + 2u * wk, 2u * kB + 2u * wk + 1u, 4u * kB, 4u * kB + 1u};
+                    ulonglong2 c[6];
+                    const long long t0 = clock64();
+                    for (;;) {
+                        bool ok = true;
+#pragma unroll
+                        for (int q6 = 0; q6 < 6; ++q6) {
+                            c[q6] = ld_sys_v2(cell + ci[q6]);
+                            ok = ok && uint32_t(c[q6].x >> 32) == main_id && uint32_t(c[q6].y >> 32) == main_id;
+                        }
+                        if (ok) break;
+                        if ((sh.err & 2u) || clock64() - t0 > 6000000000LL) { sh.err |= 2u; break; }   // ~3 s: a peer is gone; fail, do not hang
+                    }
+                    auto val = [](const ulonglong2 &x) { return (long long)((x.x & 0xffffffffULL) | (x.y << 32)); };
+                    tlo += val(c[0]); thi += val(c[1]); sm_hi += val(c[2]); sm_lo += val(c[3]); e_hi += val(c[4]); e_lo += val(c[5]);
                 }
                 const double eps_sum_total = (double(e_hi) * 4294967296.0 + double(e_lo)) * inv_scale;
                 // tlo = sum_l S_l 2^(8l) over limbs 0..3, thi over limbs 4..7 (combined per CTA before the reduction)
@@ -1398,7 +1429,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             if (lane == 0) {
                 p.out_scalars[0] = s; p.out_scalars[1] = q;
                 p.out_counts[0] = sh.n_nonskipped_total; p.out_counts[1] = nBlocks; p.out_counts[3] = bar_gen;
-                if (p.world > 1) *p.round_ctr = round_base + xround;
+                if (world > 1) *p.round_ctr = round_base + xround;
             }
         }
         __syncthreads();
