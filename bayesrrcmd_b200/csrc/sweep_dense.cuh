@@ -133,7 +133,11 @@ __host__ __device__ inline size_t xchg_mailbox_ints(int world) { return size_t(w
 constexpr int kMainVals = 4 * kB + 2;
 __host__ __device__ inline size_t xchg_ll_off_ints(int world) { return xchg_mailbox_ints(world) + size_t(world) * kXchgCtas * 2; }
 __host__ __device__ inline size_t xchg_ll_ints(int world) { return size_t(world) * kXchgRot * kMainVals * 4; }
-__host__ __device__ inline size_t xchg_total_ints(int world) { return xchg_ll_off_ints(world) + xchg_ll_ints(world) + 8; }
+// The Gram rows of a lazy round travel the same way when every CTA consumes them at read-back (the usual case: the block's rows
+// fit the shared-memory row slots): value i of the round = u64 #(i & 1) of entry (row - r0, column) = i >> 1.
+constexpr int kLazyCells = 2 * kB * kCols;
+__host__ __device__ inline size_t xchg_lazy_ll_off_ints(int world) { return xchg_ll_off_ints(world) + xchg_ll_ints(world); }
+__host__ __device__ inline size_t xchg_total_ints(int world) { return xchg_lazy_ll_off_ints(world) + size_t(world) * kXchgRot * kLazyCells * 4 + 8; }
 enum { kXAbs = 0, kXMain = 1, kXLazy = 2 };
 
 // phases of the block loop, as timed by thread 0 of CTA 0 (a walker) when DenseSweepParams::prof is set;
@@ -430,6 +434,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     int main_rot = 0;                                       // mailbox rotation of the current per-block round
     unsigned mcount = 0;                                    // per-block rounds done in this launch (their mailbox rotation)
     uint32_t main_id = 0u;                                  // LL id of the current per-block round
+    unsigned lcount = 0;                                    // Gram-row rounds sent in LL form in this launch
+    uint32_t ll_rows = 0;                                   // Gram rows of the current block sent in LL form (not merged in the global slot)
     auto xchg = [&](int kind, int *slot, uint32_t r0, uint32_t nrows, int t, int nthr, auto &&sync) {
         if (world <= 1) return;
         ++xround;
@@ -439,8 +445,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         if (kind == kXMain) {
             // CTA 0 pushes the block's reduced sums to every peer as LL cells; the walkers of EVERY CTA then poll the cells they
             // need in their own mailbox while they read the local sums back (peer_cells below): no flag, no fence, no merge
+            // (ids: the walkers alone count the per-block rounds in xround, so round ids differ between the threads of a CTA; LL ids
+            //  come from counters every participant shares.  round_ctr grows by more than either counter per launch: no reuse.)
+            main_id = uint32_t(round_base + 1u + mcount);
             main_rot = int(mcount++ % kXchgRot);
-            main_id = uint32_t(rid);
             if (cta == 0) {
                 unsigned long long v[(kMainVals + 32 * kWalkWarps - 1) / (32 * kWalkWarps)];
 #pragma unroll
@@ -967,7 +975,32 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         // (3) the grid-wide round
         grid_arrive(p.bar);
         grid_wait(p.bar, (++bar_gen) * p.nCTA);
-        xchg(kXLazy, slot, r0, nnew, tid, kThreads, cta_sync);
+        // several GPUs: when the rows keep their next-block half in shared memory (keep_next) nobody reads the global slot after
+        // this read-back, so the peers' counts are added as they are read (LL cells, one NVLink trip); else the merging exchange
+        bool ll_round = false;
+        uint32_t lazy_id = 0u;
+        int lrot = 0;
+        if (MG && world > 1 && keep_next) {
+            ll_round = true;
+            ++xround;
+            lazy_id = uint32_t(round_base + 1u + lcount);
+            lrot = int(lcount++ % kXchgRot);
+            ll_rows += nnew;
+            const uint32_t E = p.xchg_ctas;
+            if (cta < E) {
+                const uint32_t totv = nnew * 2 * kCols, per = (totv + E - 1) / E, vlo = min(totv, cta * per), vhi = min(totv, vlo + per);
+                const unsigned long long idh = (unsigned long long)lazy_id << 32;
+                for (uint32_t i = vlo + tid; i < vhi; i += kThreads) {
+                    const unsigned long long v = __ldcg(reinterpret_cast<const unsigned long long *>(slot + kSlotLazy + (size_t(r0) * kCols + (i >> 1)) * kLine) + (i & 1u));
+                    for (int pr = 0; pr < world; ++pr)
+                        if (pr != p.rank)
+                            st_sys_v2(reinterpret_cast<ulonglong2 *>(p.peer_xchg[pr] + xchg_lazy_ll_off_ints(world)) + (size_t(p.rank) * kXchgRot + lrot) * kLazyCells + i,
+                                      (v & 0xffffffffULL) | idh, (v >> 32) | idh);
+                }
+            }
+        } else {
+            xchg(kXLazy, slot, r0, nnew, tid, kThreads, cta_sync);
+        }
         PHASE(kProfLazyBarrier);
         // (4) read back and standardise into x_j . x_k (all loads of a thread in flight at once): the block-b half into row slot
         //     r of G; the block-(b+1) half, when the block's rows fit 32 slots (keep_next), into row slot 32 + r -- the carry pass
@@ -981,6 +1014,26 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             for (int t = 0; t < 4; ++t) {
                 const uint32_t en = base + tid + t * kThreads;
                 if (en < tot) v[t] = __ldcg(reinterpret_cast<const int4 *>(slot + kSlotLazy + (size_t(r0 + (en >> csh)) * kCols + (en & (ncol - 1u))) * kLine));
+            }
+            if (MG && ll_round) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t en = base + tid + t * kThreads;
+                    if (en >= tot) continue;
+                    const size_t ci = 2 * (size_t(en >> csh) * kCols + (en & (ncol - 1u)));
+                    for (int pr = 0; pr < world; ++pr) {
+                        if (pr == p.rank) continue;
+                        const ulonglong2 *cell = reinterpret_cast<const ulonglong2 *>(p.peer_xchg[p.rank] + xchg_lazy_ll_off_ints(world)) + (size_t(pr) * kXchgRot + lrot) * kLazyCells + ci;
+                        ulonglong2 c0, c1;
+                        const long long t0 = clock64();
+                        for (;;) {
+                            c0 = ld_sys_v2(cell); c1 = ld_sys_v2(cell + 1);
+                            if (uint32_t(c0.x >> 32) == lazy_id && uint32_t(c0.y >> 32) == lazy_id && uint32_t(c1.x >> 32) == lazy_id && uint32_t(c1.y >> 32) == lazy_id) break;
+                            if ((sh.err & 2u) || clock64() - t0 > 6000000000LL) { sh.err |= 2u; break; }   // ~3 s: a peer is gone; fail, do not hang
+                        }
+                        v[t].x += int(uint32_t(c0.x)); v[t].y += int(uint32_t(c0.y)); v[t].z += int(uint32_t(c1.x)); v[t].w += int(uint32_t(c1.y));
+                    }
+                }
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -1190,6 +1243,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         // Thread k < 64 samples marker k of the block; warp 0 runs the solve for both halves.
         // Asynchronous mode: no in-block correction; the rows are only needed for the next block's carry.
         uint32_t have0 = 0, have1 = 0, lz_used = 0;             // Gram rows known so far (identical in every CTA)
+        ll_rows = 0;
         bool g2_ok = true;                                       // all rows so far kept their block-(b+1) half in shared memory
         // A quiet block (nothing sampled away from zero) ends here for the dot warps: they go straight to the dot pass of
         // block b+2 while the walkers file the results and wait for block b+1's round; no CTA-wide barrier in between.
@@ -1205,7 +1259,17 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             }
             if (need0 | need1) {
                 const uint32_t nnew = __popc(need0) + __popc(need1);
+                const bool g2_was = g2_ok;
                 g2_ok = g2_ok && have_next && lz_used + nnew <= 32u;
+                if (MG && world > 1 && g2_was && !g2_ok && ll_rows) {
+                    // the block outgrows the shared-memory row slots: its carry will read ALL rows from the global slot, where the
+                    // rows sent in LL form so far hold local sums only -- merge them now (after a grid barrier: no CTA of this GPU
+                    // may still be reading the local values).  Chain start only.
+                    grid_arrive(p.bar);
+                    grid_wait(p.bar, (++bar_gen) * p.nCTA);
+                    xchg(kXLazy, slot, 0, ll_rows, tid, kThreads, cta_sync);
+                    ll_rows = 0;
+                }
                 lazy_round(pk, pk_next, slot, meta, meta_next, nb, nb_next, need0, need1, lz_used, g2_ok);
                 have0 |= need0; have1 |= need1; lz_used += nnew;
             }
