@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libbrr_gpu.so")
+LIB_PATH = os.environ.get("BRR_GPU_LIB") or os.path.join(PKG, "libbrr_gpu.so")   # BRR_GPU_LIB: another build of the same ABI (A/B timing)
 ABI_VERSION = 1
 LAYOUT_DENSE2BIT, LAYOUT_RAGGED, LAYOUT_EIGEN = 0, 1, 2
 _LAYOUTS = {"dense": 0, "ragged": 1, "eigen": 2}
