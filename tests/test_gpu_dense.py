@@ -102,10 +102,28 @@ def _random_problem(seed, N, M, p_miss, nG=1, K=4):
     (1200, 300, 0.6, 1, 3, 64, 0),     # mostly missing genotypes
 ])
 def test_sweep_matches_oracle_on_random_inputs(N, M, p_miss, nG, K, block, tokens):
+    _compare_sweeps_with_oracle(N, M, p_miss, nG, K, block, tokens)
+
+
+@pytest.mark.parametrize("N,max_ctas,slice_inds", [
+    (3000, 10, 320),      # 5 k-steps per slice: two word pairs + a half pair, dot warps without any item
+    (3000, 7, 448),       # 7 k-steps: 3 pairs + half
+    (8000, 10, 832),      # 13 k-steps: the half pair lands on another warp of the tile
+    (11000, 7, 1600),     # 25 k-steps: several items per dot warp (the software-pipelined loop)
+    (9000, 5, 1856),      # 29 k-steps
+])
+def test_slice_shapes_of_the_mma_loops(N, max_ctas, slice_inds):
+    """The dot and Gram-row loops split a slice's word pairs over the warps of a marker tile (4+4+3+3) and handle an odd
+    number of 64-individual k-steps by a half pair: every split is compared with the oracle (the full-size tests cover 53)."""
+    info = _compare_sweeps_with_oracle(N, 200, 0.02, 2, 4, 64, 0, max_ctas=max_ctas)
+    assert info["slice_inds"] == slice_inds
+
+
+def _compare_sweeps_with_oracle(N, M, p_miss, nG, K, block, tokens, max_ctas=0):
     O.build()
     pr = _random_problem(N * 7 + M, N, M, p_miss, nG, K)
     rng = pr["rng"]
-    e = Engine(N, M, K, nG, block_markers=block)
+    e = Engine(N, M, K, nG, block_markers=block, max_ctas=max_ctas)
     e.upload_bed(pr["bed"]); e.finalize(); e.set_model(pr["S"], pr["groups"])
     beta = np.where(rng.random(M) < 0.3, rng.normal(size=M) * 0.05, 0.0)
     comp = (beta != 0).astype(np.float64); acum = rng.random(M)
@@ -128,6 +146,7 @@ def test_sweep_matches_oracle_on_random_inputs(N, M, p_miss, nG, K, block, token
         assert np.max(np.abs(eps - eps_o)) <= 1e-9
         assert np.max(np.abs(bs - bs_o)) <= 1e-9 * (1 + np.abs(bs_o).max())
         assert abs(out.eps_sqnorm - (eps_o ** 2).sum()) <= 1e-9 * (eps_o ** 2).sum()
+    return e.info()
 
 
 def test_empty_and_single_marker_sweeps():
