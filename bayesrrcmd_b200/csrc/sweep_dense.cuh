@@ -76,6 +76,11 @@ constexpr int kSlotMainLines = 128 + 128 + 2;
 constexpr int kSlotLazy = kSlotEps + 2 * kLine;    // [64 row slots][128 columns], one line each, first 16 bytes:
                                                    //   u64 #0 = a | cw << 32,  u64 #1 = cy | cz << 32   (see gram_entry)
 constexpr int kSlotInts = kSlotLazy + kB * kCols * kLine;
+// Cross-GPU accumulators carry their own arrival count: every peer adds kCnt1 + its (signed) reduced sum to the word, |total| < 2^55,
+// so count = (total + 2^55) >> 56 and value = total - count * 2^56; a reader polls ONE word per value until count == world - 1.
+constexpr unsigned long long kCnt1 = 1ULL << 56;
+__host__ __device__ inline unsigned line_count(unsigned long long total) { return unsigned((total + (1ULL << 55)) >> 56); }
+__host__ __device__ inline long long line_value(unsigned long long total) { return (long long)(total - ((unsigned long long)line_count(total) << 56)); }
 constexpr int kSlots = 4;              // blocks b-2 (being recycled), b-1 (still read by slow CTAs), b, b+1 (being published)
 
 struct DenseSweepParams {
@@ -247,6 +252,16 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_sys_add_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_sys_v2(ulonglong2 *p, unsigned long long a, unsigned long long b)
@@ -433,7 +448,6 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     unsigned bar2_target = 0;
     int main_rot = 0;                                       // mailbox rotation of the current per-block round
     unsigned mcount = 0;                                    // per-block rounds done in this launch (their mailbox rotation)
-    uint32_t main_id = 0u;                                  // LL id of the current per-block round
     unsigned lcount = 0;                                    // Gram-row rounds sent in LL form in this launch
     uint32_t ll_rows = 0;                                   // Gram rows of the current block sent in LL form (not merged in the global slot)
     auto xchg = [&](int kind, int *slot, uint32_t r0, uint32_t nrows, int t, int nthr, auto &&sync) {
@@ -443,28 +457,19 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         const int rot = int(rid % kXchgRot);
         const uint32_t E = (kind == kXLazy) ? p.xchg_ctas : 1u;
         if (kind == kXMain) {
-            // CTA 0 pushes the block's reduced sums to every peer as LL cells; the walkers of EVERY CTA then poll the cells they
-            // need in their own mailbox while they read the local sums back (peer_cells below): no flag, no fence, no merge
-            // (ids: the walkers alone count the per-block rounds in xround, so round ids differ between the threads of a CTA; LL ids
-            //  come from counters every participant shares.  round_ctr grows by more than either counter per launch: no reuse.)
-            main_id = uint32_t(round_base + 1u + mcount);
+            // Every GPU keeps, per rotation, one 64-bit ACCUMULATOR per value of the round (at the head of the LL region); the peers
+            // ADD their reduced sums into it over NVLink (red.add, value + kCnt1), the push spread over all CTAs (value i by CTA
+            // i mod nCTA, one thread per (value, peer)).  The walkers of every CTA then poll ONE word per value until it carries the
+            // count of all peers (read-back below): the cost of a round does not grow with the number of GPUs.  The accumulators
+            // of block b-2 are cleared with its slot; all of them at the start of a launch.
             main_rot = int(mcount++ % kXchgRot);
-            if (cta == 0) {
-                unsigned long long v[(kMainVals + 32 * kWalkWarps - 1) / (32 * kWalkWarps)];
-#pragma unroll
-                for (int k = 0; k < int(sizeof(v) / sizeof(v[0])); ++k) {
-                    const uint32_t i = t + k * nthr;
-                    if (i < uint32_t(kMainVals)) v[k] = __ldcg(reinterpret_cast<const unsigned long long *>(slot + kSlotDots + i * kLine));
-                }
-                const unsigned long long idh = (unsigned long long)main_id << 32;
-#pragma unroll
-                for (int k = 0; k < int(sizeof(v) / sizeof(v[0])); ++k) {
-                    const uint32_t i = t + k * nthr;
-                    if (i < uint32_t(kMainVals))
-                        for (int pr = 0; pr < world; ++pr)
-                            if (pr != p.rank)
-                                st_sys_v2(reinterpret_cast<ulonglong2 *>(p.peer_xchg[pr] + xchg_ll_off_ints(world)) + (size_t(p.rank) * kXchgRot + main_rot) * kMainVals + i,
-                                          (v[k] & 0xffffffffULL) | idh, (v[k] >> 32) | idh);
+            {
+                const uint32_t np = MG ? uint32_t(world - 1) : 1u;       // (never 0: this code is dead in the single-GPU instantiations)
+                const uint32_t nv = cta < uint32_t(kMainVals) ? (uint32_t(kMainVals) - 1u - cta) / p.nCTA + 1u : 0u;
+                for (uint32_t idx = t; idx < nv * np; idx += nthr) {
+                    const uint32_t k = idx / np, pj = idx - k * np, pr = pj < uint32_t(p.rank) ? pj : pj + 1u, i = cta + k * p.nCTA;
+                    const unsigned long long v = __ldcg(reinterpret_cast<const unsigned long long *>(slot + kSlotDots + i * kLine));
+                    red_sys_add_u64(reinterpret_cast<unsigned long long *>(p.peer_xchg[pr] + xchg_ll_off_ints(world)) + size_t(main_rot) * kMainVals + i, v + kCnt1);
                 }
             }
             return;
@@ -529,6 +534,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     auto cta_sync = [&]() { __syncthreads(); };
     auto wlk_sync = [&]() { walker_sync(); };
 
+    if (MG && world > 1 && cta == 0) {                        // all per-block accumulators start at zero (the peers add only after the exchange below)
+        unsigned long long *acc = reinterpret_cast<unsigned long long *>(p.peer_xchg[p.rank] + xchg_ll_off_ints(world));
+        for (int i = tid; i < kXchgRot * kMainVals; i += kThreads) acc[i] = 0ULL;
+        __threadfence_system();
+    }
     grid_arrive(p.bar);
     grid_wait(p.bar, (++bar_gen) * p.nCTA);
     xchg(kXAbs, nullptr, 0, 0, tid, kThreads, cta_sync);   // max |eps| over all GPUs
@@ -1138,24 +1148,20 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                 long long sm_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotSm + (2 * wk + 1) * kLine));
                 long long e_hi = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps));
                 long long e_lo = __ldcg(reinterpret_cast<const long long *>(slot + kSlotEps + kLine));
-                for (int pr = 0; pr < world; ++pr) {              // + the peers' sums, as their LL cells arrive
-                    if (pr == p.rank) continue;
-                    const ulonglong2 *cell = reinterpret_cast<const ulonglong2 *>(p.peer_xchg[p.rank] + xchg_ll_off_ints(world)) + (size_t(pr) * kXchgRot + main_rot) * kMainVals;
+                if (MG && world > 1) {                              // + the peers' sums: one accumulator word per value, complete at count world-1
+                    const unsigned long long *acc = reinterpret_cast<const unsigned long long *>(p.peer_xchg[p.rank] + xchg_ll_off_ints(world)) + size_t(main_rot) * kMainVals;
                     const uint32_t ci[6] = {2u * wk, 2u * wk + 1u, 2u * kB + 2u * wk, 2u * kB + 2u * wk + 1u, 4u * kB, 4u * kB + 1u};
-                    ulonglong2 c[6];
+                    unsigned long long c[6];
                     const long long t0 = clock64();
                     for (;;) {
                         bool ok = true;
 #pragma unroll
-                        for (int q6 = 0; q6 < 6; ++q6) {
-                            c[q6] = ld_sys_v2(cell + ci[q6]);
-                            ok = ok && uint32_t(c[q6].x >> 32) == main_id && uint32_t(c[q6].y >> 32) == main_id;
-                        }
+                        for (int q6 = 0; q6 < 6; ++q6) { c[q6] = ld_sys_u64(acc + ci[q6]); ok = ok && line_count(c[q6]) == unsigned(world - 1); }
                         if (ok) break;
                         if ((sh.err & 2u) || clock64() - t0 > 6000000000LL) { sh.err |= 2u; break; }   // ~3 s: a peer is gone; fail, do not hang
                     }
-                    auto val = [](const ulonglong2 &x) { return (long long)((x.x & 0xffffffffULL) | (x.y << 32)); };
-                    tlo += val(c[0]); thi += val(c[1]); sm_hi += val(c[2]); sm_lo += val(c[3]); e_hi += val(c[4]); e_lo += val(c[5]);
+                    tlo += line_value(c[0]); thi += line_value(c[1]); sm_hi += line_value(c[2]); sm_lo += line_value(c[3]);
+                    e_hi += line_value(c[4]); e_lo += line_value(c[5]);
                 }
                 const double eps_sum_total = (double(e_hi) * 4294967296.0 + double(e_lo)) * inv_scale;
                 // tlo = sum_l S_l 2^(8l) over limbs 0..3, thi over limbs 4..7 (combined per CTA before the reduction)
@@ -1218,6 +1224,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             zero_turn += int(p.nCTA);
             int *old = p.slots + size_t((b - 2) % kSlots) * kSlotInts;
             for (int i = tid; i < kSlotMainLines; i += kThreads) *reinterpret_cast<unsigned long long *>(old + i * kLine) = 0ULL;
+            if (MG && world > 1) {
+                unsigned long long *acc = reinterpret_cast<unsigned long long *>(p.peer_xchg[p.rank] + xchg_ll_off_ints(world)) + size_t((b - 2) % kXchgRot) * kMainVals;
+                for (int i = tid; i < kMainVals; i += kThreads) acc[i] = 0ULL;
+            }
             const uint32_t used = sh.lz_hist[(b - 2) % kSlots];
             for (uint32_t i = tid; i < used * kCols; i += kThreads) *reinterpret_cast<int4 *>(old + kSlotLazy + size_t(i) * kLine) = make_int4(0, 0, 0, 0);
         }
