@@ -1,4 +1,4 @@
-// Persistent cooperative Gibbs-sweep kernel, dense 2-bit layout (sm_100a), version 3.
+// Persistent cooperative Gibbs-sweep kernel, dense 2-bit layout (sm_100a), version 4.
 //
 // One launch = one AnalysisGraph::exec (reference src/sequential.cpp:10-27 driving
 // src/BayesRBase.cpp:287-392 over all markers of the sweep, in the given order).
@@ -12,7 +12,8 @@
 //     (the next 64 of the permutation) is fetched with TMA 1-D bulk copies (cp.async.bulk + mbarrier),
 //     double buffered, two blocks ahead.
 //   * All O(N) arithmetic runs on the tensor cores as INTEGER matrix products (mma.sync m16n8k32,
-//     u8 x u8 / u8 x s8 -> s32): a register-only 2-bit -> int8 expansion ((w >> 2c) & 0x03030303) feeds
+//     u8 x u8 / u8 x s8 -> s32): a register-only 2-bit -> int8 expansion (class c of a code word in place, w & (0x03030303 << 2c),
+//     one accumulator per class) feeds
 //       - the DOT pass:   64 markers x 8 limbs,   S[m][l] = sum_i g_mi * limb_l(q_i)
 //       - the GRAM rows:  u x 64 marker pairs,    GG[j][k] = sum_i g_ji * g_ki, ONLY for the rows j of
 //         markers that change the residual (not skipUpdate, src/BayesRBase.cpp:372) -- computed on demand.
@@ -23,7 +24,10 @@
 //     barrier of block b, read the reduced dots back and sample the 64 markers, while warps 2-15 already
 //     run the dot pass of block b+1 against the current residual -- speculating that block b leaves the
 //     residual untouched (true for most blocks once the chain has left burn-in).  If block b does update
-//     the residual, the speculative partial sums are dropped and the dot pass is repeated after the update.
+//     the residual, the published sums of block b+1 are completed by a carry taken from the block-(b+1) half of block
+//     b's Gram rows: a dot pass is never repeated.
+//   * Several GPUs (individuals sharded): the per-block sums of the peers are ADDED into count-carrying accumulators over
+//     NVLink and polled at read-back; Gram rows travel as LL cells (see "cross-GPU exchange").
 //   * The walk: lane k samples marker k with
 //         num_k = x_k.eps_blockstart - sum_{j<k updated} (beta_j,new - beta_j,old) x_j.x_k + beta_old,k (N-1),
 //     which is exactly the dot against the residual the one-by-one loop would have seen.  Lanes
