@@ -145,6 +145,11 @@ __host__ __device__ inline size_t xchg_ll_ints(int world) { return size_t(world)
 // The Gram rows of a lazy round travel the same way when every CTA consumes them at read-back (the usual case: the block's rows
 // fit the shared-memory row slots): value i of the round = u64 #(i & 1) of entry (row - r0, column) = i >> 1.
 constexpr int kLazyCells = 2 * kB * kCols;
+// Alternative for the Gram-row rounds, NOT enabled yet (correct on one device, to be measured on 8 GPUs next round): count-carrying
+// accumulators as for the per-block round (one word per value at the head of the lazy LL region, peers add value + kCnt1, the push
+// spread over all CTAs, readers poll two words per entry whatever the number of GPUs).  The counts a, cw, cy, cz are non-negative
+// and below 2^24 in the upper halves, so count = word >> 56 and value = word & (2^56 - 1).
+constexpr bool kLazyAcc = false;
 __host__ __device__ inline size_t xchg_lazy_ll_off_ints(int world) { return xchg_ll_off_ints(world) + xchg_ll_ints(world); }
 __host__ __device__ inline size_t xchg_total_ints(int world) { return xchg_lazy_ll_off_ints(world) + size_t(world) * kXchgRot * kLazyCells * 4 + 8; }
 enum { kXAbs = 0, kXMain = 1, kXLazy = 2 };
@@ -198,6 +203,7 @@ struct SweepShared {   // fixed-size part; limbs, code buffers, scratch and the 
     unsigned long long wq[kWarps][2]; // per-warp sums of q over the slice, (hi, lo) parts
     double scale, inv_scale;
     uint32_t ns_list[kB];
+    uint32_t lza_hist[4];            // kLazyAcc: Gram rows sent through each rotation of the lazy accumulators by its last round
     uint32_t n_ns;
     uint32_t n_nonskipped_total;
     uint32_t err;
@@ -541,6 +547,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
     if (MG && world > 1 && cta == 0) {                        // all per-block accumulators start at zero (the peers add only after the exchange below)
         unsigned long long *acc = reinterpret_cast<unsigned long long *>(p.peer_xchg[p.rank] + xchg_ll_off_ints(world));
         for (int i = tid; i < kXchgRot * kMainVals; i += kThreads) acc[i] = 0ULL;
+        __threadfence_system();
+    }
+    if (MG && kLazyAcc && world > 1) {                        // ... and the Gram-row accumulators (all CTAs share the 512 KB)
+        unsigned long long *accl = reinterpret_cast<unsigned long long *>(p.peer_xchg[p.rank] + xchg_lazy_ll_off_ints(world));
+        for (uint32_t i = cta * kThreads + tid; i < uint32_t(kXchgRot * kLazyCells); i += p.nCTA * kThreads) accl[i] = 0ULL;
+        if (tid < kXchgRot) sh.lza_hist[tid] = 0u;
         __threadfence_system();
     }
     grid_arrive(p.bar);
@@ -987,6 +999,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
         }
         PHASE(kProfLazyMma);
         // (3) the grid-wide round
+        if (MG && kLazyAcc && world > 1 && keep_next) {
+            // the rotation this round's successor-but-one will use was last used two rounds ago: every CTA of this GPU has left that
+            // round's read-back (it passed the previous round's barrier), and no peer adds into it before it has seen this GPU's next
+            // round.  One CTA clears the rows used then; the arrive below publishes the zeros.
+            const uint32_t zr = (lcount + 2u) % kXchgRot;
+            if (cta == lcount % p.nCTA) {
+                unsigned long long *accl = reinterpret_cast<unsigned long long *>(p.peer_xchg[p.rank] + xchg_lazy_ll_off_ints(world)) + size_t(zr) * kLazyCells;
+                for (uint32_t i = tid; i < sh.lza_hist[zr] * 2u * kCols; i += kThreads) accl[i] = 0ULL;
+            }
+        }
         grid_arrive(p.bar);
         grid_wait(p.bar, (++bar_gen) * p.nCTA);
         // several GPUs: when the rows keep their next-block half in shared memory (keep_next) nobody reads the global slot after
@@ -1001,7 +1023,15 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
             lrot = int(lcount++ % kXchgRot);
             ll_rows += nnew;
             const uint32_t E = p.xchg_ctas;
-            if (cta < E) {
+            if (kLazyAcc) {
+                const uint32_t totv = nnew * 2 * kCols, np = MG ? uint32_t(world - 1) : 1u;
+                for (uint32_t idx = cta * kThreads + tid; idx < totv * np; idx += p.nCTA * kThreads) {
+                    const uint32_t i = idx / np, pj = idx - i * np, pr = pj < uint32_t(p.rank) ? pj : pj + 1u;
+                    const unsigned long long v = __ldcg(reinterpret_cast<const unsigned long long *>(slot + kSlotLazy + (size_t(r0) * kCols + (i >> 1)) * kLine) + (i & 1u));
+                    red_sys_add_u64(reinterpret_cast<unsigned long long *>(p.peer_xchg[pr] + xchg_lazy_ll_off_ints(world)) + size_t(lrot) * kLazyCells + i, v + kCnt1);
+                }
+                if (tid == 0) sh.lza_hist[lrot] = nnew;         // (read two rounds later, behind CTA barriers)
+            } else if (cta < E) {
                 const uint32_t totv = nnew * 2 * kCols, per = (totv + E - 1) / E, vlo = min(totv, cta * per), vhi = min(totv, vlo + per);
                 const unsigned long long idh = (unsigned long long)lazy_id << 32;
                 for (uint32_t i = vlo + tid; i < vhi; i += kThreads) {
@@ -1035,6 +1065,19 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense_kernel(const DenseSwe
                     const uint32_t en = base + tid + t * kThreads;
                     if (en >= tot) continue;
                     const size_t ci = 2 * (size_t(en >> csh) * kCols + (en & (ncol - 1u)));
+                    if (kLazyAcc) {
+                        const unsigned long long *accl = reinterpret_cast<const unsigned long long *>(p.peer_xchg[p.rank] + xchg_lazy_ll_off_ints(world)) + size_t(lrot) * kLazyCells + ci;
+                        unsigned long long c0, c1;
+                        const long long t0 = clock64();
+                        for (;;) {
+                            c0 = ld_sys_u64(accl); c1 = ld_sys_u64(accl + 1);
+                            if (unsigned(c0 >> 56) == unsigned(world - 1) && unsigned(c1 >> 56) == unsigned(world - 1)) break;
+                            if ((sh.err & 2u) || clock64() - t0 > 6000000000LL) { sh.err |= 2u; break; }   // ~3 s: a peer is gone; fail, do not hang
+                        }
+                        c0 &= kCnt1 - 1ULL; c1 &= kCnt1 - 1ULL;
+                        v[t].x += int(uint32_t(c0)); v[t].y += int(uint32_t(c0 >> 32)); v[t].z += int(uint32_t(c1)); v[t].w += int(uint32_t(c1 >> 32));
+                        continue;
+                    }
                     for (int pr = 0; pr < world; ++pr) {
                         if (pr == p.rank) continue;
                         const ulonglong2 *cell = reinterpret_cast<const ulonglong2 *>(p.peer_xchg[p.rank] + xchg_lazy_ll_off_ints(world)) + (size_t(pr) * kXchgRot + lrot) * kLazyCells + ci;
