@@ -21,7 +21,7 @@ SYMBOLS = [
     "brr_gpu_sweep", "brr_gpu_sweep_stage", "brr_gpu_sweep_run", "brr_gpu_sweep_fetch", "brr_gpu_compute_num",
     "brr_gpu_apply_delta", "brr_gpu_ipc_export", "brr_gpu_ipc_attach", "brr_gpu_attach_local",
     "brr_gpu_num_blocks", "brr_gpu_stream", "brr_gpu_synth_dense", "brr_gpu_synth_ragged", "brr_gpu_synth_bed_host", "brr_gpu_info",
-    "brr_gpu_launch_count", "brr_gpu_profile_cycles",
+    "brr_gpu_launch_count", "brr_gpu_profile_cycles", "brr_gpu_kernel_version",
 ]
 
 
@@ -90,6 +90,7 @@ def load_library():
     lib.brr_gpu_launch_count.argtypes = [vp]
     lib.brr_gpu_launch_count.restype = C.c_uint64
     lib.brr_gpu_profile_cycles.argtypes = [vp, vp, C.c_int]
+    lib.brr_gpu_kernel_version.restype = C.c_char_p
     _lib = lib
     return lib
 
@@ -264,7 +265,8 @@ class Engine:
     def info(self):
         a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
         self._check(self.lib.brr_gpu_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
-        return dict(n_ctas=a.value, slice_inds=b.value, block_markers=c.value, genotype_bytes=d.value)
+        return dict(n_ctas=a.value, slice_inds=b.value, block_markers=c.value, genotype_bytes=d.value,
+                    kernel_version=self.lib.brr_gpu_kernel_version().decode())
 
     def launch_count(self):
         return int(self.lib.brr_gpu_launch_count(self._h))

@@ -173,6 +173,12 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
     if (cfg->layout < BRR_GPU_LAYOUT_DENSE2BIT || cfg->layout > BRR_GPU_LAYOUT_EIGEN) return fail(BRR_GPU_EINVAL, "unknown layout %d", cfg->layout);
     if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(BRR_GPU_EINVAL, "bad rank/world");
     if (cfg->n_inds_total < cfg->n_inds) return fail(BRR_GPU_EINVAL, "n_inds_total < n_inds");
+    if (cfg->layout != BRR_GPU_LAYOUT_DENSE2BIT && (cfg->world > 1 || cfg->n_inds_total != cfg->n_inds))
+        return fail(BRR_GPU_EINVAL, "the ragged / eigen layouts have no cross-shard exchange: world must be 1 and n_inds_total == n_inds "
+                                    "(got world=%d, n_inds=%u, n_inds_total=%u); shard the dense 2-bit layout instead", cfg->world, cfg->n_inds, cfg->n_inds_total);
+    if (cfg->world == 1 && cfg->n_inds_total != cfg->n_inds) return fail(BRR_GPU_EINVAL, "world=1 but n_inds_total (%u) != n_inds (%u)", cfg->n_inds_total, cfg->n_inds);
+    // the cross-GPU accumulators carry an arrival count above bit 56: |sum of 3 * limb-combined q| must stay below 2^55
+    if (cfg->world > 1 && cfg->n_inds_total > 5500000u) return fail(BRR_GPU_EINVAL, "n_inds_total=%u exceeds the 5.5M bound of the cross-GPU accumulators", cfg->n_inds_total);
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -297,7 +303,7 @@ extern "C" int brr_gpu_upload_dense2bit(brr_gpu_ctx *c, const uint8_t *bed, size
 {
     CHECK_CTX(c);
     if (c->cfg.layout != BRR_GPU_LAYOUT_DENSE2BIT) return fail(BRR_GPU_ESTATE, "context layout is not dense2bit");
-    if (!bed || first + count > c->cfg.n_markers) return fail(BRR_GPU_EINVAL, "bad marker range");
+    if (!bed || uint64_t(first) + uint64_t(count) > uint64_t(c->cfg.n_markers)) return fail(BRR_GPU_EINVAL, "bad marker range");
     const size_t col_bytes = (size_t(c->cfg.n_inds) + 3) / 4;
     if (col_stride < col_bytes) return fail(BRR_GPU_EINVAL, "col_stride %zu < %zu", col_stride, col_bytes);
     const size_t chunk_markers = std::max<size_t>(1, std::min<size_t>(count, (size_t(256) << 20) / col_bytes));
@@ -513,6 +519,8 @@ static int launch_dense(brr_gpu_ctx *c)
     CUDA_TRY(cudaMemsetAsync(c->slots, 0, sizeof(int) * (size_t(kSlots) * kSlotInts + 8), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->out_counts, 0, sizeof(unsigned) * 4, c->stream));
     void *args[] = {&p};
+    // per-function state, shared by every context of the process: re-apply this context's size before each launch
+    CUDA_TRY(cudaFuncSetAttribute(dense_sweep_fn(c->cfg.world > 1, p.prof != nullptr), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
     CUDA_TRY(cudaLaunchCooperativeKernel(dense_sweep_fn(c->cfg.world > 1, p.prof != nullptr), dim3(c->nCTA), dim3(kThreads), args,
                                          c->smem_bytes, c->stream));
@@ -546,7 +554,9 @@ extern "C" int brr_gpu_sweep_fetch(brr_gpu_ctx *c, double *v, double *betasqn, b
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(BRR_GPU_ECUDA, "sweep failed: %s", cudaGetErrorString(e));
     if (c->h_counts[2] != 0)
-        return fail(BRR_GPU_ESTATE, "sweep failed: the residual grew past the fixed-point range of the dot products inside one sweep (flags 0x%x)", c->h_counts[2]);
+        return fail(BRR_GPU_ESTATE, "sweep failed (flags 0x%x):%s%s; the chain state on the device is no longer valid -- restore it with brr_gpu_set_state", c->h_counts[2],
+                    (c->h_counts[2] & 1u) ? " the residual grew past the fixed-point range of the dot products inside one sweep" : "",
+                    (c->h_counts[2] & 2u) ? " a peer GPU did not deliver its sums in time (is every rank calling brr_gpu_sweep?)" : "");
     if (v) memcpy(v, h, sizeof(double) * nG * K);
     if (betasqn) memcpy(betasqn, h + kMaxGK, sizeof(double) * nG);
     cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
@@ -687,6 +697,7 @@ extern "C" int brr_gpu_info(brr_gpu_ctx *c, uint32_t *n_ctas, uint32_t *slice_in
 }
 
 extern "C" uint64_t brr_gpu_launch_count(brr_gpu_ctx *c) { return c ? c->launches : 0; }
+extern "C" const char *brr_gpu_kernel_version(void) { return kDenseKernelVersion; }
 
 extern "C" int brr_gpu_profile_cycles(brr_gpu_ctx *c, uint64_t *cycles40, int reset)
 {

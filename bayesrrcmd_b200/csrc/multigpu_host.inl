@@ -7,6 +7,7 @@ extern "C" int brr_gpu_ipc_export(brr_gpu_ctx *c, void *handle_out)
 {
     CHECK_CTX(c);
     if (!handle_out) return fail(BRR_GPU_EINVAL, "null handle buffer");
+    if (c->cfg.layout != BRR_GPU_LAYOUT_DENSE2BIT) return fail(BRR_GPU_ESTATE, "the multi-GPU exchange exists for the dense 2-bit layout only (this context's layout is %d)", c->cfg.layout);
     if (c->cfg.world < 2 || !c->xchg) return fail(BRR_GPU_ESTATE, "context was created with world=1: nothing to exchange");
     static_assert(sizeof(cudaIpcMemHandle_t) == BRR_GPU_IPC_HANDLE_BYTES, "IPC handle size");
     cudaIpcMemHandle_t h;

@@ -197,6 +197,7 @@ static int launch_ragged(brr_gpu_ctx *c)
     CUDA_TRY(cudaMemsetAsync(c->bar, 0, sizeof(unsigned) * 4, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->out_counts, 0, sizeof(unsigned) * 4, c->stream));      // [2] = error flags read by sweep_fetch
     void *args[] = {&p};
+    CUDA_TRY(cudaFuncSetAttribute(sweep_ragged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));   // per-function state: see launch_dense
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
     CUDA_TRY(cudaLaunchCooperativeKernel((const void *)sweep_ragged_kernel, dim3(c->nCTA), dim3(kThreads), args, c->smem_bytes, c->stream));
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));

@@ -47,6 +47,7 @@
 
 namespace brr {
 
+constexpr const char *kDenseKernelVersion = "v4";
 constexpr int kB = 64;                 // markers per block = tile structure of the MMA passes
 constexpr int kLimbs = 8;
 constexpr uint32_t kM3 = 0x03030303u;

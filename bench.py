@@ -30,6 +30,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SEED = 20260101
+# ONE metric string for both arms (the driver pairs the lines by it); sizes live in `config`.
+METRIC = "marker updates/sec (ppbayes Gibbs sweep, dense)"
+ARITHMETIC = ("fp64 chain state (eps, beta, draws); x_j.eps as exact 64-bit fixed-point integer dots (eps quantised per sweep to "
+              "2^-s with >= 57 significant bits relative to max|eps|, 8 int8 limbs x 2-bit codes on integer MMA, int64 reductions)")
 MAF_LO, MAF_HI, P_MISSING = 0.01, 0.5, 0.001
 S_CVA = np.array([[0.01, 0.001, 0.0001]])
 N_CAUSAL, H2 = 1000, 0.5
@@ -99,17 +103,37 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def reference_phenotype(n_inds, n_markers):
+    """The bench phenotype rebuilt WITHOUT the product library (reference arm): the same rng stream as the engine arm
+    (causal markers, effects, noise), the causal columns from the numpy twin of the synthetic generator, standardised by the
+    reference's own DenseMarkerBuilder (oracle/_ref), y = noise + sum_j b_j x_j, then BayesRBase::init's standardisation."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_lib as R
+    import synth_np
+    rng = np.random.default_rng(SEED)
+    causal = rng.choice(n_markers, N_CAUSAL, replace=False)
+    bcausal = rng.standard_normal(N_CAUSAL) * np.sqrt(H2 / N_CAUSAL)
+    y = rng.standard_normal(n_inds) * np.sqrt(1.0 - H2)
+    for j, b in zip(causal, bcausal):
+        col = synth_np.synth_bed(SEED, n_inds, [int(j)], MAF_LO, MAF_HI, False, P_MISSING)[0]
+        y += b * R.dense_column(col, n_inds)
+    y = y.astype(np.float32).astype(np.float64)
+    y -= y.sum() / n_inds
+    return y / np.sqrt((y ** 2).sum() / (n_inds - 1))
+
+
 def cpu_reference_leg(n_inds, n_markers, eps_y, steps, warmup=0):
     """The reference's own CPU implementation of the path (oracle/_ref, built from /root/reference with the
     shipped -O3 -ffast-math flags), on a bounded sample: the first `n_markers` markers of the SAME synthetic
-    data set, all N individuals, dense layout, marker cache (Sequential graph: 1 core by construction)."""
+    data set, all N individuals, dense layout, marker cache (Sequential graph: 1 core by construction).
+    No product library is mapped by this leg: the data set comes from oracle/synth_np.py (numpy twin of the device generator)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_lib as R
-    from bayesrrcmd_b200.capi import synth_bed_host
+    import synth_np
     fast = R.ref_available(fast=True)
     if not fast and not R.ref_available():
         return None
-    bed = synth_bed_host(SEED, n_inds, 0, n_markers, MAF_LO, MAF_HI, False, P_MISSING)
+    bed = synth_np.synth_bed(SEED, n_inds, np.arange(n_markers), MAF_LO, MAF_HI, False, P_MISSING)
     y = np.asarray(eps_y, dtype=np.float32)
     _, t = R.run_chain(bed, n_inds, n_markers, y, S_CVA, seed=1, iterations=warmup + steps, layout=0, dump=False, fast=fast)
     per_sweep = t["total_s"] / (warmup + steps)
@@ -141,17 +165,18 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        rng = np.random.default_rng(SEED)
-        y = rng.standard_normal(N).astype(np.float32)
-        leg = cpu_reference_leg(N, a.cpu_markers, y, a.steps, a.warmup)
-        if leg is None:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_lib as R
+        if not (R.ref_available(fast=True) or R.ref_available()):
             emit({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"})
             return
-        line = {"impl": "reference", "metric": "marker updates/sec (ppbayes Gibbs sweep, dense)", "value": leg["value"],
+        y = reference_phenotype(N, M)          # y = X beta + e, as the engine arm
+        leg = cpu_reference_leg(N, a.cpu_markers, y, a.steps, a.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": leg["value"],
                 "unit": "marker updates/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * leg["s_per_sweep_sample"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "sample": leg["sample"]},
+                "config": {"workload": workload, "sample": leg["sample"], "arithmetic": "fp64 (Eigen), -O3 -ffast-math as shipped"},
                 "cpu_baseline": leg,
                 "e2e": {"value": leg["value"], "unit": "marker updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
@@ -203,6 +228,8 @@ def main():
     mu = 0.0
 
     kernel_ms, e2e_s, nonskipped, blocks = [], [], [], []
+    warm = []                                  # (kernel ms, non-skipped markers) of the warm-up sweeps: the chain's update-heavy start
+    state_hash = [None]
     h2d = d2h = 0
     sampler = None
 
@@ -220,6 +247,9 @@ def main():
         v, bs, out = eng.sweep(order, rand_uz, pi, sigmaG, sigmaE)     # the plugin call: host buffers in, host out
         _, beta, comp, acum = eng.get_state(eps=False)
         t1 = time.perf_counter()
+        state_hash[0] = (beta, comp)
+        if not timed:
+            warm.append((out.kernel_ms, out.n_nonskipped))
         if timed:
             kernel_ms.append(out.kernel_ms); e2e_s.append(t1 - t0)
             nonskipped.append(out.n_nonskipped); blocks.append(out.n_blocks)
@@ -256,41 +286,56 @@ def main():
                          + "  | overlapped: " + "  ".join("%s=%d" % (k, pc[k] // nblk) for k in eng.PROFILE_OVERLAPPED)
                          + "  | per block: " + "  ".join("%s=%.3f" % (k, pc[k] / nblk) for k in eng.PROFILE_COUNTERS) + "\n")
     ksum = sum(kernel_ms) / 1e3; esum = sum(e2e_s)
+    ranks_identical = None
     if world > 1:
         t = torch.tensor([ksum, esum], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ksum, esum = float(t[0]), float(t[1])
+        # every rank walks the same chain from the same integer sums: beta / components must be BIT-identical on all ranks
+        import hashlib
+        h = hashlib.sha256(state_hash[0][0].tobytes() + state_hash[0][1].tobytes()).hexdigest()
+        hs = grp.gather(h)
+        ranks_identical = all(x == hs[0] for x in hs)
+        if not ranks_identical:
+            raise SystemExit("bench: beta/components differ between ranks after the timed sweeps: %s" % hs)
     if rank != 0:
         dist.destroy_process_group()
         return
 
     peak, peak_src = measured_peak()
-    traffic = None                              # DRAM bytes of one full-size launch, from the committed ncu capture (one GPU only)
+    # DRAM bytes of one full-size launch: from the committed ncu capture (profiles/ncu_traffic.json), only when that capture
+    # was taken on THIS kernel version and problem size (null otherwise: a stale figure explains nothing)
+    traffic, traffic_src = None, None
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        if world == 1 and N == 500000 and M == 1000000:
+        if world == 1 and N == int(t.get("n_inds", 0)) and M == int(t.get("n_markers", 0)) and t.get("kernel_version") == info.get("kernel_version"):
             traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+            traffic_src = "ncu --set full capture of one launch of kernel version %s, committed as profiles/ncu_traffic.json" % t.get("kernel_version")
     except Exception:
         pass
     alg_bytes = ((n_loc + 3) // 4) * M                  # ceil(N_shard/4) genotype bytes per marker update
     achieved = alg_bytes / (ksum / a.steps) / 1e9
     line = {
-        "metric": "marker updates/sec (ppbayes Gibbs sweep, dense 2-bit, N=500k x M=1M)",
+        "metric": METRIC,
         "value": M * a.steps / ksum, "unit": "marker updates/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * ksum / a.steps, "s_per_sweep": ksum / a.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "parallelism": "individuals sharded over %d GPU(s)" % world,
                    "block_markers": info["block_markers"], "ctas": info["n_ctas"], "slice_inds": info["slice_inds"],
                    "genotype_bytes_per_gpu": info["genotype_bytes"], "l2": "inputs (%.1f GB/GPU) are larger than L2" % (info["genotype_bytes"] / 1e9),
+                   "n_inds": N, "n_markers": M, "arithmetic": ARITHMETIC, "kernel_version": info.get("kernel_version"),
+                   "regime": "timed sweeps = sweeps %d..%d of a chain started from BayesRBase::init's state; %.4f%% of the markers non-skipped "
+                             "(beta_old != 0 or beta_new != 0) per timed sweep; the cost of a sweep depends on that fraction" % (
+                                 a.warmup, a.warmup + a.steps - 1, 100.0 * float(np.mean(nonskipped)) / M),
+                   "chain_start": [{"sweep": i, "ms": float(ms), "nonskipped_fraction": ns / M} for i, (ms, ns) in enumerate(warm[:3])],
                    "nonskipped_fraction": float(np.mean(nonskipped)) / M, "exchanges_per_sweep": int(np.mean(blocks)),
-                   "setup_s": gen_s},
+                   "ranks_bit_identical": ranks_identical, "setup_s": gen_s},
         "e2e": {"value": M * a.steps / esum, "unit": "marker updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "s_per_sweep": esum / a.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "sweep_dense_kernel",
-                     "algorithmic_bytes_per_launch": int(alg_bytes),
-                     "note": "traffic = dram bytes of one launch (ncu, profiles/ncu_traffic.json): 1.05x the algorithmic bytes (row tails); the gap to the roofline is per-block latency, not traffic (DESIGN.md 4.1)"},
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "sweep_dense_kernel",
+                     "algorithmic_bytes_per_launch": int(alg_bytes)},
         "clocks": sampler.summary() if sampler else None,
     }
     if not a.no_cpu_baseline:

@@ -72,7 +72,9 @@ typedef struct {
                                  markers of a block are corrected with the block's Gram matrix. */
     uint32_t max_ctas;        /* 0 = one CTA per SM */
     int32_t rank;             /* shard index, 0..world-1 */
-    int32_t world;            /* number of shards (GPUs); individuals are split across them */
+    int32_t world;            /* number of shards (GPUs); individuals are split across them.  Dense 2-bit layout only:
+                                 the ragged / eigen layouts have no cross-shard exchange and brr_gpu_create rejects
+                                 world > 1 (or n_inds_total != n_inds) for them with BRR_GPU_EINVAL */
 } brr_gpu_config;
 
 /* Outputs of one sweep: what runGibbs needs after exec() (src/BayesRBase.cpp:238-247). */
@@ -141,7 +143,8 @@ int brr_gpu_eps_reduce(brr_gpu_ctx *ctx, double *sum_out, double *sqnorm_out);
  * rand_uz: M x 2 (u, z) indexed by MARKER ID (src/BayesRBase.cpp:343-344);
  * pi: n_groups x K; sigmaG: n_groups; eps_sum_in: m_epsilonSum (ragged layout only);
  * async_tokens: 0 = synchronous ppbayes; T > 0 = bounded-staleness asyncppbayes with T markers in
- * flight (Options::analysisTokens, src/options.hpp:33), T <= 32.
+ * flight (Options::analysisTokens, src/options.hpp:33), T <= 64 for the dense layout, T <= 32 for the
+ * ragged / eigen layouts (BRR_GPU_EINVAL beyond).
  * v (n_groups x K) and betasqn (n_groups) are OVERWRITTEN with this sweep's counts / sums
  * (runGibbs zeroes them before exec, src/BayesRBase.cpp:200-202). */
 int brr_gpu_sweep(brr_gpu_ctx *ctx, const uint32_t *marker_order, uint32_t n_order, const double *rand_uz,
@@ -205,6 +208,8 @@ int brr_gpu_synth_bed_host(uint64_t seed, double maf_lo, double maf_hi, int log_
 int brr_gpu_info(brr_gpu_ctx *ctx, uint32_t *n_ctas, uint32_t *slice_inds, uint32_t *block_markers,
                  uint64_t *genotype_bytes);
 uint64_t brr_gpu_launch_count(brr_gpu_ctx *ctx);
+/* Version tag of the dense sweep kernel this library was built with (bench lines and ncu captures carry it). */
+const char *brr_gpu_kernel_version(void);
 /* Phase breakdown of the dense sweep kernel (SM cycles of CTA 0, accumulated over sweeps), available when
  * the environment has BRR_GPU_PROFILE=1 at brr_gpu_create: 40 counters in the order wait (grid barrier),
  * cross-GPU exchange, read-back, sampling, join (walkers waiting for the dot warps), publish (next block's
