@@ -21,7 +21,7 @@ SYMBOLS = [
     "brr_gpu_sweep", "brr_gpu_sweep_stage", "brr_gpu_sweep_run", "brr_gpu_sweep_fetch", "brr_gpu_compute_num",
     "brr_gpu_apply_delta", "brr_gpu_ipc_export", "brr_gpu_ipc_attach", "brr_gpu_attach_local",
     "brr_gpu_num_blocks", "brr_gpu_stream", "brr_gpu_synth_dense", "brr_gpu_synth_ragged", "brr_gpu_synth_bed_host", "brr_gpu_info",
-    "brr_gpu_launch_count", "brr_gpu_profile_cycles", "brr_gpu_kernel_version",
+    "brr_gpu_launch_count", "brr_gpu_profile_cycles", "brr_gpu_kernel_version", "brr_gpu_profile_cycles5", "brr_gpu_last_sweep_info",
 ]
 
 
@@ -91,6 +91,8 @@ def load_library():
     lib.brr_gpu_launch_count.restype = C.c_uint64
     lib.brr_gpu_profile_cycles.argtypes = [vp, vp, C.c_int]
     lib.brr_gpu_kernel_version.restype = C.c_char_p
+    lib.brr_gpu_profile_cycles5.argtypes = [vp, vp, C.c_int]
+    lib.brr_gpu_last_sweep_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     _lib = lib
     return lib
 
@@ -284,6 +286,21 @@ class Engine:
         a = np.zeros(40, dtype=np.uint64)
         self._check(self.lib.brr_gpu_profile_cycles(self._h, _ptr(a), int(reset)))
         return dict(zip(self.PROFILE_PHASES, (int(x) for x in a)))
+
+    PROFILE5 = ["w_plan", "w_bar", "w_read", "w_sample", "w_fix", "w_file", "d_gate", "d_apply", "d_tma", "d_loop", "d_post", "d_comb",
+                "blocks", "gram_blocks", "restarts", "applies", "p0_plan", "p0_issue"]
+
+    def profile_cycles5(self, reset=True):
+        """Phase cycle counters of the version-5 dense kernel (walker warp 0 / first dot warp / planner warp of CTA 0)."""
+        a = np.zeros(24, dtype=np.uint64)
+        self._check(self.lib.brr_gpu_profile_cycles5(self._h, _ptr(a), int(reset)))
+        return dict(zip(self.PROFILE5, (int(x) for x in a)))
+
+    def last_sweep_info(self):
+        """-> (dense kernel version of the last sweep: 4 or 5, pipeline restarts of a version-5 sweep)."""
+        k, r = C.c_uint32(), C.c_uint32()
+        self._check(self.lib.brr_gpu_last_sweep_info(self._h, C.byref(k), C.byref(r)))
+        return k.value, r.value
 
     def stream(self):
         return self.lib.brr_gpu_stream(self._h)

@@ -7,6 +7,7 @@
 #include "sampler.cuh"
 #include "store_kernels.cuh"
 #include "sweep_dense.cuh"
+#include "sweep_dense5.cuh"
 #include "sweep_ragged.cuh"
 
 #include <algorithm>
@@ -74,6 +75,17 @@ struct brr_gpu_ctx {
     double *v = nullptr, *betasq = nullptr, *out_scalars = nullptr;
     unsigned *out_counts = nullptr;
     unsigned long long *prof = nullptr;     // phase cycle counters (BRR_GPU_PROFILE=1)
+    // version-5 dense kernel (single GPU, synchronous): ring of per-block slots, per-CTA partial outputs
+    int *slots5 = nullptr;
+    double *part_bsq = nullptr;
+    int *part_v = nullptr;
+    unsigned long long *prof5 = nullptr;
+    size_t smem5_bytes = 0;
+    bool v5_ok = false;
+    int dense_mode = 0;                     // 0 = auto (per sweep), 4 / 5 = forced (BRR_GPU_DENSE_KERNEL)
+    bool have_last = false;                 // the previous sweep's non-skipped count is known and the chain state was not replaced since
+    double last_nonskipped_frac = 1.0;
+    uint32_t last_kernel = 0, last_restarts = 0;
     // multi-GPU exchange (world > 1)
     int *xchg = nullptr;                    // this rank's exchange buffer (mailboxes + flags), cudaMalloc'd, IPC-exported
     int **peer_ptrs_dev = nullptr;          // device array [world] of every rank's exchange buffer
@@ -116,6 +128,7 @@ extern "C" void brr_gpu_destroy(brr_gpu_ctx *c)
     void *ptrs[] = {c->codes, c->lut, c->counts_local, c->counts_global, c->group, c->cva, c->eps, c->beta, c->comp,
                     c->acum, c->order, c->rand_uz, c->pi, c->sigmaG, c->part_dot, c->cta_red,
                     c->red_partial, c->slots, c->v, c->betasq, c->out_scalars, c->out_counts, c->prof, c->round_ctr,
+                    c->slots5, c->part_bsq, c->part_v, c->prof5,
                     c->rag.idx16, c->rag.cta_base, c->rag.stats, c->rag.seg};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *q : c->peer_opened) cudaIpcCloseMemHandle(q);
@@ -232,6 +245,29 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
         c->absmax = reinterpret_cast<unsigned long long *>(c->slots + size_t(kSlots) * kSlotInts);
         c->bar = reinterpret_cast<unsigned *>(c->slots + size_t(kSlots) * kSlotInts + 2);
         c->bar2 = c->bar + 1;
+        if (const char *e = getenv("BRR_GPU_DENSE_KERNEL")) {
+            if (!strcmp(e, "v4")) c->dense_mode = 4; else if (!strcmp(e, "v5")) c->dense_mode = 5;
+        }
+        c->smem5_bytes = v5::sweep5_smem_bytes(c->RS);
+        if (cfg->world == 1 && c->dense_mode != 4 && c->smem5_bytes <= size_t(prop.sharedMemPerBlockOptin)) {
+            bool fits = true;
+            for (const void *fn : {(const void *)v5::sweep_dense5_kernel<false>, (const void *)v5::sweep_dense5_kernel<true>}) {
+                CUDA_OR_DESTROY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem5_bytes));
+                int o = 0;
+                CUDA_OR_DESTROY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, kThreads, c->smem5_bytes));
+                fits = fits && o >= 1 && uint32_t(o) * c->numSMs >= c->nCTA;
+            }
+            if (fits) {
+                TRY_OR_DESTROY(dev_alloc(&c->slots5, size_t(v5::kSlotRing) * v5::kSlotInts5));
+                TRY_OR_DESTROY(dev_alloc(&c->part_bsq, size_t(c->nCTA) * 2 * cfg->n_groups));
+                TRY_OR_DESTROY(dev_alloc(&c->part_v, size_t(c->nCTA) * cfg->n_groups * cfg->n_components));
+                c->v5_ok = true;
+            }
+        }
+        if (c->dense_mode == 5 && !c->v5_ok) {
+            int rc_ = fail(BRR_GPU_EINVAL, "BRR_GPU_DENSE_KERNEL=v5 but the version-5 kernel is not available for this context (world=%d, %zu bytes of shared memory per CTA)", cfg->world, c->smem5_bytes);
+            brr_gpu_destroy(c); return rc_;
+        }
         if (cfg->world > 1) {
             TRY_OR_DESTROY(dev_alloc(&c->xchg, xchg_total_ints(cfg->world)));
             CUDA_OR_DESTROY(cudaMemset(c->xchg, 0, sizeof(int) * xchg_total_ints(cfg->world)));
@@ -276,6 +312,8 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
         if (e[0] == '1') {
             TRY_OR_DESTROY(dev_alloc(&c->prof, kProfPhases));
             CUDA_OR_DESTROY(cudaMemset(c->prof, 0, sizeof(unsigned long long) * kProfPhases));
+            TRY_OR_DESTROY(dev_alloc(&c->prof5, v5::kPfN));
+            CUDA_OR_DESTROY(cudaMemset(c->prof5, 0, sizeof(unsigned long long) * v5::kPfN));
         }
     }
     CUDA_OR_DESTROY(cudaMallocHost(reinterpret_cast<void **>(&c->h_small), sizeof(double) * (2 * kMaxGK + 8 + 2 * kRedBlocks)));
@@ -424,6 +462,7 @@ extern "C" int brr_gpu_set_state(brr_gpu_ctx *c, const double *eps, const double
     if (components) CUDA_TRY(cudaMemcpyAsync(c->comp, components, sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
     if (acum) CUDA_TRY(cudaMemcpyAsync(c->acum, acum, sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (beta) c->have_last = false;          // the kernel choice of the next sweep must not rely on the previous chain
     return 0;
 }
 
@@ -529,13 +568,59 @@ static int launch_dense(brr_gpu_ctx *c)
     return 0;
 }
 
+// Version 5 (sweep_dense5.cuh): the steady-state kernel.  Chosen per sweep: it restarts its pipeline at every marker that ENTERS
+// the model, so it is used when the previous sweep of this chain had few non-skipped markers (the chain has left its start), and
+// version 4 (on-demand Gram rows) otherwise -- both produce the same chain.  BRR_GPU_DENSE_KERNEL=v4|v5 forces one of them.
+static const double kV5MaxNonskipped = 0.03;
+static bool use_v5(const brr_gpu_ctx *c)
+{
+    if (!c->v5_ok || c->async_tokens || c->cfg.world > 1) return false;
+    if (c->dense_mode == 5) return true;
+    if (c->dense_mode == 4) return false;
+    return c->have_last && c->last_nonskipped_frac <= kV5MaxNonskipped;
+}
+
+static int launch_dense5(brr_gpu_ctx *c)
+{
+    v5::Sweep5Params p{};
+    p.n_local = c->cfg.n_inds; p.n_total = c->cfg.n_inds_total; p.M = c->cfg.n_markers; p.K = c->cfg.n_components;
+    p.nG = c->cfg.n_groups; p.nCTA = c->nCTA; p.SL = c->SL; p.PW = c->PW; p.RS = c->RS;
+    p.codes = c->codes; p.lut = c->lut; p.counts = c->counts_global; p.group = c->group;
+    p.order = c->order; p.n_order = c->n_order; p.rand_uz = c->rand_uz; p.pi = c->pi; p.sigmaG = c->sigmaG; p.cva = c->cva;
+    p.sigmaE = c->sigmaE;
+    p.eps = c->eps; p.beta = c->beta; p.comp = c->comp; p.acum = c->acum;
+    p.slots = c->slots5; p.absmax = c->absmax; p.bar = c->bar; p.cta_red = c->cta_red;
+    p.part_bsq = c->part_bsq; p.part_v = c->part_v;
+    p.v = c->v; p.betasq = c->betasq; p.out_scalars = c->out_scalars; p.out_counts = c->out_counts;
+    p.prof = c->prof5;
+    CUDA_TRY(cudaMemsetAsync(c->slots5, 0, sizeof(int) * size_t(v5::kSlotRing) * v5::kSlotInts5, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->slots + size_t(kSlots) * kSlotInts, 0, sizeof(int) * 8, c->stream));     // absmax + barrier counters
+    CUDA_TRY(cudaMemsetAsync(c->out_counts, 0, sizeof(unsigned) * 4, c->stream));
+    const void *fn = p.prof ? (const void *)v5::sweep_dense5_kernel<true> : (const void *)v5::sweep_dense5_kernel<false>;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem5_bytes));
+    void *args[] = {&p};
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(c->nCTA), dim3(kThreads), args, c->smem5_bytes, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 1; c->last_launches = 1;
+    return 0;
+}
+
 static int launch_ragged(brr_gpu_ctx *c);
 
 extern "C" int brr_gpu_sweep_run(brr_gpu_ctx *c)
 {
     CHECK_CTX(c);
     if (!c->staged) return fail(BRR_GPU_ESTATE, "brr_gpu_sweep_stage not called");
-    int rc = (c->cfg.layout == BRR_GPU_LAYOUT_DENSE2BIT) ? launch_dense(c) : launch_ragged(c);
+    int rc;
+    if (c->cfg.layout == BRR_GPU_LAYOUT_DENSE2BIT) {
+        const bool five = use_v5(c);
+        rc = five ? launch_dense5(c) : launch_dense(c);
+        c->last_kernel = five ? 5u : 4u;
+    } else {
+        rc = launch_ragged(c);
+        c->last_kernel = 0;
+    }
     if (rc) return rc;
     c->ran = true;
     return 0;
@@ -554,11 +639,15 @@ extern "C" int brr_gpu_sweep_fetch(brr_gpu_ctx *c, double *v, double *betasqn, b
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(BRR_GPU_ECUDA, "sweep failed: %s", cudaGetErrorString(e));
     if (c->h_counts[2] != 0)
-        return fail(BRR_GPU_ESTATE, "sweep failed (flags 0x%x):%s%s; the chain state on the device is no longer valid -- restore it with brr_gpu_set_state", c->h_counts[2],
+        return fail(BRR_GPU_ESTATE, "sweep failed (flags 0x%x):%s%s%s; the chain state on the device is no longer valid -- restore it with brr_gpu_set_state", c->h_counts[2],
                     (c->h_counts[2] & 1u) ? " the residual grew past the fixed-point range of the dot products inside one sweep" : "",
-                    (c->h_counts[2] & 2u) ? " a peer GPU did not deliver its sums in time (is every rank calling brr_gpu_sweep?)" : "");
+                    (c->h_counts[2] & 2u) ? " a peer GPU did not deliver its sums in time (is every rank calling brr_gpu_sweep?)" : "",
+                    (c->h_counts[2] & 4u) ? " a wait inside the sweep pipeline timed out (internal protocol error)" : "");
     if (v) memcpy(v, h, sizeof(double) * nG * K);
     if (betasqn) memcpy(betasqn, h + kMaxGK, sizeof(double) * nG);
+    c->have_last = c->n_order > 0 && c->n_order == c->cfg.n_markers;
+    c->last_nonskipped_frac = c->n_order ? double(c->h_counts[0]) / double(c->n_order) : 1.0;
+    c->last_restarts = c->last_kernel == 5 ? c->h_counts[3] : 0u;
     cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
     if (out) {
         out->eps_sum = h[2 * kMaxGK]; out->eps_sqnorm = h[2 * kMaxGK + 1];
@@ -707,6 +796,25 @@ extern "C" int brr_gpu_profile_cycles(brr_gpu_ctx *c, uint64_t *cycles40, int re
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaMemcpy(cycles40, c->prof, sizeof(uint64_t) * kProfPhases, cudaMemcpyDeviceToHost));
     if (reset) CUDA_TRY(cudaMemset(c->prof, 0, sizeof(uint64_t) * kProfPhases));
+    return 0;
+}
+
+extern "C" int brr_gpu_profile_cycles5(brr_gpu_ctx *c, uint64_t *cycles24, int reset)
+{
+    CHECK_CTX(c);
+    if (!cycles24) return fail(BRR_GPU_EINVAL, "null output");
+    if (!c->prof5) return fail(BRR_GPU_ESTATE, "phase profiling is off: set BRR_GPU_PROFILE=1 before brr_gpu_create");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(cycles24, c->prof5, sizeof(uint64_t) * v5::kPfN, cudaMemcpyDeviceToHost));
+    if (reset) CUDA_TRY(cudaMemset(c->prof5, 0, sizeof(uint64_t) * v5::kPfN));
+    return 0;
+}
+
+extern "C" int brr_gpu_last_sweep_info(brr_gpu_ctx *c, uint32_t *kernel_version, uint32_t *restarts)
+{
+    if (!c) return fail(BRR_GPU_EINVAL, "null context");
+    if (kernel_version) *kernel_version = c->last_kernel;
+    if (restarts) *restarts = c->last_restarts;
     return 0;
 }
 

@@ -228,7 +228,8 @@ def main():
     mu = 0.0
 
     kernel_ms, e2e_s, nonskipped, blocks = [], [], [], []
-    warm = []                                  # (kernel ms, non-skipped markers) of the warm-up sweeps: the chain's update-heavy start
+    warm = []                                  # (kernel ms, non-skipped markers, dense kernel version) of the warm-up sweeps: the chain's update-heavy start
+    kernels, restarts = [], []                 # timed sweeps: dense kernel version the library chose, pipeline restarts (version 5)
     state_hash = [None]
     h2d = d2h = 0
     sampler = None
@@ -248,8 +249,11 @@ def main():
         _, beta, comp, acum = eng.get_state(eps=False)
         t1 = time.perf_counter()
         state_hash[0] = (beta, comp)
+        kv, rst = eng.last_sweep_info()
         if not timed:
-            warm.append((out.kernel_ms, out.n_nonskipped))
+            warm.append((out.kernel_ms, out.n_nonskipped, kv))
+        else:
+            kernels.append(kv); restarts.append(rst)
         if timed:
             kernel_ms.append(out.kernel_ms); e2e_s.append(t1 - t0)
             nonskipped.append(out.n_nonskipped); blocks.append(out.n_blocks)
@@ -276,7 +280,14 @@ def main():
     if sampler:
         sampler.stop_flag = True; sampler.join(timeout=2)
 
-    if profiling and rank == 0:           # phase breakdown of the timed sweeps (cycles of CTA 0 per block) -> stderr
+    if profiling and rank == 0 and 5 in kernels:      # version-5 kernel: cycles per walked block of one warp per role of CTA 0 -> stderr
+        pc = eng.profile_cycles5(reset=True)
+        nblk = max(1, pc["blocks"] if pc.get("blocks") else int(np.sum(blocks)))
+        sys.stderr.write("v5 phase cycles/block over %d timed sweeps (%d blocks): " % (a.steps, int(np.sum(blocks)))
+                         + "  ".join("%s=%d" % (k, pc[k] // max(1, int(np.sum(blocks)))) for k in eng.PROFILE5 if k not in ("blocks", "gram_blocks", "restarts", "applies"))
+                         + "  | per block: gram_blocks=%.3f applies=%.3f  restarts/sweep=%.1f\n" % (
+                             pc["gram_blocks"] / max(1, int(np.sum(blocks))), pc["applies"] / max(1, int(np.sum(blocks))), float(np.mean(restarts))))
+    if profiling and rank == 0 and 4 in kernels:      # phase breakdown of the timed sweeps (cycles of CTA 0 per block) -> stderr
         pc = eng.profile_cycles(reset=True)
         nblk = max(1, int(np.sum(blocks)))
         skip = set(eng.PROFILE_COUNTERS) | set(eng.PROFILE_OVERLAPPED) | {"prologue"}
@@ -327,7 +338,8 @@ def main():
                    "regime": "timed sweeps = sweeps %d..%d of a chain started from BayesRBase::init's state; %.4f%% of the markers non-skipped "
                              "(beta_old != 0 or beta_new != 0) per timed sweep; the cost of a sweep depends on that fraction" % (
                                  a.warmup, a.warmup + a.steps - 1, 100.0 * float(np.mean(nonskipped)) / M),
-                   "chain_start": [{"sweep": i, "ms": float(ms), "nonskipped_fraction": ns / M} for i, (ms, ns) in enumerate(warm[:3])],
+                   "chain_start": [{"sweep": i, "ms": float(ms), "nonskipped_fraction": ns / M, "dense_kernel": kv} for i, (ms, ns, kv) in enumerate(warm[:3])],
+                   "dense_kernel_timed_sweeps": sorted(set(kernels)), "pipeline_restarts_per_sweep": float(np.mean(restarts)) if restarts else None,
                    "nonskipped_fraction": float(np.mean(nonskipped)) / M, "exchanges_per_sweep": int(np.mean(blocks)),
                    "ranks_bit_identical": ranks_identical, "setup_s": gen_s},
         "e2e": {"value": M * a.steps / esum, "unit": "marker updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -219,6 +219,15 @@ const char *brr_gpu_kernel_version(void);
  * their dot pass (these two overlap the walker phases); then finer marks inside publish (reduce, missing sums,
  * arrive, preamble) and the Gram-row round (loop, reduction, three marks of the cross counts), and 4 spare.  reset != 0 clears them. */
 int brr_gpu_profile_cycles(brr_gpu_ctx *ctx, uint64_t *cycles40, int reset);
+/* The same for the version-5 dense kernel (sweep_dense5.cuh), 24 counters: walker warp 0 of CTA 0: wait for the plan, wait for
+ * the block's counter, read-back (+ Gram rows), sampling, in-block corrections, filing; first dot warp: block-start gate,
+ * residual update, wait for the rows, MMA loop, missing sums + cross counts, combine + REDs; then 4 counts (blocks walked with
+ * Gram rows, -, restarts, residual updates); planner warp: plan, TMA issue. */
+int brr_gpu_profile_cycles5(brr_gpu_ctx *ctx, uint64_t *cycles24, int reset);
+/* Which dense kernel the last sweep ran (4 = on-demand Gram rows, 5 = steady-state pipeline; 0 = not dense) and, for version 5,
+ * how often its pipeline restarted behind a marker that entered the model.  The library chooses per sweep (version 5 when the
+ * previous sweep of the chain had <= 3% non-skipped markers); the environment variable BRR_GPU_DENSE_KERNEL=v4|v5 forces one. */
+int brr_gpu_last_sweep_info(brr_gpu_ctx *ctx, uint32_t *kernel_version, uint32_t *restarts);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,19 @@ from helpers import Golden, check_iteration, num_tol, replay
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["v4", "v5"])
+def dense_kernel(request, monkeypatch):
+    """Every test of this module runs against both dense sweep kernels (BRR_GPU_DENSE_KERNEL is read at brr_gpu_create): version 4
+    (on-demand Gram rows; also the asynchronous and the sharded path) and version 5 (steady-state pipeline; synchronous, one GPU)."""
+    if request.param == "v5":
+        cs = getattr(request.node, "callspec", None)
+        prm = cs.params if cs else {}
+        if prm.get("tokens", 0) or prm.get("world", 1) > 1 or request.node.name.startswith(("test_world_gt_1", "test_mu_update", "test_synthetic", "test_tier1")):
+            pytest.skip("asynchronous / sharded / marker-level paths do not run the version-5 kernel")
+    monkeypatch.setenv("BRR_GPU_DENSE_KERNEL", request.param)
+    return request.param
+
+
 def make_engine(g, layout="dense", **kw):
     e = Engine(g.N, g.M, g.K, g.nG, layout=layout, **kw)
     e.upload_bed(g.bed)
