@@ -32,7 +32,7 @@
 namespace brr {
 namespace v5 {
 
-constexpr int kD = 2;                       // the dot pass of block c sees the residual updates of blocks <= c - kD - 1
+constexpr int kD = 3;                       // the dot pass of block c sees the residual updates of blocks <= c - kD - 1
 constexpr int kRowsPerBlock = 2;            // in-model markers of a block (a third one ends the block before it)
 constexpr int kGramRows = (kD + 1) * kRowsPerBlock;   // rows whose Gram counts ride on a dot pass (<= 8 = one MMA N-tile)
 static_assert(kGramRows <= 8, "one N-tile of Gram rows");
@@ -101,11 +101,11 @@ struct Shared5 {
     uint32_t rs_pos, rs_c, rs_seq, ne_id, ne_uses;
     double ne_dbeta, ne_lut[4];
     Decision dec[2];
-    uint32_t upd_row[8]; double upd_dB[8]; double upd_lut[8][4];
+    uint32_t upd_row[12]; double upd_dB[12]; double upd_lut[12][4];
     // sequencer's chain (one thread)
     uint32_t hist[kD + 1], hist_n, seq_epoch;
     unsigned long long wq[kDotW][2], sumq[2];
-    uint32_t pubcnt[kSeq];
+    uint32_t pubcnt[kSeq], tilecnt[12];
     double scale, inv_scale, warp_tmp[kWarps];
     // walkers
     double d0[kB], G[kGramRows][kB], bcast[2];
@@ -123,7 +123,7 @@ __host__ __device__ inline size_t sweep5_smem_bytes(uint32_t RS)
     s += size_t(kLimbs) * RS * 16;                    // limbs
     s += size_t(kStages) * kTileRows * RS * 4;        // code stages
     s += size_t(kStash) * RS * 4;                     // stashed rows
-    s += size_t(2) * kDotW * 128 * 4;                 // per-warp partial sums: dots, Gram
+    s += size_t(3) * 4 * 256 * 4;                      // tile accumulators (three sets in rotation)
     return s + 16;
 }
 
@@ -145,6 +145,19 @@ __device__ __forceinline__ double gram_std(const RowConst &rj, const RowConst &r
     return rj.sj * rk.sj * t;
 }
 
+// the slow half of a guarded spin (every 1024 polls): has the launch been given up, or has this wait lasted ~2 s?
+__device__ __noinline__ bool spin_check(uint32_t *abort_flag, unsigned *global_flags, long long &t0)
+{
+    if (ldv(abort_flag)) return true;
+    const long long t = clock64();
+    if (t0 == 0) { t0 = t; return false; }
+    if (t - t0 > 4000000000LL || (*reinterpret_cast<volatile unsigned *>(global_flags) & 4u)) {
+        stv(abort_flag, 1u); atomicOr(global_flags, 4u);
+        return true;
+    }
+    return false;
+}
+
 template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) sweep_dense5_kernel(const Sweep5Params p)
 {
@@ -155,8 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense5_kernel(const Sweep5P
     uint4 *limbs = reinterpret_cast<uint4 *>(smem_raw + off0);                                      // [8][RS]
     uint32_t *stages = reinterpret_cast<uint32_t *>(smem_raw + off0 + size_t(kLimbs) * RS * 16);     // [8][16][RS]
     uint32_t *stash = stages + size_t(kStages) * kTileRows * RS;                                    // [kStash][RS]
-    int *part_dot = reinterpret_cast<int *>(stash + size_t(kStash) * RS);                           // [12][128]
-    int *part_gram = part_dot + kDotW * 128;                                                        // [12][128]
+    int *tile_acc = reinterpret_cast<int *>(stash + size_t(kStash) * RS);                           // [3][4 tiles][128 dots + 128 Gram]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t gid = lane >> 2, tig = lane & 3;
@@ -178,15 +190,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense5_kernel(const Sweep5P
     // other waits of the grid see the flag and fall through, the launch ends, the host reports error flag 4 -- instead of hanging the GPU.
     long long spin_t0 = 0; uint32_t spin_it = 0;
     auto spin_fail = [&]() -> bool {
-        if ((++spin_it & 2047u) != 0u) return false;
-        if (ldv(&sh.abort)) return true;
-        const long long t = clock64();
-        if (spin_t0 == 0) { spin_t0 = t; return false; }
-        if (t - spin_t0 > 4000000000LL || (*reinterpret_cast<volatile unsigned *>(p.out_counts + 2) & 4u)) {
-            stv(&sh.abort, 1u); atomicOr(p.out_counts + 2, 4u);
-            return true;
-        }
-        return false;
+        __nanosleep(20);                               // a spinning warp must not take issue slots / shared-memory cycles from the dot warps
+        if ((++spin_it & 1023u) != 0u) return false;
+        return spin_check(&sh.abort, p.out_counts + 2, spin_t0);
     };
     auto spin_ok = [&]() { spin_t0 = 0; spin_it = 0; };
     auto mbar_wait_g = [&](uint64_t *bar, unsigned parity) {
@@ -216,9 +222,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense5_kernel(const Sweep5P
     }
     fill_group_consts(sh.gc, p.nG, K, NM1, p.sigmaE, p.pi, p.sigmaG, p.cva);
     for (int i = tid; i < kMaxGK; i += kThreads) { sh.v_s[i] = 0; sh.betasq_w[0][i] = 0.0; sh.betasq_w[1][i] = 0.0; }
+    for (int i = tid; i < 3 * 4 * 256; i += kThreads) tile_acc[i] = 0;
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 3); }
         for (int i = 0; i < kSeq; ++i) { mbar_init(&sh.stash_full[i], 1); sh.pubcnt[i] = 0; }
+        for (int i = 0; i < 12; ++i) sh.tilecnt[i] = 0;
         mbar_init(&sh.ne_full, 1);
         mbar_fence_init();
         sh.abort = 0; sh.planned_seq = 0; sh.walk_done_seq = 0; sh.applied_seq = 0; sh.epoch_w = 0; sh.finished = 0; sh.ne_uses = 0;
@@ -309,6 +317,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense5_kernel(const Sweep5P
                 const uint32_t k = lane + 32 * h, id = h ? idB : idA;
                 m.id[k] = id;
                 if (pos + k < p.n_order) {
+                    // the walk reads the marker's value table and class counts straight from L2: pull the lines in now
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.lut + 4 * size_t(id)));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.counts + 4 * size_t(id)));
                     cp_async16(&m.uz[k][0], p.rand_uz + 2 * size_t(id));
                     cp_async8(&m.beta_old[k], p.beta + id);
                     if (p.group) cp_async4(&m.grp[k], p.group + id); else m.grp[k] = 0;
@@ -692,9 +703,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense5_kernel(const Sweep5P
                 }
             }
             // ---- missing-genotype cross counts of the (Gram row, column) pairs of this tile: one pair per thread ----
-            if (present && nt) {
-                const uint32_t col = ti & 15u, r = ti >> 4;
-                if (r < uint32_t(kGramRows) && ((present >> r) & 1u) && col < nt) {
+            if (present && nt)
+            for (uint32_t pidx = ti; pidx < 16u * kGramRows; pidx += 96u) {
+                const uint32_t col = pidx & 15u, r = pidx >> 4;
+                if (((present >> r) & 1u) && col < nt) {
                     const uint32_t back = kD - r / kRowsPerBlock, i = r % kRowsPerBlock;
                     const uint32_t hs = back ? B.back_seq[back - 1] : d;
                     const bool self = back == 0u && B.rowk[i] == 16 * tile + col;
@@ -739,48 +751,63 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense5_kernel(const Sweep5P
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.empty[st]);
             PHASE(kPfDPost);
-            // ---- combine the three warps of the tile and add into the block's slot ----
+            // ---- combine the three warps of the tile WITHOUT a barrier: every warp adds its partial sums into the tile's accumulator in
+            //      shared memory; the last of the three to arrive adds the totals into the block's slot (and leaves the accumulator zero).
+            //      Three accumulator sets in rotation: a warp can be two blocks ahead of its tile mates (stage ring), never three. ----
+            {
+                const uint32_t ai = (d % 3u) * 4u + tile;
+                int *tacc = tile_acc + ai * 256;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                part_dot[dw * 128 + q * 32 + lane] = acc[0][q] + (acc[1][q] >> 2) + (acc[2][q] >> 4) + (acc[3][q] >> 6);
-                if (present) part_gram[dw * 128 + q * 32 + lane] = gacc[0][q] + (gacc[1][q] >> 4) + (gacc[2][q] >> 8) + (gacc[3][q] >> 12);
-            }
-            bar_named(3 + int(tile), 96);
-            if (ti < 32u) {
-                // (marker m, half h): the limb sums 4h..4h+3 combined into sum_l S_l 2^(8l), exact, as ONE signed 64-bit RED
-                const uint32_t m = ti >> 1, h = ti & 1u;
-                if (m < nt) {
-                    long long v = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t l = 4 * h + j, idx = ((l & 1u) + 2 * (m >> 3)) * 32 + (m & 7u) * 4 + (l >> 1);
-                        const long long sl = (long long)part_dot[tile * 128 + idx] + (long long)part_dot[(4 + tile) * 128 + idx] + (long long)part_dot[(8 + tile) * 128 + idx];
-                        v += sl * (1LL << (8 * j));
-                    }
-                    if (v) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLDots + 2 * (16 * tile + m) + h) * kLine), (unsigned long long)v);
-                }
-            } else if (present) {
-                const uint32_t u = ti - 32u, m = u & 15u;
-                if (m < nt) {
-#pragma unroll
-                    for (uint32_t r = u >> 4; r < uint32_t(kGramRows); r += 4) {
-                        if (!((present >> r) & 1u)) continue;
-                        const uint32_t idx = ((r & 1u) + 2 * (m >> 3)) * 32 + (m & 7u) * 4 + (r >> 1);
-                        const int a = part_gram[tile * 128 + idx] + part_gram[(4 + tile) * 128 + idx] + part_gram[(8 + tile) * 128 + idx];
-                        if (a) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLGram + r * kB + 16 * tile + m) * kLine), (unsigned long long)(unsigned)a);
+                for (int q = 0; q < 4; ++q) {
+                    const int v = acc[0][q] + (acc[1][q] >> 2) + (acc[2][q] >> 4) + (acc[3][q] >> 6);
+                    if (v) atomicAdd(&tacc[q * 32 + lane], v);
+                    if (present) {
+                        const int g = gacc[0][q] + (gacc[1][q] >> 4) + (gacc[2][q] >> 8) + (gacc[3][q] >> 12);
+                        if (g) atomicAdd(&tacc[128 + q * 32 + lane], g);
                     }
                 }
-            }
-            if (tile == 0 && ti >= 32u && ti < 34u) {
-                const unsigned long long v = sh.sumq[ti - 32u];
-                if (v) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLEps + (ti - 32u)) * kLine), v);
-            }
-            // ---- arrive: the last of the 12 dot warps releases the block's counter for the whole grid ----
-            __syncwarp();
-            if (lane == 0) {
-                if (atom_acqrel_cta_add(&sh.pubcnt[d & (kSeq - 1)], 1u) == uint32_t(kDotW - 1)) {
-                    sh.pubcnt[d & (kSeq - 1)] = 0u;
-                    red_release_add(reinterpret_cast<unsigned *>(slot + kLCnt * kLine), 1u);
+                __syncwarp();
+                unsigned last = 0;
+                if (lane == 0) last = atom_acqrel_cta_add(&sh.tilecnt[ai], 1u) == 2u ? 1u : 0u;
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    __threadfence_block();
+                    {   // (marker m, half h): the limb sums 4h..4h+3 combined into sum_l S_l 2^(8l), exact, as ONE signed 64-bit RED
+                        const uint32_t m = lane >> 1, h = lane & 1u;
+                        long long v = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t l = 4 * h + j, idx = ((l & 1u) + 2 * (m >> 3)) * 32 + (m & 7u) * 4 + (l >> 1);
+                            v += (long long)tacc[idx] * (1LL << (8 * j));
+                            tacc[idx] = 0;
+                        }
+                        if (v && m < nt) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLDots + 2 * (16 * tile + m) + h) * kLine), (unsigned long long)v);
+                    }
+                    if (present) {
+#pragma unroll
+                        for (uint32_t i2 = lane; i2 < 128u; i2 += 32u) {
+                            const int a = tacc[128 + i2];
+                            if (a) {
+                                tacc[128 + i2] = 0;
+                                const uint32_t q = i2 >> 5, l2 = i2 & 31u, m = (l2 >> 2) + 8 * (q >> 1), r = 2 * (l2 & 3u) + (q & 1u);
+                                if (m < nt && ((present >> r) & 1u))
+                                    atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLGram + r * kB + 16 * tile + m) * kLine), (unsigned long long)(unsigned)a);
+                            }
+                        }
+                    }
+                    if (tile == 0 && lane < 2) {
+                        const unsigned long long v = sh.sumq[lane];
+                        if (v) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLEps + lane) * kLine), v);
+                    }
+                    __syncwarp();
+                    // ---- arrive: the last of the four tiles releases the block's counter for the whole grid ----
+                    if (lane == 0) {
+                        sh.tilecnt[ai] = 0u;
+                        if (atom_acqrel_cta_add(&sh.pubcnt[d & (kSeq - 1)], 1u) == 3u) {
+                            sh.pubcnt[d & (kSeq - 1)] = 0u;
+                            red_release_add(reinterpret_cast<unsigned *>(slot + kLCnt * kLine), 1u);
+                        }
+                    }
                 }
             }
             PHASE(kPfDComb);
@@ -834,19 +861,22 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense5_kernel(const Sweep5P
                 for (int r = 0; r < kGramRows; ++r)
                     if ((present >> r) & 1u) gv[r] = __ldcg(reinterpret_cast<const int4 *>(slot + size_t(kLGram + r * kB + wk) * kLine));
                 L[0] = l01.x; L[1] = l01.y; L[2] = l23.x; L[3] = l23.y;
-                const double sx = 0.5 * (L[2] - L[0]), inv_s = 1.0 / sx, cc = -L[0] * inv_s;
-                rc.sj = sx; rc.cj = cc; rc.ej = L[3] * inv_s + cc;
-                rc.sumg = double(cn.y) + 2.0 * double(cn.z); rc.nmiss = double(cn.w);
+                const double sx = 0.5 * (L[2] - L[0]);
                 const double eps_sum_total = (double(e_hi) * 4294967296.0 + double(e_lo)) * inv_scale;
                 const double dprime = (double(thi) * 4294967296.0 + double(tlo)) * inv_scale;
                 const double smd = (double(sm_hi) * 4294967296.0 + double(sm_lo)) * inv_scale;
-                base = L[0] * eps_sum_total + rc.sj * (dprime - 3.0 * smd) + (L[3] - L[0]) * smd;
+                base = L[0] * eps_sum_total + sx * (dprime - 3.0 * smd) + (L[3] - L[0]) * smd;
                 bo = m.beta_old[wk]; uu = m.uz[wk][0]; zz = m.uz[wk][1]; gg = m.grp[wk];
-                for (uint32_t i = 0; i < B.nrows; ++i)
-                    if (B.rowk[i] == uint32_t(wk)) {
-                        sh.rowc[s & (kSeq - 1)][i] = rc;
-                        for (int q = 0; q < 4; ++q) sh.rowlut[s & (kSeq - 1)][i][q] = L[q];
-                    }
+                if (present) {                                  // only blocks with Gram rows need the standardisation constants (a division)
+                    const double inv_s = 1.0 / sx, cc = -L[0] * inv_s;
+                    rc.sj = sx; rc.cj = cc; rc.ej = L[3] * inv_s + cc;
+                    rc.sumg = double(cn.y) + 2.0 * double(cn.z); rc.nmiss = double(cn.w);
+                    for (uint32_t i = 0; i < B.nrows; ++i)
+                        if (B.rowk[i] == uint32_t(wk)) {
+                            sh.rowc[s & (kSeq - 1)][i] = rc;
+                            for (int q = 0; q < 4; ++q) sh.rowlut[s & (kSeq - 1)][i][q] = L[q];
+                        }
+                }
             }
             if (present) {
                 bar_named(1, 64);
@@ -879,10 +909,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense5_kernel(const Sweep5P
                     const uint32_t hi_k = i < B.nrows ? B.rowk[i] : n;      // segment [lo_k, hi_k): no in-model marker inside
                     const bool enters = act && uint32_t(wk) >= lo_k && uint32_t(wk) < hi_k && bo == 0.0 && dr.beta_new != 0.0;
                     const unsigned bal = __ballot_sync(0xffffffffu, enters);
-                    if (lane == 0) sh.w_flag[warp] = bal;
+                    uint32_t *fl = sh.w_flag + 2 * ((s + i) & 1u);          // alternating pairs: the next write is two barriers away
+                    if (lane == 0) fl[warp] = bal;
                     bar_named(1, 64);
-                    const unsigned b0 = sh.w_flag[0], b1 = sh.w_flag[1];
-                    bar_named(1, 64);
+                    const unsigned b0 = fl[0], b1 = fl[1];
                     if (b0 | b1) { n_final = (b0 ? uint32_t(__ffs(b0) - 1) : 32u + uint32_t(__ffs(b1) - 1)) + 1u; restart = true; break; }
                     if (i == B.nrows) break;
                     // marker hi_k (in the model): its draw is final; everything behind it moves by dB x_j.x_k

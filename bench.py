@@ -272,6 +272,7 @@ def main():
     profiling = os.environ.get("BRR_GPU_PROFILE") == "1"
     if profiling:
         eng.profile_cycles(reset=True)
+        eng.profile_cycles5(reset=True)
     if rank == 0:
         sampler = ClockSampler(local_rank); sampler.start()
     for _ in range(a.steps):
