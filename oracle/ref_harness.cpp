@@ -16,6 +16,8 @@
 #include "DenseBayesRRmz.hpp"
 #include "SparseBayesRRG.hpp"
 #include "analysisgraph.hpp"
+#include "parallelgraph.h"
+#include "markercache.h"
 #include "bayesrkernel.h"
 #include "sparsebayesrkernel.h"
 #include "eigenbayesrkernel.h"
@@ -180,7 +182,70 @@ private:
     double m_execSeconds = 0;
 };
 
+// The reference's asynchronous scheduler itself (src/parallelgraph.cpp: TBB flow graph, bounded staleness of `analysisTokens`
+// markers, all host cores), unmodified, behind the same tap.  It reads its columns from the process-wide MarkerCache singleton
+// (src/parallelgraph.cpp:19-24), which normally fills itself from a preprocessed file (src/markercache.cpp:19-45); here the
+// markers built in memory are installed into it through the protected member (pointer-to-member of a derived class: legal).
+struct CacheAccess : MarkerCache { using MarkerCache::m_markers; };
+void installMarkerCache(const std::vector<ConstMarkerPtr> &markers)
+{
+    (markerCache().get()->*(&CacheAccess::m_markers)) = markers;
+}
+
+class TapParallelGraph : public AnalysisGraph
+{
+public:
+    explicit TapParallelGraph(size_t analysisTokens) : m_inner(40, analysisTokens, true) {}      // defaults of src/options.hpp:32-33
+    bool isAsynchronous() const override { return true; }
+    void exec(Analysis *analysis, unsigned numInds, unsigned numSnps, const std::vector<unsigned> &order) override
+    {
+        auto *tap = dynamic_cast<TapIface *>(analysis);
+        if (tap) tap->before(m_iteration, order);
+        const auto t0 = std::chrono::steady_clock::now();
+        m_inner.exec(analysis, numInds, numSnps, order);
+        m_execSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (tap) tap->after(m_iteration);
+        ++m_iteration;
+    }
+    double execSeconds() const { return m_execSeconds; }
+    unsigned iterations() const { return m_iteration; }
+
+private:
+    ParallelGraph m_inner;
+    unsigned m_iteration = 0;
+    double m_execSeconds = 0;
+};
+
+// A graph that wraps any AnalysisGraph with the tap (used for the GPU graph of oracle/gpu_graph_ref.cpp)
+class TapWrapGraph : public AnalysisGraph
+{
+public:
+    explicit TapWrapGraph(AnalysisGraph *inner) : m_inner(inner) {}
+    bool isAsynchronous() const override { return m_inner->isAsynchronous(); }
+    void exec(Analysis *analysis, unsigned numInds, unsigned numSnps, const std::vector<unsigned> &order) override
+    {
+        auto *tap = dynamic_cast<TapIface *>(analysis);
+        if (tap) tap->before(m_iteration, order);
+        const auto t0 = std::chrono::steady_clock::now();
+        m_inner->exec(analysis, numInds, numSnps, order);
+        m_execSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (tap) tap->after(m_iteration);
+        ++m_iteration;
+    }
+    double execSeconds() const { return m_execSeconds; }
+    unsigned iterations() const { return m_iteration; }
+
+private:
+    std::unique_ptr<AnalysisGraph> m_inner;
+    unsigned m_iteration = 0;
+    double m_execSeconds = 0;
+};
+
 } // namespace
+
+#ifdef BRR_REF_WITH_GPU
+AnalysisGraph *makeGpuSweepGraph(const Data *data, const Options *opt, bool async, const uint8_t *bedPayload, std::string *err);
+#endif
 
 extern "C" {
 
@@ -279,6 +344,9 @@ struct ref_chain_args {
     double execSeconds;     // out: total seconds spent inside exec() (the marker loop)
     double totalSeconds;    // out: seconds inside runGibbs
     double buildSeconds;    // out: seconds building markers
+    int32_t graphKind;      // 0 = sequential (TapGraph = Sequential::exec), 1 = the reference's ParallelGraph (asyncppbayes),
+                            // 2 / 3 = GpuSweepGraph of oracle/gpu_graph_ref.cpp (ppbayes / asyncppbayes) -- libbrr_ref_gpu.so only
+    uint32_t analysisTokens; // ParallelGraph: markers in flight between forced synchronisations (Options::analysisTokens, default 20)
 };
 
 int ref_run_chain(ref_chain_args *a)
@@ -316,19 +384,41 @@ int ref_run_chain(ref_chain_args *a)
     opt.fixedEffectNumber = 0;
     opt.useMarkerCache = true;
 
-    TapGraph graph(&markers);
     std::unique_ptr<BayesRBase> analysis;
     if (a->layout == 0)
         analysis.reset(new Tap<DenseBayesRRmz>(&data, &opt, a->dump, a->M, a->N, a->nGroups, a->K));
     else
         analysis.reset(new Tap<SparseBayesRRG>(&data, &opt, a->dump, a->M, a->N, a->nGroups, a->K));
 
+    int rc;
+    unsigned iters;
     const auto t0 = std::chrono::steady_clock::now();
-    const int rc = analysis->runGibbs(&graph);
+    if (a->graphKind == 2 || a->graphKind == 3) {
+#ifdef BRR_REF_WITH_GPU
+        opt.analysisTokens = a->analysisTokens ? a->analysisTokens : 20;
+        std::string err;
+        AnalysisGraph *g = makeGpuSweepGraph(&data, &opt, a->graphKind == 3, a->bed, &err);
+        if (!g) { std::cerr << "GpuSweepGraph: " << err << std::endl; return 10; }
+        TapWrapGraph graph(g);
+        rc = analysis->runGibbs(&graph);
+        a->execSeconds = graph.execSeconds(); iters = graph.iterations();
+#else
+        return 11;
+#endif
+    } else if (a->graphKind == 1) {
+        installMarkerCache(markers);
+        TapParallelGraph graph(a->analysisTokens ? a->analysisTokens : 20);
+        rc = analysis->runGibbs(&graph);
+        a->execSeconds = graph.execSeconds(); iters = graph.iterations();
+        markerCache()->clear();
+    } else {
+        TapGraph graph(&markers);
+        rc = analysis->runGibbs(&graph);
+        a->execSeconds = graph.execSeconds(); iters = graph.iterations();
+    }
     a->totalSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    a->execSeconds = graph.execSeconds();
-    if (a->dump && graph.iterations() > 0)
-        dynamic_cast<TapIface *>(analysis.get())->post(graph.iterations() - 1);
+    if (a->dump && iters > 0)
+        dynamic_cast<TapIface *>(analysis.get())->post(iters - 1);
     return rc;
 }
 

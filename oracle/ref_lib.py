@@ -24,7 +24,7 @@ class ChainArgs(C.Structure):
                 ("groups", C.c_void_p), ("nGroups", C.c_uint32), ("S", C.c_void_p), ("K", C.c_uint32),
                 ("seed", C.c_uint32), ("iterations", C.c_uint32), ("layout", C.c_int32),
                 ("dump", C.c_void_p), ("execSeconds", C.c_double), ("totalSeconds", C.c_double),
-                ("buildSeconds", C.c_double)]
+                ("buildSeconds", C.c_double), ("graphKind", C.c_int32), ("analysisTokens", C.c_uint32)]
 
 
 def ref_available(fast=False):
@@ -32,6 +32,8 @@ def ref_available(fast=False):
 
 
 def _path(fast):
+    if fast == "gpu":       # the strict reference build + the GpuSweepGraph of oracle/gpu_graph_ref.cpp, linked against the product library
+        return os.path.join(HERE, "_ref", "libbrr_ref_gpu.so")
     return os.path.join(HERE, "_ref", "libbrr_ref_fast.so" if fast else "libbrr_ref.so")
 
 
@@ -103,8 +105,11 @@ class _Quiet:
         os.close(self.null); os.close(self.saved)
 
 
-def run_chain(bed, N, M, y, S, seed, iterations, layout=0, groups=None, dump=True, fast=False):
-    """Run the reference's BayesRBase::runGibbs; returns (dict of per-iteration arrays, timings)."""
+def run_chain(bed, N, M, y, S, seed, iterations, layout=0, groups=None, dump=True, fast=False, graph="sequential", tokens=20,
+              keep=None):
+    """Run the reference's BayesRBase::runGibbs; returns (dict of per-iteration arrays, timings).
+    graph="parallel": through the reference's own ParallelGraph (asyncppbayes: TBB, all cores, `tokens` markers in flight).
+    keep: names of the per-iteration arrays to record (None = all); the others share one scratch row (long chains)."""
     S = np.ascontiguousarray(np.atleast_2d(S), dtype=np.float64)
     nG, K = S.shape[0], S.shape[1] + 1
     bed = np.ascontiguousarray(bed, dtype=np.uint8)
@@ -119,13 +124,17 @@ def run_chain(bed, N, M, y, S, seed, iterations, layout=0, groups=None, dump=Tru
     arrays = {}
     d = ChainDump()
     if dump:
+        assert keep is None, "keep= needs the harness to index per iteration: record everything (dump=True) on short chains instead"
         for k, shp in shapes.items():
             arrays[k] = np.zeros(shp, dtype=np.uint32 if k == "order" else np.float64)
             setattr(d, k, arrays[k].ctypes.data)
     a = ChainArgs(bed=bed.ctypes.data, N=N, M=M, y=y.ctypes.data,
                   groups=None if g is None else g.ctypes.data, nGroups=nG, S=S.ctypes.data, K=K,
                   seed=seed, iterations=iterations, layout=layout,
-                  dump=C.addressof(d) if dump else None)
+                  dump=C.addressof(d) if dump else None, analysisTokens=tokens,
+                  graphKind={"sequential": 0, "parallel": 1, "gpu": 2, "gpu-async": 3}[graph])
+    if graph.startswith("gpu"):
+        fast = "gpu"
     C.CDLL(None).srand(1)   # glibc rand() drives std::random_shuffle; fresh-process state
     lib = load(fast)
     with _Quiet():

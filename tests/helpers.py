@@ -84,3 +84,37 @@ def check_iteration(chain, it, res, tol=1e-8, check_acum=True):
         if check_acum:
             close(res["acum"], chain["acum_full"][k], "acum")
         close(res["eps"], chain["eps_full"][k], "eps")
+
+
+def run_host_chain(N, M, S, y, iters, seed, sweep_fn, add_scalar_fn, eps_sum_fn=None):
+    """The host part of BayesRBase::runGibbs (reference src/BayesRBase.cpp:186-253, one group) around a sweep callback, with numpy's
+    generator for the draws: mu, the per-marker (u, z) table, the marker order, sigmaE, sigmaG, pi.  Used for STATISTICAL comparisons
+    (posterior means), not for replay parity.
+
+    sweep_fn(order, rand_uz, pi, sigmaG, sigmaE) -> (v[K], betasq, eps_sqnorm, n_nonzero);  add_scalar_fn(c) -> sum(eps) after eps += c
+    Returns per-iteration arrays: mu, sigmaE, sigmaG, betasq, nonzero."""
+    rng = np.random.default_rng(seed)
+    K = S.shape[1] + 1
+    pi = np.full((1, K), 0.5 / K); pi[0, 0] = 0.5
+    sigmaG = np.array([rng.random()])
+    sigmaE = float((y ** 2).sum()) / N * 0.5
+    mu = 0.0
+    v0 = s0 = 1e-4
+    out = {k: np.zeros(iters) for k in ("mu", "sigmaE", "sigmaG", "betasq", "nonzero")}
+
+    def inv_scaled_chisq(dof, scale):
+        return 1.0 / rng.gamma(0.5 * dof, 1.0 / (0.5 * dof * scale))
+
+    for it in range(iters):
+        s = add_scalar_fn(mu)
+        mu = rng.normal(s / N, np.sqrt(sigmaE / N))
+        add_scalar_fn(-mu)
+        rand_uz = np.c_[rng.random(M), rng.standard_normal(M)]
+        order = rng.permutation(M).astype(np.uint32)
+        v, bs, sq, nz = sweep_fn(order, rand_uz, pi, sigmaG, sigmaE)
+        sigmaE = inv_scaled_chisq(v0 + N, (sq + v0 * s0) / (v0 + N))
+        m0 = v[1:].sum()
+        sigmaG = np.array([inv_scaled_chisq(v0 + m0, (bs * m0 + v0 * s0) / (v0 + m0))])
+        pi = rng.dirichlet(v + 1.0)[None, :]
+        out["mu"][it] = mu; out["sigmaE"][it] = sigmaE; out["sigmaG"][it] = sigmaG[0]; out["betasq"][it] = bs; out["nonzero"][it] = nz
+    return out
