@@ -321,6 +321,30 @@ def main():
         ranks_identical = all(x == hs[0] for x in hs)
         if not ranks_identical:
             raise SystemExit("bench: beta/components differ between ranks after the timed sweeps: %s" % hs)
+    # NCCL baseline of the per-block exchange (north_star: "in-kernel P2P flag-based exchange or an NCCL allreduce baseline, each
+    # measured"): the 258 64-bit sums a block reduces across GPUs, as one ncclAllReduce(sum, int64) per block, back to back on one
+    # stream -- the exchange ALONE, without any of the sweep's arithmetic.  The in-kernel exchange is inside `ms_per_step`.
+    nccl_base = None
+    if world > 1:
+        buf = torch.zeros(258, dtype=torch.int64, device="cuda")
+        for _ in range(50):
+            dist.all_reduce(buf)
+        torch.cuda.synchronize()
+        n_ar = 2000
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(); torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(n_ar):
+            dist.all_reduce(buf)
+        ev1.record(); torch.cuda.synchronize()
+        us = 1e3 * ev0.elapsed_time(ev1) / n_ar
+        t = torch.tensor([us], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nblk = int(np.mean(blocks))
+        nccl_base = {"what": "ncclAllReduce(sum) of the 258 int64 sums of one block, %d calls back to back on one stream (torch.distributed, NCCL)" % n_ar,
+                     "us_per_allreduce": float(t[0]), "blocks_per_sweep": nblk,
+                     "exchange_only_s_per_sweep": float(t[0]) * 1e-6 * nblk,
+                     "in_kernel_p2p_whole_sweep_s": ksum / a.steps}
     if rank != 0:
         dist.destroy_process_group()
         return
@@ -362,6 +386,9 @@ def main():
                      "algorithmic_bytes_per_launch": int(alg_bytes)},
         "clocks": sampler.summary() if sampler else None,
     }
+    if nccl_base:
+        line["exchange"] = {"in_kernel": "integer sums added into count-carrying accumulators of every peer over NVLink inside the sweep kernel",
+                            "nccl_allreduce_baseline": nccl_base}
     if not a.no_cpu_baseline:
         try:
             leg = cpu_reference_leg(N, a.cpu_markers, y_full, a.cpu_sweeps)

@@ -234,6 +234,20 @@ def test_sharded_individuals_exchange_on_one_device(world, N, M, p_miss, block, 
     """The in-kernel cross-shard exchange (the multi-GPU path) with all shards on ONE device: the kernels of
     the shards run concurrently on their own streams and exchange through 'peer' pointers that happen to be
     local.  The chain must be BIT-identical to the unsharded one (the cross-shard sums are integers)."""
+    _sharded_exchange(world, N, M, p_miss, block, tokens, devices=[0] * world)
+
+
+@pytest.mark.parametrize("world,N,M,p_miss,block,tokens", [(2, 200000, 400, 0.002, 64, 0), (2, 60000, 300, 0.01, 64, 20), (4, 300000, 300, 0.001, 64, 0)])
+def test_sharded_individuals_exchange_on_several_devices(world, N, M, p_miss, block, tokens):
+    """The same bit-identity with every shard on its OWN GPU (NVLink peer memory between real devices).  Needs `world` visible
+    devices: skipped on a single-GPU box, run by `gpurun --gpus N`."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    _sharded_exchange(world, N, M, p_miss, block, tokens, devices=list(range(world)))
+
+
+def _sharded_exchange(world, N, M, p_miss, block, tokens, devices):
     O.build()
     pr = _random_problem(N + M + world, N, M, p_miss)
     rng = pr["rng"]
@@ -242,7 +256,7 @@ def test_sharded_individuals_exchange_on_one_device(world, N, M, p_miss, block, 
     bounds = _shard_bounds(N, world)
     shards = []
     for r, (lo, hi) in enumerate(bounds):
-        e = Engine(hi - lo, M, pr["K"], 1, block_markers=block, n_inds_total=N, rank=r, world=world)
+        e = Engine(hi - lo, M, pr["K"], 1, block_markers=block, n_inds_total=N, rank=r, world=world, device=devices[r])
         e.upload_bed(_shard_bed(pr["bed"], lo, hi))
         shards.append(e)
     counts = sum(e.counts().astype(np.int64) for e in shards).astype(np.uint32)
