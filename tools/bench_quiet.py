@@ -1,0 +1,22 @@
+"""Timing experiment: the dense sweep on a chain that never leaves beta = 0 (pure-noise phenotype, a prior that keeps everything out
+of the model): no Gram rows, no restarts, no residual updates -- what remains is the streaming pipeline itself."""
+import os, sys, json
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bayesrrcmd_b200 import Engine
+N, M = 500000, int(os.environ.get("BRR_BENCH_M", 400000))
+e = Engine(N, M, 4, 1, layout="dense")
+e.synth_dense(20260101, 0.01, 0.5, False, 0.001)
+e.finalize(); e.set_model(np.array([[0.01, 0.001, 0.0001]]))
+rng = np.random.default_rng(1)
+y = rng.standard_normal(N); y = (y - y.mean()) / y.std(ddof=1)
+e.set_state(eps=y, beta=np.zeros(M), comp=np.zeros(M), acum=np.zeros(M))
+pi = np.array([[1.0 - 3e-12, 1e-12, 1e-12, 1e-12]]); sigmaG = np.array([0.5])
+ms = []
+for it in range(6):
+    order = rng.permutation(M).astype(np.uint32); uz = np.c_[rng.random(M), rng.standard_normal(M)]
+    v, bs, out = e.sweep(order, uz, pi, sigmaG, 0.9)
+    ms.append(out.kernel_ms)
+    assert out.n_nonskipped == 0
+k, r = e.last_sweep_info()
+print(json.dumps({"kernel": k, "dbg": os.environ.get("BRR_GPU_V5_DBG"), "ms_per_sweep": float(np.mean(ms[2:])), "us_per_block": 1e3 * float(np.mean(ms[2:])) / (M / 64), "M": M}))
