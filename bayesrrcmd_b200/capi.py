@@ -21,7 +21,7 @@ SYMBOLS = [
     "brr_gpu_sweep", "brr_gpu_sweep_stage", "brr_gpu_sweep_run", "brr_gpu_sweep_fetch", "brr_gpu_compute_num",
     "brr_gpu_apply_delta", "brr_gpu_ipc_export", "brr_gpu_ipc_attach", "brr_gpu_attach_local",
     "brr_gpu_num_blocks", "brr_gpu_stream", "brr_gpu_synth_dense", "brr_gpu_synth_ragged", "brr_gpu_synth_bed_host", "brr_gpu_info",
-    "brr_gpu_launch_count", "brr_gpu_profile_cycles", "brr_gpu_kernel_version", "brr_gpu_profile_cycles5", "brr_gpu_last_sweep_info",
+    "brr_gpu_launch_count", "brr_gpu_profile_cycles", "brr_gpu_kernel_version", "brr_gpu_profile_cycles5", "brr_gpu_profile_cycles6", "brr_gpu_last_sweep_info",
 ]
 
 
@@ -92,6 +92,7 @@ def load_library():
     lib.brr_gpu_profile_cycles.argtypes = [vp, vp, C.c_int]
     lib.brr_gpu_kernel_version.restype = C.c_char_p
     lib.brr_gpu_profile_cycles5.argtypes = [vp, vp, C.c_int]
+    lib.brr_gpu_profile_cycles6.argtypes = [vp, vp, C.c_int]
     lib.brr_gpu_last_sweep_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     _lib = lib
     return lib
@@ -295,6 +296,16 @@ class Engine:
         a = np.zeros(24, dtype=np.uint64)
         self._check(self.lib.brr_gpu_profile_cycles5(self._h, _ptr(a), int(reset)))
         return dict(zip(self.PROFILE5, (int(x) for x in a)))
+
+    PROFILE6 = ["d_dec", "d_apply", "d_full", "d_loop", "d_acc", "po_wait", "po_work", "pu_wait", "pu_work", "pr_plan", "pr_empty", "pr_issue",
+                "c_poll", "c_plan", "c_decide", "w_cnt", "w_read", "w_pred", "w_sample", "w_fix", "w_valid", "blocks", "walks", "applies", "restarts",
+                "gram_blocks"]
+
+    def profile_cycles6(self, reset=True):
+        """Phase cycle counters of the version-6 dense kernel (one warp per role of CTA 0)."""
+        a = np.zeros(32, dtype=np.uint64)
+        self._check(self.lib.brr_gpu_profile_cycles6(self._h, _ptr(a), int(reset)))
+        return dict(zip(self.PROFILE6, (int(x) for x in a)))
 
     def last_sweep_info(self):
         """-> (dense kernel version of the last sweep: 4 or 5, pipeline restarts of a version-5 sweep)."""

@@ -8,6 +8,7 @@
 #include "store_kernels.cuh"
 #include "sweep_dense.cuh"
 #include "sweep_dense5.cuh"
+#include "sweep_dense6.cuh"
 #include "sweep_ragged.cuh"
 
 #include <algorithm>
@@ -82,7 +83,14 @@ struct brr_gpu_ctx {
     unsigned long long *prof5 = nullptr;
     size_t smem5_bytes = 0;
     bool v5_ok = false;
-    int dense_mode = 0;                     // 0 = auto (per sweep), 4 / 5 = forced (BRR_GPU_DENSE_KERNEL)
+    // version-6 dense kernel (walk distributed over the CTAs): result lines, per-CTA constant tables, in-model mask of the sweep's positions
+    int *results6 = nullptr;
+    GroupConsts *gc6 = nullptr;
+    uint32_t *inmask6 = nullptr;
+    unsigned long long *prof6 = nullptr;
+    size_t smem6_bytes = 0;
+    bool v6_ok = false;
+    int dense_mode = 0;                     // 0 = auto (per sweep), 4 / 5 / 6 = forced (BRR_GPU_DENSE_KERNEL)
     bool have_last = false;                 // the previous sweep's non-skipped count is known and the chain state was not replaced since
     double last_nonskipped_frac = 1.0;
     uint32_t last_kernel = 0, last_restarts = 0;
@@ -128,7 +136,7 @@ extern "C" void brr_gpu_destroy(brr_gpu_ctx *c)
     void *ptrs[] = {c->codes, c->lut, c->counts_local, c->counts_global, c->group, c->cva, c->eps, c->beta, c->comp,
                     c->acum, c->order, c->rand_uz, c->pi, c->sigmaG, c->part_dot, c->cta_red,
                     c->red_partial, c->slots, c->v, c->betasq, c->out_scalars, c->out_counts, c->prof, c->round_ctr,
-                    c->slots5, c->part_bsq, c->part_v, c->prof5,
+                    c->slots5, c->part_bsq, c->part_v, c->prof5, c->results6, c->gc6, c->inmask6, c->prof6,
                     c->rag.idx16, c->rag.cta_base, c->rag.stats, c->rag.seg};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *q : c->peer_opened) cudaIpcCloseMemHandle(q);
@@ -246,7 +254,7 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
         c->bar = reinterpret_cast<unsigned *>(c->slots + size_t(kSlots) * kSlotInts + 2);
         c->bar2 = c->bar + 1;
         if (const char *e = getenv("BRR_GPU_DENSE_KERNEL")) {
-            if (!strcmp(e, "v4")) c->dense_mode = 4; else if (!strcmp(e, "v5")) c->dense_mode = 5;
+            if (!strcmp(e, "v4")) c->dense_mode = 4; else if (!strcmp(e, "v5")) c->dense_mode = 5; else if (!strcmp(e, "v6")) c->dense_mode = 6;
         }
         c->smem5_bytes = v5::sweep5_smem_bytes(c->RS);
         if (cfg->world == 1 && c->dense_mode != 4 && c->smem5_bytes <= size_t(prop.sharedMemPerBlockOptin)) {
@@ -263,6 +271,29 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
                 TRY_OR_DESTROY(dev_alloc(&c->part_v, size_t(c->nCTA) * cfg->n_groups * cfg->n_components));
                 c->v5_ok = true;
             }
+        }
+        c->smem6_bytes = v6::sweep6_smem_bytes(c->RS, c->SL);
+        if (cfg->world == 1 && c->dense_mode != 4 && c->dense_mode != 5 && c->smem6_bytes <= size_t(prop.sharedMemPerBlockOptin)) {
+            bool fits = true;
+            for (const void *fn : {(const void *)v6::sweep_dense6_kernel<false>, (const void *)v6::sweep_dense6_kernel<true>}) {
+                CUDA_OR_DESTROY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem6_bytes));
+                int o = 0;
+                CUDA_OR_DESTROY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, kThreads, c->smem6_bytes));
+                fits = fits && o >= 1 && uint32_t(o) * c->numSMs >= c->nCTA;
+            }
+            if (fits) {
+                if (!c->slots5) TRY_OR_DESTROY(dev_alloc(&c->slots5, size_t(v5::kSlotRing) * v5::kSlotInts5));
+                if (!c->part_bsq) TRY_OR_DESTROY(dev_alloc(&c->part_bsq, size_t(c->nCTA) * 2 * cfg->n_groups));
+                if (!c->part_v) TRY_OR_DESTROY(dev_alloc(&c->part_v, size_t(c->nCTA) * cfg->n_groups * cfg->n_components));
+                TRY_OR_DESTROY(dev_alloc(&c->results6, size_t(v6::kResRing) * 32));
+                TRY_OR_DESTROY(dev_alloc(&c->gc6, size_t(c->nCTA)));
+                TRY_OR_DESTROY(dev_alloc(&c->inmask6, size_t(M) / 32 + 4));
+                c->v6_ok = true;
+            }
+        }
+        if (c->dense_mode == 6 && !c->v6_ok) {
+            int rc_ = fail(BRR_GPU_EINVAL, "BRR_GPU_DENSE_KERNEL=v6 but the version-6 kernel is not available for this context (world=%d, %zu bytes of shared memory per CTA)", cfg->world, c->smem6_bytes);
+            brr_gpu_destroy(c); return rc_;
         }
         if (c->dense_mode == 5 && !c->v5_ok) {
             int rc_ = fail(BRR_GPU_EINVAL, "BRR_GPU_DENSE_KERNEL=v5 but the version-5 kernel is not available for this context (world=%d, %zu bytes of shared memory per CTA)", cfg->world, c->smem5_bytes);
@@ -314,6 +345,8 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
             CUDA_OR_DESTROY(cudaMemset(c->prof, 0, sizeof(unsigned long long) * kProfPhases));
             TRY_OR_DESTROY(dev_alloc(&c->prof5, v5::kPfN));
             CUDA_OR_DESTROY(cudaMemset(c->prof5, 0, sizeof(unsigned long long) * v5::kPfN));
+            TRY_OR_DESTROY(dev_alloc(&c->prof6, v6::kPfN));
+            CUDA_OR_DESTROY(cudaMemset(c->prof6, 0, sizeof(unsigned long long) * v6::kPfN));
         }
     }
     CUDA_OR_DESTROY(cudaMallocHost(reinterpret_cast<void **>(&c->h_small), sizeof(double) * (2 * kMaxGK + 8 + 2 * kRedBlocks)));
@@ -576,8 +609,45 @@ static bool use_v5(const brr_gpu_ctx *c)
 {
     if (!c->v5_ok || c->async_tokens || c->cfg.world > 1) return false;
     if (c->dense_mode == 5) return true;
-    if (c->dense_mode == 4) return false;
+    if (c->dense_mode == 4 || c->dense_mode == 6) return false;
+    return !c->v6_ok && c->have_last && c->last_nonskipped_frac <= kV5MaxNonskipped;
+}
+// Version 6 (sweep_dense6.cuh): as version 5 with the walk distributed over the CTAs; preferred over version 5 when it fits.
+static bool use_v6(const brr_gpu_ctx *c)
+{
+    if (!c->v6_ok || c->async_tokens || c->cfg.world > 1) return false;
+    if (c->dense_mode == 6) return true;
+    if (c->dense_mode == 4 || c->dense_mode == 5) return false;
     return c->have_last && c->last_nonskipped_frac <= kV5MaxNonskipped;
+}
+
+static int launch_dense6(brr_gpu_ctx *c)
+{
+    v6::Sweep6Params p{};
+    p.n_local = c->cfg.n_inds; p.n_total = c->cfg.n_inds_total; p.M = c->cfg.n_markers; p.K = c->cfg.n_components;
+    p.nG = c->cfg.n_groups; p.nCTA = c->nCTA; p.SL = c->SL; p.PW = c->PW; p.RS = c->RS;
+    p.codes = c->codes; p.lut = c->lut; p.counts = c->counts_global; p.group = c->group;
+    p.order = c->order; p.n_order = c->n_order; p.inmask = c->inmask6; p.rand_uz = c->rand_uz; p.pi = c->pi; p.sigmaG = c->sigmaG; p.cva = c->cva;
+    p.sigmaE = c->sigmaE;
+    p.eps = c->eps; p.beta = c->beta; p.comp = c->comp; p.acum = c->acum;
+    p.slots = c->slots5; p.results = c->results6; p.gc = c->gc6; p.absmax = c->absmax; p.bar = c->bar; p.cta_red = c->cta_red;
+    p.part_bsq = c->part_bsq; p.part_v = c->part_v;
+    p.v = c->v; p.betasq = c->betasq; p.out_scalars = c->out_scalars; p.out_counts = c->out_counts;
+    p.prof = c->prof6;
+    CUDA_TRY(cudaMemsetAsync(c->slots5, 0, sizeof(int) * size_t(v5::kSlotRing) * v5::kSlotInts5, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->results6, 0, sizeof(int) * size_t(v6::kResRing) * 32, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->slots + size_t(kSlots) * kSlotInts, 0, sizeof(int) * 8, c->stream));     // absmax + barrier counters
+    CUDA_TRY(cudaMemsetAsync(c->out_counts, 0, sizeof(unsigned) * 4, c->stream));
+    const void *fn = p.prof ? (const void *)v6::sweep_dense6_kernel<true> : (const void *)v6::sweep_dense6_kernel<false>;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem6_bytes));
+    void *args[] = {&p};
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    const uint32_t n_words = (c->n_order + 31) / 32;
+    if (n_words) v6::inmodel_mask_kernel<<<(n_words * 32 + 255) / 256, 256, 0, c->stream>>>(c->order, c->n_order, c->beta, c->inmask6, n_words);
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(c->nCTA), dim3(kThreads), args, c->smem6_bytes, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 1 + (n_words ? 1 : 0); c->last_launches = 1 + (n_words ? 1 : 0);
+    return 0;
 }
 
 static int launch_dense5(brr_gpu_ctx *c)
@@ -614,9 +684,9 @@ extern "C" int brr_gpu_sweep_run(brr_gpu_ctx *c)
     if (!c->staged) return fail(BRR_GPU_ESTATE, "brr_gpu_sweep_stage not called");
     int rc;
     if (c->cfg.layout == BRR_GPU_LAYOUT_DENSE2BIT) {
-        const bool five = use_v5(c);
-        rc = five ? launch_dense5(c) : launch_dense(c);
-        c->last_kernel = five ? 5u : 4u;
+        const bool six = use_v6(c), five = !six && use_v5(c);
+        rc = six ? launch_dense6(c) : five ? launch_dense5(c) : launch_dense(c);
+        c->last_kernel = six ? 6u : five ? 5u : 4u;
     } else {
         rc = launch_ragged(c);
         c->last_kernel = 0;
@@ -647,7 +717,7 @@ extern "C" int brr_gpu_sweep_fetch(brr_gpu_ctx *c, double *v, double *betasqn, b
     if (betasqn) memcpy(betasqn, h + kMaxGK, sizeof(double) * nG);
     c->have_last = c->n_order > 0 && c->n_order == c->cfg.n_markers;
     c->last_nonskipped_frac = c->n_order ? double(c->h_counts[0]) / double(c->n_order) : 1.0;
-    c->last_restarts = c->last_kernel == 5 ? c->h_counts[3] : 0u;
+    c->last_restarts = c->last_kernel >= 5 ? c->h_counts[3] : 0u;
     cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
     if (out) {
         out->eps_sum = h[2 * kMaxGK]; out->eps_sqnorm = h[2 * kMaxGK + 1];
@@ -807,6 +877,17 @@ extern "C" int brr_gpu_profile_cycles5(brr_gpu_ctx *c, uint64_t *cycles24, int r
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaMemcpy(cycles24, c->prof5, sizeof(uint64_t) * v5::kPfN, cudaMemcpyDeviceToHost));
     if (reset) CUDA_TRY(cudaMemset(c->prof5, 0, sizeof(uint64_t) * v5::kPfN));
+    return 0;
+}
+
+extern "C" int brr_gpu_profile_cycles6(brr_gpu_ctx *c, uint64_t *cycles32, int reset)
+{
+    CHECK_CTX(c);
+    if (!cycles32) return fail(BRR_GPU_EINVAL, "null output");
+    if (!c->prof6) return fail(BRR_GPU_ESTATE, "phase profiling is off: set BRR_GPU_PROFILE=1 before brr_gpu_create");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(cycles32, c->prof6, sizeof(uint64_t) * v6::kPfN, cudaMemcpyDeviceToHost));
+    if (reset) CUDA_TRY(cudaMemset(c->prof6, 0, sizeof(uint64_t) * v6::kPfN));
     return 0;
 }
 

@@ -1,0 +1,1147 @@
+// Persistent cooperative Gibbs-sweep kernel, dense 2-bit layout (sm_100a), version 6: the steady-state kernel with the walk
+// DISTRIBUTED over the CTAs.
+//
+// One launch = one AnalysisGraph::exec (reference src/sequential.cpp:10-27 driving src/BayesRBase.cpp:287-392 over all
+// markers of the sweep, in the given order), single GPU, synchronous mode.  Same arithmetic as versions 4 / 5 (exact integer
+// dots of the 2-bit codes against 8 int8 limbs of the fixed-point residual on mma.sync.m16n8k32, integer reductions over
+// CTAs, fp64 sampling, Gram counts of the in-model rows riding on the dot pass, restart behind a marker that enters the
+// model), re-organised around what versions 4 / 5 were measured to be bound by (profiles/r2_v5_phase_cycles.txt): every CTA
+// walked every block (read-back of 258 sums + sampling of 64 markers, ~10 k cycles on two warps), and the dot warps
+// themselves published, took the missing sums and waited for the walk.
+//
+//   * The walk of block c is done by ONE CTA, c mod nCTA ("owner").  It reads the block's reduced sums from the block's global
+//     slot, samples, and writes a 128-byte RESULT line (markers final, did one enter the model, the residual update of the
+//     block's in-model row).  Every CTA consumes the result lines in block order -- one line per block instead of 258 sums
+//     and 64 draws.  beta / components / acum are written by the owner once its block is known to be part of the chain.
+//   * Inside a CTA every stage of a block has its own warps and nothing waits for a later stage:
+//       warp 12      control: plans the blocks (<= 64 consecutive markers, at most ONE in-model marker each: a second one ends the
+//                    block before it), consumes the result lines, decides for every block which residual updates precede its dot
+//                    pass (those of the block kD + 1 blocks back: a fixed lag, so that all CTAs agree) and which stashed in-model
+//                    rows ride on it;
+//       warps 13-15  producers: TMA bulk copies of the code rows into a ring of 8 stages of 16 rows (one warp issues one copy
+//                    per ~100 cycles: profiles/r2_tma_gather_bench.txt);
+//       warps 2-9    dot warps: two 16-marker tiles each (one load of the limb fragments feeds both), a quarter of the
+//                    individuals each; partial sums go into a shared-memory accumulator set;
+//       warp 10      post: sums of q over the rows' missing individuals, missing-genotype cross counts of the Gram pairs;
+//       warp 11      publisher: combines an accumulator set into 64-bit sums, adds them to the block's global slot, arrives at
+//                    the slot's counter (the release fence is paid here, off the dot warps);
+//       warps 0-1    walkers: the walk of the blocks this CTA owns.
+//   * The residual lives in shared memory (fp64, item order) next to its int8 limbs: updates are applied by the dot warps at
+//     the block boundary the control warp names.
+// A sweep that starts from beta = 0 (many markers entering) should use version 4 (brr_gpu.cu chooses per sweep).
+#pragma once
+#include "sweep_dense5.cuh"
+
+namespace brr {
+namespace v6 {
+
+using v5::ldv; using v5::stv; using v5::bar_named; using v5::mbar_arrive; using v5::gram_std; using v5::RowConst; using v5::spin_check;
+using v5::kSlotRing; using v5::kSkip; using v5::kEnd; using v5::kLCnt; using v5::kLDots; using v5::kLSm; using v5::kLEps; using v5::kLGram;
+using v5::kSlotLines; using v5::kSlotInts5;
+
+constexpr int kD = 7;                       // the dot pass of a block sees the residual updates of the chain blocks more than kD back
+constexpr int kGramRows = kD + 1;           // one in-model row per block: the rows of the last kD blocks and the block's own
+static_assert(kGramRows <= 8, "one N-tile of Gram rows");
+constexpr int kSeq = 32;                    // ring of block descriptors
+constexpr int kAhead = kD + 4;              // blocks planned beyond the last consumed result
+constexpr int kIdRing = 16;                 // marker ids of planned blocks (>= kAhead)
+constexpr int kStashRing = 32;              // stashed in-model rows, slot = seq % kStashRing.  A row of seq s is last used by the residual update that
+                                            // precedes the dot pass of seq s + kD + 1 -- or, behind a restart, of the first block of the new epoch, at most
+                                            // seq s + kD + kAhead; its slot is planned again when the result of seq s + kStashRing - kAhead has been consumed
+static_assert(kStashRing - kAhead > kD + kAhead, "a stashed row must outlive the update that applies it");
+constexpr int kNeSlot = kStashRing;         // + one row for a marker that entered the model
+constexpr int kStages = 8, kTileRows = 16;
+constexpr int kAcc = 3;                     // accumulator sets in rotation
+constexpr int kAccInts = 4 * 256 + 4;       // per set: [4 tiles][128 dot sums + 128 Gram counts] + the change of sum q (2 x u64)
+constexpr int kMaxUpd = kD + 3;
+constexpr uint32_t kResRing = 512;          // result lines (32 ints each)
+constexpr int kWalkW = 2, kDotW = 8;
+constexpr int kWPost = kWalkW + kDotW, kWPub = kWPost + 1, kWCtrl = kWPub + 1, kWProd0 = kWCtrl + 1, kProdW = 3;
+static_assert(kWProd0 + kProdW == kWarps, "16 warps");
+constexpr int kDotThreads = 32 * kDotW;
+enum { kActSkip = 0, kActDot = 1, kActExit = 2 };
+enum { kPfDDec = 0, kPfDApply, kPfDFull, kPfDLoop, kPfDAcc, kPfPoWait, kPfPoWork, kPfPuWait, kPfPuWork, kPfPrPlan, kPfPrEmpty, kPfPrIssue,
+       kPfCPoll, kPfCPlan, kPfCDecide, kPfWCnt, kPfWRead, kPfWPred, kPfWSample, kPfWFix, kPfWValid, kPfBlocks, kPfWalks, kPfApplies, kPfRestarts,
+       kPfGramBlocks, kPfN = 32 };
+
+struct Sweep6Params {
+    uint32_t n_local, n_total, M, K, nG, nCTA, SL, PW, RS;
+    const uint32_t *codes; const double *lut; const uint32_t *counts; const int32_t *group;
+    const uint32_t *order; uint32_t n_order;
+    const uint32_t *inmask;      // bit p of word p / 32: beta[order[p]] != 0 at the start of the sweep (inmodel_mask_kernel)
+    const double *rand_uz, *pi, *sigmaG, *cva;
+    double sigmaE;
+    double *eps, *beta, *comp, *acum;
+    int *slots;                  // [kSlotRing][kSlotInts5], zero at launch
+    int *results;                // [kResRing][32], zero at launch
+    GroupConsts *gc;             // [nCTA] scratch: each CTA's table of per-(group, component) constants
+    unsigned long long *absmax;  // zero at launch
+    unsigned *bar;               // prologue / epilogue grid barrier counter, zero at launch
+    double *cta_red;             // [nCTA][2]
+    double *part_bsq;            // [nCTA][2][nG]   per-CTA, per-walker-warp sums of beta^2
+    int *part_v;                 // [nCTA][nG*K]
+    double *v, *betasq, *out_scalars;
+    unsigned *out_counts;        // [0] non-skipped, [1] blocks walked, [2] error flags, [3] restarts (zero at launch)
+    unsigned long long *prof;    // optional [kPfN]
+};
+
+struct Blk6 {
+    // planned
+    uint32_t c, pos, n, epoch, nrows, rowk, row_id;
+    // decided
+    uint32_t action, present, n_upd;
+    uint32_t back_seq[kD];       // seq of the chain blocks 1..kD back (kEnd = none)
+    uint32_t upd_slot[kMaxUpd];
+    double upd_dB[kMaxUpd];
+};
+
+struct Shared6 {
+    Blk6 blk[kSeq];
+    uint32_t ids[kIdRing][kB];
+    double rowlut[kStashRing + 1][4];
+    uint32_t valid_tag[kSeq];
+    // control words (volatile accesses)
+    uint32_t epoch_w, finished, abort, dots_done;
+    // control warp's private lists
+    uint32_t pend_slot[kMaxUpd + 4], pend_seq[kMaxUpd + 4]; double pend_dB[kMaxUpd + 4];
+    uint32_t hist[kD + 1];
+    unsigned long long wq[kWarps][2], sumq[2];
+    double scale, inv_scale, warp_tmp[kWarps];
+    // walkers
+    double bcast[2];
+    uint32_t w_flag[4], w_ctl[4];
+    uint32_t n_nonskipped, n_blocks, n_restarts, err;
+    unsigned long long prof[kPfN];
+    alignas(8) uint64_t full[kStages], empty[kStages], stash_full[kStashRing], ne_full, plan_bar[kSeq], dec_bar[kSeq], acc_full[kAcc], acc_empty[kAcc],
+        apply_done;
+};
+
+__host__ __device__ inline size_t sweep6_smem_bytes(uint32_t RS, uint32_t SL)
+{
+    size_t s = (sizeof(Shared6) + 15) & ~size_t(15);
+    s += size_t(kLimbs) * RS * 16;                    // limbs
+    s += size_t(kStages) * kTileRows * RS * 4;        // code stages
+    s += size_t(kStashRing + 1) * RS * 4;             // stashed rows
+    s += size_t(kAcc) * kAccInts * 4;                 // accumulator sets
+    s += size_t(SL) * 8;                              // residual, fp64
+    return s + 16;
+}
+
+// bit p of word p / 32 = the marker at position p of the sweep is in the model (src/BayesRBase.cpp:372: its update is never skipped)
+__global__ void inmodel_mask_kernel(const uint32_t *__restrict__ order, uint32_t n_order, const double *__restrict__ beta, uint32_t *__restrict__ mask, uint32_t n_words)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = p < n_order && beta[order[p]] != 0.0;
+    const unsigned b = __ballot_sync(0xffffffffu, in);
+    if ((threadIdx.x & 31) == 0 && (p >> 5) < n_words) mask[p >> 5] = b;
+}
+
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+template <bool PROF>
+__global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6Params p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Shared6 &sh = *reinterpret_cast<Shared6 *>(smem_raw);
+    const uint32_t RS = p.RS, PW = p.PW, SL = p.SL;
+    const size_t off0 = (sizeof(Shared6) + 15) & ~size_t(15);
+    uint4 *limbs = reinterpret_cast<uint4 *>(smem_raw + off0);                                      // [8][RS]
+    uint32_t *stages = reinterpret_cast<uint32_t *>(smem_raw + off0 + size_t(kLimbs) * RS * 16);     // [8][16][RS]
+    uint32_t *stash = stages + size_t(kStages) * kTileRows * RS;                                    // [kStashRing + 1][RS]
+    int *accs = reinterpret_cast<int *>(stash + size_t(kStashRing + 1) * RS);                       // [kAcc][kAccInts]
+    double *e_s = reinterpret_cast<double *>(accs + size_t(kAcc) * kAccInts);                       // [SL], item order: e_s[4 * item + t]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t gid = lane >> 2, tig = lane & 3;
+    const uint32_t cta = blockIdx.x, K = p.K;
+    const uint32_t NP = SL / 64, NI = SL / 4, NF = NP / 2;
+    const uint32_t PWT = PW + kTail, CB = PWT * 4;
+    const double NM1 = double(p.n_total - 1), Nt = double(p.n_total);
+    const uint32_t slice0 = cta * SL;
+    const bool is_dot = warp >= kWalkW && warp < kWPost;
+    const int dt = tid - 32 * kWalkW;                 // dot-thread index 0..255
+    const uint32_t dw = uint32_t(warp - kWalkW);      // dot-warp index 0..7
+    GroupConsts &gc = p.gc[cta];
+    const bool prof_on = PROF && p.prof != nullptr && cta == 0 && lane == 0;
+    long long t_prev = prof_on ? clock64() : 0;
+    auto PHASE = [&](int ph) { if (PROF && prof_on) { const long long t = clock64(); sh.prof[ph] += (unsigned long long)(t - t_prev); t_prev = t; } };
+    auto PMARK = [&]() { if (PROF && prof_on) t_prev = clock64(); };
+    auto PCOUNT = [&](int ph) { if (PROF && prof_on) sh.prof[ph] += 1; };
+    // Every wait of the pipeline can be given up: a wait that lasts ~2 s means a protocol error (or a lost CTA).  All other waits of
+    // the grid see the flag and fall through, the launch ends, the host reports error flag 4 -- instead of hanging the GPU.
+    long long spin_t0 = 0; uint32_t spin_it = 0;
+    auto spin_fail = [&]() -> bool {                  // slow half every 256 polls
+        if ((++spin_it & 255u) != 0u) return ldv(&sh.abort) != 0u;
+        return spin_check(&sh.abort, p.out_counts + 2, spin_t0);
+    };
+    auto spin_ok = [&]() { spin_t0 = 0; spin_it = 0; };
+    auto mbw = [&](uint64_t *bar, unsigned parity) -> bool {      // false = the launch was given up
+        for (;;) {
+            if (mbar_test(bar, parity)) { spin_ok(); return true; }
+            if (spin_fail()) return false;
+        }
+    };
+
+    // ---- prologue -----------------------------------------------------------------------------------------------------
+    double amax = 0.0;
+    for (uint32_t idx = tid; idx < SL; idx += kThreads) {          // e_s[4 * item + t] = eps of individual 16 w + 4 t + c, item = 4 w + c
+        const uint32_t item = idx >> 2, t = idx & 3u;
+        const uint32_t i = 16 * (item >> 2) + 4 * t + (item & 3u);
+        const uint32_t gi = slice0 + i;
+        const double x = gi < p.n_local ? p.eps[gi] : 0.0;
+        e_s[idx] = x;
+        amax = fmax(amax, fabs(x));
+    }
+    fill_group_consts(gc, p.nG, K, NM1, p.sigmaE, p.pi, p.sigmaG, p.cva);
+    for (int i = tid; i < kAcc * kAccInts; i += kThreads) accs[i] = 0;
+    for (uint32_t i = tid; i < p.nG * K; i += kThreads) p.part_v[size_t(cta) * p.nG * K + i] = 0;
+    for (uint32_t i = tid; i < 2 * p.nG; i += kThreads) p.part_bsq[size_t(cta) * 2 * p.nG + i] = 0.0;
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 5); }      // 4 dot warps + the post warp release a stage
+        for (int i = 0; i < kStashRing; ++i) mbar_init(&sh.stash_full[i], 1);
+        for (int i = 0; i < kSeq; ++i) { mbar_init(&sh.plan_bar[i], 1); mbar_init(&sh.dec_bar[i], 1); sh.valid_tag[i] = 0; }
+        for (int i = 0; i < kAcc; ++i) { mbar_init(&sh.acc_full[i], kDotW + 1); mbar_init(&sh.acc_empty[i], 1); }
+        mbar_init(&sh.ne_full, 1); mbar_init(&sh.apply_done, kDotW);
+        mbar_fence_init();
+        sh.abort = 0; sh.epoch_w = 0; sh.finished = 0; sh.dots_done = 0;
+        sh.n_nonskipped = 0; sh.n_blocks = 0; sh.n_restarts = 0; sh.err = 0;
+        if (PROF) for (int i = 0; i < kPfN; ++i) sh.prof[i] = 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0) sh.warp_tmp[warp] = amax;
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0;
+        for (int w = 0; w < kWarps; ++w) a = fmax(a, sh.warp_tmp[w]);
+        atomicMax(p.absmax, (unsigned long long)__double_as_longlong(a));
+    }
+    grid_arrive(p.bar);
+    grid_wait(p.bar, p.nCTA);
+    {   // common fixed-point scale: |q| <= 2^(62 - headroom) at the start of the sweep
+        const double a = __longlong_as_double((long long)__ldcg(p.absmax));
+        int ex = 0;
+        if (a > 0.0) frexp(a, &ex);
+        const int s = 62 - kHeadroomBits - ex;
+        if (tid == 0) { sh.scale = ldexp(1.0, s); sh.inv_scale = ldexp(1.0, -s); }
+    }
+    __syncthreads();
+    const double scale = sh.scale, inv_scale = sh.inv_scale;
+
+    // one item (word w, class c: the individuals 16 w + 4 t + c) of the residual -> its 8 limb words; returns q of the four (hi, lo sums)
+    auto quantize_item = [&](uint32_t item, const double (&ev)[4], long long &shi, unsigned long long &slo) {
+        uint32_t lo[4], hi[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const double x = ev[t] * scale;
+            if (!(fabs(x) < 4.0e18)) sh.err = 1u;                       // 2^62 = 4.6e18
+            const long long q = __double2ll_rn(x);
+            shi += q >> 32; slo += (unsigned long long)(q & 0xffffffffLL);
+            const unsigned long long uq = ((unsigned long long)q + 0x8080808080808080ULL) ^ 0x8080808080808080ULL;
+            lo[t] = (uint32_t)uq; hi[t] = (uint32_t)(uq >> 32);
+        }
+        const uint32_t w = item >> 2, c = item & 3u;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(limbs) + c;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const uint32_t sel = uint32_t(l) | (uint32_t(4 + l) << 4);
+            const uint32_t x01 = __byte_perm(lo[0], lo[1], sel), x23 = __byte_perm(lo[2], lo[3], sel);
+            dst[(size_t(l) * RS + w) * 4] = __byte_perm(x01, x23, 0x5410);
+            const uint32_t y01 = __byte_perm(hi[0], hi[1], sel), y23 = __byte_perm(hi[2], hi[3], sel);
+            dst[(size_t(4 + l) * RS + w) * 4] = __byte_perm(y01, y23, 0x5410);
+        }
+    };
+    {
+        long long shi = 0; unsigned long long slo = 0;
+        for (uint32_t item = tid; item < NI; item += kThreads) {
+            double ev[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) ev[t] = e_s[4 * item + t];
+            quantize_item(item, ev, shi, slo);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { shi += __shfl_xor_sync(0xffffffffu, shi, o); slo += __shfl_xor_sync(0xffffffffu, slo, o); }
+        if (lane == 0) { sh.wq[warp][0] = (unsigned long long)shi; sh.wq[warp][1] = slo; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long h = 0, l = 0;
+        for (int w = 0; w < kWarps; ++w) { h += sh.wq[w][0]; l += sh.wq[w][1]; }
+        sh.sumq[0] = h; sh.sumq[1] = l;
+    }
+    __syncthreads();
+
+    // =====================================================================================================================
+    if (warp == kWCtrl) {
+        // ---- control warp (warp-uniform: every lane carries the same state) ------------------------------------------------
+        uint32_t epoch = 0, pos = 0, next_c = 0;
+        uint32_t s_plan = 0, s_cons = 0, s_dec = 0;
+        uint32_t pend_n = 0, hist_n = 0, n_restarts = 0;
+        bool plan_end = false, restart_pending = false;
+        uint32_t ne_user = 0; bool ne_used = false; uint32_t ne_uses = 0;
+        uint32_t idA = 0, idB = 0, mw0 = 0, mw1 = 0, mw2 = 0;           // prefetched inputs of the block at pos
+        const uint32_t n_mw = (p.n_order + 31) / 32;
+        auto prefetch = [&]() {
+            idA = pos + lane < p.n_order ? __ldg(p.order + pos + lane) : 0u;
+            idB = pos + 32 + lane < p.n_order ? __ldg(p.order + pos + 32 + lane) : 0u;
+            const uint32_t w = pos >> 5;
+            mw0 = w < n_mw ? __ldg(p.inmask + w) : 0u;
+            mw1 = w + 1 < n_mw ? __ldg(p.inmask + w + 1) : 0u;
+            mw2 = w + 2 < n_mw ? __ldg(p.inmask + w + 2) : 0u;
+        };
+        prefetch();
+        for (;;) {
+            if (ldv(&sh.abort)) break;
+            bool progress = false;
+            PMARK();
+            // ---- (1) consume the result of the oldest block not yet consumed -------------------------------------------------
+            if (s_cons < s_plan) {
+                Blk6 &B = sh.blk[s_cons & (kSeq - 1)];
+                if (B.epoch != epoch) {                             // planned before a restart: no result to wait for
+                    if (ldv(&sh.dots_done) > s_cons) { ++s_cons; progress = true; }
+                } else if (B.c != kEnd) {
+                    const uint32_t c = B.c;
+                    const int *line = p.results + size_t(c % kResRing) * 32;
+                    const unsigned tag = ld_acquire(reinterpret_cast<const unsigned *>(line));
+                    if (tag == c + 1u) {
+                        const uint32_t u = __ldcg(line + 1);
+                        const uint32_t n_final = u & 0xffffu; const bool restart = (u >> 16) & 1u;
+                        const double dB = __ldcg(reinterpret_cast<const double *>(line + 2));
+                        const double ne_dB = __ldcg(reinterpret_cast<const double *>(line + 4));
+                        if (B.nrows && dB != 0.0) {
+                            if (lane == 0) { sh.pend_slot[pend_n] = (s_cons % kStashRing) | (((s_cons / kStashRing) & 1u) << 8); sh.pend_dB[pend_n] = dB; sh.pend_seq[pend_n] = s_cons; }
+                            ++pend_n;
+                        }
+                        if (lane == 0) stv(&sh.valid_tag[s_cons & (kSeq - 1)], s_cons + 1u);
+                        if (restart) {
+                            const uint32_t ne_pos = B.pos + n_final - 1u;
+                            if (ne_dB != 0.0) {                     // the marker that entered the model: fetch its row and value table
+                                const uint32_t ne_id = __ldg(p.order + ne_pos);
+                                if (ne_used) { while (ldv(&sh.dots_done) <= ne_user) { if (spin_fail()) break; } spin_ok(); }
+                                if (lane < 4) sh.rowlut[kNeSlot][lane] = __ldg(p.lut + 4 * size_t(ne_id) + lane);
+                                if (lane == 0) {
+                                    fence_proxy_async();
+                                    mbar_arrive_expect_tx(&sh.ne_full, CB);
+                                    bulk_g2s(stash + size_t(kNeSlot) * RS, p.codes + (size_t(ne_id) * p.nCTA + cta) * PWT, CB, &sh.ne_full);
+                                }
+                                mbw(&sh.ne_full, ne_uses & 1u);
+                                ++ne_uses;
+                                if (lane == 0) { sh.pend_slot[pend_n] = kNeSlot; sh.pend_dB[pend_n] = ne_dB; sh.pend_seq[pend_n] = s_cons; }
+                                ++pend_n;
+                            }
+                            ++epoch; pos = B.pos + n_final; next_c = c + kSkip;
+                            restart_pending = true; plan_end = false; ++n_restarts;
+                            __syncwarp();
+                            if (lane == 0) stv(&sh.epoch_w, epoch);
+                            prefetch();
+                        }
+                        ++s_cons; progress = true;
+                    }
+                }
+                __syncwarp();
+            }
+            PHASE(kPfCPoll);
+            // ---- (2) plan the next block -------------------------------------------------------------------------------------
+            if (!plan_end && s_plan < s_cons + uint32_t(kAhead)) {
+                const uint32_t s = s_plan;
+                Blk6 &B = sh.blk[s & (kSeq - 1)];
+                const uint32_t rem = p.n_order - pos;
+                uint32_t n = min(uint32_t(kB), rem);
+                const uint32_t shf = pos & 31u;
+                const uint32_t lo = __funnelshift_r(mw0, mw1, shf), hi = __funnelshift_r(mw1, mw2, shf);
+                unsigned long long im = (unsigned long long)lo | ((unsigned long long)hi << 32);
+                if (n < 64u) im &= (1ULL << n) - 1ULL;
+                uint32_t nrows = 0, rowk = 0;
+                if (im) {
+                    rowk = uint32_t(__ffsll((long long)im) - 1); nrows = 1; im &= im - 1;
+                    if (im) n = uint32_t(__ffsll((long long)im) - 1);   // a second in-model marker: the block ends before it
+                }
+                uint32_t *ids = sh.ids[s & (kIdRing - 1)];
+                ids[lane] = idA; ids[32 + lane] = idB;
+                const uint32_t row_id = __shfl_sync(0xffffffffu, rowk < 32u ? idA : idB, rowk & 31u);
+                const uint32_t slot = s % kStashRing;
+                if (nrows && lane < 4) sh.rowlut[slot][lane] = __ldg(p.lut + 4 * size_t(row_id) + lane);
+                const bool end = rem == 0;
+                if (lane == 0) {
+                    B.c = end ? kEnd : next_c; B.pos = pos; B.n = n; B.epoch = epoch; B.nrows = nrows; B.rowk = rowk; B.row_id = row_id;
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(&sh.stash_full[slot], nrows * CB);
+                    if (nrows) bulk_g2s(stash + size_t(slot) * RS, p.codes + (size_t(row_id) * p.nCTA + cta) * PWT, CB, &sh.stash_full[slot]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.plan_bar[s & (kSeq - 1)]);
+                ++s_plan; progress = true;
+                if (end) plan_end = true;
+                else { pos += n; ++next_c; prefetch(); }
+            }
+            PHASE(kPfCPlan);
+            // ---- (3) decide the next block for the dot / post / publisher warps --------------------------------------------
+            if (s_dec < s_plan) {
+                const uint32_t d = s_dec;
+                Blk6 &B = sh.blk[d & (kSeq - 1)];
+                uint32_t action = kActDot, n_take = 0, present = 0;
+                bool can = true;
+                if (B.epoch != epoch) {
+                    action = kActSkip;
+                } else if (B.c == kEnd) {
+                    if (s_cons == d) { action = kActExit; n_take = pend_n; } else can = false;
+                } else {
+                    if (restart_pending) { n_take = pend_n; hist_n = 0; }
+                    else if (hist_n == uint32_t(kD + 1)) {
+                        const uint32_t oldest = sh.hist[kD];
+                        if (s_cons <= oldest) can = false;
+                        else {
+                            while (n_take < pend_n && sh.pend_seq[n_take] <= oldest) ++n_take;
+                            hist_n = kD;
+                        }
+                    }
+                }
+                if (can) {
+                    if (action == kActDot) {
+                        restart_pending = false;
+                        for (uint32_t back = 1; back <= uint32_t(kD); ++back) {
+                            const uint32_t hs = back <= hist_n ? sh.hist[back - 1] : kEnd;
+                            if (lane == 0) B.back_seq[back - 1] = hs;
+                            if (hs != kEnd && sh.blk[hs & (kSeq - 1)].nrows) present |= 1u << (kD - back);
+                        }
+                        if (B.nrows) present |= 1u << kD;
+                        __syncwarp();
+                        if (lane == 0) {
+                            for (int h = int(hist_n); h > 0; --h) sh.hist[h] = sh.hist[h - 1];
+                            sh.hist[0] = d;
+                        }
+                        ++hist_n;
+                    }
+                    if (lane == 0) {
+                        for (uint32_t q = 0; q < n_take; ++q) { B.upd_slot[q] = sh.pend_slot[q]; B.upd_dB[q] = sh.pend_dB[q]; }
+                        for (uint32_t q = n_take; q < pend_n; ++q) {
+                            sh.pend_slot[q - n_take] = sh.pend_slot[q]; sh.pend_dB[q - n_take] = sh.pend_dB[q]; sh.pend_seq[q - n_take] = sh.pend_seq[q];
+                        }
+                        B.action = action; B.present = present; B.n_upd = n_take;
+                    }
+                    pend_n -= n_take;
+                    __syncwarp();
+                    for (uint32_t q = 0; q < n_take; ++q)
+                        if (B.upd_slot[q] == uint32_t(kNeSlot)) { ne_user = d; ne_used = true; }
+                    if (lane == 0) mbar_arrive(&sh.dec_bar[d & (kSeq - 1)]);
+                    ++s_dec; progress = true;
+                    if (action == kActExit) {
+                        if (lane == 0) { stv(&sh.finished, 1u); sh.n_restarts = n_restarts; }
+                        break;
+                    }
+                }
+            }
+            PHASE(kPfCDecide);
+            if (progress) spin_ok(); else if (spin_fail()) break;
+        }
+    } else if (warp >= kWProd0) {
+        // ---- producers: stage q = 4 s + t (tile t of block seq s) -> ring entry q % 8; producer w takes every third stage ----
+        const uint32_t pw = uint32_t(warp - kWProd0);
+        for (uint32_t q = pw;; q += kProdW) {
+            const uint32_t s = q >> 2, t = q & 3u, st = q & (kStages - 1);
+            PMARK();
+            bool ok = true;
+            for (;;) {                                              // the block's plan (or the end of the sweep)
+                if (mbar_test(&sh.plan_bar[s & (kSeq - 1)], (s / kSeq) & 1u)) break;
+                if (ldv(&sh.finished) || spin_fail()) { ok = false; break; }
+            }
+            spin_ok();
+            if (!ok) break;
+            PHASE(kPfPrPlan);
+            const Blk6 &B = sh.blk[s & (kSeq - 1)];
+            const uint32_t n = B.n;
+            const uint32_t nt = n > 16 * t ? min(16u, n - 16 * t) : 0u;
+            const uint32_t id = sh.ids[s & (kIdRing - 1)][16 * t + (lane & 15)];
+            if (q >= uint32_t(kStages)) {
+                for (;;) {
+                    if (mbar_test(&sh.empty[st], ((q >> 3) - 1u) & 1u)) break;
+                    if (ldv(&sh.finished) || spin_fail()) { ok = false; break; }
+                }
+                spin_ok();
+                if (!ok) break;
+            }
+            PHASE(kPfPrEmpty);
+            fence_proxy_async();
+            if (lane == 0) mbar_arrive_expect_tx(&sh.full[st], nt * CB);
+            __syncwarp();
+            if (uint32_t(lane) < nt)
+                bulk_g2s(stages + (size_t(st) * kTileRows + lane) * RS, p.codes + (size_t(id) * p.nCTA + cta) * PWT, CB, &sh.full[st]);
+            PHASE(kPfPrIssue);
+        }
+    } else if (is_dot) {
+        // ---- dot warps: tiles 2 tp, 2 tp + 1 of every block; the 128-individual chunks kp, kp + 4, ... --------------------------------
+        const uint32_t tp = dw >> 2, kp = dw & 3u;
+        uint32_t n_apply = 0;
+        for (uint32_t d = 0;; ++d) {
+            PMARK();
+            if (!mbw(&sh.dec_bar[d & (kSeq - 1)], (d / kSeq) & 1u)) break;
+            const Blk6 &B = sh.blk[d & (kSeq - 1)];
+            const uint32_t action = B.action, n_upd = B.n_upd;
+            // the block's accumulator set (released by the publisher kAcc blocks ago): the change of sum q of an update goes there too
+            if (d >= uint32_t(kAcc) && !mbw(&sh.acc_empty[d % kAcc], ((d / kAcc) - 1u) & 1u)) break;
+            PHASE(kPfDDec);
+            if (n_upd) {
+                // ---- residual update (src/BayesRBase.cpp:375-378 for every update not yet applied, in chain order) ----
+                // everything that reads the limbs of the previous block (dot warps, post warp) must be through
+                if (d > 0 && !mbw(&sh.acc_full[(d - 1) % kAcc], ((d - 1) / kAcc) & 1u)) break;
+                {
+                    bool ok = true;
+                    for (uint32_t q = 0; q < n_upd; ++q) {
+                        const uint32_t us = B.upd_slot[q];
+                        if ((us & 0xffu) != uint32_t(kNeSlot)) ok = ok && mbw(&sh.stash_full[us & 0xffu], (us >> 8) & 1u);
+                    }
+                    if (!ok) break;
+                }
+                long long shi = 0; unsigned long long slo = 0;
+                for (uint32_t item = uint32_t(dt); item < NI; item += kDotThreads) {
+                    const uint32_t w = item >> 2, c2 = 2 * (item & 3u);
+                    double ev[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) ev[t] = e_s[4 * item + t];
+                    long long ohi = 0; unsigned long long olo = 0;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) { const long long q = __double2ll_rn(ev[t] * scale); ohi += q >> 32; olo += (unsigned long long)(q & 0xffffffffLL); }
+                    for (uint32_t q = 0; q < n_upd; ++q) {
+                        const uint32_t slot = B.upd_slot[q] & 0xffu;
+                        const double dB = B.upd_dB[q];
+                        const uint32_t r = (stash[size_t(slot) * RS + w] >> c2) & kM3;
+                        const double *L = sh.rowlut[slot];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) ev[t] += dB * L[(r >> (8 * t)) & 3u];
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {      // individuals past n_local carry eps = 0 and code 0: their lut[0] increments must not stick
+                        const uint32_t gi = slice0 + 16 * w + 4 * t + (item & 3u);
+                        if (gi >= p.n_local) ev[t] = 0.0;
+                        e_s[4 * item + t] = ev[t];
+                    }
+                    quantize_item(item, ev, shi, slo);
+                    shi -= ohi; slo -= olo;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { shi += __shfl_xor_sync(0xffffffffu, shi, o); slo += __shfl_xor_sync(0xffffffffu, slo, o); }
+                if (lane == 0) {
+                    unsigned long long *dq = reinterpret_cast<unsigned long long *>(accs + size_t(d % kAcc) * kAccInts + 1024);
+                    atomicAdd(dq, (unsigned long long)shi); atomicAdd(dq + 1, slo);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.apply_done);
+                if (!mbw(&sh.apply_done, n_apply & 1u)) break;
+                ++n_apply;
+                if (dt == 0) PCOUNT(kPfApplies);
+                PHASE(kPfDApply);
+            }
+            if (action == kActExit) break;
+            const uint32_t st0 = (4 * d + 2 * tp) & (kStages - 1);
+            const uint32_t *pk = stages + size_t(st0) * kTileRows * RS;      // 32 rows: the two tiles are neighbours in the ring
+            if (!mbw(&sh.full[st0], (d >> 1) & 1u)) break;
+            if (!mbw(&sh.full[st0 + 1], (d >> 1) & 1u)) break;
+            if (action == kActSkip) {
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&sh.empty[st0]); mbar_arrive(&sh.empty[st0 + 1]); mbar_arrive(&sh.acc_full[d % kAcc]); }
+                continue;
+            }
+            const uint32_t n = B.n, present = B.present;
+            const bool any = n > 32 * tp;                                   // rows of this tile pair in the block
+            // Gram row r of this lane (as the B operand's column gid): the stashed row of the chain block kD - r back
+            const uint32_t *urow = stash;
+            uint32_t um = 0u;
+            if (present) {
+                bool bad = false;
+                const uint32_t r = gid;
+                if ((present >> r) & 1u) {
+                    const uint32_t back = kD - r;
+                    const uint32_t hs = back ? B.back_seq[back - 1] : d;
+                    if (!mbw(&sh.stash_full[hs % kStashRing], (hs / kStashRing) & 1u)) bad = true;
+                    urow = stash + size_t(hs % kStashRing) * RS;
+                    um = 0xffffffffu;
+                }
+                if (__any_sync(0xffffffffu, bad)) break;
+            }
+            PHASE(kPfDFull);
+            int acc[2][4][4];
+#pragma unroll
+            for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[tl][cc][q] = 0;
+            int gacc[2][4][4];
+            if (any) {
+                const uint32_t lo = gid * RS + tig;
+                uint32_t aR = smem_u32(pk + lo + 8 * kp);
+                const uint32_t dR8 = 32u * RS, dR16 = 64u * RS, dR24 = 96u * RS;       // byte offsets of rows + 8, + 16, + 24
+                uint32_t aL = smem_u32(limbs + lo + 8 * kp);
+                uint32_t cnt = NF > kp ? (NF - kp + 3u) / 4u : 0u;
+                if (present == 0u) {
+                    // ---- dots only: S[m][l] = sum_i g'_mi limb_l(q_i), one MMA per code class and tile (sweep_dense.cuh) ----
+                    if (cnt) {
+                        uint4 LA = lds_v4<0>(aL), LB = lds_v4<64>(aL);
+                        uint32_t x0 = lds_u32<0>(aR), x1 = lds_u32<0>(aR + dR8), x2 = lds_u32<16>(aR), x3 = lds_u32<16>(aR + dR8);
+                        uint32_t y0 = lds_u32<0>(aR + dR16), y1 = lds_u32<0>(aR + dR24), y2 = lds_u32<16>(aR + dR16), y3 = lds_u32<16>(aR + dR24);
+#pragma unroll 1
+                        for (;;) {
+                            const bool more = --cnt != 0u;
+                            if (more) { aR += 128u; aL += 512u; }
+                            const uint4 LAn = lds_v4<0>(aL), LBn = lds_v4<64>(aL);
+                            const uint32_t x0n = lds_u32<0>(aR), x1n = lds_u32<0>(aR + dR8), x2n = lds_u32<16>(aR), x3n = lds_u32<16>(aR + dR8);
+                            const uint32_t y0n = lds_u32<0>(aR + dR16), y1n = lds_u32<0>(aR + dR24), y2n = lds_u32<16>(aR + dR16), y3n = lds_u32<16>(aR + dR24);
+                            mma_u8s8(acc[0][0], x0 & kC0, x1 & kC0, x2 & kC0, x3 & kC0, LA.x, LB.x);
+                            mma_u8s8(acc[1][0], y0 & kC0, y1 & kC0, y2 & kC0, y3 & kC0, LA.x, LB.x);
+                            mma_u8s8(acc[0][1], x0 & kC1, x1 & kC1, x2 & kC1, x3 & kC1, LA.y, LB.y);
+                            mma_u8s8(acc[1][1], y0 & kC1, y1 & kC1, y2 & kC1, y3 & kC1, LA.y, LB.y);
+                            mma_u8s8(acc[0][2], x0 & kC2, x1 & kC2, x2 & kC2, x3 & kC2, LA.z, LB.z);
+                            mma_u8s8(acc[1][2], y0 & kC2, y1 & kC2, y2 & kC2, y3 & kC2, LA.z, LB.z);
+                            mma_u8s8(acc[0][3], x0 & kC3, x1 & kC3, x2 & kC3, x3 & kC3, LA.w, LB.w);
+                            mma_u8s8(acc[1][3], y0 & kC3, y1 & kC3, y2 & kC3, y3 & kC3, LA.w, LB.w);
+                            if (!more) break;
+                            LA = LAn; LB = LBn; x0 = x0n; x1 = x1n; x2 = x2n; x3 = x3n; y0 = y0n; y1 = y1n; y2 = y2n; y3 = y3n;
+                        }
+                    }
+                } else {
+                    // ---- dots + the Gram counts of the stashed rows against the 32 columns of the pair (same A fragments) ----
+#pragma unroll
+                    for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) gacc[tl][cc][q] = 0;
+                    uint32_t aU = smem_u32(urow + tig + 8 * kp);
+                    if (cnt) {
+#pragma unroll 1
+                        for (;;) {
+                            const uint4 LA = lds_v4<0>(aL), LB = lds_v4<64>(aL);
+                            const uint32_t uA = lds_u32<0>(aU) & um, uB = lds_u32<16>(aU) & um;
+#pragma unroll
+                            for (int tl = 0; tl < 2; ++tl) {
+                                const uint32_t rb = tl ? dR16 : 0u;
+                                const uint32_t a0 = lds_u32<0>(aR + rb), a1 = lds_u32<0>(aR + rb + dR8), b0 = lds_u32<16>(aR + rb), b1 = lds_u32<16>(aR + rb + dR8);
+                                uint32_t x0 = a0 & kC0, x1 = a1 & kC0, x2 = b0 & kC0, x3 = b1 & kC0;
+                                mma_u8s8(acc[tl][0], x0, x1, x2, x3, LA.x, LB.x); mma_u8u8(gacc[tl][0], x0, x1, x2, x3, uA & kC0, uB & kC0);
+                                x0 = a0 & kC1; x1 = a1 & kC1; x2 = b0 & kC1; x3 = b1 & kC1;
+                                mma_u8s8(acc[tl][1], x0, x1, x2, x3, LA.y, LB.y); mma_u8u8(gacc[tl][1], x0, x1, x2, x3, uA & kC1, uB & kC1);
+                                x0 = a0 & kC2; x1 = a1 & kC2; x2 = b0 & kC2; x3 = b1 & kC2;
+                                mma_u8s8(acc[tl][2], x0, x1, x2, x3, LA.z, LB.z); mma_u8u8(gacc[tl][2], x0, x1, x2, x3, uA & kC2, uB & kC2);
+                                x0 = a0 & kC3; x1 = a1 & kC3; x2 = b0 & kC3; x3 = b1 & kC3;
+                                mma_u8s8(acc[tl][3], x0, x1, x2, x3, LA.w, LB.w); mma_u8u8(gacc[tl][3], x0, x1, x2, x3, uA & kC3, uB & kC3);
+                            }
+                            if (--cnt == 0u) break;
+                            aR += 128u; aL += 512u; aU += 128u;
+                        }
+                    }
+                }
+                if ((NP & 1u) && (NF & 3u) == kp) {                                     // the half chunk at the end of the slice
+                    const uint32_t *r0p = pk + lo + 8 * NF;
+                    const uint4 LA = limbs[lo + 8 * NF];
+                    const uint32_t uA = urow[tig + 8 * NF] & um;
+#pragma unroll
+                    for (int tl = 0; tl < 2; ++tl) {
+                        const uint32_t a0 = r0p[(16 * tl) * RS], a1 = r0p[(16 * tl + 8) * RS];
+                        mma_u8s8(acc[tl][0], a0 & kC0, a1 & kC0, 0u, 0u, LA.x, 0u);
+                        mma_u8s8(acc[tl][1], a0 & kC1, a1 & kC1, 0u, 0u, LA.y, 0u);
+                        mma_u8s8(acc[tl][2], a0 & kC2, a1 & kC2, 0u, 0u, LA.z, 0u);
+                        mma_u8s8(acc[tl][3], a0 & kC3, a1 & kC3, 0u, 0u, LA.w, 0u);
+                        if (present) {
+                            mma_u8u8(gacc[tl][0], a0 & kC0, a1 & kC0, 0u, 0u, uA & kC0, 0u);
+                            mma_u8u8(gacc[tl][1], a0 & kC1, a1 & kC1, 0u, 0u, uA & kC1, 0u);
+                            mma_u8u8(gacc[tl][2], a0 & kC2, a1 & kC2, 0u, 0u, uA & kC2, 0u);
+                            mma_u8u8(gacc[tl][3], a0 & kC3, a1 & kC3, 0u, 0u, uA & kC3, 0u);
+                        }
+                    }
+                }
+            }
+            // the rows are no longer needed by this warp
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&sh.empty[st0]); mbar_arrive(&sh.empty[st0 + 1]); }
+            PHASE(kPfDLoop);
+            // ---- partial sums into the block's accumulator set ----
+            if (any) {
+                int *aset = accs + size_t(d % kAcc) * kAccInts;
+#pragma unroll
+                for (int tl = 0; tl < 2; ++tl) {
+                    int *tacc = aset + (2 * tp + tl) * 256;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int v = acc[tl][0][q] + (acc[tl][1][q] >> 2) + (acc[tl][2][q] >> 4) + (acc[tl][3][q] >> 6);
+                        if (v) atomicAdd(&tacc[q * 32 + lane], v);
+                        if (present) {
+                            const int g = gacc[tl][0][q] + (gacc[tl][1][q] >> 4) + (gacc[tl][2][q] >> 8) + (gacc[tl][3][q] >> 12);
+                            if (g) atomicAdd(&tacc[128 + q * 32 + lane], g);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.acc_full[d % kAcc]);
+            PHASE(kPfDAcc);
+        }
+    } else if (warp == kWPost) {
+        // ---- post warp: per row the sum of q over its missing individuals; per Gram pair the missing-genotype cross counts ----
+        uint32_t n_apply = 0;
+        auto q_of = [&](uint32_t i) -> long long {
+            const uint8_t *lb = reinterpret_cast<const uint8_t *>(limbs) + ((i >> 4) * 4 + (i & 3u)) * 4 + ((i >> 2) & 3u);
+            uint32_t ulo = 0, uhi = 0;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                ulo |= uint32_t(lb[size_t(l) * RS * 16]) << (8 * l);
+                uhi |= uint32_t(lb[size_t(4 + l) * RS * 16]) << (8 * l);
+            }
+            const unsigned long long uq = (unsigned long long)ulo | ((unsigned long long)uhi << 32);
+            return (long long)((uq ^ 0x8080808080808080ULL) - 0x8080808080808080ULL);
+        };
+        for (uint32_t d = 0;; ++d) {
+            PMARK();
+            if (!mbw(&sh.dec_bar[d & (kSeq - 1)], (d / kSeq) & 1u)) break;
+            const Blk6 &B = sh.blk[d & (kSeq - 1)];
+            const uint32_t action = B.action;
+            if (action == kActExit) break;
+            if (B.n_upd) { if (!mbw(&sh.apply_done, n_apply & 1u)) break; ++n_apply; }
+            const uint32_t stb = (4 * d) & (kStages - 1);                          // the block's four stages are neighbours: rows 0..63
+            bool ok = true;
+            for (uint32_t t = 0; t < 4; ++t) ok = ok && mbw(&sh.full[stb + t], (d >> 1) & 1u);
+            if (!ok) break;
+            PHASE(kPfPoWait);
+            if (action == kActDot) {
+                const uint32_t n = B.n, c = B.c, present = B.present;
+                int *slot = p.slots + size_t(c % kSlotRing) * kSlotInts5;
+                const uint32_t *pk = stages + size_t(stb) * kTileRows * RS;
+                for (uint32_t m = lane; m < n; m += 32) {
+                    const uint32_t *row = pk + size_t(m) * RS;
+                    const uint16_t *tail = reinterpret_cast<const uint16_t *>(row + PW);
+                    const uint32_t cntm = tail[0];
+                    if (cntm == 0u) continue;
+                    long long qh = 0; unsigned long long ql = 0;
+                    if (cntm <= 15u) {
+                        for (uint32_t en = 0; en < cntm; ++en) { const long long q = q_of(tail[1 + en]); qh += q >> 32; ql += (unsigned long long)(q & 0xffffffffLL); }
+                    } else {                                   // a long list: scan the row's words
+                        for (uint32_t w = 0; w < PW; ++w) {
+                            const uint32_t x = row[w];
+                            uint32_t mm = x & (x >> 1) & 0x55555555u;
+                            while (mm) {
+                                const int bit = __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                const long long q = q_of(16 * w + (bit >> 1)); qh += q >> 32; ql += (unsigned long long)(q & 0xffffffffLL);
+                            }
+                        }
+                    }
+                    if (qh) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLSm + 2 * m) * kLine), (unsigned long long)qh);
+                    if (ql) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLSm + 2 * m + 1) * kLine), ql);
+                }
+                if (present) {
+                    for (uint32_t r = 0; r < uint32_t(kGramRows); ++r) {
+                        if (!((present >> r) & 1u)) continue;
+                        const uint32_t back = kD - r;
+                        const uint32_t hs = back ? B.back_seq[back - 1] : d;
+                        if (!mbw(&sh.stash_full[hs % kStashRing], (hs / kStashRing) & 1u)) { ok = false; break; }
+                        const uint32_t *rowj = stash + size_t(hs % kStashRing) * RS;
+                        const uint16_t *tlj = reinterpret_cast<const uint16_t *>(rowj + PW);
+                        const uint32_t cntj = tlj[0];
+                        for (uint32_t col = lane; col < n; col += 32) {
+                            if (back == 0u && B.rowk == col) continue;               // the row against itself: not needed
+                            const uint32_t *rowa = pk + size_t(col) * RS;
+                            const uint16_t *tla = reinterpret_cast<const uint16_t *>(rowa + PW);
+                            const uint32_t cnta = tla[0];
+                            uint32_t z = 0, wv = 0, y = 0;
+                            if (cntj <= 15u && cnta <= 15u) {
+                                for (uint32_t en = 0; en < cntj; ++en) {
+                                    const uint32_t ii = tlj[1 + en];
+                                    const uint32_t cc = (rowa[ii >> 4] >> (2 * (ii & 15u))) & 3u;
+                                    if (cc == 3u) ++wv; else z += cc;
+                                }
+                                for (uint32_t en = 0; en < cnta; ++en) {
+                                    const uint32_t ii = tla[1 + en];
+                                    const uint32_t cc = (rowj[ii >> 4] >> (2 * (ii & 15u))) & 3u;
+                                    if (cc != 3u) y += cc;
+                                }
+                            } else if (cntj | cnta) {
+                                for (uint32_t w = 0; w < PW; ++w) {
+                                    const uint32_t xj = rowj[w], xa = rowa[w];
+                                    const uint32_t mj = xj & (xj >> 1) & 0x55555555u, ma = xa & (xa >> 1) & 0x55555555u;
+                                    uint32_t mm = mj | ma;
+                                    while (mm) {
+                                        const int bit = __ffs(mm) - 1;
+                                        mm &= mm - 1;
+                                        const uint32_t cj2 = (xj >> bit) & 3u, ca2 = (xa >> bit) & 3u;
+                                        if (cj2 == 3u) { if (ca2 == 3u) ++wv; else z += ca2; }
+                                        else y += cj2;                               // column missing, row present
+                                    }
+                                }
+                            }
+                            unsigned long long *ln = reinterpret_cast<unsigned long long *>(slot + size_t(kLGram + r * kB + col) * kLine);
+                            if (wv) atomicAdd(ln, (unsigned long long)wv << 32);
+                            if (y | z) atomicAdd(ln + 1, (unsigned long long)y | ((unsigned long long)z << 32));
+                        }
+                    }
+                    if (!ok) break;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                for (uint32_t t = 0; t < 4; ++t) mbar_arrive(&sh.empty[stb + t]);
+                mbar_arrive(&sh.acc_full[d % kAcc]);
+            }
+            PHASE(kPfPoWork);
+        }
+    } else if (warp == kWPub) {
+        // ---- publisher: accumulator set -> the block's global slot, arrive at its counter; recycling of the global slots ----
+        unsigned long long sq = lane < 2 ? sh.sumq[lane] : 0ULL;
+        uint32_t last_c = 0, n_apply = 0; bool have_c = false;
+        for (uint32_t d = 0;; ++d) {
+            PMARK();
+            if (!mbw(&sh.dec_bar[d & (kSeq - 1)], (d / kSeq) & 1u)) break;
+            const Blk6 &B = sh.blk[d & (kSeq - 1)];
+            const uint32_t action = B.action;
+            int *aset = accs + size_t(d % kAcc) * kAccInts;
+            if (action == kActExit) {
+                if (B.n_upd) mbw(&sh.apply_done, n_apply & 1u);     // the last updates of the sweep: their change of sum q is in the set
+                break;
+            }
+            if (B.n_upd) ++n_apply;
+            if (!mbw(&sh.acc_full[d % kAcc], (d / kAcc) & 1u)) break;
+            if (lane == 0) stv(&sh.dots_done, d + 1u);
+            PHASE(kPfPuWait);
+            if (lane < 2) {                                         // residual updates applied before this block's dot pass
+                unsigned long long *dq = reinterpret_cast<unsigned long long *>(aset + 1024);
+                sq += dq[lane]; dq[lane] = 0ULL;
+            }
+            if (action == kActDot) {
+                const uint32_t n = B.n, c = B.c, present = B.present;
+                int *slot = p.slots + size_t(c % kSlotRing) * kSlotInts5;
+#pragma unroll
+                for (int rep = 0; rep < 4; ++rep) {
+                    // (marker m, half h): the limb sums 4h..4h+3 combined into sum_l S_l 2^(8l), exact, as ONE signed 64-bit RED
+                    const uint32_t i = uint32_t(lane) + 32u * rep, m = i >> 1, h = i & 1u, mt = m & 15u;
+                    int *tacc = aset + (m >> 4) * 256;
+                    long long v = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t l = 4 * h + j, idx = ((l & 1u) + 2 * (mt >> 3)) * 32 + (mt & 7u) * 4 + (l >> 1);
+                        v += (long long)tacc[idx] * (1LL << (8 * j));
+                        tacc[idx] = 0;
+                    }
+                    if (v && m < n) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLDots + 2 * m + h) * kLine), (unsigned long long)v);
+                }
+                if (present) {
+                    for (uint32_t i2 = lane; i2 < 512u; i2 += 32u) {
+                        const uint32_t tile = i2 >> 7, j2 = i2 & 127u;
+                        int *tacc = aset + tile * 256 + 128;
+                        const int a = tacc[j2];
+                        if (a) {
+                            tacc[j2] = 0;
+                            const uint32_t q = j2 >> 5, l2 = j2 & 31u, m = 16 * tile + (l2 >> 2) + 8 * (q >> 1), r = 2 * (l2 & 3u) + (q & 1u);
+                            if (m < n && ((present >> r) & 1u))
+                                atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLGram + r * kB + m) * kLine), (unsigned long long)(unsigned)a);
+                        }
+                    }
+                }
+                if (lane < 2 && sq) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLEps + lane) * kLine), sq);
+                __syncwarp();
+                if (lane == 0) red_release_add(reinterpret_cast<unsigned *>(slot + kLCnt * kLine), 1u);
+                // block indices (last_c, c] are passed: their slots' next users (256 blocks on) get zeroed by the CTA they map to
+                uint32_t i0 = have_c ? last_c + 1 : 0u;
+                for (uint32_t idx = i0; idx <= c; ++idx) {
+                    if (idx % p.nCTA != cta) continue;
+                    int *z = p.slots + size_t((idx + kSlotRing / 2) % kSlotRing) * kSlotInts5;
+                    for (int ln = lane; ln < kSlotLines; ln += 32) *reinterpret_cast<int4 *>(z + size_t(ln) * kLine) = make_int4(0, 0, 0, 0);
+                }
+                last_c = c; have_c = true;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.acc_empty[d % kAcc]);
+            PHASE(kPfPuWork);
+        }
+        // updates applied at the end of the sweep (or left in a set nobody published): their change of sum q
+        __syncwarp();
+        if (lane < 2) {
+            for (int a = 0; a < kAcc; ++a) sq += *(reinterpret_cast<volatile unsigned long long *>(accs + size_t(a) * kAccInts + 1024) + lane);
+            sh.wq[0][lane] = sq;                                    // (added again after the CTA barrier of the epilogue, see there)
+        }
+    } else {
+        // ---- walkers: the walk of the blocks this CTA owns; thread k = marker k of the block ------------------------------------
+        const int wk = tid;
+        uint32_t nonskipped = 0, nblocks = 0;
+        double bsq_acc = 0.0;   // (unused accumulator slot kept for symmetry with the per-group sums below)
+        (void)bsq_acc;
+        for (uint32_t s = 0;; ++s) {
+            PMARK();
+            // the block's plan, or the end of the sweep
+            if (tid == 0) {
+                uint32_t ctl = 1;
+                for (;;) {
+                    if (mbar_test(&sh.plan_bar[s & (kSeq - 1)], (s / kSeq) & 1u)) break;
+                    if (ldv(&sh.finished) || spin_fail()) { ctl = 0; break; }
+                }
+                spin_ok();
+                sh.w_ctl[0] = ctl;
+            }
+            bar_named(1, 64);
+            if (!sh.w_ctl[0] || ldv(&sh.abort)) break;
+            const Blk6 &B = sh.blk[s & (kSeq - 1)];
+            const uint32_t c = B.c, n = B.n, pos = B.pos, b_epoch = B.epoch, nrows = B.nrows, rowk = B.rowk;
+            bar_named(1, 64);                                       // (w_ctl is rewritten below)
+            if (c == kEnd || c % p.nCTA != cta) continue;
+            // ---- per-marker inputs (latency hidden behind the waits below) ----
+            const bool act = uint32_t(wk) < n;
+            uint32_t my_id = 0;
+            double bo = 0.0, uu = 2.0, zz = 0.0; int gg = 0;
+            double L[4] = {0.0, 0.0, 0.0, 0.0};
+            uint4 cn = make_uint4(0, 0, 0, 0);
+            if (act) {
+                my_id = __ldg(p.order + pos + wk);
+                const double2 l01 = __ldg(reinterpret_cast<const double2 *>(p.lut + 4 * size_t(my_id)));
+                const double2 l23 = __ldg(reinterpret_cast<const double2 *>(p.lut + 4 * size_t(my_id) + 2));
+                cn = __ldg(reinterpret_cast<const uint4 *>(p.counts + 4 * size_t(my_id)));
+                const double2 uz = __ldg(reinterpret_cast<const double2 *>(p.rand_uz + 2 * size_t(my_id)));
+                bo = __ldcg(p.beta + my_id);
+                gg = p.group ? __ldg(p.group + my_id) : 0;
+                L[0] = l01.x; L[1] = l01.y; L[2] = l23.x; L[3] = l23.y; uu = uz.x; zz = uz.y;
+            }
+            // ---- the decision (Gram rows present, chain blocks behind), then the slot's counter ----
+            if (tid == 0) {
+                uint32_t ctl = 1;
+                if (!mbw(&sh.dec_bar[s & (kSeq - 1)], (s / kSeq) & 1u)) ctl = 0;
+                else if (B.action != kActDot) ctl = 2;              // dropped by a restart
+                else {
+                    const int *slot0 = p.slots + size_t(c % kSlotRing) * kSlotInts5;
+                    while (ld_acquire(reinterpret_cast<const unsigned *>(slot0 + kLCnt * kLine)) < p.nCTA) {
+                        if (ldv(&sh.epoch_w) != b_epoch) { ctl = 2; break; }
+                        if (spin_fail()) { ctl = 0; break; }
+                        __nanosleep(100);
+                    }
+                    spin_ok();
+                }
+                sh.w_ctl[1] = ctl;
+            }
+            bar_named(1, 64);
+            {
+                const uint32_t ctl = sh.w_ctl[1];
+                if (ctl == 0) break;
+                if (ctl == 2) continue;
+            }
+            __threadfence_block();
+            PHASE(kPfWCnt);
+            const int *slot = p.slots + size_t(c % kSlotRing) * kSlotInts5;
+            const uint32_t present = B.present;
+            double base = 0.0;
+            RowConst rc; rc.sj = rc.cj = rc.ej = rc.sumg = rc.nmiss = 0.0;
+            int4 gv[kGramRows];
+            if (act) {
+                const long long tlo = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLDots + 2 * wk) * kLine));
+                const long long thi = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLDots + 2 * wk + 1) * kLine));
+                const long long sm_hi = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLSm + 2 * wk) * kLine));
+                const long long sm_lo = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLSm + 2 * wk + 1) * kLine));
+                const long long e_hi = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLEps) * kLine));
+                const long long e_lo = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLEps + 1) * kLine));
+#pragma unroll
+                for (int r = 0; r < kGramRows; ++r)
+                    if ((present >> r) & 1u) gv[r] = __ldcg(reinterpret_cast<const int4 *>(slot + size_t(kLGram + r * kB + wk) * kLine));
+                const double sx = 0.5 * (L[2] - L[0]);
+                const double eps_sum_total = (double(e_hi) * 4294967296.0 + double(e_lo)) * inv_scale;
+                const double dprime = (double(thi) * 4294967296.0 + double(tlo)) * inv_scale;
+                const double smd = (double(sm_hi) * 4294967296.0 + double(sm_lo)) * inv_scale;
+                base = L[0] * eps_sum_total + sx * (dprime - 3.0 * smd) + (L[3] - L[0]) * smd;
+                if (present) {
+                    const double inv_s = 1.0 / sx, cc = -L[0] * inv_s;
+                    rc.sj = sx; rc.cj = cc; rc.ej = L[3] * inv_s + cc;
+                    rc.sumg = double(cn.y) + 2.0 * double(cn.z); rc.nmiss = double(cn.w);
+                }
+            }
+            PHASE(kPfWRead);
+            // ---- Gram rows: standardise; the rows of earlier blocks complete this block's dots (their updates were not in the residual yet) ----
+            double G_own = 0.0;
+            bool dropped = false, given_up = false;
+            if (present) {
+                for (int r = 0; r < kGramRows; ++r) {
+                    if (!((present >> r) & 1u)) continue;
+                    const uint32_t back = kD - r;
+                    const uint32_t hs = back ? B.back_seq[back - 1] : s;
+                    const Blk6 &H = sh.blk[hs & (kSeq - 1)];
+                    const uint32_t jid = H.row_id;
+                    // the row's standardisation constants (every thread derives them: same loads, broadcast by the cache)
+                    RowConst rj;
+                    {
+                        const double2 l01 = __ldg(reinterpret_cast<const double2 *>(p.lut + 4 * size_t(jid)));
+                        const double2 l23 = __ldg(reinterpret_cast<const double2 *>(p.lut + 4 * size_t(jid) + 2));
+                        const uint4 cj4 = __ldg(reinterpret_cast<const uint4 *>(p.counts + 4 * size_t(jid)));
+                        const double sxj = 0.5 * (l23.x - l01.x), inv_s = 1.0 / sxj, cc = -l01.x * inv_s;
+                        rj.sj = sxj; rj.cj = cc; rj.ej = l23.y * inv_s + cc;
+                        rj.sumg = double(cj4.y) + 2.0 * double(cj4.z); rj.nmiss = double(cj4.w);
+                    }
+                    double g = 0.0;
+                    if (act) g = gram_std(rj, rc, double(unsigned(gv[r].x)), double(unsigned(gv[r].y)), double(unsigned(gv[r].z)), double(unsigned(gv[r].w)), Nt);
+                    if (back) {
+                        // the update of that row: in the result line of its block (written by that block's owner)
+                        const uint32_t hc = H.c;
+                        if (tid == 0) {
+                            uint32_t ctl = 1;
+                            const int *line = p.results + size_t(hc % kResRing) * 32;
+                            while (ld_acquire(reinterpret_cast<const unsigned *>(line)) != hc + 1u) {
+                                if (ldv(&sh.epoch_w) != b_epoch) { ctl = 2; break; }
+                                if (spin_fail()) { ctl = 0; break; }
+                            }
+                            spin_ok();
+                            if (ctl == 1) sh.bcast[1] = __ldcg(reinterpret_cast<const double *>(line + 2));
+                            sh.w_ctl[2] = ctl;
+                        }
+                        bar_named(1, 64);
+                        const uint32_t ctl = sh.w_ctl[2];
+                        const double dBj = sh.bcast[1];
+                        bar_named(1, 64);
+                        if (ctl == 0) { given_up = true; break; }
+                        if (ctl == 2) { dropped = true; break; }
+                        if (dBj != 0.0) base += dBj * g;
+                    } else G_own = g;
+                }
+            }
+            if (given_up) break;
+            if (dropped) continue;
+            base += bo * NM1;
+            PHASE(kPfWPred);
+            Draw dr; dr.beta_new = bo; dr.acum0 = 0.0; dr.comp = -1;
+            if (act) dr = sample_marker_k(gc, gg, K, base, p.sigmaE, bo, uu, zz);
+            PHASE(kPfWSample);
+            // ---- in marker order: the block's in-model marker changes the dots of the markers behind it; a marker that enters the
+            //      model ends the block right behind itself ----
+            uint32_t n_final = n;
+            bool restart = false;
+            {
+                uint32_t lo_k = 0;
+                for (uint32_t i = 0; i <= nrows; ++i) {
+                    const uint32_t hi_k = i < nrows ? rowk : n;             // segment [lo_k, hi_k): no in-model marker inside
+                    const bool enters = act && uint32_t(wk) >= lo_k && uint32_t(wk) < hi_k && bo == 0.0 && dr.beta_new != 0.0;
+                    const unsigned bal = __ballot_sync(0xffffffffu, enters);
+                    uint32_t *fl = sh.w_flag + 2 * (i & 1u);
+                    if (lane == 0) fl[warp] = bal;
+                    bar_named(1, 64);
+                    const unsigned b0 = fl[0], b1 = fl[1];
+                    if (b0 | b1) { n_final = (b0 ? uint32_t(__ffs(b0) - 1) : 32u + uint32_t(__ffs(b1) - 1)) + 1u; restart = true; break; }
+                    if (i == nrows) break;
+                    // marker hi_k (in the model): its draw is final; everything behind it moves by dB x_j.x_k
+                    if (uint32_t(wk) == hi_k) sh.bcast[0] = bo - dr.beta_new;
+                    bar_named(1, 64);
+                    const double dB = sh.bcast[0];
+                    if (dB != 0.0 && act && uint32_t(wk) > hi_k) {
+                        base += dB * G_own;
+                        dr = sample_marker_k(gc, gg, K, base, p.sigmaE, bo, uu, zz);
+                    }
+                    lo_k = hi_k + 1;
+                    if (tid == 0) PCOUNT(kPfGramBlocks);
+                }
+            }
+            bar_named(1, 64);                                       // (w_flag / bcast are reused by the next owned block)
+            const bool fin = act && uint32_t(wk) < n_final;
+            const double dBm = fin ? (bo - dr.beta_new) : 0.0;
+            // ---- the result line: what every CTA needs to know about this block ----
+            {
+                int *line = p.results + size_t(c % kResRing) * 32;
+                if (nrows && uint32_t(wk) == rowk) *reinterpret_cast<volatile double *>(line + 2) = dBm;
+                if (restart && uint32_t(wk) == n_final - 1u) *reinterpret_cast<volatile double *>(line + 4) = dBm;
+                if (tid == 0) {
+                    *reinterpret_cast<volatile int *>(line + 1) = int(n_final | (restart ? 0x10000u : 0u));
+                    if (!nrows) *reinterpret_cast<volatile double *>(line + 2) = 0.0;
+                }
+                __threadfence();
+                bar_named(1, 64);
+                if (tid == 0) st_release_gpu(reinterpret_cast<unsigned *>(line), c + 1u);
+            }
+            PHASE(kPfWFix);
+            // ---- the block is part of the chain once this CTA's control warp has consumed its result in chain order ----
+            if (tid == 0) {
+                uint32_t ctl = 1;
+                while (ldv(&sh.valid_tag[s & (kSeq - 1)]) != s + 1u) {
+                    if (ldv(&sh.epoch_w) != b_epoch) { ctl = ldv(&sh.valid_tag[s & (kSeq - 1)]) == s + 1u ? 1u : 2u; break; }
+                    if (spin_fail()) { ctl = 0; break; }
+                }
+                spin_ok();
+                sh.w_ctl[3] = ctl;
+            }
+            bar_named(1, 64);
+            {
+                const uint32_t ctl = sh.w_ctl[3];
+                if (ctl == 0) break;
+                if (ctl == 2) continue;
+            }
+            PHASE(kPfWValid);
+            // ---- file the block: src/BayesRBase.cpp:341, :350-356, the sweep's counts (:355) and sums of squares (:353) ----
+            const bool nonskip = fin && !(bo == 0.0 && dr.beta_new == 0.0);
+            nonskipped += __popc(__ballot_sync(0xffffffffu, nonskip));
+            {
+                double b2 = 0.0; int gk = -1;
+                if (fin) {
+                    p.acum[my_id] = dr.acum0;
+                    if (dr.comp >= 0) {
+                        p.beta[my_id] = dr.beta_new;
+                        p.comp[my_id] = double(dr.comp);
+                        atomicAdd(&p.part_v[size_t(cta) * p.nG * K + gg * K + dr.comp], 1);
+                        if (dr.comp > 0) { b2 = dr.beta_new * dr.beta_new; gk = gg; }
+                    }
+                }
+                unsigned pend = __ballot_sync(0xffffffffu, gk >= 0);
+                while (pend) {                                  // one pass per group that gained a non-zero effect (fixed summation order)
+                    const int g = __shfl_sync(0xffffffffu, gk, __ffs(pend) - 1);
+                    const double s0 = warp_sum(gk == g ? b2 : 0.0);
+                    if (lane == 0) p.part_bsq[size_t(cta) * 2 * p.nG + size_t(warp) * p.nG + g] += s0;
+                    pend &= ~__ballot_sync(0xffffffffu, gk == g);
+                }
+            }
+            ++nblocks;
+            if (tid == 0) PCOUNT(kPfWalks);
+        }
+        if (lane == 0) atomicAdd(&sh.n_nonskipped, nonskipped);           // each warp counted its own lanes
+        if (tid == 0) sh.n_blocks = nblocks;
+    }
+
+    // ---- epilogue: every update has been applied; eps back to HBM, sweep scalars -----------------------------------------
+    __syncthreads();
+    double sq = 0.0;
+    for (uint32_t idx = tid; idx < SL; idx += kThreads) {
+        const uint32_t item = idx >> 2, t = idx & 3u;
+        const uint32_t gi = slice0 + 16 * (item >> 2) + 4 * t + (item & 3u);
+        if (gi < p.n_local) { const double x = e_s[idx]; p.eps[gi] = x; sq += x * x; }
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) sh.warp_tmp[warp] = sq;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < kWarps; ++w) s += sh.warp_tmp[w];
+        p.cta_red[2 * cta + 0] = (double((long long)sh.wq[0][0]) * 4294967296.0 + double((long long)sh.wq[0][1])) * inv_scale;
+        p.cta_red[2 * cta + 1] = s;
+        if (sh.err) atomicOr(p.out_counts + 2, sh.err);
+        atomicAdd(p.out_counts + 0, sh.n_nonskipped);
+        atomicAdd(p.out_counts + 1, sh.n_blocks);
+        if (cta == 0) p.out_counts[3] = sh.n_restarts;
+    }
+    __threadfence();
+    grid_arrive(p.bar);
+    if (cta == 0) {
+        grid_wait(p.bar, 2 * p.nCTA);
+        if (warp == 0) {
+            double s = 0.0, q = 0.0;
+            for (uint32_t cc = lane; cc < p.nCTA; cc += 32) { s += ld_cg(p.cta_red + 2 * cc); q += ld_cg(p.cta_red + 2 * cc + 1); }
+            s = warp_sum(s); q = warp_sum(q);
+            if (lane == 0) { p.out_scalars[0] = s; p.out_scalars[1] = q; }
+        }
+        for (uint32_t i = tid; i < p.nG * K; i += kThreads) {
+            int a = 0;
+            for (uint32_t cc = 0; cc < p.nCTA; ++cc) a += ld_cg(p.part_v + size_t(cc) * p.nG * K + i);
+            p.v[i] = double(a);
+        }
+        for (uint32_t i = tid; i < p.nG; i += kThreads) {
+            double a = 0.0;
+            for (uint32_t cc = 0; cc < p.nCTA; ++cc) { a += ld_cg(p.part_bsq + size_t(cc) * 2 * p.nG + i); a += ld_cg(p.part_bsq + size_t(cc) * 2 * p.nG + p.nG + i); }
+            p.betasq[i] = a;
+        }
+        if (PROF && p.prof && tid == 0) for (int i = 0; i < kPfN; ++i) p.prof[i] += sh.prof[i];
+    }
+}
+
+} // namespace v6
+} // namespace brr

@@ -224,9 +224,16 @@ int brr_gpu_profile_cycles(brr_gpu_ctx *ctx, uint64_t *cycles40, int reset);
  * residual update, wait for the rows, MMA loop, missing sums + cross counts, combine + REDs; then 4 counts (blocks walked with
  * Gram rows, -, restarts, residual updates); planner warp: plan, TMA issue. */
 int brr_gpu_profile_cycles5(brr_gpu_ctx *ctx, uint64_t *cycles24, int reset);
-/* Which dense kernel the last sweep ran (4 = on-demand Gram rows, 5 = steady-state pipeline; 0 = not dense) and, for version 5,
- * how often its pipeline restarted behind a marker that entered the model.  The library chooses per sweep (version 5 when the
- * previous sweep of the chain had <= 3% non-skipped markers); the environment variable BRR_GPU_DENSE_KERNEL=v4|v5 forces one. */
+/* The same for the version-6 dense kernel (sweep_dense6.cuh), 32 counters, one warp of CTA 0 per role: first dot warp (wait for the
+ * decision, residual update, wait for the rows, MMA loop, accumulate), post warp (wait, work), publisher (wait, work), first
+ * producer (wait for the plan, wait for a free stage, issue), control warp (result poll, plan, decide), walker warp 0 (wait for the
+ * slot counter, read-back, rows of earlier blocks, sampling, in-block corrections + result line, validation); then counts:
+ * -, blocks walked by CTA 0, residual updates, -, blocks walked with an in-model row. */
+int brr_gpu_profile_cycles6(brr_gpu_ctx *ctx, uint64_t *cycles32, int reset);
+/* Which dense kernel the last sweep ran (4 = on-demand Gram rows, 5 = steady-state pipeline, 6 = steady-state pipeline with the
+ * walk distributed over the CTAs; 0 = not dense) and, for versions 5 / 6, how often the pipeline restarted behind a marker that
+ * entered the model.  The library chooses per sweep (version 6 when the previous sweep of the chain had <= 3% non-skipped
+ * markers, version 4 otherwise); the environment variable BRR_GPU_DENSE_KERNEL=v4|v5|v6 forces one. */
 int brr_gpu_last_sweep_info(brr_gpu_ctx *ctx, uint32_t *kernel_version, uint32_t *restarts);
 
 #ifdef __cplusplus

@@ -14,15 +14,16 @@ from helpers import Golden, check_iteration, num_tol, replay
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["v4", "v5"])
+@pytest.fixture(autouse=True, params=["v4", "v5", "v6"])
 def dense_kernel(request, monkeypatch):
     """Every test of this module runs against both dense sweep kernels (BRR_GPU_DENSE_KERNEL is read at brr_gpu_create): version 4
-    (on-demand Gram rows; also the asynchronous and the sharded path) and version 5 (steady-state pipeline; synchronous, one GPU)."""
-    if request.param == "v5":
+    (on-demand Gram rows; also the asynchronous and the sharded path), version 5 (steady-state pipeline; synchronous, one GPU) and
+    version 6 (the same with the walk distributed over the CTAs)."""
+    if request.param in ("v5", "v6"):
         cs = getattr(request.node, "callspec", None)
         prm = cs.params if cs else {}
         if prm.get("tokens", 0) or prm.get("world", 1) > 1 or request.node.name.startswith(("test_world_gt_1", "test_mu_update", "test_synthetic", "test_tier1")):
-            pytest.skip("asynchronous / sharded / marker-level paths do not run the version-5 kernel")
+            pytest.skip("asynchronous / sharded / marker-level paths do not run the version-5 / 6 kernels")
     monkeypatch.setenv("BRR_GPU_DENSE_KERNEL", request.param)
     return request.param
 
