@@ -297,9 +297,9 @@ class Engine:
         self._check(self.lib.brr_gpu_profile_cycles5(self._h, _ptr(a), int(reset)))
         return dict(zip(self.PROFILE5, (int(x) for x in a)))
 
-    PROFILE6 = ["d_dec", "d_apply", "d_full", "d_loop", "d_acc", "po_wait", "po_work", "pu_wait", "pu_work", "pr_plan", "pr_empty", "pr_issue",
+    PROFILE6 = ["d_dec", "d_apply", "d_full", "d_loop", "d_miss", "d_cross", "d_acc", "pu_wait", "pu_work", "pr_plan", "pr_empty", "pr_issue",
                 "c_poll", "c_plan", "c_decide", "w_cnt", "w_read", "w_pred", "w_sample", "w_fix", "w_valid", "blocks", "walks", "applies", "restarts",
-                "gram_blocks"]
+                "gram_blocks", "row_blocks"]
 
     def profile_cycles6(self, reset=True):
         """Phase cycle counters of the version-6 dense kernel (one warp per role of CTA 0)."""

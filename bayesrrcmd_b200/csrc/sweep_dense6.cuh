@@ -22,9 +22,10 @@
 //                    per ~100 cycles: profiles/r2_tma_gather_bench.txt);
 //       warps 2-9    dot warps: two 16-marker tiles each (one load of the limb fragments feeds both), a quarter of the
 //                    individuals each; partial sums go into a shared-memory accumulator set;
-//       warp 10      post: sums of q over the rows' missing individuals, missing-genotype cross counts of the Gram pairs;
-//       warp 11      publisher: combines an accumulator set into 64-bit sums, adds them to the block's global slot, arrives at
-//                    the slot's counter (the release fence is paid here, off the dot warps);
+//                    the sums of q over the rows' missing individuals (from the fp64 residual) and the missing-genotype cross
+//                    counts of the Gram pairs follow, four lanes per row;
+//       warps 10-11  publishers (alternating blocks): combine an accumulator set into 64-bit sums, add them to the block's global
+//                    slot, arrive at the slot's counter (the release fence is paid here, off the dot warps);
 //       warps 0-1    walkers: the walk of the blocks this CTA owns.
 //   * The residual lives in shared memory (fp64, item order) next to its int8 limbs: updates are applied by the dot warps at
 //     the block boundary the control warp names.
@@ -56,13 +57,13 @@ constexpr int kAccInts = 4 * 256 + 4;       // per set: [4 tiles][128 dot sums +
 constexpr int kMaxUpd = kD + 3;
 constexpr uint32_t kResRing = 512;          // result lines (32 ints each)
 constexpr int kWalkW = 2, kDotW = 8;
-constexpr int kWPost = kWalkW + kDotW, kWPub = kWPost + 1, kWCtrl = kWPub + 1, kWProd0 = kWCtrl + 1, kProdW = 3;
+constexpr int kWPub = kWalkW + kDotW, kPubW = 2, kWCtrl = kWPub + kPubW, kWProd0 = kWCtrl + 1, kProdW = 3;
 static_assert(kWProd0 + kProdW == kWarps, "16 warps");
 constexpr int kDotThreads = 32 * kDotW;
 enum { kActSkip = 0, kActDot = 1, kActExit = 2 };
-enum { kPfDDec = 0, kPfDApply, kPfDFull, kPfDLoop, kPfDAcc, kPfPoWait, kPfPoWork, kPfPuWait, kPfPuWork, kPfPrPlan, kPfPrEmpty, kPfPrIssue,
+enum { kPfDDec = 0, kPfDApply, kPfDFull, kPfDLoop, kPfDMiss, kPfDCross, kPfDAcc, kPfPuWait, kPfPuWork, kPfPrPlan, kPfPrEmpty, kPfPrIssue,
        kPfCPoll, kPfCPlan, kPfCDecide, kPfWCnt, kPfWRead, kPfWPred, kPfWSample, kPfWFix, kPfWValid, kPfBlocks, kPfWalks, kPfApplies, kPfRestarts,
-       kPfGramBlocks, kPfN = 32 };
+       kPfGramBlocks, kPfRowBlocks, kPfN = 32 };
 
 struct Sweep6Params {
     uint32_t n_local, n_total, M, K, nG, nCTA, SL, PW, RS;
@@ -165,11 +166,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
     const uint32_t PWT = PW + kTail, CB = PWT * 4;
     const double NM1 = double(p.n_total - 1), Nt = double(p.n_total);
     const uint32_t slice0 = cta * SL;
-    const bool is_dot = warp >= kWalkW && warp < kWPost;
+    const bool is_dot = warp >= kWalkW && warp < kWPub;
     const int dt = tid - 32 * kWalkW;                 // dot-thread index 0..255
     const uint32_t dw = uint32_t(warp - kWalkW);      // dot-warp index 0..7
     GroupConsts &gc = p.gc[cta];
-    const bool prof_on = PROF && p.prof != nullptr && cta == 0 && lane == 0;
+    const bool prof_on = PROF && p.prof != nullptr && cta == 0 && lane == 0 &&
+                         (warp == 0 || warp == kWalkW || warp == kWPub || warp == kWCtrl || warp == kWProd0);   // one warp per role
     long long t_prev = prof_on ? clock64() : 0;
     auto PHASE = [&](int ph) { if (PROF && prof_on) { const long long t = clock64(); sh.prof[ph] += (unsigned long long)(t - t_prev); t_prev = t; } };
     auto PMARK = [&]() { if (PROF && prof_on) t_prev = clock64(); };
@@ -204,10 +206,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
     for (uint32_t i = tid; i < p.nG * K; i += kThreads) p.part_v[size_t(cta) * p.nG * K + i] = 0;
     for (uint32_t i = tid; i < 2 * p.nG; i += kThreads) p.part_bsq[size_t(cta) * 2 * p.nG + i] = 0.0;
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 5); }      // 4 dot warps + the post warp release a stage
+        for (int i = 0; i < kStages; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 4); }      // the 4 dot warps of a tile pair release a stage
         for (int i = 0; i < kStashRing; ++i) mbar_init(&sh.stash_full[i], 1);
         for (int i = 0; i < kSeq; ++i) { mbar_init(&sh.plan_bar[i], 1); mbar_init(&sh.dec_bar[i], 1); sh.valid_tag[i] = 0; }
-        for (int i = 0; i < kAcc; ++i) { mbar_init(&sh.acc_full[i], kDotW + 1); mbar_init(&sh.acc_empty[i], 1); }
+        for (int i = 0; i < kAcc; ++i) { mbar_init(&sh.acc_full[i], kDotW); mbar_init(&sh.acc_empty[i], 1); }
         mbar_init(&sh.ne_full, 1); mbar_init(&sh.apply_done, kDotW);
         mbar_fence_init();
         sh.abort = 0; sh.epoch_w = 0; sh.finished = 0; sh.dots_done = 0;
@@ -527,10 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { shi += __shfl_xor_sync(0xffffffffu, shi, o); slo += __shfl_xor_sync(0xffffffffu, slo, o); }
-                if (lane == 0) {
-                    unsigned long long *dq = reinterpret_cast<unsigned long long *>(accs + size_t(d % kAcc) * kAccInts + 1024);
-                    atomicAdd(dq, (unsigned long long)shi); atomicAdd(dq + 1, slo);
-                }
+                if (lane == 0) { atomicAdd(&sh.sumq[0], (unsigned long long)shi); atomicAdd(&sh.sumq[1], slo); }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh.apply_done);
                 if (!mbw(&sh.apply_done, n_apply & 1u)) break;
@@ -539,6 +538,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 PHASE(kPfDApply);
             }
             if (action == kActExit) break;
+            if (dw == 0 && lane < 2)        // sum q as this block's dot pass sees it (no update touches it before every dot warp has arrived at acc_full)
+                *(reinterpret_cast<unsigned long long *>(accs + size_t(d % kAcc) * kAccInts + 1024) + lane) = sh.sumq[lane];
             const uint32_t st0 = (4 * d + 2 * tp) & (kStages - 1);
             const uint32_t *pk = stages + size_t(st0) * kTileRows * RS;      // 32 rows: the two tiles are neighbours in the ring
             if (!mbw(&sh.full[st0], (d >> 1) & 1u)) break;
@@ -657,10 +658,108 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                     }
                 }
             }
+            PHASE(kPfDLoop);
+            // ---- sums of q over the missing individuals of the pair's rows: 4 lanes per row, 8 rows per warp.  q is taken from the fp64
+            //      residual (the same rounding as the limbs: one load instead of eight) ----
+            {
+                const uint32_t rr = 8 * kp + (lane >> 2), e4 = lane & 3u, m = 32 * tp + rr;
+                uint32_t cntm = 0;
+                long long qh = 0; unsigned long long ql = 0;
+                auto q_of = [&](uint32_t i) -> long long { return __double2ll_rn(e_s[16 * (i >> 4) + 4 * (i & 3u) + ((i >> 2) & 3u)] * scale); };
+                if (m < n) {
+                    const uint32_t *row = pk + size_t(rr) * RS;
+                    const uint16_t *tail = reinterpret_cast<const uint16_t *>(row + PW);
+                    cntm = tail[0];
+                    if (cntm <= 15u) {
+#pragma unroll 1
+                        for (uint32_t en = e4; en < cntm; en += 4) { const long long q = q_of(tail[1 + en]); qh += q >> 32; ql += (unsigned long long)(q & 0xffffffffLL); }
+                    } else {                                   // a long list: the four lanes scan the row's words
+#pragma unroll 1
+                        for (uint32_t w = e4; w < PW; w += 4) {
+                            const uint32_t x = row[w];
+                            uint32_t mm = x & (x >> 1) & 0x55555555u;
+                            while (mm) {
+                                const int bit = __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                const long long q = q_of(16 * w + (bit >> 1)); qh += q >> 32; ql += (unsigned long long)(q & 0xffffffffLL);
+                            }
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, cntm != 0u)) {
+#pragma unroll
+                    for (int o2 = 1; o2 < 4; o2 <<= 1) {
+                        qh += __shfl_xor_sync(0xffffffffu, qh, o2);
+                        ql += __shfl_xor_sync(0xffffffffu, ql, o2);
+                    }
+                    if (e4 == 0 && m < n && cntm) {
+                        int *slot = p.slots + size_t(B.c % kSlotRing) * kSlotInts5;
+                        if (qh) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLSm + 2 * m) * kLine), (unsigned long long)qh);
+                        if (ql) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLSm + 2 * m + 1) * kLine), ql);
+                    }
+                }
+                PHASE(kPfDMiss);
+                // ---- missing-genotype cross counts of the (stashed row, this row) pairs: the row's four lanes share both lists ----
+                if (present) {
+                    bool bad = false;
+                    for (uint32_t r = 0; r < uint32_t(kGramRows); ++r) {
+                        if (!((present >> r) & 1u)) continue;
+                        PCOUNT(kPfRowBlocks);
+                        const uint32_t back = kD - r;
+                        const uint32_t hs = back ? B.back_seq[back - 1] : d;
+                        if (!mbw(&sh.stash_full[hs % kStashRing], (hs / kStashRing) & 1u)) { bad = true; break; }
+                        const uint32_t *rowj = stash + size_t(hs % kStashRing) * RS;
+                        const uint16_t *tlj = reinterpret_cast<const uint16_t *>(rowj + PW);
+                        const uint32_t cntj = tlj[0];
+                        const bool pair = m < n && !(back == 0u && B.rowk == m);            // (the row against itself: not needed)
+                        uint32_t z = 0, wv = 0, y = 0;
+                        if (pair) {
+                            const uint32_t *rowa = pk + size_t(rr) * RS;
+                            const uint16_t *tla = reinterpret_cast<const uint16_t *>(rowa + PW);
+                            if (cntj <= 15u && cntm <= 15u) {
+                                for (uint32_t en = e4; en < cntj; en += 4) {
+                                    const uint32_t ii = tlj[1 + en];
+                                    const uint32_t cc = (rowa[ii >> 4] >> (2 * (ii & 15u))) & 3u;
+                                    if (cc == 3u) ++wv; else z += cc;
+                                }
+                                for (uint32_t en = e4; en < cntm; en += 4) {
+                                    const uint32_t ii = tla[1 + en];
+                                    const uint32_t cc = (rowj[ii >> 4] >> (2 * (ii & 15u))) & 3u;
+                                    if (cc != 3u) y += cc;
+                                }
+                            } else if (cntj | cntm) {
+                                for (uint32_t w = e4; w < PW; w += 4) {
+                                    const uint32_t xj = rowj[w], xa = rowa[w];
+                                    const uint32_t mj = xj & (xj >> 1) & 0x55555555u, ma = xa & (xa >> 1) & 0x55555555u;
+                                    uint32_t mm = mj | ma;
+                                    while (mm) {
+                                        const int bit = __ffs(mm) - 1;
+                                        mm &= mm - 1;
+                                        const uint32_t cj2 = (xj >> bit) & 3u, ca2 = (xa >> bit) & 3u;
+                                        if (cj2 == 3u) { if (ca2 == 3u) ++wv; else z += ca2; }
+                                        else y += cj2;                               // column missing, row present
+                                    }
+                                }
+                            }
+                        }
+                        unsigned long long pk3 = (unsigned long long)wv | ((unsigned long long)y << 20) | ((unsigned long long)z << 40);
+                        pk3 += __shfl_xor_sync(0xffffffffu, pk3, 1);
+                        pk3 += __shfl_xor_sync(0xffffffffu, pk3, 2);
+                        if (e4 == 0 && pair && pk3) {
+                            const unsigned long long wv4 = pk3 & 0xfffffULL, y4 = (pk3 >> 20) & 0xfffffULL, z4 = pk3 >> 40;
+                            int *slot = p.slots + size_t(B.c % kSlotRing) * kSlotInts5;
+                            unsigned long long *ln = reinterpret_cast<unsigned long long *>(slot + size_t(kLGram + r * kB + m) * kLine);
+                            if (wv4) atomicAdd(ln, wv4 << 32);
+                            if (y4 | z4) atomicAdd(ln + 1, y4 | (z4 << 32));
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, bad)) break;
+                }
+            }
             // the rows are no longer needed by this warp
             __syncwarp();
             if (lane == 0) { mbar_arrive(&sh.empty[st0]); mbar_arrive(&sh.empty[st0 + 1]); }
-            PHASE(kPfDLoop);
+            PHASE(kPfDCross);
             // ---- partial sums into the block's accumulator set ----
             if (any) {
                 int *aset = accs + size_t(d % kAcc) * kAccInts;
@@ -682,151 +781,51 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             if (lane == 0) mbar_arrive(&sh.acc_full[d % kAcc]);
             PHASE(kPfDAcc);
         }
-    } else if (warp == kWPost) {
-        // ---- post warp: per row the sum of q over its missing individuals; per Gram pair the missing-genotype cross counts ----
-        uint32_t n_apply = 0;
-        auto q_of = [&](uint32_t i) -> long long {
-            const uint8_t *lb = reinterpret_cast<const uint8_t *>(limbs) + ((i >> 4) * 4 + (i & 3u)) * 4 + ((i >> 2) & 3u);
-            uint32_t ulo = 0, uhi = 0;
-#pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                ulo |= uint32_t(lb[size_t(l) * RS * 16]) << (8 * l);
-                uhi |= uint32_t(lb[size_t(4 + l) * RS * 16]) << (8 * l);
-            }
-            const unsigned long long uq = (unsigned long long)ulo | ((unsigned long long)uhi << 32);
-            return (long long)((uq ^ 0x8080808080808080ULL) - 0x8080808080808080ULL);
-        };
-        for (uint32_t d = 0;; ++d) {
+    } else if (warp >= kWPub && warp < kWPub + kPubW) {
+        // ---- publishers (two, alternating blocks): accumulator set -> the block's global slot, arrive at its counter; recycling of the global slots ----
+        uint32_t last_c = 0; bool have_c = false;
+        for (uint32_t d = uint32_t(warp - kWPub);; d += kPubW) {
             PMARK();
-            if (!mbw(&sh.dec_bar[d & (kSeq - 1)], (d / kSeq) & 1u)) break;
-            const Blk6 &B = sh.blk[d & (kSeq - 1)];
-            const uint32_t action = B.action;
-            if (action == kActExit) break;
-            if (B.n_upd) { if (!mbw(&sh.apply_done, n_apply & 1u)) break; ++n_apply; }
-            const uint32_t stb = (4 * d) & (kStages - 1);                          // the block's four stages are neighbours: rows 0..63
-            bool ok = true;
-            for (uint32_t t = 0; t < 4; ++t) ok = ok && mbw(&sh.full[stb + t], (d >> 1) & 1u);
-            if (!ok) break;
-            PHASE(kPfPoWait);
-            if (action == kActDot) {
-                const uint32_t n = B.n, c = B.c, present = B.present;
-                int *slot = p.slots + size_t(c % kSlotRing) * kSlotInts5;
-                const uint32_t *pk = stages + size_t(stb) * kTileRows * RS;
-                for (uint32_t m = lane; m < n; m += 32) {
-                    const uint32_t *row = pk + size_t(m) * RS;
-                    const uint16_t *tail = reinterpret_cast<const uint16_t *>(row + PW);
-                    const uint32_t cntm = tail[0];
-                    if (cntm == 0u) continue;
-                    long long qh = 0; unsigned long long ql = 0;
-                    if (cntm <= 15u) {
-                        for (uint32_t en = 0; en < cntm; ++en) { const long long q = q_of(tail[1 + en]); qh += q >> 32; ql += (unsigned long long)(q & 0xffffffffLL); }
-                    } else {                                   // a long list: scan the row's words
-                        for (uint32_t w = 0; w < PW; ++w) {
-                            const uint32_t x = row[w];
-                            uint32_t mm = x & (x >> 1) & 0x55555555u;
-                            while (mm) {
-                                const int bit = __ffs(mm) - 1;
-                                mm &= mm - 1;
-                                const long long q = q_of(16 * w + (bit >> 1)); qh += q >> 32; ql += (unsigned long long)(q & 0xffffffffLL);
-                            }
-                        }
-                    }
-                    if (qh) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLSm + 2 * m) * kLine), (unsigned long long)qh);
-                    if (ql) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLSm + 2 * m + 1) * kLine), ql);
-                }
-                if (present) {
-                    for (uint32_t r = 0; r < uint32_t(kGramRows); ++r) {
-                        if (!((present >> r) & 1u)) continue;
-                        const uint32_t back = kD - r;
-                        const uint32_t hs = back ? B.back_seq[back - 1] : d;
-                        if (!mbw(&sh.stash_full[hs % kStashRing], (hs / kStashRing) & 1u)) { ok = false; break; }
-                        const uint32_t *rowj = stash + size_t(hs % kStashRing) * RS;
-                        const uint16_t *tlj = reinterpret_cast<const uint16_t *>(rowj + PW);
-                        const uint32_t cntj = tlj[0];
-                        for (uint32_t col = lane; col < n; col += 32) {
-                            if (back == 0u && B.rowk == col) continue;               // the row against itself: not needed
-                            const uint32_t *rowa = pk + size_t(col) * RS;
-                            const uint16_t *tla = reinterpret_cast<const uint16_t *>(rowa + PW);
-                            const uint32_t cnta = tla[0];
-                            uint32_t z = 0, wv = 0, y = 0;
-                            if (cntj <= 15u && cnta <= 15u) {
-                                for (uint32_t en = 0; en < cntj; ++en) {
-                                    const uint32_t ii = tlj[1 + en];
-                                    const uint32_t cc = (rowa[ii >> 4] >> (2 * (ii & 15u))) & 3u;
-                                    if (cc == 3u) ++wv; else z += cc;
-                                }
-                                for (uint32_t en = 0; en < cnta; ++en) {
-                                    const uint32_t ii = tla[1 + en];
-                                    const uint32_t cc = (rowj[ii >> 4] >> (2 * (ii & 15u))) & 3u;
-                                    if (cc != 3u) y += cc;
-                                }
-                            } else if (cntj | cnta) {
-                                for (uint32_t w = 0; w < PW; ++w) {
-                                    const uint32_t xj = rowj[w], xa = rowa[w];
-                                    const uint32_t mj = xj & (xj >> 1) & 0x55555555u, ma = xa & (xa >> 1) & 0x55555555u;
-                                    uint32_t mm = mj | ma;
-                                    while (mm) {
-                                        const int bit = __ffs(mm) - 1;
-                                        mm &= mm - 1;
-                                        const uint32_t cj2 = (xj >> bit) & 3u, ca2 = (xa >> bit) & 3u;
-                                        if (cj2 == 3u) { if (ca2 == 3u) ++wv; else z += ca2; }
-                                        else y += cj2;                               // column missing, row present
-                                    }
-                                }
-                            }
-                            unsigned long long *ln = reinterpret_cast<unsigned long long *>(slot + size_t(kLGram + r * kB + col) * kLine);
-                            if (wv) atomicAdd(ln, (unsigned long long)wv << 32);
-                            if (y | z) atomicAdd(ln + 1, (unsigned long long)y | ((unsigned long long)z << 32));
-                        }
-                    }
-                    if (!ok) break;
-                }
+            if (d > 0) {                                            // the end of the sweep may be the other publisher's block
+                if (!mbw(&sh.dec_bar[(d - 1) & (kSeq - 1)], ((d - 1) / kSeq) & 1u)) break;
+                if (sh.blk[(d - 1) & (kSeq - 1)].action == kActExit) break;
             }
-            __syncwarp();
-            if (lane == 0) {
-                for (uint32_t t = 0; t < 4; ++t) mbar_arrive(&sh.empty[stb + t]);
-                mbar_arrive(&sh.acc_full[d % kAcc]);
-            }
-            PHASE(kPfPoWork);
-        }
-    } else if (warp == kWPub) {
-        // ---- publisher: accumulator set -> the block's global slot, arrive at its counter; recycling of the global slots ----
-        unsigned long long sq = lane < 2 ? sh.sumq[lane] : 0ULL;
-        uint32_t last_c = 0, n_apply = 0; bool have_c = false;
-        for (uint32_t d = 0;; ++d) {
-            PMARK();
             if (!mbw(&sh.dec_bar[d & (kSeq - 1)], (d / kSeq) & 1u)) break;
             const Blk6 &B = sh.blk[d & (kSeq - 1)];
             const uint32_t action = B.action;
             int *aset = accs + size_t(d % kAcc) * kAccInts;
-            if (action == kActExit) {
-                if (B.n_upd) mbw(&sh.apply_done, n_apply & 1u);     // the last updates of the sweep: their change of sum q is in the set
-                break;
-            }
-            if (B.n_upd) ++n_apply;
+            if (action == kActExit) break;
             if (!mbw(&sh.acc_full[d % kAcc], (d / kAcc) & 1u)) break;
-            if (lane == 0) stv(&sh.dots_done, d + 1u);
+            if (lane == 0) atomicMax(&sh.dots_done, d + 1u);
             PHASE(kPfPuWait);
-            if (lane < 2) {                                         // residual updates applied before this block's dot pass
-                unsigned long long *dq = reinterpret_cast<unsigned long long *>(aset + 1024);
-                sq += dq[lane]; dq[lane] = 0ULL;
-            }
             if (action == kActDot) {
                 const uint32_t n = B.n, c = B.c, present = B.present;
                 int *slot = p.slots + size_t(c % kSlotRing) * kSlotInts5;
+                {   // (marker m, half h): the limb sums 4h..4h+3 combined into sum_l S_l 2^(8l), exact, as ONE signed 64-bit RED; all loads first
+                    int pv[4][4];
 #pragma unroll
-                for (int rep = 0; rep < 4; ++rep) {
-                    // (marker m, half h): the limb sums 4h..4h+3 combined into sum_l S_l 2^(8l), exact, as ONE signed 64-bit RED
-                    const uint32_t i = uint32_t(lane) + 32u * rep, m = i >> 1, h = i & 1u, mt = m & 15u;
-                    int *tacc = aset + (m >> 4) * 256;
-                    long long v = 0;
+                    for (int rep = 0; rep < 4; ++rep) {
+                        const uint32_t i = uint32_t(lane) + 32u * rep, m = i >> 1, h = i & 1u, mt = m & 15u;
+                        int *tacc = aset + (m >> 4) * 256;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t l = 4 * h + j, idx = ((l & 1u) + 2 * (mt >> 3)) * 32 + (mt & 7u) * 4 + (l >> 1);
-                        v += (long long)tacc[idx] * (1LL << (8 * j));
-                        tacc[idx] = 0;
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t l = 4 * h + j, idx = ((l & 1u) + 2 * (mt >> 3)) * 32 + (mt & 7u) * 4 + (l >> 1);
+                            pv[rep][j] = tacc[idx];
+                        }
                     }
-                    if (v && m < n) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLDots + 2 * m + h) * kLine), (unsigned long long)v);
+#pragma unroll
+                    for (int rep = 0; rep < 4; ++rep) {
+                        const uint32_t i = uint32_t(lane) + 32u * rep, m = i >> 1, h = i & 1u, mt = m & 15u;
+                        int *tacc = aset + (m >> 4) * 256;
+                        long long v = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t l = 4 * h + j, idx = ((l & 1u) + 2 * (mt >> 3)) * 32 + (mt & 7u) * 4 + (l >> 1);
+                            v += (long long)pv[rep][j] * (1LL << (8 * j));
+                            tacc[idx] = 0;
+                        }
+                        if (v && m < n) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLDots + 2 * m + h) * kLine), (unsigned long long)v);
+                    }
                 }
                 if (present) {
                     for (uint32_t i2 = lane; i2 < 512u; i2 += 32u) {
@@ -841,10 +840,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                         }
                     }
                 }
-                if (lane < 2 && sq) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLEps + lane) * kLine), sq);
+                if (lane < 2) {
+                    const unsigned long long sq = *(reinterpret_cast<const unsigned long long *>(aset + 1024) + lane);
+                    if (sq) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLEps + lane) * kLine), sq);
+                }
                 __syncwarp();
                 if (lane == 0) red_release_add(reinterpret_cast<unsigned *>(slot + kLCnt * kLine), 1u);
                 // block indices (last_c, c] are passed: their slots' next users (256 blocks on) get zeroed by the CTA they map to
+                // (both publishers do it for the ranges they see: the stores are idempotent)
                 uint32_t i0 = have_c ? last_c + 1 : 0u;
                 for (uint32_t idx = i0; idx <= c; ++idx) {
                     if (idx % p.nCTA != cta) continue;
@@ -856,12 +859,6 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.acc_empty[d % kAcc]);
             PHASE(kPfPuWork);
-        }
-        // updates applied at the end of the sweep (or left in a set nobody published): their change of sum q
-        __syncwarp();
-        if (lane < 2) {
-            for (int a = 0; a < kAcc; ++a) sq += *(reinterpret_cast<volatile unsigned long long *>(accs + size_t(a) * kAccInts + 1024) + lane);
-            sh.wq[0][lane] = sq;                                    // (added again after the CTA barrier of the epilogue, see there)
         }
     } else {
         // ---- walkers: the walk of the blocks this CTA owns; thread k = marker k of the block ------------------------------------
@@ -1112,7 +1109,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
     if (tid == 0) {
         double s = 0.0;
         for (int w = 0; w < kWarps; ++w) s += sh.warp_tmp[w];
-        p.cta_red[2 * cta + 0] = (double((long long)sh.wq[0][0]) * 4294967296.0 + double((long long)sh.wq[0][1])) * inv_scale;
+        p.cta_red[2 * cta + 0] = (double((long long)sh.sumq[0]) * 4294967296.0 + double((long long)sh.sumq[1])) * inv_scale;
         p.cta_red[2 * cta + 1] = s;
         if (sh.err) atomicOr(p.out_counts + 2, sh.err);
         atomicAdd(p.out_counts + 0, sh.n_nonskipped);
