@@ -88,6 +88,7 @@ struct brr_gpu_ctx {
     GroupConsts *gc6 = nullptr;
     uint32_t *inmask6 = nullptr;
     unsigned long long *prof6 = nullptr;
+    unsigned *dbg6 = nullptr;
     size_t smem6_bytes = 0;
     bool v6_ok = false;
     int dense_mode = 0;                     // 0 = auto (per sweep), 4 / 5 / 6 = forced (BRR_GPU_DENSE_KERNEL)
@@ -136,7 +137,7 @@ extern "C" void brr_gpu_destroy(brr_gpu_ctx *c)
     void *ptrs[] = {c->codes, c->lut, c->counts_local, c->counts_global, c->group, c->cva, c->eps, c->beta, c->comp,
                     c->acum, c->order, c->rand_uz, c->pi, c->sigmaG, c->part_dot, c->cta_red,
                     c->red_partial, c->slots, c->v, c->betasq, c->out_scalars, c->out_counts, c->prof, c->round_ctr,
-                    c->slots5, c->part_bsq, c->part_v, c->prof5, c->results6, c->gc6, c->inmask6, c->prof6,
+                    c->slots5, c->part_bsq, c->part_v, c->prof5, c->results6, c->gc6, c->inmask6, c->prof6, c->dbg6,
                     c->rag.idx16, c->rag.cta_base, c->rag.stats, c->rag.seg};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *q : c->peer_opened) cudaIpcCloseMemHandle(q);
@@ -278,7 +279,7 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
             for (const void *fn : {(const void *)v6::sweep_dense6_kernel<false>, (const void *)v6::sweep_dense6_kernel<true>}) {
                 CUDA_OR_DESTROY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem6_bytes));
                 int o = 0;
-                CUDA_OR_DESTROY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, kThreads, c->smem6_bytes));
+                CUDA_OR_DESTROY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, v6::kThreads6, c->smem6_bytes));
                 fits = fits && o >= 1 && uint32_t(o) * c->numSMs >= c->nCTA;
             }
             if (fits) {
@@ -288,6 +289,7 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
                 TRY_OR_DESTROY(dev_alloc(&c->results6, size_t(v6::kResRing) * 32));
                 TRY_OR_DESTROY(dev_alloc(&c->gc6, size_t(c->nCTA)));
                 TRY_OR_DESTROY(dev_alloc(&c->inmask6, size_t(M) / 32 + 4));
+                TRY_OR_DESTROY(dev_alloc(&c->dbg6, size_t(c->nCTA) * 32));
                 c->v6_ok = true;
             }
         }
@@ -633,7 +635,8 @@ static int launch_dense6(brr_gpu_ctx *c)
     p.slots = c->slots5; p.results = c->results6; p.gc = c->gc6; p.absmax = c->absmax; p.bar = c->bar; p.cta_red = c->cta_red;
     p.part_bsq = c->part_bsq; p.part_v = c->part_v;
     p.v = c->v; p.betasq = c->betasq; p.out_scalars = c->out_scalars; p.out_counts = c->out_counts;
-    p.prof = c->prof6;
+    p.prof = c->prof6; p.dbg = c->dbg6;
+    CUDA_TRY(cudaMemsetAsync(c->dbg6, 0, sizeof(unsigned) * size_t(c->nCTA) * 32, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->slots5, 0, sizeof(int) * size_t(v5::kSlotRing) * v5::kSlotInts5, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->results6, 0, sizeof(int) * size_t(v6::kResRing) * 32, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->slots + size_t(kSlots) * kSlotInts, 0, sizeof(int) * 8, c->stream));     // absmax + barrier counters
@@ -644,7 +647,7 @@ static int launch_dense6(brr_gpu_ctx *c)
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
     const uint32_t n_words = (c->n_order + 31) / 32;
     if (n_words) v6::inmodel_mask_kernel<<<(n_words * 32 + 255) / 256, 256, 0, c->stream>>>(c->order, c->n_order, c->beta, c->inmask6, n_words);
-    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(c->nCTA), dim3(kThreads), args, c->smem6_bytes, c->stream));
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(c->nCTA), dim3(v6::kThreads6), args, c->smem6_bytes, c->stream));
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     c->launches += 1 + (n_words ? 1 : 0); c->last_launches = 1 + (n_words ? 1 : 0);
     return 0;
@@ -708,11 +711,29 @@ extern "C" int brr_gpu_sweep_fetch(brr_gpu_ctx *c, double *v, double *betasqn, b
     CUDA_TRY(cudaMemcpyAsync(c->h_counts, c->out_counts, sizeof(unsigned) * 4, cudaMemcpyDeviceToHost, c->stream));
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(BRR_GPU_ECUDA, "sweep failed: %s", cudaGetErrorString(e));
+    if ((c->h_counts[2] & 4u) && c->last_kernel == 6 && c->dbg6 && getenv("BRR_GPU_V6_DBG")) {     // where every warp of the reported CTA (and of CTA 0) was waiting
+        std::vector<unsigned> h(size_t(c->nCTA) * 32);
+        cudaMemcpy(h.data(), c->dbg6, sizeof(unsigned) * h.size(), cudaMemcpyDeviceToHost);
+        for (uint32_t cta = 1; cta < c->nCTA; ++cta) {          // CTAs whose warps 2..19 wait somewhere else than CTA 0's
+            bool same = true;
+            for (int w = 2; w < 20; ++w) same = same && h[size_t(cta) * 32 + w] == h[w];
+            if (same) continue;
+            fprintf(stderr, "[brr_gpu v6] differs: CTA %u:", cta);
+            for (int w = 0; w < 20; ++w) { const unsigned x = h[size_t(cta) * 32 + w]; fprintf(stderr, " w%d:%u@%u", w, x & 0xfffu, (x >> 12) & 0x7ffffu); }
+            fprintf(stderr, "\n");
+        }
+        for (uint32_t cta : {0u, (c->h_counts[3] >> 16) & 0x7fffu, ((h[12] >> 12) & 1023u) % c->nCTA, (((h[12] >> 12) & 1023u) + 1) % c->nCTA}) {
+            if (cta >= c->nCTA) continue;
+            fprintf(stderr, "[brr_gpu v6] CTA %u:", cta);
+            for (int w = 0; w < 20; ++w) { const unsigned x = h[size_t(cta) * 32 + w]; fprintf(stderr, " w%d:%u@%u", w, x & 0xfffu, (x >> 12) & 0x7ffffu); }
+            fprintf(stderr, "\n");
+        }
+    }
     if (c->h_counts[2] != 0)
         return fail(BRR_GPU_ESTATE, "sweep failed (flags 0x%x):%s%s%s; the chain state on the device is no longer valid -- restore it with brr_gpu_set_state", c->h_counts[2],
                     (c->h_counts[2] & 1u) ? " the residual grew past the fixed-point range of the dot products inside one sweep" : "",
                     (c->h_counts[2] & 2u) ? " a peer GPU did not deliver its sums in time (is every rank calling brr_gpu_sweep?)" : "",
-                    (c->h_counts[2] & 4u) ? " a wait inside the sweep pipeline timed out (internal protocol error)" : "");
+                    (c->h_counts[2] & 4u) ? (std::string(" a wait inside the sweep pipeline timed out (internal protocol error; site ") + std::to_string(c->h_counts[3] & 0xffu) + ", warp " + std::to_string((c->h_counts[3] >> 8) & 0xffu) + ", CTA " + std::to_string((c->h_counts[3] >> 16) & 0x7fffu) + ")").c_str() : "");
     if (v) memcpy(v, h, sizeof(double) * nG * K);
     if (betasqn) memcpy(betasqn, h + kMaxGK, sizeof(double) * nG);
     c->have_last = c->n_order > 0 && c->n_order == c->cfg.n_markers;

@@ -40,7 +40,10 @@ using v5::ldv; using v5::stv; using v5::bar_named; using v5::mbar_arrive; using 
 using v5::kSlotRing; using v5::kSkip; using v5::kEnd; using v5::kLCnt; using v5::kLDots; using v5::kLSm; using v5::kLEps; using v5::kLGram;
 using v5::kSlotLines; using v5::kSlotInts5;
 
-constexpr int kD = 7;                       // the dot pass of a block sees the residual updates of the chain blocks more than kD back
+#ifndef BRR_V6_KD
+#define BRR_V6_KD 4
+#endif
+constexpr int kD = BRR_V6_KD;                       // the dot pass of a block sees the residual updates of the chain blocks more than kD back
 constexpr int kGramRows = kD + 1;           // one in-model row per block: the rows of the last kD blocks and the block's own
 static_assert(kGramRows <= 8, "one N-tile of Gram rows");
 constexpr int kSeq = 32;                    // ring of block descriptors
@@ -52,11 +55,15 @@ constexpr int kStashRing = 32;              // stashed in-model rows, slot = seq
 static_assert(kStashRing - kAhead > kD + kAhead, "a stashed row must outlive the update that applies it");
 constexpr int kNeSlot = kStashRing;         // + one row for a marker that entered the model
 constexpr int kStages = 8, kTileRows = 16;
-constexpr int kAcc = 3;                     // accumulator sets in rotation
-constexpr int kAccInts = 4 * 256 + 4;       // per set: [4 tiles][128 dot sums + 128 Gram counts] + the change of sum q (2 x u64)
+constexpr int kThreads6 = kThreads;
+constexpr int kWalkW = 2, kDotW = 8;
+constexpr int kAcc = 2;                     // accumulator sets in rotation (one per publisher)
+constexpr int kAccDots = kDotW * 256;       // per set: every dot warp's own partial sums [2 tiles][4][32] (plain stores, summed by the publisher),
+constexpr int kAccGram = kAccDots;          //          then [4 tiles][128] Gram counts (shared-memory atomics: only blocks that carry Gram rows),
+constexpr int kAccSumQ = kAccGram + 4 * 128; //         then sum q as the block's dot pass sees it (2 x u64)
+constexpr int kAccInts = kAccSumQ + 4;
 constexpr int kMaxUpd = kD + 3;
 constexpr uint32_t kResRing = 512;          // result lines (32 ints each)
-constexpr int kWalkW = 2, kDotW = 8;
 constexpr int kWPub = kWalkW + kDotW, kPubW = 2, kWCtrl = kWPub + kPubW, kWProd0 = kWCtrl + 1, kProdW = 3;
 static_assert(kWProd0 + kProdW == kWarps, "16 warps");
 constexpr int kDotThreads = 32 * kDotW;
@@ -84,6 +91,7 @@ struct Sweep6Params {
     double *v, *betasq, *out_scalars;
     unsigned *out_counts;        // [0] non-skipped, [1] blocks walked, [2] error flags, [3] restarts (zero at launch)
     unsigned long long *prof;    // optional [kPfN]
+    unsigned *dbg;               // [nCTA][32]: the wait each warp was in when the launch was given up (site | aux << 12 | 0x80000000), zero at launch
 };
 
 struct Blk6 {
@@ -102,7 +110,7 @@ struct Shared6 {
     double rowlut[kStashRing + 1][4];
     uint32_t valid_tag[kSeq];
     // control words (volatile accesses)
-    uint32_t epoch_w, finished, abort, dots_done;
+    uint32_t epoch_w, finished, abort, dots_done, arm_cnt[kStages];
     // control warp's private lists
     uint32_t pend_slot[kMaxUpd + 4], pend_seq[kMaxUpd + 4]; double pend_dB[kMaxUpd + 4];
     uint32_t hist[kD + 1];
@@ -137,11 +145,16 @@ __global__ void inmodel_mask_kernel(const uint32_t *__restrict__ order, uint32_t
     if ((threadIdx.x & 31) == 0 && (p >> 5) < n_words) mask[p >> 5] = b;
 }
 
+#ifndef BRR_V6_SUSPEND_NS
+#define BRR_V6_SUSPEND_NS 20000
+#endif
+constexpr uint32_t kSuspendNs = BRR_V6_SUSPEND_NS;
 __device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)
 {
     unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    // (with a suspend-time hint: a waiting warp sleeps in the barrier unit instead of spinning through the issue slots of the dot warps)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendNs) : "memory");
     return ok != 0u;
 }
 __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -179,12 +192,35 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
     // Every wait of the pipeline can be given up: a wait that lasts ~2 s means a protocol error (or a lost CTA).  All other waits of
     // the grid see the flag and fall through, the launch ends, the host reports error flag 4 -- instead of hanging the GPU.
     long long spin_t0 = 0; uint32_t spin_it = 0;
+    // (which wait a thread is in -- the index of the mbarrier in Shared6, or 200.. for the other waits -- and at which block: written to
+    //  Sweep6Params::dbg when the launch is given up, printed by the host with BRR_GPU_V6_DBG=1)
+#ifdef BRR_V6_DEBUG
+    uint32_t spin_site = 0, spin_aux = 0;
+#define BRR_SITE(site_) (spin_site = (site_))
+#define BRR_AUX(aux_) (spin_aux = (aux_))
+    auto spin_fail = [&]() -> bool {                  // slow half every 256 polls
+        if ((++spin_it & 255u) != 0u) {
+            if (ldv(&sh.abort) == 0u) return false;
+            if (p.dbg) p.dbg[cta * 32 + warp] = 0x80000000u | spin_site | (spin_aux << 12);
+            return true;
+        }
+        const bool was = ldv(&sh.abort) != 0u || (*reinterpret_cast<volatile unsigned *>(p.out_counts + 2) & 4u);
+        const bool r = spin_check(&sh.abort, p.out_counts + 2, spin_t0);
+        if (r && p.dbg) p.dbg[cta * 32 + warp] = 0x80000000u | spin_site | (spin_aux << 12);
+        if (r && !was) atomicCAS(p.out_counts + 3, 0u, 0x80000000u | spin_site | (uint32_t(warp) << 8) | (cta << 16));
+        return r;
+    };
+#else
+#define BRR_SITE(site_) ((void)0)
+#define BRR_AUX(aux_) ((void)0)
     auto spin_fail = [&]() -> bool {                  // slow half every 256 polls
         if ((++spin_it & 255u) != 0u) return ldv(&sh.abort) != 0u;
         return spin_check(&sh.abort, p.out_counts + 2, spin_t0);
     };
+#endif
     auto spin_ok = [&]() { spin_t0 = 0; spin_it = 0; };
     auto mbw = [&](uint64_t *bar, unsigned parity) -> bool {      // false = the launch was given up
+        BRR_SITE((smem_u32(bar) - smem_u32(&sh.full[0])) / 8u);
         for (;;) {
             if (mbar_test(bar, parity)) { spin_ok(); return true; }
             if (spin_fail()) return false;
@@ -213,6 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
         mbar_init(&sh.ne_full, 1); mbar_init(&sh.apply_done, kDotW);
         mbar_fence_init();
         sh.abort = 0; sh.epoch_w = 0; sh.finished = 0; sh.dots_done = 0;
+        for (int i = 0; i < kStages; ++i) sh.arm_cnt[i] = 0;
         sh.n_nonskipped = 0; sh.n_blocks = 0; sh.n_restarts = 0; sh.err = 0;
         if (PROF) for (int i = 0; i < kPfN; ++i) sh.prof[i] = 0;
     }
@@ -441,15 +478,23 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 }
             }
             PHASE(kPfCDecide);
+            BRR_SITE(210 + (s_cons < s_plan ? 1u : 0u) + (s_dec < s_plan ? 2u : 0u) + (plan_end ? 4u : 0u)); BRR_AUX(s_cons | (s_dec << 10));
             if (progress) spin_ok(); else if (spin_fail()) break;
         }
     } else if (warp >= kWProd0) {
-        // ---- producers: stage q = 4 s + t (tile t of block seq s) -> ring entry q % 8; producer w takes every third stage ----
+        // ---- producers: stage q = 4 s + t (tile t of block seq s) -> ring entry q % 8; producer w takes every third stage.  Consecutive
+        //      uses of a ring entry belong to different producers, and a parity wait may be at most one phase ahead of its barrier.  That
+        //      holds because a tile pair's two entries are released together and in block order, and every producer meets all four tiles
+        //      within four of its stages: it is stopped by a legitimate wait before it could get a whole ring ahead of another producer
+        //      (with one releasing warp per TILE, tried in this round, it does not hold: a producer then passed an entry's barrier one use
+        //      early).  BRR_V6_DEBUG builds check it (sh.arm_cnt). ----
         const uint32_t pw = uint32_t(warp - kWProd0);
         for (uint32_t q = pw;; q += kProdW) {
             const uint32_t s = q >> 2, t = q & 3u, st = q & (kStages - 1);
             PMARK();
+            BRR_AUX(s);
             bool ok = true;
+            BRR_SITE(220);
             for (;;) {                                              // the block's plan (or the end of the sweep)
                 if (mbar_test(&sh.plan_bar[s & (kSeq - 1)], (s / kSeq) & 1u)) break;
                 if (ldv(&sh.finished) || spin_fail()) { ok = false; break; }
@@ -462,6 +507,13 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             const uint32_t nt = n > 16 * t ? min(16u, n - 16 * t) : 0u;
             const uint32_t id = sh.ids[s & (kIdRing - 1)][16 * t + (lane & 15)];
             if (q >= uint32_t(kStages)) {
+#ifdef BRR_V6_DEBUG
+                BRR_SITE(222);
+                while (ldv(&sh.arm_cnt[st]) != (q >> 3)) { if (ldv(&sh.finished) || spin_fail()) { ok = false; break; } }
+                spin_ok();
+                if (!ok) break;
+#endif
+                BRR_SITE(221);
                 for (;;) {
                     if (mbar_test(&sh.empty[st], ((q >> 3) - 1u) & 1u)) break;
                     if (ldv(&sh.finished) || spin_fail()) { ok = false; break; }
@@ -471,7 +523,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             }
             PHASE(kPfPrEmpty);
             fence_proxy_async();
-            if (lane == 0) mbar_arrive_expect_tx(&sh.full[st], nt * CB);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&sh.full[st], nt * CB);
+#ifdef BRR_V6_DEBUG
+                stv(&sh.arm_cnt[st], (q >> 3) + 1u);
+#endif
+            }
             __syncwarp();
             if (uint32_t(lane) < nt)
                 bulk_g2s(stages + (size_t(st) * kTileRows + lane) * RS, p.codes + (size_t(id) * p.nCTA + cta) * PWT, CB, &sh.full[st]);
@@ -483,6 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
         uint32_t n_apply = 0;
         for (uint32_t d = 0;; ++d) {
             PMARK();
+            BRR_AUX(d);
             if (!mbw(&sh.dec_bar[d & (kSeq - 1)], (d / kSeq) & 1u)) break;
             const Blk6 &B = sh.blk[d & (kSeq - 1)];
             const uint32_t action = B.action, n_upd = B.n_upd;
@@ -539,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             }
             if (action == kActExit) break;
             if (dw == 0 && lane < 2)        // sum q as this block's dot pass sees it (no update touches it before every dot warp has arrived at acc_full)
-                *(reinterpret_cast<unsigned long long *>(accs + size_t(d % kAcc) * kAccInts + 1024) + lane) = sh.sumq[lane];
+                *(reinterpret_cast<unsigned long long *>(accs + size_t(d % kAcc) * kAccInts + kAccSumQ) + lane) = sh.sumq[lane];
             const uint32_t st0 = (4 * d + 2 * tp) & (kStages - 1);
             const uint32_t *pk = stages + size_t(st0) * kTileRows * RS;      // 32 rows: the two tiles are neighbours in the ring
             if (!mbw(&sh.full[st0], (d >> 1) & 1u)) break;
@@ -761,18 +819,18 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             if (lane == 0) { mbar_arrive(&sh.empty[st0]); mbar_arrive(&sh.empty[st0 + 1]); }
             PHASE(kPfDCross);
             // ---- partial sums into the block's accumulator set ----
-            if (any) {
+            {
                 int *aset = accs + size_t(d % kAcc) * kAccInts;
+                int *wacc = aset + dw * 256;
 #pragma unroll
                 for (int tl = 0; tl < 2; ++tl) {
-                    int *tacc = aset + (2 * tp + tl) * 256;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const int v = acc[tl][0][q] + (acc[tl][1][q] >> 2) + (acc[tl][2][q] >> 4) + (acc[tl][3][q] >> 6);
-                        if (v) atomicAdd(&tacc[q * 32 + lane], v);
-                        if (present) {
+                        const int v = any ? acc[tl][0][q] + (acc[tl][1][q] >> 2) + (acc[tl][2][q] >> 4) + (acc[tl][3][q] >> 6) : 0;
+                        wacc[(4 * tl + q) * 32 + lane] = v;
+                        if (present && any) {
                             const int g = gacc[tl][0][q] + (gacc[tl][1][q] >> 4) + (gacc[tl][2][q] >> 8) + (gacc[tl][3][q] >> 12);
-                            if (g) atomicAdd(&tacc[128 + q * 32 + lane], g);
+                            if (g) atomicAdd(&aset[kAccGram + (2 * tp + tl) * 128 + q * 32 + lane], g);
                         }
                     }
                 }
@@ -786,6 +844,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
         uint32_t last_c = 0; bool have_c = false;
         for (uint32_t d = uint32_t(warp - kWPub);; d += kPubW) {
             PMARK();
+            BRR_AUX(d);
             if (d > 0) {                                            // the end of the sweep may be the other publisher's block
                 if (!mbw(&sh.dec_bar[(d - 1) & (kSeq - 1)], ((d - 1) / kSeq) & 1u)) break;
                 if (sh.blk[(d - 1) & (kSeq - 1)].action == kActExit) break;
@@ -801,36 +860,34 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             if (action == kActDot) {
                 const uint32_t n = B.n, c = B.c, present = B.present;
                 int *slot = p.slots + size_t(c % kSlotRing) * kSlotInts5;
-                {   // (marker m, half h): the limb sums 4h..4h+3 combined into sum_l S_l 2^(8l), exact, as ONE signed 64-bit RED; all loads first
-                    int pv[4][4];
+                {   // (marker m, half h): the limb sums 4h..4h+3, each summed over the four dot warps of the tile pair, combined into
+                    // sum_l S_l 2^(8l), exact, as ONE signed 64-bit RED; all loads first
+                    int2 pv[4][4][2];
 #pragma unroll
                     for (int rep = 0; rep < 4; ++rep) {
-                        const uint32_t i = uint32_t(lane) + 32u * rep, m = i >> 1, h = i & 1u, mt = m & 15u;
-                        int *tacc = aset + (m >> 4) * 256;
+                        const uint32_t i = uint32_t(lane) + 32u * rep, m = i >> 1, h = i & 1u, mt = m & 15u, tl = (m >> 4) & 1u, tpm = m >> 5;
+                        // warp (tpm, kp): value (tile tl, q, lane gid * 4 + tig) with l = 2 tig + (q & 1), marker gid + 8 (q >> 1)
+                        const int *base = aset + (4 * tpm) * 256 + (4 * tl + 2 * (mt >> 3)) * 32 + (mt & 7u) * 4 + 2 * h;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t l = 4 * h + j, idx = ((l & 1u) + 2 * (mt >> 3)) * 32 + (mt & 7u) * 4 + (l >> 1);
-                            pv[rep][j] = tacc[idx];
+                        for (int kp2 = 0; kp2 < 4; ++kp2) {
+                            pv[rep][kp2][0] = *reinterpret_cast<const int2 *>(base + kp2 * 256);           // q & 1 = 0: limbs 4h, 4h + 2
+                            pv[rep][kp2][1] = *reinterpret_cast<const int2 *>(base + kp2 * 256 + 32);      // q & 1 = 1: limbs 4h + 1, 4h + 3
                         }
                     }
 #pragma unroll
                     for (int rep = 0; rep < 4; ++rep) {
-                        const uint32_t i = uint32_t(lane) + 32u * rep, m = i >> 1, h = i & 1u, mt = m & 15u;
-                        int *tacc = aset + (m >> 4) * 256;
-                        long long v = 0;
+                        const uint32_t i = uint32_t(lane) + 32u * rep, m = i >> 1, h = i & 1u;
+                        int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t l = 4 * h + j, idx = ((l & 1u) + 2 * (mt >> 3)) * 32 + (mt & 7u) * 4 + (l >> 1);
-                            v += (long long)pv[rep][j] * (1LL << (8 * j));
-                            tacc[idx] = 0;
-                        }
+                        for (int kp2 = 0; kp2 < 4; ++kp2) { l0 += pv[rep][kp2][0].x; l2 += pv[rep][kp2][0].y; l1 += pv[rep][kp2][1].x; l3 += pv[rep][kp2][1].y; }
+                        const long long v = (long long)l0 + (long long)l1 * 256LL + (long long)l2 * 65536LL + (long long)l3 * 16777216LL;
                         if (v && m < n) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLDots + 2 * m + h) * kLine), (unsigned long long)v);
                     }
                 }
                 if (present) {
                     for (uint32_t i2 = lane; i2 < 512u; i2 += 32u) {
                         const uint32_t tile = i2 >> 7, j2 = i2 & 127u;
-                        int *tacc = aset + tile * 256 + 128;
+                        int *tacc = aset + kAccGram + tile * 128;
                         const int a = tacc[j2];
                         if (a) {
                             tacc[j2] = 0;
@@ -841,7 +898,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                     }
                 }
                 if (lane < 2) {
-                    const unsigned long long sq = *(reinterpret_cast<const unsigned long long *>(aset + 1024) + lane);
+                    const unsigned long long sq = *(reinterpret_cast<const unsigned long long *>(aset + kAccSumQ) + lane);
                     if (sq) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLEps + lane) * kLine), sq);
                 }
                 __syncwarp();
@@ -871,6 +928,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             // the block's plan, or the end of the sweep
             if (tid == 0) {
                 uint32_t ctl = 1;
+                BRR_SITE(200); BRR_AUX(s);
                 for (;;) {
                     if (mbar_test(&sh.plan_bar[s & (kSeq - 1)], (s / kSeq) & 1u)) break;
                     if (ldv(&sh.finished) || spin_fail()) { ctl = 0; break; }
@@ -907,6 +965,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 else if (B.action != kActDot) ctl = 2;              // dropped by a restart
                 else {
                     const int *slot0 = p.slots + size_t(c % kSlotRing) * kSlotInts5;
+                    BRR_SITE(201);
                     while (ld_acquire(reinterpret_cast<const unsigned *>(slot0 + kLCnt * kLine)) < p.nCTA) {
                         if (ldv(&sh.epoch_w) != b_epoch) { ctl = 2; break; }
                         if (spin_fail()) { ctl = 0; break; }
@@ -979,6 +1038,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                         if (tid == 0) {
                             uint32_t ctl = 1;
                             const int *line = p.results + size_t(hc % kResRing) * 32;
+                            BRR_SITE(202);
                             while (ld_acquire(reinterpret_cast<const unsigned *>(line)) != hc + 1u) {
                                 if (ldv(&sh.epoch_w) != b_epoch) { ctl = 2; break; }
                                 if (spin_fail()) { ctl = 0; break; }
@@ -1044,14 +1104,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                     *reinterpret_cast<volatile int *>(line + 1) = int(n_final | (restart ? 0x10000u : 0u));
                     if (!nrows) *reinterpret_cast<volatile double *>(line + 2) = 0.0;
                 }
-                __threadfence();
-                bar_named(1, 64);
-                if (tid == 0) st_release_gpu(reinterpret_cast<unsigned *>(line), c + 1u);
+                bar_named(1, 64);                                   // (the release below is cumulative over the writes this barrier orders before it)
+                if (tid == 0) { __threadfence(); st_release_gpu(reinterpret_cast<unsigned *>(line), c + 1u); }
             }
             PHASE(kPfWFix);
             // ---- the block is part of the chain once this CTA's control warp has consumed its result in chain order ----
             if (tid == 0) {
                 uint32_t ctl = 1;
+                BRR_SITE(203);
                 while (ldv(&sh.valid_tag[s & (kSeq - 1)]) != s + 1u) {
                     if (ldv(&sh.epoch_w) != b_epoch) { ctl = ldv(&sh.valid_tag[s & (kSeq - 1)]) == s + 1u ? 1u : 2u; break; }
                     if (spin_fail()) { ctl = 0; break; }
@@ -1114,7 +1174,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
         if (sh.err) atomicOr(p.out_counts + 2, sh.err);
         atomicAdd(p.out_counts + 0, sh.n_nonskipped);
         atomicAdd(p.out_counts + 1, sh.n_blocks);
-        if (cta == 0) p.out_counts[3] = sh.n_restarts;
+        if (cta == 0 && !(*reinterpret_cast<volatile unsigned *>(p.out_counts + 3) & 0x80000000u)) p.out_counts[3] = sh.n_restarts;
     }
     __threadfence();
     grid_arrive(p.bar);

@@ -19,4 +19,8 @@ for it in range(6):
     ms.append(out.kernel_ms)
     assert out.n_nonskipped == 0
 k, r = e.last_sweep_info()
+if os.environ.get("BRR_GPU_PROFILE") == "1" and k == 6:
+    pc = e.profile_cycles6(reset=True)
+    nblk = 6 * (M / 64)
+    sys.stderr.write("v6 quiet chain, cycles per block: " + "  ".join("%s=%d" % (kk, v / nblk) for kk, v in pc.items() if not kk.startswith("w_") and v > nblk) + "\n")
 print(json.dumps({"kernel": k, "dbg": os.environ.get("BRR_GPU_V5_DBG"), "ms_per_sweep": float(np.mean(ms[2:])), "us_per_block": 1e3 * float(np.mean(ms[2:])) / (M / 64), "M": M}))
