@@ -14,17 +14,17 @@
 //     block's in-model row).  Every CTA consumes the result lines in block order -- one line per block instead of 258 sums
 //     and 64 draws.  beta / components / acum are written by the owner once its block is known to be part of the chain.
 //   * Inside a CTA every stage of a block has its own warps and nothing waits for a later stage:
-//       warp 12      control: plans the blocks (<= 64 consecutive markers, at most ONE in-model marker each: a second one ends the
+//       warp 11      control: plans the blocks (<= 64 consecutive markers, at most ONE in-model marker each: a second one ends the
 //                    block before it), consumes the result lines, decides for every block which residual updates precede its dot
 //                    pass (those of the block kD + 1 blocks back: a fixed lag, so that all CTAs agree) and which stashed in-model
 //                    rows ride on it;
-//       warps 13-15  producers: TMA bulk copies of the code rows into a ring of 8 stages of 16 rows (one warp issues one copy
+//       warps 12-15  producers (one per 16-marker tile): TMA bulk copies of the code rows into a ring of 8 stages of 16 rows (one warp issues one copy
 //                    per ~100 cycles: profiles/r2_tma_gather_bench.txt);
 //       warps 2-9    dot warps: two 16-marker tiles each (one load of the limb fragments feeds both), a quarter of the
 //                    individuals each; partial sums go into a shared-memory accumulator set;
 //                    the sums of q over the rows' missing individuals (from the fp64 residual) and the missing-genotype cross
 //                    counts of the Gram pairs follow, four lanes per row;
-//       warps 10-11  publishers (alternating blocks): combine an accumulator set into 64-bit sums, add them to the block's global
+//       warp 10      publisher: combines an accumulator set into 64-bit sums, adds them to the block's global
 //                    slot, arrive at the slot's counter (the release fence is paid here, off the dot warps);
 //       warps 0-1    walkers: the walk of the blocks this CTA owns.
 //   * The residual lives in shared memory (fp64, item order) next to its int8 limbs: updates are applied by the dot warps at
@@ -57,14 +57,14 @@ constexpr int kNeSlot = kStashRing;         // + one row for a marker that enter
 constexpr int kStages = 8, kTileRows = 16;
 constexpr int kThreads6 = kThreads;
 constexpr int kWalkW = 2, kDotW = 8;
-constexpr int kAcc = 2;                     // accumulator sets in rotation (one per publisher)
+constexpr int kAcc = 2;                     // accumulator sets in rotation
 constexpr int kAccDots = kDotW * 256;       // per set: every dot warp's own partial sums [2 tiles][4][32] (plain stores, summed by the publisher),
 constexpr int kAccGram = kAccDots;          //          then [4 tiles][128] Gram counts (shared-memory atomics: only blocks that carry Gram rows),
 constexpr int kAccSumQ = kAccGram + 4 * 128; //         then sum q as the block's dot pass sees it (2 x u64)
 constexpr int kAccInts = kAccSumQ + 4;
 constexpr int kMaxUpd = kD + 3;
 constexpr uint32_t kResRing = 512;          // result lines (32 ints each)
-constexpr int kWPub = kWalkW + kDotW, kPubW = 2, kWCtrl = kWPub + kPubW, kWProd0 = kWCtrl + 1, kProdW = 3;
+constexpr int kWPub = kWalkW + kDotW, kPubW = 1, kWCtrl = kWPub + kPubW, kWProd0 = kWCtrl + 1, kProdW = 4;
 static_assert(kWProd0 + kProdW == kWarps, "16 warps");
 constexpr int kDotThreads = 32 * kDotW;
 enum { kActSkip = 0, kActDot = 1, kActExit = 2 };
@@ -482,12 +482,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             if (progress) spin_ok(); else if (spin_fail()) break;
         }
     } else if (warp >= kWProd0) {
-        // ---- producers: stage q = 4 s + t (tile t of block seq s) -> ring entry q % 8; producer w takes every third stage.  Consecutive
-        //      uses of a ring entry belong to different producers, and a parity wait may be at most one phase ahead of its barrier.  That
-        //      holds because a tile pair's two entries are released together and in block order, and every producer meets all four tiles
-        //      within four of its stages: it is stopped by a legitimate wait before it could get a whole ring ahead of another producer
-        //      (with one releasing warp per TILE, tried in this round, it does not hold: a producer then passed an entry's barrier one use
-        //      early).  BRR_V6_DEBUG builds check it (sh.arm_cnt). ----
+        // ---- producers: producer t takes tile t of every block: stage q = 4 s + t -> ring entry q % 8, i.e. entries t and t + 4 in turn.
+        //      The waits on an entry's empty barrier are thus in ONE warp's program order (a parity wait may be at most one phase ahead of
+        //      its barrier; with the stages dealt round-robin to three producers this held only because tile pairs are released together and
+        //      in block order -- BRR_V6_DEBUG builds check it through sh.arm_cnt) ----
         const uint32_t pw = uint32_t(warp - kWProd0);
         for (uint32_t q = pw;; q += kProdW) {
             const uint32_t s = q >> 2, t = q & 3u, st = q & (kStages - 1);
@@ -717,6 +715,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 }
             }
             PHASE(kPfDLoop);
+            bool early = false;
             // ---- sums of q over the missing individuals of the pair's rows: 4 lanes per row, 8 rows per warp.  q is taken from the fp64
             //      residual (the same rounding as the limbs: one load instead of eight) ----
             {
@@ -724,13 +723,28 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 uint32_t cntm = 0;
                 long long qh = 0; unsigned long long ql = 0;
                 auto q_of = [&](uint32_t i) -> long long { return __double2ll_rn(e_s[16 * (i >> 4) + 4 * (i & 3u) + ((i >> 2) & 3u)] * scale); };
+                // this lane's share of the row's list (entries e4, e4 + 4, ...) goes to registers first: with it, a block without Gram rows
+                // needs the code rows no longer, and the stages go back to the producers before the look-ups
+                const uint32_t *row = pk + size_t(rr) * RS;
+                const uint16_t *tail = reinterpret_cast<const uint16_t *>(row + PW);
+                uint32_t idv[4] = {0u, 0u, 0u, 0u};
                 if (m < n) {
-                    const uint32_t *row = pk + size_t(rr) * RS;
-                    const uint16_t *tail = reinterpret_cast<const uint16_t *>(row + PW);
                     cntm = tail[0];
                     if (cntm <= 15u) {
-#pragma unroll 1
-                        for (uint32_t en = e4; en < cntm; en += 4) { const long long q = q_of(tail[1 + en]); qh += q >> 32; ql += (unsigned long long)(q & 0xffffffffLL); }
+#pragma unroll
+                        for (uint32_t k4 = 0; k4 < 4; ++k4) if (e4 + 4 * k4 < cntm) idv[k4] = tail[1 + e4 + 4 * k4];
+                    }
+                }
+                early = !present && __all_sync(0xffffffffu, cntm <= 15u);
+                if (early) {
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(&sh.empty[st0]); mbar_arrive(&sh.empty[st0 + 1]); }
+                }
+                if (m < n) {
+                    if (cntm <= 15u) {
+#pragma unroll
+                        for (uint32_t k4 = 0; k4 < 4; ++k4)
+                            if (e4 + 4 * k4 < cntm) { const long long q = q_of(idv[k4]); qh += q >> 32; ql += (unsigned long long)(q & 0xffffffffLL); }
                     } else {                                   // a long list: the four lanes scan the row's words
 #pragma unroll 1
                         for (uint32_t w = e4; w < PW; w += 4) {
@@ -816,7 +830,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             }
             // the rows are no longer needed by this warp
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&sh.empty[st0]); mbar_arrive(&sh.empty[st0 + 1]); }
+            if (!early && lane == 0) { mbar_arrive(&sh.empty[st0]); mbar_arrive(&sh.empty[st0 + 1]); }
             PHASE(kPfDCross);
             // ---- partial sums into the block's accumulator set ----
             {

@@ -360,12 +360,14 @@ def main():
         return
 
     peak, peak_src = measured_peak()
+    kv_timed = max(set(kernels)) if kernels else 4              # dense kernel version of the timed sweeps (the library chooses per sweep)
+    kname = {4: "sweep_dense_kernel", 5: "sweep_dense5_kernel", 6: "sweep_dense6_kernel"}.get(kv_timed, "sweep_dense_kernel")
     # DRAM bytes of one full-size launch: from the committed ncu capture (profiles/ncu_traffic.json), only when that capture
     # was taken on THIS kernel version and problem size (null otherwise: a stale figure explains nothing)
     traffic, traffic_src = None, None
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        if world == 1 and N == int(t.get("n_inds", 0)) and M == int(t.get("n_markers", 0)) and t.get("kernel_version") == info.get("kernel_version"):
+        if world == 1 and N == int(t.get("n_inds", 0)) and M == int(t.get("n_markers", 0)) and t.get("kernel_version") == "v%d" % kv_timed:
             traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
             traffic_src = "ncu --set full capture of one launch of kernel version %s, committed as profiles/ncu_traffic.json" % t.get("kernel_version")
     except Exception:
@@ -380,7 +382,7 @@ def main():
         "config": {"workload": workload, "parallelism": "individuals sharded over %d GPU(s)" % world,
                    "block_markers": info["block_markers"], "ctas": info["n_ctas"], "slice_inds": info["slice_inds"],
                    "genotype_bytes_per_gpu": info["genotype_bytes"], "l2": "inputs (%.1f GB/GPU) are larger than L2" % (info["genotype_bytes"] / 1e9),
-                   "n_inds": N, "n_markers": M, "arithmetic": ARITHMETIC, "kernel_version": info.get("kernel_version"),
+                   "n_inds": N, "n_markers": M, "arithmetic": ARITHMETIC, "kernel_version": "v%d" % kv_timed,
                    "regime": "timed sweeps = sweeps %d..%d of a chain started from BayesRBase::init's state; %.4f%% of the markers non-skipped "
                              "(beta_old != 0 or beta_new != 0) per timed sweep; the cost of a sweep depends on that fraction" % (
                                  a.warmup, a.warmup + a.steps - 1, 100.0 * float(np.mean(nonskipped)) / M),
@@ -392,7 +394,7 @@ def main():
                 "s_per_sweep": esum / a.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "sweep_dense_kernel",
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kname,
                      "algorithmic_bytes_per_launch": int(alg_bytes)},
         "clocks": sampler.summary() if sampler else None,
     }
