@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 const bool end = rem == 0;
                 if (lane == 0) {
                     B.c = end ? kEnd : next_c; B.pos = pos; B.n = n; B.epoch = epoch; B.nrows = nrows; B.rowk = rowk; B.row_id = row_id;
-                    fence_proxy_async();
+                    if (nrows) fence_proxy_async();             // (only with a copy to issue: the fence is a MEMBAR, and this thread paces the CTA)
                     mbar_arrive_expect_tx(&sh.stash_full[slot], nrows * CB);
                     if (nrows) bulk_g2s(stash + size_t(slot) * RS, p.codes + (size_t(row_id) * p.nCTA + cta) * PWT, CB, &sh.stash_full[slot]);
                 }
@@ -520,7 +520,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 if (!ok) break;
             }
             PHASE(kPfPrEmpty);
-            fence_proxy_async();
+            // (no fence.proxy.async here: the entry's last readers released it through the mbarrier, which orders their generic-proxy
+            //  reads before these async-proxy writes; the fence cost the producers ~a third of the kernel's stall samples as MEMBAR)
             if (lane == 0) {
                 mbar_arrive_expect_tx(&sh.full[st], nt * CB);
 #ifdef BRR_V6_DEBUG
