@@ -57,10 +57,10 @@ def build_host(force=False):
     if force or _newer(lib, srcs) or _newer(exe, srcs):
         common = ["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-Wall", "-Wno-deprecated-declarations",
                   "-I" + os.path.join(ROOT, "include"), "-I" + hdir]
-        subprocess.check_call(common + ["-shared", "-o", lib] + cpps + ["-L" + PKG, "-lbrr_gpu", "-Wl,-rpath,$ORIGIN"])
+        subprocess.check_call(common + ["-shared", "-o", lib] + cpps + ["-L" + PKG, "-lbrr_gpu", "-lz", "-Wl,-rpath,$ORIGIN"])
         main = os.path.join(hdir, "main.cpp")
         if os.path.exists(main):
-            subprocess.check_call(common + ["-o", exe, main, "-L" + PKG, "-lbrr_host", "-lbrr_gpu", "-Wl,-rpath,$ORIGIN"])
+            subprocess.check_call(common + ["-o", exe, main, "-L" + PKG, "-lbrr_host", "-lbrr_gpu", "-lz", "-Wl,-rpath,$ORIGIN"])
     return lib
 
 

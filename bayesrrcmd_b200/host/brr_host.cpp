@@ -1,5 +1,6 @@
 // Host side of the B200 BayesR engine: see brr_host.hpp for the map to the reference's sources.
 #include "brr_host.hpp"
+#include "markers.hpp"
 
 #include <algorithm>
 #include <chrono>
@@ -91,7 +92,9 @@ bool Options::inputOptions(int argc, const char *const argv[])
         else if (a == "--sample-precision") { if (!(v = need(i))) return false; g_samplePrecision = std::atoi(v); }
         else if (a == "--no-epsilon") writeEpsilon = false;
         // accepted for command-line compatibility; they configure the reference's TBB graphs / .ppbed cache, which do not exist here
-        else if (a == "--marker-cache" || a == "--compress" || a == "--preprocess") { }
+        else if (a == "--marker-cache") useMarkerCache = true;       // genotypes from the reference's preprocessed files (markers.hpp)
+        else if (a == "--compress") compress = true;
+        else if (a == "--preprocess") { }
         else if (a == "--thread" || a == "--thread-spawned" || a == "--decompression-concurrency" || a == "--decompression-tokens" ||
                  a == "--analysis-concurrency" || a == "--preprocess-chunks") { if (!need(i)) return false; }
         else { std::cerr << "Error: invalid option \"" << a << "\"." << std::endl; return false; }
@@ -225,12 +228,19 @@ bool GpuDevice::open(const Data &data, const Options &opt)
     cfg.rank = 0; cfg.world = 1;
     auto fail = [&](const char *what) { std::cerr << "Error: " << what << ": " << brr_gpu_last_error() << std::endl; return false; };
     if (brr_gpu_create(&cfg, &m_ctx)) return fail("cannot create the GPU context (there is no CPU fallback)");
-    // the .bed payload IS the device layout: no .ppbed is written (replaces PreprocessGraph, src/preprocessgraph.cpp:10-73,
-    // and MarkerCache::populate, src/markercache.cpp:19-45)
-    const int rc = m_layout == BRR_GPU_LAYOUT_DENSE2BIT ? brr_gpu_upload_dense2bit(m_ctx, data.bed.data(), data.colStride, 0, data.numSnps)
-                                                         : brr_gpu_upload_ragged_from_bed(m_ctx, data.bed.data(), data.colStride);
-    if (rc) return fail("genotype upload failed");
-    if (brr_gpu_finalize_markers(m_ctx, nullptr)) return fail("marker statistics failed");
+    if (opt.useMarkerCache) {
+        // --marker-cache: the reference's preprocessed files (.ppbed / .ragged.sparsebed / .eigen.sparsebed + index, --compress for
+        // deflated markers) through MarkerCache::populate, then the cache becomes the device store (src/markercache.cpp:19-45)
+        if (!markerCache()->populate(opt.dataFile, opt.preprocessDataType, data.numSnps, data.numInds, opt.compress)) return false;
+        if (!markerCache()->upload(m_ctx)) return false;
+        markerCache()->clear();
+    } else {
+        // the .bed payload IS the device layout: no .ppbed is written (replaces PreprocessGraph, src/preprocessgraph.cpp:10-73)
+        const int rc = m_layout == BRR_GPU_LAYOUT_DENSE2BIT ? brr_gpu_upload_dense2bit(m_ctx, data.bed.data(), data.colStride, 0, data.numSnps)
+                                                             : brr_gpu_upload_ragged_from_bed(m_ctx, data.bed.data(), data.colStride);
+        if (rc) return fail("genotype upload failed");
+        if (brr_gpu_finalize_markers(m_ctx, nullptr)) return fail("marker statistics failed");
+    }
     std::vector<int32_t> groups(data.G.begin(), data.G.end());
     std::vector<double> cva;
     for (const auto &row : opt.S) cva.insert(cva.end(), row.begin(), row.end());
@@ -485,7 +495,8 @@ int brr_main(int argc, const char *const argv[])
     }
     Data data;
     if (!data.readFamFile(replaceExtension(opt.dataFile, ".fam")) || !data.readBimFile(replaceExtension(opt.dataFile, ".bim")) ||
-        !data.readBedFile(opt.dataFile) || !data.readPhenotypeFile(opt.phenotypeFile))
+        (!opt.useMarkerCache && !data.readBedFile(opt.dataFile)) ||      // (--marker-cache: the preprocessed files replace the .bed)
+        !data.readPhenotypeFile(opt.phenotypeFile))
         return 1;
     if (!opt.groupFile.empty() && !data.readGroupFile(opt.groupFile)) return 1;
     if (opt.S.size() != data.numGroups) {

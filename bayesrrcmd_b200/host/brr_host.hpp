@@ -55,6 +55,8 @@ struct Options {                                   // src/options.hpp:20-112 (th
     int device = 0;                                // --gpu n
     unsigned blockMarkers = 0;                     // --block-markers n (0 = engine default)
     bool writeEpsilon = true;                      // --no-epsilon drops the N residual columns from the sample file
+    bool useMarkerCache = false;                   // --marker-cache: genotypes from the preprocessed files of --data-file (markers.hpp)
+    bool compress = false;                         // --compress: those files hold deflated markers
     bool inputOptions(int argc, const char *const argv[]);   // false + message on std::cerr when the line is unusable
     static bool parseVarianceComponents(const std::string &arg, std::vector<std::vector<double>> &S);   // src/options.cpp:20-93
 };

@@ -26,10 +26,13 @@
 #include "eigensparsemarker.h"
 #include "markerbuilder.h"
 #include "common.h"
+#include "compression.h"
 
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <fstream>
+#include <sstream>
 #include <memory>
 #include <vector>
 
@@ -285,6 +288,35 @@ int ref_eigen_stats(const uint8_t *bedCol, uint32_t N, double *stats)
     if (!m) return 1;
     stats[0] = m->mean; stats[1] = m->sd; stats[2] = m->sqrdZ; stats[3] = m->Zsum;
     return 0;
+}
+
+// The reference's preprocessed files, written by the reference's own markers (Marker::write / Marker::compress, src/marker.cpp:10-37,
+// src/densemarker.cpp, src/raggedsparsemarker.cpp:43-66, src/eigensparsemarker.cpp:38-57) and index writer
+// (src/compression.cpp:128-154), as `brr --preprocess` leaves them: test input for the host side's readers.
+// layout: 0 dense (.ppbed), 1 ragged, 2 eigen.  Returns 0 on success.
+int ref_write_pp_files(const uint8_t *bed, size_t colStride, uint32_t N, uint32_t M, int layout, int compress,
+                       const char *markerFile, const char *indexFile)
+{
+    const auto type = layoutType(layout);
+    if (type == PreprocessDataType::None) return 1;
+    std::ofstream out(markerFile, std::ios::binary), idx(indexFile, std::ios::binary);
+    if (!out || !idx) return 2;
+    std::unique_ptr<MarkerBuilder> b(builderForType(type));
+    unsigned long pos = 0;
+    for (uint32_t j = 0; j < M; ++j) {
+        auto m = buildMarker(b.get(), j, bed + size_t(j) * colStride, N);
+        if (!m) return 3;
+        if (compress) {
+            const auto c = m->compress();
+            writeCompressedDataWithIndex(c.buffer.get(), c.index.compressedSize, c.index.originalSize, out, idx, pos);
+        } else {
+            std::ostringstream raw;
+            m->write(&raw);
+            const std::string bytes = raw.str();
+            writeUncompressedDataWithIndex(reinterpret_cast<const unsigned char *>(bytes.data()), bytes.size(), out, idx, pos);
+        }
+    }
+    return (out && idx) ? 0 : 4;
 }
 
 // computeNum and the epsilon change for one marker in one layout

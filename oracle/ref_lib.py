@@ -46,6 +46,7 @@ def load(fast=False):
         lib.ref_dense_column.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         lib.ref_ragged_marker.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 7
         lib.ref_eigen_stats.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.ref_write_pp_files.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
         lib.ref_marker_ops.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_double,
                                        C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ref_run_chain.argtypes = [C.POINTER(ChainArgs)]
@@ -76,6 +77,14 @@ def eigen_stats(bedcol, N):
     stats = np.empty(4)
     assert load().ref_eigen_stats(_p(bedcol), N, _p(stats)) == 0
     return stats
+
+
+def write_pp_files(bed, N, M, layout, compress, marker_file, index_file):
+    """The reference's preprocessed marker file + index file for a PLINK payload (its own Marker::write / compress)."""
+    bed = np.ascontiguousarray(bed, dtype=np.uint8)
+    rc = load().ref_write_pp_files(_p(bed), bed.shape[1], N, M, layout, int(compress), marker_file.encode(), index_file.encode())
+    if rc:
+        raise RuntimeError("ref_write_pp_files failed: %d" % rc)
 
 
 def marker_ops(layout, bedcol, N, eps, beta_old, beta_new, eps_sum=0.0):

@@ -191,3 +191,29 @@ def test_posterior_on_test_gauss_agrees_with_the_reference_chain(built, tmp_path
     assert abs((beta ** 2).sum() - (ref ** 2).sum()) <= 0.5 * max((ref ** 2).sum(), 1e-12) + 1e-6
     top = np.argsort(-np.abs(ref))[:20]
     assert np.corrcoef(beta[top], ref[top])[0, 1] > 0.5 or n_same == iters
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sparse", [None, "ragged"])
+def test_marker_cache_run_from_the_references_preprocessed_files(built, tmp_path, sparse):
+    """`--marker-cache --compress`: the chain fed from files the REFERENCE's markers wrote (no .bed on disk) equals the .bed-fed chain."""
+    import ref_lib as R
+    if not R.ref_available():
+        pytest.skip("oracle/_ref is not built")
+    g = Golden("missing_small")
+    base = write_plink(g, str(tmp_path))
+    layout, ext = (0, ".ppbed") if sparse is None else (1, ".ragged.sparsebed")
+    R.write_pp_files(g.bed, g.N, g.M, layout, 1, base + ext, base + ext + "index")
+    S = ";".join(",".join("%.9g" % x for x in row) for row in g.S)
+    common = ["--data-file", base + ".bed", "--pheno", base + ".phen", "--analysis-type", "ppbayes", "--chain-length", "4", "--burn-in", "0",
+              "--thin", "1", "--seed", "7", "--S", S, "--sample-precision", "17"] + (["--sparse-data", sparse] if sparse else [])
+    if g.groups is not None:
+        write_plink(g, str(tmp_path), groups_file=True)
+        common += ["--group", base + ".group"]
+    r1 = run(built, common + ["--mcmc-samples", base + "_bed.csv"])
+    assert r1.returncode == 0, r1.stderr
+    os.rename(base + ".bed", base + ".bed.away")
+    r2 = run(built, common + ["--marker-cache", "--compress", "--mcmc-samples", base + "_pp.csv"])
+    assert r2.returncode == 0, r2.stderr
+    a = np.loadtxt(base + "_bed.csv", delimiter=",", skiprows=1); b = np.loadtxt(base + "_pp.csv", delimiter=",", skiprows=1)
+    assert a.shape == b.shape and np.max(np.abs(a - b) / (1 + np.abs(a))) <= 1e-8
