@@ -79,6 +79,8 @@ bool Options::inputOptions(int argc, const char *const argv[])
         else if (a == "--thin") { if (!(v = need(i))) return false; thin = unsigned(std::atoi(v)); }
         else if (a == "--S") { if (!(v = need(i))) return false; if (!parseVarianceComponents(v, S)) return false; }
         else if (a == "--group") { if (!(v = need(i))) return false; groupFile = v; }
+        else if (a == "--fixed_effects") { if (!(v = need(i))) return false; fixedFile = v; }
+        else if (a == "--fixedEffectNumber") { if (!(v = need(i))) return false; fixedEffectNumber = unsigned(std::atoi(v)); }
         else if (a == "--analysis-tokens") { if (!(v = need(i))) return false; analysisTokens = unsigned(std::atoi(v)); }
         else if (a == "--sparse-data") {
             if (!(v = need(i))) return false;
@@ -198,6 +200,26 @@ bool Data::readGroupFile(const std::string &groupFile)
     if (G.size() != numSnps) { std::cerr << "Error: the group file lists " << G.size() << " markers, the .bim " << numSnps << std::endl; return false; }
     for (int v : G)
         if (v < 0 || unsigned(v) >= numGroups) { std::cerr << "Error: group labels must be 0.." << numGroups - 1 << std::endl; return false; }
+    return true;
+}
+
+bool Data::readCSV(const std::string &filename, int cols)
+{
+    // src/data.cpp:369-403: one line per individual, comma-separated, atof per cell, values kept as float
+    std::ifstream in(filename);
+    if (!in) { std::cerr << "Error: can not open the file [" << filename << "] to read." << std::endl; return false; }
+    X.assign(size_t(numInds) * size_t(cols), 0.0f);
+    std::string line;
+    unsigned row = 0;
+    while (row < numInds && std::getline(in, line)) {
+        int col = 0;
+        size_t start = 0;
+        for (size_t i = 0; i <= line.size() && col < cols; ++i)
+            if (i == line.size() || line[i] == ',') { X[size_t(col) * numInds + row] = float(std::atof(line.c_str() + start)); ++col; start = i + 1; }
+        ++row;
+    }
+    if (row != numInds) { std::cerr << "Error: [" << filename << "] has " << row << " lines for " << numInds << " individuals" << std::endl; return false; }
+    numFixedEffects = unsigned(cols);
     return true;
 }
 
@@ -351,8 +373,13 @@ int GpuBayesR::runGibbs(AnalysisGraph *analysis)
     init(K, M, N);
     if (m_failed) return 1;
 
+    const unsigned nF = m_opt->fixedEffectNumber;
     SampleWriter writer;
+    writer.setFixedCount(nF);
     if (!writer.openGroups(m_opt->mcmcSampleFile, M, N, nGroups, m_opt->writeEpsilon)) return 1;
+    m_gamma.assign(nF, 0.0);
+    std::vector<int> xI(nF);
+    std::iota(xI.begin(), xI.end(), 0);
 
     std::vector<unsigned> markerI(M);
     std::iota(markerI.begin(), markerI.end(), 0);
@@ -378,6 +405,7 @@ int GpuBayesR::runGibbs(AnalysisGraph *analysis)
         analysis->exec(this, N, M, markerI);
         const auto sweepEnd = std::chrono::high_resolution_clock::now();
         if (m_failed) return 1;
+        if (nF > 0 && !updateFixedEffects(xI)) { std::cerr << "Error: " << brr_gpu_last_error() << std::endl; return 1; }
 
         m_sigmaE = m_dist.inv_scaled_chisq_rng(m_opt->v0E + N, (m_epsilonSqNorm + m_opt->v0E * m_opt->s02E) / (m_opt->v0E + N));   // :238-239
         for (unsigned g = 0; g < nGroups; ++g) {                                                                                    // :243-247
@@ -396,7 +424,7 @@ int GpuBayesR::runGibbs(AnalysisGraph *analysis)
                 std::cerr << "Error: " << brr_gpu_last_error() << std::endl;
                 return 1;
             }
-            writer.write(iteration, m_mu, m_beta, m_sigmaE, m_sigmaG, m_components, m_acum, m_epsilon);
+            writer.write(iteration, m_mu, m_beta, m_sigmaE, m_sigmaG, m_gamma, m_components, m_acum, m_epsilon);
         }
         const auto endTime = std::chrono::high_resolution_clock::now();
         const double it = std::chrono::duration<double>(endTime - startTime).count(), sw = std::chrono::duration<double>(sweepEnd - sweepStart).count();
@@ -414,6 +442,38 @@ int GpuBayesR::runGibbs(AnalysisGraph *analysis)
     std::cout << "mean iteration duration: " << m_meanIteration << "s" << std::endl
               << "mean flowgraph duration: " << m_meanSweep << "s" << std::endl;
     return 0;
+}
+
+// Fixed effects (src/BayesRBase.cpp:214-235): per covariate, in shuffled order, gamma ~ N(num / denom, sigmaE / denom) with
+// num = x . (eps + gamma_old x), denom = (N - 1) + sigmaE / sigmaF, then eps += (gamma_old - gamma) x -- the reference's scalar loops
+// over the float covariates.  Once per sweep and O(N nF): the residual makes one round trip over PCIe (8 N bytes each way) and the
+// loop runs here; ||eps||^2 (and the dense sum) are taken again on the device.
+bool GpuBayesR::updateFixedEffects(std::vector<int> &xI)
+{
+    const unsigned N = m_data->numInds, nF = m_opt->fixedEffectNumber;
+    if (m_data->X.size() != size_t(N) * nF) { std::cerr << "Error: --fixedEffectNumber " << nF << " without matching --fixed_effects data" << std::endl; return false; }
+    if (brr_gpu_get_state(m_dev->ctx(), m_epsilon.data(), nullptr, nullptr, nullptr)) return false;
+#pragma GCC diagnostic push
+#pragma GCC diagnostic ignored "-Wdeprecated-declarations"
+    std::random_shuffle(xI.begin(), xI.end());
+#pragma GCC diagnostic pop
+    const double dNm1 = double(N - 1), sigE_sigF = m_sigmaE / m_sigmaF;
+    for (unsigned i = 0; i < nF; ++i) {
+        const float *x = m_data->X.data() + size_t(xI[i]) * N;
+        const double gamma_old = m_gamma[xI[i]];
+        double num_f = 0.0;
+        for (unsigned k = 0; k < N; ++k) num_f += double(x[k]) * (m_epsilon[k] + gamma_old * double(x[k]));
+        const double denom_f = dNm1 + sigE_sigF;
+        m_gamma[xI[i]] = m_dist.norm_rng(num_f / denom_f, m_sigmaE / denom_f);
+        const double d = gamma_old - m_gamma[xI[i]];
+        for (unsigned k = 0; k < N; ++k) m_epsilon[k] = m_epsilon[k] + d * double(x[k]);
+    }
+    m_sigmaF = s02F;
+    if (brr_gpu_set_state(m_dev->ctx(), m_epsilon.data(), nullptr, nullptr, nullptr)) return false;
+    double sum = 0, sq = 0;
+    if (brr_gpu_eps_reduce(m_dev->ctx(), &sum, &sq)) return false;
+    m_epsilonSqNorm = sq;                                   // (m_epsilonSum of the sparse layouts is NOT touched: neither does the reference)
+    return true;
 }
 
 void GpuSweepGraph::exec(Analysis *analysis, unsigned numInds, unsigned numSnps, const std::vector<unsigned> &markerIndices)
@@ -449,6 +509,7 @@ bool SampleWriter::openGroups(const std::string &file, unsigned markers, unsigne
     for (unsigned i = 0; i < markers; ++i) m_out << "beta[" << (i + 1) << "],";
     m_out << "sigmaE,";
     for (unsigned i = 0; i < groups; ++i) m_out << "sigmaG[" << (i + 1) << "],";
+    for (unsigned i = 0; i < m_fixed; ++i) m_out << "gamma[" << (i + 1) << "],";
     for (unsigned i = 0; i < markers; ++i) m_out << "comp[" << (i + 1) << "],";
     for (unsigned i = 0; i < markers; ++i) m_out << "acum[" << (i + 1) << "]" << ((i + 1 < markers || epsilon) ? "," : "");
     if (epsilon)
@@ -458,13 +519,14 @@ bool SampleWriter::openGroups(const std::string &file, unsigned markers, unsigne
     return true;
 }
 
-void SampleWriter::write(unsigned iteration, double mu, const VectorXd &beta, double sigmaE, const VectorXd &sigmaG, const VectorXd &components,
-                         const VectorXd &acum, const VectorXd &epsilon)
+void SampleWriter::write(unsigned iteration, double mu, const VectorXd &beta, double sigmaE, const VectorXd &sigmaG, const VectorXd &gamma,
+                         const VectorXd &components, const VectorXd &acum, const VectorXd &epsilon)
 {
     m_out << iteration << ", " << mu;
     for (double b : beta) m_out << ", " << b;
     m_out << ", " << sigmaE;
     for (double s : sigmaG) m_out << ", " << s;
+    for (double g : gamma) m_out << ", " << g;
     for (double c : components) m_out << ", " << c;
     for (double a : acum) m_out << ", " << a;
     if (m_eps)
@@ -499,6 +561,7 @@ int brr_main(int argc, const char *const argv[])
         !data.readPhenotypeFile(opt.phenotypeFile))
         return 1;
     if (!opt.groupFile.empty() && !data.readGroupFile(opt.groupFile)) return 1;
+    if (!opt.fixedFile.empty() && !data.readCSV(opt.fixedFile, int(opt.fixedEffectNumber))) return 1;      // src/analysisrunner.cpp:125-127
     if (opt.S.size() != data.numGroups) {
         std::cerr << "Error: --S has " << opt.S.size() << " group(s) of variance components, the data " << data.numGroups << std::endl;
         return 1;

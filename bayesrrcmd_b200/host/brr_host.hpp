@@ -50,6 +50,8 @@ struct Options {                                   // src/options.hpp:20-112 (th
     AnalysisType analysisType = AnalysisType::Unknown;
     PreprocessDataType preprocessDataType = PreprocessDataType::Dense;
     std::string dataFile, phenotypeFile, groupFile, mcmcSampleFile = "bayesOutput.csv";
+    std::string fixedFile;                         // --fixed_effects <csv>: N rows of comma-separated covariates (src/options.cpp:162-165)
+    unsigned fixedEffectNumber = 0;                // --fixedEffectNumber n   (src/options.cpp:167-170)
     std::vector<std::vector<double>> S{{0.01, 0.001, 0.0001}};     // [groups][K-1]
     double v0E = 0.0001, s02E = 0.0001, v0G = 0.0001, s02G = 0.0001;
     int device = 0;                                // --gpu n
@@ -65,6 +67,8 @@ struct Data {                                      // src/data.hpp (what the pat
     unsigned numInds = 0, numSnps = 0, numGroups = 1;
     std::vector<float> y;                          // VectorXf y (src/data.hpp:92): phenotypes pass through float
     std::vector<int> G;                            // group of every marker (src/data.cpp:130, :424-450)
+    std::vector<float> X;                          // MatrixXf X (src/data.hpp:89): fixed-effect covariates, column-major N x numFixedEffects
+    unsigned numFixedEffects = 0;
     std::vector<uint8_t> bed;                      // PLINK SNP-major payload without the 3-byte magic
     size_t colStride = 0;
     bool readFamFile(const std::string &famFile);              // src/data.cpp:85-107
@@ -72,6 +76,7 @@ struct Data {                                      // src/data.hpp (what the pat
     bool readBedFile(const std::string &bedFile);              // payload only: the .bed IS the device layout
     bool readPhenotypeFile(const std::string &phenFile);       // src/data.cpp:334-367
     bool readGroupFile(const std::string &groupFile);          // src/data.cpp:424-453
+    bool readCSV(const std::string &filename, int cols);       // src/data.cpp:369-403 (fixed-effect covariates)
 private:
     std::vector<std::string> m_ids;                // fid:pid in fam order
 };
@@ -165,6 +170,7 @@ public:
     double mu() const { return m_mu; }
     double sigmaE() const { return m_sigmaE; }
     const VectorXd &sigmaG() const { return m_sigmaG; }
+    const VectorXd &gamma() const { return m_gamma; }
     double meanIterationSeconds() const { return m_meanIteration; }
     double meanSweepSeconds() const { return m_meanSweep; }
     bool failed() const { return m_failed; }
@@ -172,6 +178,10 @@ protected:
     void init(int K, unsigned markerCount, unsigned individualCount);   // :39-99
     void prepareForAnylsis();                                           // :101-110 (the reference's spelling)
     bool updateMu(double old_mu, double N);                             // src/DenseBayesRRmz.cpp:36-42, src/SparseBayesRRG.cpp:106-113
+    bool updateFixedEffects(std::vector<int> &xI);                      // src/BayesRBase.cpp:214-235
+    VectorXd m_gamma;                                                   // fixed effects
+    const double s02F = 1.0;
+    double m_sigmaF = 1.0;                                              // (the reference reads it uninitialised in iteration 0, :218; it is s02F from then on)
     GpuDevice *m_dev;
     Distributions m_dist;
     bool m_sparse = false, m_failed = false;
@@ -198,12 +208,14 @@ private:
 
 class SampleWriter {                               // src/samplewriter.cpp:82-118
 public:
+    void setFixedCount(unsigned n) { m_fixed = n; }                    // gamma[1..n] columns (src/samplewriter.cpp:82-118)
     bool openGroups(const std::string &file, unsigned markers, unsigned individuals, unsigned groups, bool epsilon);
-    void write(unsigned iteration, double mu, const VectorXd &beta, double sigmaE, const VectorXd &sigmaG, const VectorXd &components,
-               const VectorXd &acum, const VectorXd &epsilon);
+    void write(unsigned iteration, double mu, const VectorXd &beta, double sigmaE, const VectorXd &sigmaG, const VectorXd &gamma,
+               const VectorXd &components, const VectorXd &acum, const VectorXd &epsilon);
 private:
     std::ofstream m_out;
     bool m_eps = true;
+    unsigned m_fixed = 0;
 };
 
 // src/main.cpp + src/analysisrunner.cpp:123-152,246-276 for --analysis-type ppbayes / asyncppbayes

@@ -87,6 +87,8 @@ struct ChainDump {
     double *sigmaE_post; // [iters]
     double *sigmaG_post; // [iters*nG]
     double *pi_post;     // [iters*nG*K]
+    double *gamma_post;  // [iters*nF] fixed effects (src/BayesRBase.cpp:214-235), may be NULL
+    double *eps_post;    // [iters*N] the residual after the fixed-effects loop, may be NULL
 };
 
 struct TapIface {
@@ -100,7 +102,12 @@ struct TapIface {
 template <class Base>
 struct Tap : Base, TapIface {
     Tap(const Data *d, const Options *o, ChainDump *dump, unsigned M, unsigned N, unsigned nG, unsigned K)
-        : Base(d, o), dump(dump), M(M), N(N), nG(nG), K(K) {}
+        : Base(d, o), dump(dump), M(M), N(N), nG(nG), K(K)
+    {
+        // src/BayesRBase.cpp:218 reads m_sigmaF in the first iteration before anything has set it (:234 sets it to s02F afterwards):
+        // the harness starts it at s02F, which is what every later iteration sees
+        this->m_sigmaF = this->s02F;
+    }
 
     void before(unsigned it, const std::vector<unsigned> &order) override
     {
@@ -149,6 +156,9 @@ struct Tap : Base, TapIface {
             for (unsigned k = 0; k < K; ++k)
                 dump->pi_post[(it * nG + g) * K + k] = this->m_pi(g, k);
         }
+        const unsigned nF = unsigned(this->m_gamma.size());
+        if (dump->gamma_post) for (unsigned f = 0; f < nF; ++f) dump->gamma_post[it * nF + f] = this->m_gamma[f];
+        if (dump->eps_post) std::memcpy(dump->eps_post + size_t(it) * N, this->m_epsilon.data(), sizeof(double) * N);
     }
 
     ChainDump *dump;
@@ -379,6 +389,8 @@ struct ref_chain_args {
     int32_t graphKind;      // 0 = sequential (TapGraph = Sequential::exec), 1 = the reference's ParallelGraph (asyncppbayes),
                             // 2 / 3 = GpuSweepGraph of oracle/gpu_graph_ref.cpp (ppbayes / asyncppbayes) -- libbrr_ref_gpu.so only
     uint32_t analysisTokens; // ParallelGraph: markers in flight between forced synchronisations (Options::analysisTokens, default 20)
+    const float *X;          // fixed-effect covariates, N x nF column-major (Data::X, src/data.cpp:369-403), or NULL
+    uint32_t nF;             // Options::fixedEffectNumber
 };
 
 int ref_run_chain(ref_chain_args *a)
@@ -413,7 +425,8 @@ int ref_run_chain(ref_chain_args *a)
     opt.mcmcSampleFile = "/dev/null";
     opt.S = Map<const Matrix<double, Dynamic, Dynamic, RowMajor>>(a->S, a->nGroups, a->K - 1);
     opt.numGroups = a->nGroups;
-    opt.fixedEffectNumber = 0;
+    opt.fixedEffectNumber = a->X ? a->nF : 0;
+    if (a->X && a->nF) { data.X = Map<const MatrixXf>(a->X, a->N, a->nF); data.numFixedEffects = a->nF; }
     opt.useMarkerCache = true;
 
     std::unique_ptr<BayesRBase> analysis;

@@ -16,7 +16,7 @@ class ChainDump(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "mu", "sigmaE_in", "sigmaG_in", "pi_in", "rand_uz", "order", "eps_in", "beta_in", "epssum_in",
         "beta_out", "comp_out", "acum_out", "eps_out", "v_out", "betasq_out", "epssum_out",
-        "sigmaE_post", "sigmaG_post", "pi_post")]
+        "sigmaE_post", "sigmaG_post", "pi_post", "gamma_post", "eps_post")]
 
 
 class ChainArgs(C.Structure):
@@ -24,7 +24,8 @@ class ChainArgs(C.Structure):
                 ("groups", C.c_void_p), ("nGroups", C.c_uint32), ("S", C.c_void_p), ("K", C.c_uint32),
                 ("seed", C.c_uint32), ("iterations", C.c_uint32), ("layout", C.c_int32),
                 ("dump", C.c_void_p), ("execSeconds", C.c_double), ("totalSeconds", C.c_double),
-                ("buildSeconds", C.c_double), ("graphKind", C.c_int32), ("analysisTokens", C.c_uint32)]
+                ("buildSeconds", C.c_double), ("graphKind", C.c_int32), ("analysisTokens", C.c_uint32),
+                ("X", C.c_void_p), ("nF", C.c_uint32)]
 
 
 def ref_available(fast=False):
@@ -115,7 +116,7 @@ class _Quiet:
 
 
 def run_chain(bed, N, M, y, S, seed, iterations, layout=0, groups=None, dump=True, fast=False, graph="sequential", tokens=20,
-              keep=None):
+              keep=None, X=None):
     """Run the reference's BayesRBase::runGibbs; returns (dict of per-iteration arrays, timings).
     graph="parallel": through the reference's own ParallelGraph (asyncppbayes: TBB, all cores, `tokens` markers in flight).
     keep: names of the per-iteration arrays to record (None = all); the others share one scratch row (long chains)."""
@@ -130,6 +131,10 @@ def run_chain(bed, N, M, y, S, seed, iterations, layout=0, groups=None, dump=Tru
                   comp_out=(it, M), acum_out=(it, M), eps_out=(it, N), v_out=(it, nG, K),
                   betasq_out=(it, nG), epssum_out=(it,), sigmaE_post=(it,), sigmaG_post=(it, nG),
                   pi_post=(it, nG, K))
+    Xf = None
+    if X is not None:                                        # fixed-effect covariates (N x nF), float32 column-major as Data::X
+        Xf = np.asfortranarray(np.atleast_2d(X), dtype=np.float32)
+        shapes["gamma_post"] = (it, Xf.shape[1]); shapes["eps_post"] = (it, N)
     arrays = {}
     d = ChainDump()
     if dump:
@@ -141,6 +146,7 @@ def run_chain(bed, N, M, y, S, seed, iterations, layout=0, groups=None, dump=Tru
                   groups=None if g is None else g.ctypes.data, nGroups=nG, S=S.ctypes.data, K=K,
                   seed=seed, iterations=iterations, layout=layout,
                   dump=C.addressof(d) if dump else None, analysisTokens=tokens,
+                  X=None if Xf is None else Xf.ctypes.data, nF=0 if Xf is None else Xf.shape[1],
                   graphKind={"sequential": 0, "parallel": 1, "gpu": 2, "gpu-async": 3}[graph])
     if graph.startswith("gpu"):
         fast = "gpu"

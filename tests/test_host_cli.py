@@ -84,7 +84,7 @@ def test_reads_plink_files_then_requires_a_gpu(built, tmp_path):
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
 
 
-def read_samples(path, M, N, nG):
+def read_samples(path, M, N, nG, nF=0):
     rows = np.loadtxt(path, delimiter=",", skiprows=1, ndmin=2)
     out = []
     for r in rows:
@@ -92,6 +92,7 @@ def read_samples(path, M, N, nG):
         d = dict(iteration=int(r[0]), mu=r[1], beta=r[o:o + M]); o += M
         d["sigmaE"] = r[o]; o += 1
         d["sigmaG"] = r[o:o + nG]; o += nG
+        d["gamma"] = r[o:o + nF]; o += nF
         d["comp"] = r[o:o + M]; o += M
         d["acum"] = r[o:o + M]; o += M
         d["eps"] = r[o:o + N]
@@ -217,3 +218,45 @@ def test_marker_cache_run_from_the_references_preprocessed_files(built, tmp_path
     assert r2.returncode == 0, r2.stderr
     a = np.loadtxt(base + "_bed.csv", delimiter=",", skiprows=1); b = np.loadtxt(base + "_pp.csv", delimiter=",", skiprows=1)
     assert a.shape == b.shape and np.max(np.abs(a - b) / (1 + np.abs(a))) <= 1e-8
+
+
+@pytest.mark.gpu
+def test_fixed_effects_chain_from_seed_reproduces_the_reference(built, tmp_path):
+    """--fixed_effects / --fixedEffectNumber (src/BayesRBase.cpp:214-235): the reference's own runGibbs with two covariates (oracle/_ref,
+    run here) against the host's chain from the same seed: mu, beta, sigmaE, sigmaG, gamma per iteration, the residual at the end."""
+    import ref_lib as R
+    if not R.ref_available():
+        pytest.skip("oracle/_ref is not built")
+    g = Golden("missing_small")
+    rng = np.random.default_rng(12)
+    X = np.c_[rng.normal(size=g.N), (rng.random(g.N) < 0.4).astype(np.float64)].astype(np.float32)
+    y = (np.asarray(g.y, dtype=np.float64) + 0.8 * X[:, 0] - 0.5 * X[:, 1]).astype(np.float32)
+    iters, seed = 5, 11
+    arr, _ = R.run_chain(g.bed, g.N, g.M, y, g.S, seed=seed, iterations=iters, layout=0, groups=g.groups, X=X)
+    g.y = y
+    base = write_plink(g, str(tmp_path), groups_file=g.groups is not None)
+    with open(base + ".cov", "w") as f:
+        for i in range(g.N):
+            f.write(",".join("%.9g" % v for v in X[i]) + "\n")
+    out = str(tmp_path / "samples.csv")
+    S = ";".join(",".join("%.17g" % x for x in row) for row in g.S)
+    args = ["--analysis-type", "ppbayes", "--data-file", base + ".bed", "--pheno", base + ".phen", "--chain-length", str(iters), "--burn-in", "0",
+            "--thin", "1", "--seed", str(seed), "--S", S, "--mcmc-samples", out, "--sample-precision", "17",
+            "--fixed_effects", base + ".cov", "--fixedEffectNumber", "2"] + (["--group", base + ".group"] if g.groups is not None else [])
+    r = run(built, args)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "gamma[2]" in open(out).readline()
+    rows = read_samples(out, g.M, g.N, g.nG, nF=2)
+
+    def close(a, b, what, it, tol=1e-8):
+        err = np.max(np.abs(np.asarray(a, float) - np.asarray(b, float)) / (1.0 + np.abs(np.asarray(b, float))))
+        assert err <= tol, "%s differs at iteration %d: %.3e" % (what, it, err)
+
+    for it, d in enumerate(rows):
+        close(d["mu"], arr["mu"][it], "mu", it)
+        close(d["beta"], arr["beta_out"][it], "beta", it)
+        close(d["sigmaE"], arr["sigmaE_post"][it], "sigmaE", it)
+        close(d["sigmaG"], arr["sigmaG_post"][it], "sigmaG", it)
+        close(d["gamma"], arr["gamma_post"][it], "gamma", it)
+    close(rows[-1]["eps"], arr["eps_post"][-1], "eps", iters - 1)
+    assert np.abs(arr["gamma_post"][-1]).max() > 0.1            # the covariates carry signal: the effects are not trivially zero
