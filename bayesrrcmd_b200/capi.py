@@ -193,11 +193,18 @@ class Engine:
         a = [_f64(x) for x in (eps, beta, comp, acum)]
         self._check(self.lib.brr_gpu_set_state(self._h, *[_ptr(x) for x in a]))
 
-    def get_state(self, eps=True, beta=True, comp=True, acum=True):
-        e = np.empty(self.N) if eps else None
-        b = np.empty(self.M) if beta else None
-        c = np.empty(self.M) if comp else None
-        a = np.empty(self.M) if acum else None
+    def get_state(self, eps=True, beta=True, comp=True, acum=True, out=None):
+        """out: optional dict of caller-owned float64 arrays (e.g. pinned host memory) for "eps" / "beta" / "comp" / "acum"."""
+        out = out or {}
+        def buf(name, want, n):
+            if not want:
+                return None
+            x = out.get(name)
+            if x is None:
+                return np.empty(n)
+            assert x.dtype == np.float64 and x.flags.c_contiguous and x.size == n
+            return x
+        e = buf("eps", eps, self.N); b = buf("beta", beta, self.M); c = buf("comp", comp, self.M); a = buf("acum", acum, self.M)
         self._check(self.lib.brr_gpu_get_state(self._h, _ptr(e), _ptr(b), _ptr(c), _ptr(a)))
         return e, b, c, a
 

@@ -107,6 +107,8 @@ struct brr_gpu_ctx {
     double *h_small = nullptr;   // [kMaxGK + kMaxGK + 2 + 2*1024]
     unsigned *h_counts = nullptr;
 
+    std::vector<uint32_t> order_stamp;      // brr_gpu_sweep_stage: marker j was seen in call number order_stamp[j]
+    uint32_t order_gen = 0;
     bool uploaded = false, finalized = false, model_set = false, staged = false, ran = false;
     uint64_t launches = 0;
     uint32_t last_launches = 0;
@@ -557,13 +559,16 @@ extern "C" int brr_gpu_sweep_stage(brr_gpu_ctx *c, const uint32_t *marker_order,
         if (async_tokens > maxb) return fail(BRR_GPU_EINVAL, "async_tokens must be <= %u for this layout", maxb);
     }
     if (!(sigmaE > 0.0)) return fail(BRR_GPU_EINVAL, "sigmaE must be positive");
-    {   // distinct, in-range marker ids
-        std::vector<uint8_t> seen(M, 0);
+    {   // distinct, in-range marker ids (stamps of the current call instead of a cleared table: this runs once per sweep on the caller's thread)
+        if (c->order_stamp.size() != M) { c->order_stamp.assign(M, 0u); c->order_gen = 0; }
+        if (++c->order_gen == 0u) { std::fill(c->order_stamp.begin(), c->order_stamp.end(), 0u); c->order_gen = 1; }
+        const uint32_t gen = c->order_gen;
+        uint32_t *stamp = c->order_stamp.data();
         for (uint32_t i = 0; i < n_order; ++i) {
             const uint32_t j = marker_order[i];
             if (j >= M) return fail(BRR_GPU_EINVAL, "marker_order[%u]=%u out of range", i, j);
-            if (seen[j]) return fail(BRR_GPU_EINVAL, "marker %u appears twice in marker_order", j);
-            seen[j] = 1;
+            if (stamp[j] == gen) return fail(BRR_GPU_EINVAL, "marker %u appears twice in marker_order", j);
+            stamp[j] = gen;
         }
     }
     CUDA_TRY(cudaMemcpyAsync(c->order, marker_order, sizeof(uint32_t) * n_order, cudaMemcpyHostToDevice, c->stream));

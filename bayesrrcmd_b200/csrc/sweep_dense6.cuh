@@ -788,17 +788,20 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                         uint32_t z = 0, wv = 0, y = 0;
                         if (pair) {
                             const uint32_t *rowa = pk + size_t(rr) * RS;
-                            const uint16_t *tla = reinterpret_cast<const uint16_t *>(rowa + PW);
                             if (cntj <= 15u && cntm <= 15u) {
-                                for (uint32_t en = e4; en < cntj; en += 4) {
-                                    const uint32_t ii = tlj[1 + en];
-                                    const uint32_t cc = (rowa[ii >> 4] >> (2 * (ii & 15u))) & 3u;
-                                    if (cc == 3u) ++wv; else z += cc;
+                                // (all look-ups of a lane issued together: its share of the row's list, then this row's list from idv)
+                                uint32_t idj[4], wj[4], wa[4];
+#pragma unroll
+                                for (uint32_t k4 = 0; k4 < 4; ++k4) idj[k4] = e4 + 4 * k4 < cntj ? tlj[1 + e4 + 4 * k4] : 0u;
+#pragma unroll
+                                for (uint32_t k4 = 0; k4 < 4; ++k4) {
+                                    wa[k4] = e4 + 4 * k4 < cntj ? rowa[idj[k4] >> 4] : 0u;
+                                    wj[k4] = e4 + 4 * k4 < cntm ? rowj[idv[k4] >> 4] : 0u;
                                 }
-                                for (uint32_t en = e4; en < cntm; en += 4) {
-                                    const uint32_t ii = tla[1 + en];
-                                    const uint32_t cc = (rowj[ii >> 4] >> (2 * (ii & 15u))) & 3u;
-                                    if (cc != 3u) y += cc;
+#pragma unroll
+                                for (uint32_t k4 = 0; k4 < 4; ++k4) {
+                                    if (e4 + 4 * k4 < cntj) { const uint32_t cc = (wa[k4] >> (2 * (idj[k4] & 15u))) & 3u; if (cc == 3u) ++wv; else z += cc; }
+                                    if (e4 + 4 * k4 < cntm) { const uint32_t cc = (wj[k4] >> (2 * (idv[k4] & 15u))) & 3u; if (cc != 3u) y += cc; }
                                 }
                             } else if (cntj | cntm) {
                                 for (uint32_t w = e4; w < PW; w += 4) {
