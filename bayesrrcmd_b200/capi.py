@@ -306,7 +306,7 @@ class Engine:
 
     PROFILE6 = ["d_dec", "d_apply", "d_full", "d_loop", "d_miss", "d_cross", "d_acc", "pu_wait", "pu_work", "pr_plan", "pr_empty", "pr_issue",
                 "c_poll", "c_plan", "c_decide", "w_cnt", "w_read", "w_pred", "w_sample", "w_fix", "w_valid", "blocks", "walks", "applies", "restarts",
-                "gram_blocks", "row_blocks"]
+                "gram_blocks", "row_blocks", "d_pre", "d_fullonly", "d_loopgram"]
 
     def profile_cycles6(self, reset=True):
         """Phase cycle counters of the version-6 dense kernel (one warp per role of CTA 0)."""

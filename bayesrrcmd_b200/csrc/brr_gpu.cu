@@ -89,6 +89,7 @@ struct brr_gpu_ctx {
     uint32_t *inmask6 = nullptr;
     unsigned long long *prof6 = nullptr;
     unsigned *dbg6 = nullptr;
+    uint32_t v6_launches = 0;               // version-6 launches so far: the tag of the cross-GPU cells
     size_t smem6_bytes = 0;
     bool v6_ok = false;
     int dense_mode = 0;                     // 0 = auto (per sweep), 4 / 5 / 6 = forced (BRR_GPU_DENSE_KERNEL)
@@ -276,9 +277,10 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
             }
         }
         c->smem6_bytes = v6::sweep6_smem_bytes(c->RS, c->SL);
-        if (cfg->world == 1 && c->dense_mode != 4 && c->dense_mode != 5 && c->smem6_bytes <= size_t(prop.sharedMemPerBlockOptin)) {
+        if (c->dense_mode != 4 && c->dense_mode != 5 && c->smem6_bytes <= size_t(prop.sharedMemPerBlockOptin)) {
             bool fits = true;
-            for (const void *fn : {(const void *)v6::sweep_dense6_kernel<false>, (const void *)v6::sweep_dense6_kernel<true>}) {
+            for (const void *fn : {(const void *)v6::sweep_dense6_kernel<false, false>, (const void *)v6::sweep_dense6_kernel<false, true>,
+                                   (const void *)v6::sweep_dense6_kernel<true, false>, (const void *)v6::sweep_dense6_kernel<true, true>}) {
                 CUDA_OR_DESTROY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem6_bytes));
                 int o = 0;
                 CUDA_OR_DESTROY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, v6::kThreads6, c->smem6_bytes));
@@ -304,8 +306,10 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
             brr_gpu_destroy(c); return rc_;
         }
         if (cfg->world > 1) {
-            TRY_OR_DESTROY(dev_alloc(&c->xchg, xchg_total_ints(cfg->world)));
-            CUDA_OR_DESTROY(cudaMemset(c->xchg, 0, sizeof(int) * xchg_total_ints(cfg->world)));
+            // (the version-6 import area follows the version-4 exchange buffer in the same, IPC-exported, allocation)
+            const size_t xints = xchg_total_ints(cfg->world) + 2 * v6::imp_u64(cfg->world);
+            TRY_OR_DESTROY(dev_alloc(&c->xchg, xints));
+            CUDA_OR_DESTROY(cudaMemset(c->xchg, 0, sizeof(int) * xints));
             const int hdr = (int)c->nCTA;       // peers read this at attach time to agree on the number of exchange CTAs
             CUDA_OR_DESTROY(cudaMemcpy(c->xchg + xchg_total_ints(cfg->world) - 8, &hdr, sizeof(int), cudaMemcpyHostToDevice));
             TRY_OR_DESTROY(dev_alloc(&c->peer_ptrs_dev, (size_t)cfg->world));
@@ -622,7 +626,7 @@ static bool use_v5(const brr_gpu_ctx *c)
 // Version 6 (sweep_dense6.cuh): as version 5 with the walk distributed over the CTAs; preferred over version 5 when it fits.
 static bool use_v6(const brr_gpu_ctx *c)
 {
-    if (!c->v6_ok || c->async_tokens || c->cfg.world > 1) return false;
+    if (!c->v6_ok || c->async_tokens || (c->cfg.world > 1 && !c->attached)) return false;
     if (c->dense_mode == 6) return true;
     if (c->dense_mode == 4 || c->dense_mode == 5) return false;
     return c->have_last && c->last_nonskipped_frac <= kV5MaxNonskipped;
@@ -641,12 +645,16 @@ static int launch_dense6(brr_gpu_ctx *c)
     p.part_bsq = c->part_bsq; p.part_v = c->part_v;
     p.v = c->v; p.betasq = c->betasq; p.out_scalars = c->out_scalars; p.out_counts = c->out_counts;
     p.prof = c->prof6; p.dbg = c->dbg6;
+    p.world = c->cfg.world; p.rank = c->cfg.rank; p.peer_xchg = c->peer_ptrs_dev; p.imp_off = xchg_total_ints(c->cfg.world);
+    p.launch_tag = ++c->v6_launches;                      // (every rank runs the same sequence of sweeps and makes the same kernel choice)
     CUDA_TRY(cudaMemsetAsync(c->dbg6, 0, sizeof(unsigned) * size_t(c->nCTA) * 32, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->slots5, 0, sizeof(int) * size_t(v5::kSlotRing) * v5::kSlotInts5, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->results6, 0, sizeof(int) * size_t(v6::kResRing) * 32, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->slots + size_t(kSlots) * kSlotInts, 0, sizeof(int) * 8, c->stream));     // absmax + barrier counters
     CUDA_TRY(cudaMemsetAsync(c->out_counts, 0, sizeof(unsigned) * 4, c->stream));
-    const void *fn = p.prof ? (const void *)v6::sweep_dense6_kernel<true> : (const void *)v6::sweep_dense6_kernel<false>;
+    const bool mg = c->cfg.world > 1;
+    const void *fn = mg ? (p.prof ? (const void *)v6::sweep_dense6_kernel<true, true> : (const void *)v6::sweep_dense6_kernel<true, false>)
+                        : (p.prof ? (const void *)v6::sweep_dense6_kernel<false, true> : (const void *)v6::sweep_dense6_kernel<false, false>);
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem6_bytes));
     void *args[] = {&p};
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));

@@ -70,7 +70,7 @@ constexpr int kDotThreads = 32 * kDotW;
 enum { kActSkip = 0, kActDot = 1, kActExit = 2 };
 enum { kPfDDec = 0, kPfDApply, kPfDFull, kPfDLoop, kPfDMiss, kPfDCross, kPfDAcc, kPfPuWait, kPfPuWork, kPfPrPlan, kPfPrEmpty, kPfPrIssue,
        kPfCPoll, kPfCPlan, kPfCDecide, kPfWCnt, kPfWRead, kPfWPred, kPfWSample, kPfWFix, kPfWValid, kPfBlocks, kPfWalks, kPfApplies, kPfRestarts,
-       kPfGramBlocks, kPfRowBlocks, kPfN = 32 };
+       kPfGramBlocks, kPfRowBlocks, kPfDPre, kPfDFullOnly, kPfDLoopGram, kPfN = 32 };
 
 struct Sweep6Params {
     uint32_t n_local, n_total, M, K, nG, nCTA, SL, PW, RS;
@@ -91,8 +91,32 @@ struct Sweep6Params {
     double *v, *betasq, *out_scalars;
     unsigned *out_counts;        // [0] non-skipped, [1] blocks walked, [2] error flags, [3] restarts (zero at launch)
     unsigned long long *prof;    // optional [kPfN]
+    // several GPUs (individuals sharded, world > 1): every GPU runs the whole protocol on its shard; the owner CTA of a block pushes
+    // the block's locally reduced sums to every peer's IMPORT area over NVLink and adds what the peers pushed before it walks
+    int world, rank;
+    int *const *peer_xchg;       // [world] base of every rank's exchange buffer (own entry = local buffer)
+    unsigned long long imp_off;  // offset (int units) of the version-6 import area inside an exchange buffer
+    uint32_t launch_tag;         // number of this launch (identical on all ranks)
     unsigned *dbg;               // [nCTA][32]: the wait each warp was in when the launch was given up (site | aux << 12 | 0x80000000), zero at launch
 };
+
+// Import area of a rank (16-byte cells {lo32 | tag << 32, hi32 | tag << 32}: 8-byte stores arrive whole, a reader that finds the tag in
+// both halves has the value -- no flag, no fence, one NVLink trip; as NCCL's LL protocol and the version-4 exchange):
+//   header: [world] cells, the peers' max |eps| of this launch;  then [kImpRing blocks][world sources][kImpVals] cells
+constexpr uint32_t kImpRing = 64;
+constexpr uint32_t kImpVals = 4 * kB + 2 + 2 * kGramRows * kB;     // per marker: dot lo / hi, missing hi / lo; sum q hi / lo; Gram words
+__host__ __device__ inline size_t imp_u64(int world) { return size_t(2) * world + size_t(2) * kImpRing * world * kImpVals; }
+__device__ __forceinline__ void ll_store(unsigned long long *cell, unsigned long long v, uint32_t tag)
+{
+    st_sys_v2(reinterpret_cast<ulonglong2 *>(cell), (v & 0xffffffffULL) | ((unsigned long long)tag << 32), (v >> 32) | ((unsigned long long)tag << 32));
+}
+__device__ __forceinline__ bool ll_load(const unsigned long long *cell, uint32_t tag, unsigned long long &v)
+{
+    const ulonglong2 x = ld_sys_v2(reinterpret_cast<const ulonglong2 *>(cell));
+    if (uint32_t(x.x >> 32) != tag || uint32_t(x.y >> 32) != tag) return false;
+    v = (x.x & 0xffffffffULL) | (x.y << 32);
+    return true;
+}
 
 struct Blk6 {
     // planned
@@ -159,7 +183,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)
 }
 __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-template <bool PROF>
+template <bool MG, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -265,7 +289,24 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
     grid_arrive(p.bar);
     grid_wait(p.bar, p.nCTA);
     {   // common fixed-point scale: |q| <= 2^(62 - headroom) at the start of the sweep
-        const double a = __longlong_as_double((long long)__ldcg(p.absmax));
+        double a = __longlong_as_double((long long)__ldcg(p.absmax));
+        if (MG && tid == 0) {                                           // max |eps| over all shards: pushed by CTA 0, polled by every CTA
+            const uint32_t tag = ((p.launch_tag & 0x3ffu) << 21) | 0x1fffffu;
+            if (cta == 0)
+                for (int q = 0; q < p.world; ++q)
+                    if (q != p.rank) ll_store(reinterpret_cast<unsigned long long *>(p.peer_xchg[q] + p.imp_off) + 2 * p.rank, (unsigned long long)__double_as_longlong(a), tag);
+            const unsigned long long *hdr = reinterpret_cast<const unsigned long long *>(p.peer_xchg[p.rank] + p.imp_off);
+            BRR_SITE(230);
+            for (int q = 0; q < p.world; ++q) {
+                if (q == p.rank) continue;
+                unsigned long long v = 0;
+                while (!ll_load(hdr + 2 * q, tag, v)) { if (spin_fail()) break; }
+                spin_ok();
+                a = fmax(a, __longlong_as_double((long long)v));
+            }
+            sh.warp_tmp[0] = a;
+        }
+        if (MG) { __syncthreads(); a = sh.warp_tmp[0]; }
         int ex = 0;
         if (a > 0.0) frexp(a, &ex);
         const int s = 62 - kHeadroomBits - ex;
@@ -599,8 +640,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 *(reinterpret_cast<unsigned long long *>(accs + size_t(d % kAcc) * kAccInts + kAccSumQ) + lane) = sh.sumq[lane];
             const uint32_t st0 = (4 * d + 2 * tp) & (kStages - 1);
             const uint32_t *pk = stages + size_t(st0) * kTileRows * RS;      // 32 rows: the two tiles are neighbours in the ring
+            PHASE(kPfDPre);
             if (!mbw(&sh.full[st0], (d >> 1) & 1u)) break;
             if (!mbw(&sh.full[st0 + 1], (d >> 1) & 1u)) break;
+            PHASE(kPfDFullOnly);
             if (action == kActSkip) {
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&sh.empty[st0]); mbar_arrive(&sh.empty[st0 + 1]); mbar_arrive(&sh.acc_full[d % kAcc]); }
@@ -715,7 +758,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                     }
                 }
             }
-            PHASE(kPfDLoop);
+            if (present) { PHASE(kPfDLoopGram); } else { PHASE(kPfDLoop); }
             bool early = false;
             // ---- sums of q over the missing individuals of the pair's rows: 4 lanes per row, 8 rows per warp.  q is taken from the fp64
             //      residual (the same rounding as the limbs: one load instead of eight) ----
@@ -1006,16 +1049,76 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             double base = 0.0;
             RowConst rc; rc.sj = rc.cj = rc.ej = rc.sumg = rc.nmiss = 0.0;
             int4 gv[kGramRows];
+            long long tlo = 0, thi = 0, sm_hi = 0, sm_lo = 0, e_hi = 0, e_lo = 0;
+            if (act || MG) {
+                e_hi = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLEps) * kLine));
+                e_lo = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLEps + 1) * kLine));
+            }
             if (act) {
-                const long long tlo = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLDots + 2 * wk) * kLine));
-                const long long thi = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLDots + 2 * wk + 1) * kLine));
-                const long long sm_hi = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLSm + 2 * wk) * kLine));
-                const long long sm_lo = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLSm + 2 * wk + 1) * kLine));
-                const long long e_hi = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLEps) * kLine));
-                const long long e_lo = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLEps + 1) * kLine));
+                tlo = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLDots + 2 * wk) * kLine));
+                thi = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLDots + 2 * wk + 1) * kLine));
+                sm_hi = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLSm + 2 * wk) * kLine));
+                sm_lo = __ldcg(reinterpret_cast<const long long *>(slot + size_t(kLSm + 2 * wk + 1) * kLine));
 #pragma unroll
                 for (int r = 0; r < kGramRows; ++r)
                     if ((present >> r) & 1u) gv[r] = __ldcg(reinterpret_cast<const int4 *>(slot + size_t(kLGram + r * kB + wk) * kLine));
+            }
+            if (MG) {
+                // ---- the other GPUs' sums of this block: push ours to every peer, add theirs (integers: the total does not depend on the order) ----
+                const uint32_t tag = ((p.launch_tag & 0x3ffu) << 21) | ((c + 1u) & 0x1fffffu);
+                const size_t blk_off = size_t(2) * p.world + size_t(2) * ((size_t(c % kImpRing) * p.world) * kImpVals);
+                for (int q = 0; q < p.world; ++q) {
+                    if (q == p.rank) continue;
+                    unsigned long long *dst = reinterpret_cast<unsigned long long *>(p.peer_xchg[q] + p.imp_off) + blk_off + size_t(2) * p.rank * kImpVals;
+                    if (act) {
+                        ll_store(dst + 2 * (4 * wk + 0), (unsigned long long)tlo, tag); ll_store(dst + 2 * (4 * wk + 1), (unsigned long long)thi, tag);
+                        ll_store(dst + 2 * (4 * wk + 2), (unsigned long long)sm_hi, tag); ll_store(dst + 2 * (4 * wk + 3), (unsigned long long)sm_lo, tag);
+#pragma unroll
+                        for (int r = 0; r < kGramRows; ++r)
+                            if ((present >> r) & 1u) {
+                                ll_store(dst + 2 * (4 * kB + 2 + 2 * (r * kB + wk) + 0), (unsigned long long)(unsigned)gv[r].x | ((unsigned long long)(unsigned)gv[r].y << 32), tag);
+                                ll_store(dst + 2 * (4 * kB + 2 + 2 * (r * kB + wk) + 1), (unsigned long long)(unsigned)gv[r].z | ((unsigned long long)(unsigned)gv[r].w << 32), tag);
+                            }
+                    }
+                    if (wk < 2) ll_store(dst + 2 * (4 * kB + wk), (unsigned long long)(wk ? e_lo : e_hi), tag);
+                }
+                uint32_t code = 0;                                  // 1 = dropped by a restart, 2 = given up
+                const unsigned long long *imp = reinterpret_cast<const unsigned long long *>(p.peer_xchg[p.rank] + p.imp_off) + blk_off;
+                BRR_SITE(231);
+                for (int q = 0; q < p.world && !code; ++q) {
+                    if (q == p.rank) continue;
+                    const unsigned long long *src = imp + size_t(2) * q * kImpVals;
+                    auto get = [&](uint32_t idx) -> unsigned long long {
+                        unsigned long long v = 0;
+                        while (!code && !ll_load(src + 2 * idx, tag, v)) {
+                            if (ldv(&sh.epoch_w) != b_epoch) code = 1;
+                            else if (spin_fail()) code = 2;
+                        }
+                        return v;
+                    };
+                    e_hi += (long long)get(4 * kB + 0); e_lo += (long long)get(4 * kB + 1);
+                    if (act) {
+                        tlo += (long long)get(4 * wk + 0); thi += (long long)get(4 * wk + 1);
+                        sm_hi += (long long)get(4 * wk + 2); sm_lo += (long long)get(4 * wk + 3);
+#pragma unroll
+                        for (int r = 0; r < kGramRows; ++r)
+                            if ((present >> r) & 1u) {
+                                const unsigned long long w0 = get(4 * kB + 2 + 2 * (r * kB + wk) + 0), w1 = get(4 * kB + 2 + 2 * (r * kB + wk) + 1);
+                                gv[r].x += int(uint32_t(w0)); gv[r].y += int(uint32_t(w0 >> 32)); gv[r].z += int(uint32_t(w1)); gv[r].w += int(uint32_t(w1 >> 32));
+                            }
+                    }
+                }
+                spin_ok();
+                if (tid == 0) sh.w_ctl[2] = 0;
+                bar_named(1, 64);
+                if (code) atomicOr(&sh.w_ctl[2], code);
+                bar_named(1, 64);
+                const uint32_t any = sh.w_ctl[2];
+                bar_named(1, 64);
+                if (any & 2u) break;
+                if (any & 1u) continue;
+            }
+            if (act) {
                 const double sx = 0.5 * (L[2] - L[0]);
                 const double eps_sum_total = (double(e_hi) * 4294967296.0 + double(e_lo)) * inv_scale;
                 const double dprime = (double(thi) * 4294967296.0 + double(tlo)) * inv_scale;

@@ -313,6 +313,7 @@ def main():
         cnts = ("blocks", "walks", "applies", "restarts", "gram_blocks", "row_blocks")
         sys.stderr.write("v6 phase cycles/block over %d timed sweeps (%d blocks): " % (a.steps, nblk)
                          + "  ".join("%s=%d" % (k, pc[k] // nblk) for k in eng.PROFILE6 if k not in cnts and not k.startswith("w_"))
+                         + " (d_full = d_pre [release of the set, snapshot] + d_fullonly [rows] + wait for stashed rows; d_loop = blocks without Gram rows, d_loopgram = with)"
                          + "  | per walk of CTA 0 (%d walks): " % pc["walks"] + "  ".join("%s=%d" % (k, pc[k] // max(1, pc["walks"])) for k in eng.PROFILE6 if k.startswith("w_"))
                          + "  | per block: applies=%.3f  Gram rows on a dot pass=%.3f  walks with a row=%.3f of CTA 0's  restarts/sweep=%.1f\n" % (
                              pc["applies"] / nblk, pc["row_blocks"] / nblk, pc["gram_blocks"] / max(1, pc["walks"]), float(np.mean(restarts))))

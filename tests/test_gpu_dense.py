@@ -4,6 +4,8 @@ Tier 1: computeNum / epsilon change per marker vs the reference's golden numbers
 Tier 2: 10-iteration replay of the reference chain consuming the recorded RNG table (<= 1e-8).
 Plus: CUDA path vs the C oracle on seeded random inputs, edge cases, async mode, block sizes.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -22,7 +24,8 @@ def dense_kernel(request, monkeypatch):
     if request.param in ("v5", "v6"):
         cs = getattr(request.node, "callspec", None)
         prm = cs.params if cs else {}
-        if prm.get("tokens", 0) or prm.get("world", 1) > 1 or request.node.name.startswith(("test_world_gt_1", "test_mu_update", "test_synthetic", "test_tier1")):
+        sharded_ok = request.param == "v6"         # version 6 also runs sharded over several GPUs (synchronous mode)
+        if prm.get("tokens", 0) or (prm.get("world", 1) > 1 and not sharded_ok) or request.node.name.startswith(("test_world_gt_1", "test_mu_update", "test_synthetic", "test_tier1")):
             pytest.skip("asynchronous / sharded / marker-level paths do not run the version-5 / 6 kernels")
     monkeypatch.setenv("BRR_GPU_DENSE_KERNEL", request.param)
     return request.param
@@ -284,7 +287,11 @@ def _sharded_exchange(world, N, M, p_miss, block, tokens, devices):
         for e, (v, bs, out) in zip(shards, res):
             _, b, c, a = e.get_state()
             assert np.array_equal(b, b0) and np.array_equal(c, c0) and np.array_equal(a, a0)
-            assert np.array_equal(v, v0) and np.array_equal(bs, bs0)
+            assert np.array_equal(v, v0)
+            if os.environ.get("BRR_GPU_DENSE_KERNEL") == "v6":      # sum(beta^2) is added up per owner CTA: the order depends on the number of CTAs
+                assert np.max(np.abs(bs - bs0)) <= 1e-13 * (1 + np.abs(bs0).max())
+            else:
+                assert np.array_equal(bs, bs0)
             assert out.n_nonskipped == out0.n_nonskipped
         assert abs(sum(o.eps_sqnorm for _, _, o in res) - out0.eps_sqnorm) <= 1e-9 * out0.eps_sqnorm
 
