@@ -40,10 +40,8 @@ using v5::ldv; using v5::stv; using v5::bar_named; using v5::mbar_arrive; using 
 using v5::kSlotRing; using v5::kSkip; using v5::kEnd; using v5::kLCnt; using v5::kLDots; using v5::kLSm; using v5::kLEps; using v5::kLGram;
 using v5::kSlotLines; using v5::kSlotInts5;
 
-#ifndef BRR_V6_KD
-#define BRR_V6_KD 4
-#endif
-constexpr int kD = BRR_V6_KD;                       // the dot pass of a block sees the residual updates of the chain blocks more than kD back
+constexpr int kD = 7;                       // LARGEST pipeline depth (array sizes).  The depth of a launch, Sweep6Params::depth = D <= kD: the dot pass of a
+                                            // block sees the residual updates of the chain blocks more than D back (4: brr_gpu.cu)
 constexpr int kGramRows = kD + 1;           // one in-model row per block: the rows of the last kD blocks and the block's own
 static_assert(kGramRows <= 8, "one N-tile of Gram rows");
 constexpr int kSeq = 32;                    // ring of block descriptors
@@ -97,6 +95,7 @@ struct Sweep6Params {
     int *const *peer_xchg;       // [world] base of every rank's exchange buffer (own entry = local buffer)
     unsigned long long imp_off;  // offset (int units) of the version-6 import area inside an exchange buffer
     uint32_t launch_tag;         // number of this launch (identical on all ranks)
+    uint32_t depth;              // D, 1..kD
     unsigned *dbg;               // [nCTA][32]: the wait each warp was in when the launch was given up (site | aux << 12 | 0x80000000), zero at launch
 };
 
@@ -198,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t gid = lane >> 2, tig = lane & 3;
-    const uint32_t cta = blockIdx.x, K = p.K;
+    const uint32_t cta = blockIdx.x, K = p.K, D = p.depth;
     const uint32_t NP = SL / 64, NI = SL / 4, NF = NP / 2;
     const uint32_t PWT = PW + kTail, CB = PWT * 4;
     const double NM1 = double(p.n_total - 1), Nt = double(p.n_total);
@@ -429,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             }
             PHASE(kPfCPoll);
             // ---- (2) plan the next block -------------------------------------------------------------------------------------
-            if (!plan_end && s_plan < s_cons + uint32_t(kAhead)) {
+            if (!plan_end && s_plan < s_cons + D + 4u) {
                 const uint32_t s = s_plan;
                 Blk6 &B = sh.blk[s & (kSeq - 1)];
                 const uint32_t rem = p.n_order - pos;
@@ -474,24 +473,24 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                     if (s_cons == d) { action = kActExit; n_take = pend_n; } else can = false;
                 } else {
                     if (restart_pending) { n_take = pend_n; hist_n = 0; }
-                    else if (hist_n == uint32_t(kD + 1)) {
-                        const uint32_t oldest = sh.hist[kD];
+                    else if (hist_n == D + 1u) {
+                        const uint32_t oldest = sh.hist[D];
                         if (s_cons <= oldest) can = false;
                         else {
                             while (n_take < pend_n && sh.pend_seq[n_take] <= oldest) ++n_take;
-                            hist_n = kD;
+                            hist_n = D;
                         }
                     }
                 }
                 if (can) {
                     if (action == kActDot) {
                         restart_pending = false;
-                        for (uint32_t back = 1; back <= uint32_t(kD); ++back) {
+                        for (uint32_t back = 1; back <= D; ++back) {
                             const uint32_t hs = back <= hist_n ? sh.hist[back - 1] : kEnd;
                             if (lane == 0) B.back_seq[back - 1] = hs;
-                            if (hs != kEnd && sh.blk[hs & (kSeq - 1)].nrows) present |= 1u << (kD - back);
+                            if (hs != kEnd && sh.blk[hs & (kSeq - 1)].nrows) present |= 1u << (D - back);
                         }
-                        if (B.nrows) present |= 1u << kD;
+                        if (B.nrows) present |= 1u << D;
                         __syncwarp();
                         if (lane == 0) {
                             for (int h = int(hist_n); h > 0; --h) sh.hist[h] = sh.hist[h - 1];
@@ -658,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 bool bad = false;
                 const uint32_t r = gid;
                 if ((present >> r) & 1u) {
-                    const uint32_t back = kD - r;
+                    const uint32_t back = D - r;
                     const uint32_t hs = back ? B.back_seq[back - 1] : d;
                     if (!mbw(&sh.stash_full[hs % kStashRing], (hs / kStashRing) & 1u)) bad = true;
                     urow = stash + size_t(hs % kStashRing) * RS;
@@ -821,7 +820,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                     for (uint32_t r = 0; r < uint32_t(kGramRows); ++r) {
                         if (!((present >> r) & 1u)) continue;
                         PCOUNT(kPfRowBlocks);
-                        const uint32_t back = kD - r;
+                        const uint32_t back = D - r;
                         const uint32_t hs = back ? B.back_seq[back - 1] : d;
                         if (!mbw(&sh.stash_full[hs % kStashRing], (hs / kStashRing) & 1u)) { bad = true; break; }
                         const uint32_t *rowj = stash + size_t(hs % kStashRing) * RS;
@@ -1137,7 +1136,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             if (present) {
                 for (int r = 0; r < kGramRows; ++r) {
                     if (!((present >> r) & 1u)) continue;
-                    const uint32_t back = kD - r;
+                    const uint32_t back = D - r;
                     const uint32_t hs = back ? B.back_seq[back - 1] : s;
                     const Blk6 &H = sh.blk[hs & (kSeq - 1)];
                     const uint32_t jid = H.row_id;
