@@ -626,7 +626,7 @@ static bool use_v5(const brr_gpu_ctx *c)
 // Version 6 (sweep_dense6.cuh): as version 5 with the walk distributed over the CTAs; preferred over version 5 when it fits.
 static bool use_v6(const brr_gpu_ctx *c)
 {
-    if (!c->v6_ok || c->async_tokens || (c->cfg.world > 1 && !c->attached)) return false;
+    if (!c->v6_ok || c->async_tokens || (c->cfg.world > 1 && !c->attached) || c->cfg.world > v6::kMaxWorld) return false;
     if (c->dense_mode == 6) return true;
     if (c->dense_mode == 4 || c->dense_mode == 5) return false;
     return c->have_last && c->last_nonskipped_frac <= kV5MaxNonskipped;
