@@ -478,6 +478,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 const bool end = rem == 0;
                 if (lane == 0) {
                     B.c = end ? kEnd : next_c; B.pos = pos; B.n = n; B.epoch = epoch; B.nrows = nrows; B.rowk = rowk; B.row_id = row_id;
+                    // (the slot's previous phase -- seq s - kStashRing, long complete -- is observed before the barrier is armed again: nobody
+                    //  waits on the phase of a block without an in-model row, and a barrier re-armed over an unobserved phase is what
+                    //  compute-sanitizer's synccheck calls a missing wait)
+                    if (s >= uint32_t(kStashRing)) while (!mbar_test(&sh.stash_full[slot], ((s / kStashRing) - 1u) & 1u)) { }
                     if (nrows) fence_proxy_async();             // (only with a copy to issue: the fence is a MEMBAR, and this thread paces the CTA)
                     mbar_arrive_expect_tx(&sh.stash_full[slot], nrows * CB);
                     if (nrows) bulk_g2s(stash + size_t(slot) * RS, p.codes + (size_t(row_id) * p.nCTA + cta) * PWT, CB, &sh.stash_full[slot]);
