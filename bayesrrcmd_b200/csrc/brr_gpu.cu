@@ -646,8 +646,10 @@ static int launch_dense6(brr_gpu_ctx *c)
     p.v = c->v; p.betasq = c->betasq; p.out_scalars = c->out_scalars; p.out_counts = c->out_counts;
     p.prof = c->prof6; p.dbg = c->dbg6;
     p.world = c->cfg.world; p.rank = c->cfg.rank; p.peer_xchg = c->peer_ptrs_dev; p.imp_off = xchg_total_ints(c->cfg.world);
-    p.depth = 4u;      // pipeline depth, the same for every world size: which updates reach a dot through the residual and which through a Gram
-                       // correction depends on it, so chains are bit-identical across shardings only at equal depth (2 GPUs: 4, 6, 7 time the same)
+    // Pipeline depth: 4 on one GPU (0.075 s per sweep; 5: 0.078, 7: 0.088), 7 across GPUs, where a walk waits for every peer's sums (8 GPUs: 0.072 s
+    // against 0.086 at depth 4; 2 GPUs: 4, 6, 7 time the same).  Which updates reach a dot through the residual and which through a Gram correction
+    // depends on the depth, so chains of different depths agree to rounding (1e-16 in a residual), not bit for bit; all ranks of one run are identical.
+    p.depth = c->cfg.world > 1 ? 7u : 4u;
     if (const char *e = getenv("BRR_GPU_V6_DEPTH")) { const int d = atoi(e); if (d >= 1 && d <= v6::kD) p.depth = uint32_t(d); }
     p.launch_tag = ++c->v6_launches;                      // (every rank runs the same sequence of sweeps and makes the same kernel choice)
     CUDA_TRY(cudaMemsetAsync(c->dbg6, 0, sizeof(unsigned) * size_t(c->nCTA) * 32, c->stream));

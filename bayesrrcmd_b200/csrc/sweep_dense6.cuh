@@ -41,7 +41,7 @@ using v5::kSlotRing; using v5::kSkip; using v5::kEnd; using v5::kLCnt; using v5:
 using v5::kSlotLines; using v5::kSlotInts5;
 
 constexpr int kD = 7;                       // LARGEST pipeline depth (array sizes).  The depth of a launch, Sweep6Params::depth = D <= kD: the dot pass of a
-                                            // block sees the residual updates of the chain blocks more than D back (4: brr_gpu.cu)
+                                            // block sees the residual updates of the chain blocks more than D back (4 on one GPU, 7 across GPUs: brr_gpu.cu)
 constexpr int kGramRows = kD + 1;           // one in-model row per block: the rows of the last kD blocks and the block's own
 static_assert(kGramRows <= 8, "one N-tile of Gram rows");
 constexpr int kSeq = 32;                    // ring of block descriptors

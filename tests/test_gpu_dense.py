@@ -252,6 +252,16 @@ def test_sharded_individuals_exchange_on_several_devices(world, N, M, p_miss, bl
 
 
 def _sharded_exchange(world, N, M, p_miss, block, tokens, devices):
+    # version 6 runs deeper across GPUs (7 blocks) than on one (4); chains of different depths agree to rounding only, so the unsharded
+    # comparison run is given the sharded depth: at equal depth the sharded chain is BIT-identical (integer cross-shard sums)
+    os.environ["BRR_GPU_V6_DEPTH"] = "7"
+    try:
+        _sharded_exchange_at_depth(world, N, M, p_miss, block, tokens, devices)
+    finally:
+        del os.environ["BRR_GPU_V6_DEPTH"]
+
+
+def _sharded_exchange_at_depth(world, N, M, p_miss, block, tokens, devices):
     O.build()
     pr = _random_problem(N + M + world, N, M, p_miss)
     rng = pr["rng"]
