@@ -2,33 +2,35 @@
 // DISTRIBUTED over the CTAs.
 //
 // One launch = one AnalysisGraph::exec (reference src/sequential.cpp:10-27 driving src/BayesRBase.cpp:287-392 over all
-// markers of the sweep, in the given order), single GPU, synchronous mode.  Same arithmetic as versions 4 / 5 (exact integer
-// dots of the 2-bit codes against 8 int8 limbs of the fixed-point residual on mma.sync.m16n8k32, integer reductions over
-// CTAs, fp64 sampling, Gram counts of the in-model rows riding on the dot pass, restart behind a marker that enters the
-// model), re-organised around what versions 4 / 5 were measured to be bound by (profiles/r2_v5_phase_cycles.txt): every CTA
-// walked every block (read-back of 258 sums + sampling of 64 markers, ~10 k cycles on two warps), and the dot warps
-// themselves published, took the missing sums and waited for the walk.
+// markers of the sweep, in the given order), synchronous mode, one GPU or several (individuals sharded).  Same arithmetic as
+// versions 4 / 5 (exact integer dots of the 2-bit codes against 8 int8 limbs of the fixed-point residual on mma.sync.m16n8k32,
+// integer reductions over CTAs and GPUs, fp64 sampling, Gram counts of the in-model rows riding on the dot pass, restart behind a
+// marker that enters the model), re-organised around what versions 4 / 5 were measured to be bound by
+// (profiles/r2_v5_phase_cycles.txt): every CTA walked every block (read-back of 258 sums + sampling of 64 markers, ~10 k cycles on
+// two warps), and the dot warps themselves published, took the missing sums and waited for the walk.
 //
 //   * The walk of block c is done by ONE CTA, c mod nCTA ("owner").  It reads the block's reduced sums from the block's global
 //     slot, samples, and writes a 128-byte RESULT line (markers final, did one enter the model, the residual update of the
 //     block's in-model row).  Every CTA consumes the result lines in block order -- one line per block instead of 258 sums
 //     and 64 draws.  beta / components / acum are written by the owner once its block is known to be part of the chain.
-//   * Inside a CTA every stage of a block has its own warps and nothing waits for a later stage:
+//   * Inside a CTA every stage of a block has its own warps and nothing waits for a later stage (mbarriers between them):
 //       warp 11      control: plans the blocks (<= 64 consecutive markers, at most ONE in-model marker each: a second one ends the
 //                    block before it), consumes the result lines, decides for every block which residual updates precede its dot
-//                    pass (those of the block kD + 1 blocks back: a fixed lag, so that all CTAs agree) and which stashed in-model
+//                    pass (those of the block D + 1 blocks back: a fixed lag, so that all CTAs agree) and which stashed in-model
 //                    rows ride on it;
-//       warps 12-15  producers (one per 16-marker tile): TMA bulk copies of the code rows into a ring of 8 stages of 16 rows (one warp issues one copy
-//                    per ~100 cycles: profiles/r2_tma_gather_bench.txt);
+//       warps 12-15  producers (one per 16-marker tile): TMA bulk copies of the code rows into a ring of 8 stages of 16 rows (one
+//                    warp issues one copy per ~100 cycles: profiles/r2_tma_gather_bench.txt);
 //       warps 2-9    dot warps: two 16-marker tiles each (one load of the limb fragments feeds both), a quarter of the
-//                    individuals each; partial sums go into a shared-memory accumulator set;
-//                    the sums of q over the rows' missing individuals (from the fp64 residual) and the missing-genotype cross
-//                    counts of the Gram pairs follow, four lanes per row;
-//       warp 10      publisher: combines an accumulator set into 64-bit sums, adds them to the block's global
-//                    slot, arrive at the slot's counter (the release fence is paid here, off the dot warps);
+//                    individuals each; per-warp partial sums by plain stores into an accumulator set; then the sums of q over
+//                    the rows' missing individuals (from the fp64 residual) and the missing-genotype cross counts of the Gram
+//                    pairs, four lanes per row;
+//       warp 10      publisher: sums the k-parts of an accumulator set, combines the limbs into 64-bit sums, adds them to the
+//                    block's global slot, arrives at the slot's counter (the release fence is paid here, off the dot warps);
 //       warps 0-1    walkers: the walk of the blocks this CTA owns.
 //   * The residual lives in shared memory (fp64, item order) next to its int8 limbs: updates are applied by the dot warps at
 //     the block boundary the control warp names.
+//   * Several GPUs: every GPU runs all of the above on its shard; inside the walk the owner pushes the block's locally reduced
+//     sums to every peer (LL cells over NVLink) and adds the peers' -- all GPUs walk every block from identical integers.
 // A sweep that starts from beta = 0 (many markers entering) should use version 4 (brr_gpu.cu chooses per sweep).
 #pragma once
 #include "sweep_dense5.cuh"
@@ -1013,8 +1015,6 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
         // ---- walkers: the walk of the blocks this CTA owns; thread k = marker k of the block ------------------------------------
         const int wk = tid;
         uint32_t nonskipped = 0, nblocks = 0;
-        double bsq_acc = 0.0;   // (unused accumulator slot kept for symmetry with the per-group sums below)
-        (void)bsq_acc;
         for (uint32_t s = 0;; ++s) {
             PMARK();
             // the block's plan, or the end of the sweep

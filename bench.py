@@ -206,7 +206,7 @@ def main():
     grp = ShardGroup(rank, world)
     lo, hi = shard_bounds(N, world)[rank]
     n_loc = hi - lo
-    eng = Engine(n_loc, M, 4, 1, layout="dense", device=local_rank, block_markers=a.block, n_inds_total=N,
+    eng = Engine(n_loc, M, 4, 1, layout="dense", device=local_rank, block_markers=a.block, n_inds_total=N, max_ctas=int(os.environ.get("BRR_BENCH_MAX_CTAS", 0)),
                  rank=rank, world=world)
     info = eng.info()
     t0 = time.time()

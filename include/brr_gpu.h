@@ -232,8 +232,11 @@ int brr_gpu_profile_cycles5(brr_gpu_ctx *ctx, uint64_t *cycles24, int reset);
 int brr_gpu_profile_cycles6(brr_gpu_ctx *ctx, uint64_t *cycles32, int reset);
 /* Which dense kernel the last sweep ran (4 = on-demand Gram rows, 5 = steady-state pipeline, 6 = steady-state pipeline with the
  * walk distributed over the CTAs; 0 = not dense) and, for versions 5 / 6, how often the pipeline restarted behind a marker that
- * entered the model.  The library chooses per sweep (version 6 when the previous sweep of the chain had <= 3% non-skipped
- * markers, version 4 otherwise); the environment variable BRR_GPU_DENSE_KERNEL=v4|v5|v6 forces one. */
+ * entered the model.  The library chooses per sweep: version 6 (one GPU or several) when the sweep is synchronous and the previous
+ * sweep of the chain had <= 3% non-skipped markers, version 4 otherwise (chain start, asynchronous mode).  Environment:
+ * BRR_GPU_DENSE_KERNEL=v4|v5|v6 forces a kernel, BRR_GPU_V6_DEPTH=1..7 the blocks version 6 keeps in flight (default 4 on one GPU,
+ * 7 across GPUs), BRR_GPU_PROFILE=1 enables the phase counters, BRR_GPU_V6_DBG=1 prints where the warps waited after a protocol
+ * time-out (builds with -DBRR_V6_DEBUG). */
 int brr_gpu_last_sweep_info(brr_gpu_ctx *ctx, uint32_t *kernel_version, uint32_t *restarts);
 
 #ifdef __cplusplus
