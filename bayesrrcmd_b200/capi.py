@@ -21,7 +21,7 @@ SYMBOLS = [
     "brr_gpu_sweep", "brr_gpu_sweep_stage", "brr_gpu_sweep_run", "brr_gpu_sweep_fetch", "brr_gpu_compute_num",
     "brr_gpu_apply_delta", "brr_gpu_ipc_export", "brr_gpu_ipc_attach", "brr_gpu_attach_local",
     "brr_gpu_num_blocks", "brr_gpu_stream", "brr_gpu_synth_dense", "brr_gpu_synth_ragged", "brr_gpu_synth_bed_host", "brr_gpu_info",
-    "brr_gpu_launch_count", "brr_gpu_profile_cycles", "brr_gpu_kernel_version", "brr_gpu_profile_cycles5", "brr_gpu_profile_cycles6", "brr_gpu_last_sweep_info",
+    "brr_gpu_launch_count", "brr_gpu_profile_cycles", "brr_gpu_kernel_version", "brr_gpu_profile_cycles5", "brr_gpu_profile_cycles6", "brr_gpu_profile_ctas6", "brr_gpu_last_sweep_info",
 ]
 
 
@@ -93,6 +93,7 @@ def load_library():
     lib.brr_gpu_kernel_version.restype = C.c_char_p
     lib.brr_gpu_profile_cycles5.argtypes = [vp, vp, C.c_int]
     lib.brr_gpu_profile_cycles6.argtypes = [vp, vp, C.c_int]
+    lib.brr_gpu_profile_ctas6.argtypes = [vp, vp, C.c_uint32, vp, C.c_int]
     lib.brr_gpu_last_sweep_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     _lib = lib
     return lib
@@ -306,13 +307,21 @@ class Engine:
 
     PROFILE6 = ["d_dec", "d_apply", "d_full", "d_loop", "d_miss", "d_cross", "d_acc", "pu_wait", "pu_work", "pr_plan", "pr_empty", "pr_issue",
                 "c_poll", "c_plan", "c_decide", "w_cnt", "w_read", "w_pred", "w_sample", "w_fix", "w_valid", "blocks", "walks", "applies", "restarts",
-                "gram_blocks", "row_blocks", "d_pre", "d_fullonly", "d_loopgram"]
+                "gram_blocks", "row_blocks", "d_pre", "d_fullonly", "d_loopgram", "c_iters"]
 
     def profile_cycles6(self, reset=True):
         """Phase cycle counters of the version-6 dense kernel (one warp per role of CTA 0)."""
         a = np.zeros(32, dtype=np.uint64)
         self._check(self.lib.brr_gpu_profile_cycles6(self._h, _ptr(a), int(reset)))
         return dict(zip(self.PROFILE6, (int(x) for x in a)))
+
+    PROFILE6_CTA = ["dec_wait", "update", "rows_wait", "mma_loop", "acc_wait", "store", "blocks", "smid"]
+
+    def profile_ctas6(self, reset=True):
+        """Version-6 dense kernel: the first dot warp's cycles per CTA -> uint64 array [nCTA, 8] (columns: PROFILE6_CTA)."""
+        a = np.zeros((1024, 8), dtype=np.uint64); n = C.c_uint32()
+        self._check(self.lib.brr_gpu_profile_ctas6(self._h, _ptr(a), 1024, C.byref(n), int(reset)))
+        return a[:n.value]
 
     def last_sweep_info(self):
         """-> (dense kernel version of the last sweep: 4 or 5, pipeline restarts of a version-5 sweep)."""

@@ -353,8 +353,8 @@ extern "C" int brr_gpu_create(const brr_gpu_config *cfg, brr_gpu_ctx **out)
             CUDA_OR_DESTROY(cudaMemset(c->prof, 0, sizeof(unsigned long long) * kProfPhases));
             TRY_OR_DESTROY(dev_alloc(&c->prof5, v5::kPfN));
             CUDA_OR_DESTROY(cudaMemset(c->prof5, 0, sizeof(unsigned long long) * v5::kPfN));
-            TRY_OR_DESTROY(dev_alloc(&c->prof6, v6::kPfN));
-            CUDA_OR_DESTROY(cudaMemset(c->prof6, 0, sizeof(unsigned long long) * v6::kPfN));
+            TRY_OR_DESTROY(dev_alloc(&c->prof6, v6::kPfN + size_t(8) * c->nCTA));
+            CUDA_OR_DESTROY(cudaMemset(c->prof6, 0, sizeof(unsigned long long) * (v6::kPfN + size_t(8) * c->nCTA)));
         }
     }
     CUDA_OR_DESTROY(cudaMallocHost(reinterpret_cast<void **>(&c->h_small), sizeof(double) * (2 * kMaxGK + 8 + 2 * kRedBlocks)));
@@ -927,6 +927,19 @@ extern "C" int brr_gpu_profile_cycles6(brr_gpu_ctx *c, uint64_t *cycles32, int r
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaMemcpy(cycles32, c->prof6, sizeof(uint64_t) * v6::kPfN, cudaMemcpyDeviceToHost));
     if (reset) CUDA_TRY(cudaMemset(c->prof6, 0, sizeof(uint64_t) * v6::kPfN));
+    return 0;
+}
+
+extern "C" int brr_gpu_profile_ctas6(brr_gpu_ctx *c, uint64_t *words, uint32_t max_ctas, uint32_t *n_ctas, int reset)
+{
+    CHECK_CTX(c);
+    if (!words || !n_ctas) return fail(BRR_GPU_EINVAL, "null output");
+    if (!c->prof6) return fail(BRR_GPU_ESTATE, "phase profiling is off: set BRR_GPU_PROFILE=1 before brr_gpu_create");
+    const uint32_t n = std::min<uint32_t>(max_ctas, c->nCTA);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(words, c->prof6 + v6::kPfN, sizeof(uint64_t) * 8 * n, cudaMemcpyDeviceToHost));
+    if (reset) CUDA_TRY(cudaMemset(c->prof6 + v6::kPfN, 0, sizeof(uint64_t) * 8 * size_t(c->nCTA)));
+    *n_ctas = n;
     return 0;
 }
 

@@ -12,18 +12,23 @@
 //   * The walk of block c is done by ONE CTA, c mod nCTA ("owner").  It reads the block's reduced sums from the block's global
 //     slot, samples, and writes a 128-byte RESULT line (markers final, did one enter the model, the residual update of the
 //     block's in-model row).  Every CTA consumes the result lines in block order -- one line per block instead of 258 sums
-//     and 64 draws.  beta / components / acum are written by the owner once its block is known to be part of the chain.
+//     and 64 draws.  The head of a line is ONE 16-byte cell, the update with a tag word (block index, markers final, restart
+//     flag) in the upper half of both 8-byte words: a reader has everything in one relaxed load (res_store / res_load below).
+//     beta / components / acum are written by the owner once its block is known to be part of the chain.
 //   * Inside a CTA every stage of a block has its own warps and nothing waits for a later stage (mbarriers between them):
 //       warp 11      control: plans the blocks (<= 64 consecutive markers, at most ONE in-model marker each: a second one ends the
 //                    block before it), consumes the result lines, decides for every block which residual updates precede its dot
 //                    pass (those of the block D + 1 blocks back: a fixed lag, so that all CTAs agree) and which stashed in-model
-//                    rows ride on it;
+//                    rows ride on it.  One pass of its loop: the load of the next result line goes out, one block is planned, one
+//                    decided, then the line is looked at; its two short lists (chain history, pending updates) are spread over
+//                    the lanes;
 //       warps 12-15  producers (one per 16-marker tile): TMA bulk copies of the code rows into a ring of 8 stages of 16 rows (one
-//                    warp issues one copy per ~100 cycles: profiles/r2_tma_gather_bench.txt);
+//                    warp issues one copy per ~100 cycles: profiles/r2_tma_gather_bench.txt); between two issues the TAIL work of
+//                    the block before, beside the dot warps' MMA loops: the sums of q over the rows' missing individuals (from the
+//                    fp64 residual) and the missing-genotype cross counts of the Gram pairs, two lanes per row;
 //       warps 2-9    dot warps: two 16-marker tiles each (one load of the limb fragments feeds both), a quarter of the
-//                    individuals each; per-warp partial sums by plain stores into an accumulator set; then the sums of q over
-//                    the rows' missing individuals (from the fp64 residual) and the missing-genotype cross counts of the Gram
-//                    pairs, four lanes per row;
+//                    individuals each; per-warp partial sums by plain stores into an accumulator set (waited for at the END of
+//                    the pass: the publisher has a whole block's time for the set of two blocks back);
 //       warp 10      publisher: sums the k-parts of an accumulator set, combines the limbs into 64-bit sums, adds them to the
 //                    block's global slot, arrives at the slot's counter (the release fence is paid here, off the dot warps);
 //       warps 0-1    walkers: the walk of the blocks this CTA owns.
@@ -70,7 +75,7 @@ constexpr int kDotThreads = 32 * kDotW;
 enum { kActSkip = 0, kActDot = 1, kActExit = 2 };
 enum { kPfDDec = 0, kPfDApply, kPfDFull, kPfDLoop, kPfDMiss, kPfDCross, kPfDAcc, kPfPuWait, kPfPuWork, kPfPrPlan, kPfPrEmpty, kPfPrIssue,
        kPfCPoll, kPfCPlan, kPfCDecide, kPfWCnt, kPfWRead, kPfWPred, kPfWSample, kPfWFix, kPfWValid, kPfBlocks, kPfWalks, kPfApplies, kPfRestarts,
-       kPfGramBlocks, kPfRowBlocks, kPfDPre, kPfDFullOnly, kPfDLoopGram, kPfN = 32 };
+       kPfGramBlocks, kPfRowBlocks, kPfDPre, kPfDFullOnly, kPfDLoopGram, kPfCIters, kPfN = 32 };
 
 struct Sweep6Params {
     uint32_t n_local, n_total, M, K, nG, nCTA, SL, PW, RS;
@@ -90,7 +95,7 @@ struct Sweep6Params {
     int *part_v;                 // [nCTA][nG*K]
     double *v, *betasq, *out_scalars;
     unsigned *out_counts;        // [0] non-skipped, [1] blocks walked, [2] error flags, [3] restarts (zero at launch)
-    unsigned long long *prof;    // optional [kPfN]
+    unsigned long long *prof;    // optional [kPfN + 8 nCTA]: the role counters of CTA 0, then per CTA the first dot warp's wait / work cycles
     // several GPUs (individuals sharded, world > 1): every GPU runs the whole protocol on its shard; the owner CTA of a block pushes
     // the block's locally reduced sums to every peer's IMPORT area over NVLink and adds what the peers pushed before it walks
     int world, rank;
@@ -164,13 +169,10 @@ struct Shared6 {
     uint32_t valid_tag[kSeq];
     // control words (volatile accesses)
     uint32_t epoch_w, finished, abort, dots_done, arm_cnt[kStages];
-    // control warp's private lists
-    uint32_t pend_slot[kMaxUpd + 4], pend_seq[kMaxUpd + 4]; double pend_dB[kMaxUpd + 4];
-    uint32_t hist[kD + 1];
     unsigned long long wq[kWarps][2], sumq[2];
     double scale, inv_scale, warp_tmp[kWarps];
     // walkers
-    double bcast[2];
+    double bcast[2], w_res;
     uint32_t w_flag[4], w_ctl[4];
     uint32_t n_nonskipped, n_blocks, n_restarts, err;
     unsigned long long prof[kPfN];
@@ -198,6 +200,10 @@ __global__ void inmodel_mask_kernel(const uint32_t *__restrict__ order, uint32_t
     if ((threadIdx.x & 31) == 0 && (p >> 5) < n_words) mask[p >> 5] = b;
 }
 
+// (timing experiments only, never in a shipped build: parts of the pipeline left out to see what the rest costs -- the results are wrong)
+#ifndef BRR_X
+#define BRR_X 0
+#endif
 #ifndef BRR_V6_SUSPEND_NS
 #define BRR_V6_SUSPEND_NS 20000
 #endif
@@ -211,6 +217,52 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)
     return ok != 0u;
 }
 __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// The head of a block's result line: the update dB of its in-model row with the line's tag word in the upper half of BOTH 8-byte words
+// (8-byte accesses are single-copy atomic: a reader that finds the tag in both halves has the whole value, in ONE load).
+//   tag word = (c + 1) mod 2^23 | 1 << 23 (a line is never valid while zero) | n_final << 24 | restart << 31
+__device__ __forceinline__ uint32_t res_tag(uint32_t c) { return ((c + 1u) & 0x7fffffu) | 0x800000u; }
+__device__ __forceinline__ void res_store(int *line, double dB, uint32_t c, uint32_t n_final, bool restart)
+{
+    const unsigned long long v = (unsigned long long)__double_as_longlong(dB);
+    const unsigned long long tw = (unsigned long long)(res_tag(c) | (n_final << 24) | (restart ? 0x80000000u : 0u)) << 32;
+    asm volatile("st.release.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(line), "l"((v & 0xffffffffULL) | tw), "l"((v >> 32) | tw) : "memory");
+}
+// second cell of the line (a restart's "marker that entered the model" update): a plain LL cell, written before the head
+__device__ __forceinline__ void res_store_ne(int *line, double dB, uint32_t c)
+{
+    const unsigned long long v = (unsigned long long)__double_as_longlong(dB);
+    const unsigned long long tw = (unsigned long long)res_tag(c) << 32;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(line + 4), "l"((v & 0xffffffffULL) | tw), "l"((v >> 32) | tw) : "memory");
+}
+__device__ __forceinline__ ulonglong2 res_load(const int *line)
+{
+    ulonglong2 x;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(x.x), "=l"(x.y) : "l"(line) : "memory");
+    return x;
+}
+// (the load is relaxed so that a poll does not hold back the memory operations behind it.  Everything a reader takes from a line is in its
+//  tagged cells; what the release / acquire pair is still needed for is the recycling of the global slots -- a slot is zeroed half a ring,
+//  256 blocks, before its next use -- and for that the control warp makes ONE acquire fence every 64 consumed blocks)
+#ifdef BRR_V6_POLL_ACQUIRE
+__device__ __forceinline__ ulonglong2 res_load_ctrl(const int *line)
+{
+    ulonglong2 x;
+    asm volatile("ld.acquire.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(x.x), "=l"(x.y) : "l"(line) : "memory");
+    return x;
+}
+#else
+__device__ __forceinline__ ulonglong2 res_load_ctrl(const int *line) { return res_load(line); }
+#endif
+#ifndef BRR_V6_IDLE_NS
+#define BRR_V6_IDLE_NS 0
+#endif
+__device__ __forceinline__ void res_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ bool res_valid(const ulonglong2 &x, uint32_t c)
+{
+    const uint32_t tw = uint32_t(x.x >> 32);
+    return tw == uint32_t(x.y >> 32) && (tw & 0xffffffu) == res_tag(c);
+}
+__device__ __forceinline__ double res_dB(const ulonglong2 &x) { return __longlong_as_double((long long)((x.x & 0xffffffffULL) | (x.y << 32))); }
 
 template <bool MG, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6Params p)
@@ -295,10 +347,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
     for (uint32_t i = tid; i < p.nG * K; i += kThreads) p.part_v[size_t(cta) * p.nG * K + i] = 0;
     for (uint32_t i = tid; i < 2 * p.nG; i += kThreads) p.part_bsq[size_t(cta) * 2 * p.nG + i] = 0.0;
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 4); }      // the 4 dot warps of a tile pair release a stage
+        for (int i = 0; i < kStages; ++i) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], 5); }      // the 4 dot warps of a tile pair release a stage
         for (int i = 0; i < kStashRing; ++i) mbar_init(&sh.stash_full[i], 1);
         for (int i = 0; i < kSeq; ++i) { mbar_init(&sh.plan_bar[i], 1); mbar_init(&sh.dec_bar[i], 1); sh.valid_tag[i] = 0; }
-        for (int i = 0; i < kAcc; ++i) { mbar_init(&sh.acc_full[i], kDotW); mbar_init(&sh.acc_empty[i], 1); }
+        for (int i = 0; i < kAcc; ++i) { mbar_init(&sh.acc_full[i], kDotW + kProdW); mbar_init(&sh.acc_empty[i], 1); }
         mbar_init(&sh.ne_full, 1); mbar_init(&sh.apply_done, kDotW);
         mbar_fence_init();
         sh.abort = 0; sh.epoch_w = 0; sh.finished = 0; sh.dots_done = 0;
@@ -389,12 +441,15 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
 
     // =====================================================================================================================
     if (warp == kWCtrl) {
-        // ---- control warp (warp-uniform: every lane carries the same state) ------------------------------------------------
+        // ---- control warp (warp-uniform state; the two short lists are spread over the lanes: lane q holds entry q) ---------------
+        const uint32_t ul = uint32_t(lane);
         uint32_t epoch = 0, pos = 0, next_c = 0;
         uint32_t s_plan = 0, s_cons = 0, s_dec = 0;
         uint32_t pend_n = 0, hist_n = 0, n_restarts = 0;
         bool plan_end = false, restart_pending = false;
         uint32_t ne_user = 0; bool ne_used = false; uint32_t ne_uses = 0;
+        uint32_t hreg = kEnd;                                           // lane h: seq of the chain block h back from the last decided one
+        uint32_t pslot = 0, pseq = 0; double pdB = 0.0;                 // lane q: pending residual update q (in chain order)
         uint32_t idA = 0, idB = 0, mw0 = 0, mw1 = 0, mw2 = 0;           // prefetched inputs of the block at pos
         const uint32_t n_mw = (p.n_order + 31) / 32;
         auto prefetch = [&]() {
@@ -410,54 +465,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             if (ldv(&sh.abort)) break;
             bool progress = false;
             PMARK();
-            // ---- (1) consume the result of the oldest block not yet consumed -------------------------------------------------
+            PCOUNT(kPfCIters);
+            // ---- (0) the load of the oldest unconsumed block's result line goes out first: its trip to L2 is covered by (1) and (2) ----
+            ulonglong2 rx = make_ulonglong2(0ULL, 0ULL);
+            bool polled = false;
             if (s_cons < s_plan) {
-                Blk6 &B = sh.blk[s_cons & (kSeq - 1)];
-                if (B.epoch != epoch) {                             // planned before a restart: no result to wait for
-                    if (ldv(&sh.dots_done) > s_cons) { ++s_cons; progress = true; }
-                } else if (B.c != kEnd) {
-                    const uint32_t c = B.c;
-                    const int *line = p.results + size_t(c % kResRing) * 32;
-                    const unsigned tag = ld_acquire(reinterpret_cast<const unsigned *>(line));
-                    if (tag == c + 1u) {
-                        const uint32_t u = __ldcg(line + 1);
-                        const uint32_t n_final = u & 0xffffu; const bool restart = (u >> 16) & 1u;
-                        const double dB = __ldcg(reinterpret_cast<const double *>(line + 2));
-                        const double ne_dB = __ldcg(reinterpret_cast<const double *>(line + 4));
-                        if (B.nrows && dB != 0.0) {
-                            if (lane == 0) { sh.pend_slot[pend_n] = (s_cons % kStashRing) | (((s_cons / kStashRing) & 1u) << 8); sh.pend_dB[pend_n] = dB; sh.pend_seq[pend_n] = s_cons; }
-                            ++pend_n;
-                        }
-                        if (lane == 0) stv(&sh.valid_tag[s_cons & (kSeq - 1)], s_cons + 1u);
-                        if (restart) {
-                            const uint32_t ne_pos = B.pos + n_final - 1u;
-                            if (ne_dB != 0.0) {                     // the marker that entered the model: fetch its row and value table
-                                const uint32_t ne_id = __ldg(p.order + ne_pos);
-                                if (ne_used) { while (ldv(&sh.dots_done) <= ne_user) { if (spin_fail()) break; } spin_ok(); }
-                                if (lane < 4) sh.rowlut[kNeSlot][lane] = __ldg(p.lut + 4 * size_t(ne_id) + lane);
-                                if (lane == 0) {
-                                    fence_proxy_async();
-                                    mbar_arrive_expect_tx(&sh.ne_full, CB);
-                                    bulk_g2s(stash + size_t(kNeSlot) * RS, p.codes + (size_t(ne_id) * p.nCTA + cta) * PWT, CB, &sh.ne_full);
-                                }
-                                mbw(&sh.ne_full, ne_uses & 1u);
-                                ++ne_uses;
-                                if (lane == 0) { sh.pend_slot[pend_n] = kNeSlot; sh.pend_dB[pend_n] = ne_dB; sh.pend_seq[pend_n] = s_cons; }
-                                ++pend_n;
-                            }
-                            ++epoch; pos = B.pos + n_final; next_c = c + kSkip;
-                            restart_pending = true; plan_end = false; ++n_restarts;
-                            __syncwarp();
-                            if (lane == 0) stv(&sh.epoch_w, epoch);
-                            prefetch();
-                        }
-                        ++s_cons; progress = true;
-                    }
-                }
-                __syncwarp();
+                const Blk6 &B = sh.blk[s_cons & (kSeq - 1)];
+                const uint32_t c = B.c;
+                if (B.epoch == epoch && c != kEnd) { rx = res_load_ctrl(p.results + size_t(c % kResRing) * 32); polled = true; }
             }
-            PHASE(kPfCPoll);
-            // ---- (2) plan the next block -------------------------------------------------------------------------------------
+            // ---- (1) plan the next block -------------------------------------------------------------------------------------
             if (!plan_end && s_plan < s_cons + D + 4u) {
                 const uint32_t s = s_plan;
                 Blk6 &B = sh.blk[s & (kSeq - 1)];
@@ -495,23 +512,25 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 else { pos += n; ++next_c; prefetch(); }
             }
             PHASE(kPfCPlan);
-            // ---- (3) decide the next block for the dot / post / publisher warps --------------------------------------------
+            // ---- (2) decide the next block for the dot / post / publisher warps --------------------------------------------
             if (s_dec < s_plan) {
                 const uint32_t d = s_dec;
                 Blk6 &B = sh.blk[d & (kSeq - 1)];
+                const uint32_t b_epoch = B.epoch, b_c = B.c, b_nrows = B.nrows;
                 uint32_t action = kActDot, n_take = 0, present = 0;
                 bool can = true;
-                if (B.epoch != epoch) {
+                if (b_epoch != epoch) {
                     action = kActSkip;
-                } else if (B.c == kEnd) {
+                } else if (b_c == kEnd) {
                     if (s_cons == d) { action = kActExit; n_take = pend_n; } else can = false;
                 } else {
                     if (restart_pending) { n_take = pend_n; hist_n = 0; }
                     else if (hist_n == D + 1u) {
-                        const uint32_t oldest = sh.hist[D];
+                        const uint32_t oldest = __shfl_sync(0xffffffffu, hreg, int(D));
                         if (s_cons <= oldest) can = false;
-                        else {
-                            while (n_take < pend_n && sh.pend_seq[n_take] <= oldest) ++n_take;
+                        else {                                      // the updates of the blocks up to the one that leaves the window
+                            const uint32_t due = __ballot_sync(0xffffffffu, ul < pend_n && pseq <= oldest);
+                            n_take = uint32_t(__ffs(int(~due))) - 1u;
                             hist_n = D;
                         }
                     }
@@ -519,30 +538,27 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 if (can) {
                     if (action == kActDot) {
                         restart_pending = false;
-                        for (uint32_t back = 1; back <= D; ++back) {
-                            const uint32_t hs = back <= hist_n ? sh.hist[back - 1] : kEnd;
-                            if (lane == 0) B.back_seq[back - 1] = hs;
-                            if (hs != kEnd && sh.blk[hs & (kSeq - 1)].nrows) present |= 1u << (D - back);
-                        }
-                        if (B.nrows) present |= 1u << D;
-                        __syncwarp();
-                        if (lane == 0) {
-                            for (int h = int(hist_n); h > 0; --h) sh.hist[h] = sh.hist[h - 1];
-                            sh.hist[0] = d;
-                        }
+                        // lane b = the chain block b back: its seq, and whether it has an in-model row (bit D - b of `present`)
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, hreg, 1);
+                        const bool is_back = ul >= 1u && ul <= D;
+                        const uint32_t hs = (is_back && ul <= hist_n) ? up : kEnd;
+                        if (is_back) B.back_seq[ul - 1u] = hs;
+                        const bool has_row = hs != kEnd && sh.blk[hs & (kSeq - 1)].nrows != 0u;
+                        const uint32_t rows = __ballot_sync(0xffffffffu, has_row);
+                        present = (__brev(rows) >> (31u - D)) & ((1u << D) - 1u);
+                        if (b_nrows) present |= 1u << D;
+                        hreg = ul == 0u ? d : up;                   // (entries beyond hist_n are never read)
                         ++hist_n;
                     }
-                    if (lane == 0) {
-                        for (uint32_t q = 0; q < n_take; ++q) { B.upd_slot[q] = sh.pend_slot[q]; B.upd_dB[q] = sh.pend_dB[q]; }
-                        for (uint32_t q = n_take; q < pend_n; ++q) {
-                            sh.pend_slot[q - n_take] = sh.pend_slot[q]; sh.pend_dB[q - n_take] = sh.pend_dB[q]; sh.pend_seq[q - n_take] = sh.pend_seq[q];
-                        }
-                        B.action = action; B.present = present; B.n_upd = n_take;
+                    if (ul < n_take) { B.upd_slot[ul] = pslot; B.upd_dB[ul] = pdB; }
+                    if (__ballot_sync(0xffffffffu, ul < n_take && pslot == uint32_t(kNeSlot))) { ne_user = d; ne_used = true; }
+                    if (n_take) {
+                        pslot = __shfl_down_sync(0xffffffffu, pslot, n_take); pseq = __shfl_down_sync(0xffffffffu, pseq, n_take);
+                        pdB = __shfl_down_sync(0xffffffffu, pdB, n_take);
+                        pend_n -= n_take;
                     }
-                    pend_n -= n_take;
+                    if (lane == 0) { B.action = action; B.present = present; B.n_upd = n_take; }
                     __syncwarp();
-                    for (uint32_t q = 0; q < n_take; ++q)
-                        if (B.upd_slot[q] == uint32_t(kNeSlot)) { ne_user = d; ne_used = true; }
                     if (lane == 0) mbar_arrive(&sh.dec_bar[d & (kSeq - 1)]);
                     ++s_dec; progress = true;
                     if (action == kActExit) {
@@ -552,73 +568,233 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 }
             }
             PHASE(kPfCDecide);
+            // ---- (3) consume the result of the oldest block not yet consumed -------------------------------------------------
+            if (s_cons < s_plan) {
+                Blk6 &B = sh.blk[s_cons & (kSeq - 1)];
+                if (B.epoch != epoch) {                             // planned before a restart: no result to wait for
+                    if (ldv(&sh.dots_done) > s_cons) { ++s_cons; progress = true; }
+                } else if (polled && res_valid(rx, B.c)) {
+                    if ((s_cons & 63u) == 63u) res_acquire();
+                    const uint32_t c = B.c;
+                    const int *line = p.results + size_t(c % kResRing) * 32;
+                    const uint32_t tw = uint32_t(rx.x >> 32);
+                    const uint32_t n_final = (tw >> 24) & 0x7fu; const bool restart = (tw >> 31) != 0u;
+                    const double dB = res_dB(rx);
+                    if (B.nrows && dB != 0.0) {
+                        if (ul == pend_n) { pslot = (s_cons % kStashRing) | (((s_cons / kStashRing) & 1u) << 8); pdB = dB; pseq = s_cons; }
+                        ++pend_n;
+                    }
+                    if (lane == 0) stv(&sh.valid_tag[s_cons & (kSeq - 1)], s_cons + 1u);
+                    if (restart) {
+                        const uint32_t ne_pos = B.pos + n_final - 1u;
+                        ulonglong2 nx;
+                        while (!res_valid(nx = res_load(line + 4), c)) { if (spin_fail()) break; }
+                        spin_ok();
+                        const double ne_dB = res_dB(nx);
+                        if (ne_dB != 0.0) {                         // the marker that entered the model: fetch its row and value table
+                            const uint32_t ne_id = __ldg(p.order + ne_pos);
+                            if (ne_used) { while (ldv(&sh.dots_done) <= ne_user) { if (spin_fail()) break; } spin_ok(); }
+                            if (lane < 4) sh.rowlut[kNeSlot][lane] = __ldg(p.lut + 4 * size_t(ne_id) + lane);
+                            if (lane == 0) {
+                                fence_proxy_async();
+                                mbar_arrive_expect_tx(&sh.ne_full, CB);
+                                bulk_g2s(stash + size_t(kNeSlot) * RS, p.codes + (size_t(ne_id) * p.nCTA + cta) * PWT, CB, &sh.ne_full);
+                            }
+                            mbw(&sh.ne_full, ne_uses & 1u);
+                            ++ne_uses;
+                            if (ul == pend_n) { pslot = kNeSlot; pdB = ne_dB; pseq = s_cons; }
+                            ++pend_n;
+                        }
+                        ++epoch; pos = B.pos + n_final; next_c = c + kSkip;
+                        restart_pending = true; plan_end = false; ++n_restarts;
+                        __syncwarp();
+                        if (lane == 0) stv(&sh.epoch_w, epoch);
+                        prefetch();
+                    }
+                    ++s_cons; progress = true;
+                }
+                __syncwarp();
+            }
+            PHASE(kPfCPoll);
             BRR_SITE(210 + (s_cons < s_plan ? 1u : 0u) + (s_dec < s_plan ? 2u : 0u) + (plan_end ? 4u : 0u)); BRR_AUX(s_cons | (s_dec << 10));
-            if (progress) spin_ok(); else if (spin_fail()) break;
+            if (progress) spin_ok();
+            else {
+                if (spin_fail()) break;
+                if (BRR_V6_IDLE_NS) __nanosleep(BRR_V6_IDLE_NS);     // (an idle pass: leave the issue slots and the result lines to the others)
+            }
         }
     } else if (warp >= kWProd0) {
         // ---- producers: producer t takes tile t of every block: stage q = 4 s + t -> ring entry q % 8, i.e. entries t and t + 4 in turn.
         //      The waits on an entry's empty barrier are thus in ONE warp's program order (a parity wait may be at most one phase ahead of
         //      its barrier; with the stages dealt round-robin to three producers this held only because tile pairs are released together and
         //      in block order -- BRR_V6_DEBUG builds check it through sh.arm_cnt) ----
-        const uint32_t pw = uint32_t(warp - kWProd0);
-        for (uint32_t q = pw;; q += kProdW) {
-            const uint32_t s = q >> 2, t = q & 3u, st = q & (kStages - 1);
-            PMARK();
-            BRR_AUX(s);
-            bool ok = true;
-            BRR_SITE(220);
-            for (;;) {                                              // the block's plan (or the end of the sweep)
-                if (mbar_test(&sh.plan_bar[s & (kSeq - 1)], (s / kSeq) & 1u)) break;
-                if (ldv(&sh.finished) || spin_fail()) { ok = false; break; }
-            }
-            spin_ok();
-            if (!ok) break;
-            PHASE(kPfPrPlan);
-            const Blk6 &B = sh.blk[s & (kSeq - 1)];
-            const uint32_t n = B.n;
-            const uint32_t nt = n > 16 * t ? min(16u, n - 16 * t) : 0u;
-            const uint32_t id = sh.ids[s & (kIdRing - 1)][16 * t + (lane & 15)];
-            if (q >= uint32_t(kStages)) {
-#ifdef BRR_V6_DEBUG
-                BRR_SITE(222);
-                while (ldv(&sh.arm_cnt[st]) != (q >> 3)) { if (ldv(&sh.finished) || spin_fail()) { ok = false; break; } }
-                spin_ok();
-                if (!ok) break;
-#endif
-                BRR_SITE(221);
-                for (;;) {
-                    if (mbar_test(&sh.empty[st], ((q >> 3) - 1u) & 1u)) break;
+        //      Between two issues the producer does the TAIL work of the block before: the sums of q over the missing individuals of its tile's
+        //      rows (q from the fp64 residual: the same rounding as the limbs, one load instead of eight), two lanes per row, and, in blocks that
+        //      carry Gram rows, the missing-genotype cross counts of the (stashed row, this row) pairs -- beside the dot warps' MMA loops. ----
+        const uint32_t pw = uint32_t(warp - kWProd0);         // tile of this producer
+        uint32_t n_apply = 0;
+        auto q_of = [&](uint32_t i) -> long long { return __double2ll_rn(e_s[16 * (i >> 4) + 4 * (i & 3u) + ((i >> 2) & 3u)] * scale); };
+        bool running = true;
+        for (uint32_t s = 0; running; ++s) {
+            // ---- issue: tile pw of block s ----
+            {
+                const uint32_t q = 4 * s + pw, st = q & (kStages - 1);
+                PMARK();
+                BRR_AUX(s);
+                bool ok = true;
+                BRR_SITE(220);
+                for (;;) {                                          // the block's plan (or the end of the sweep)
+                    if (mbar_test(&sh.plan_bar[s & (kSeq - 1)], (s / kSeq) & 1u)) break;
                     if (ldv(&sh.finished) || spin_fail()) { ok = false; break; }
                 }
                 spin_ok();
                 if (!ok) break;
+                PHASE(kPfPrPlan);
+                const Blk6 &B = sh.blk[s & (kSeq - 1)];
+                const uint32_t n = B.n;
+                const uint32_t nt = (BRR_X & 8) ? 0u : (n > 16 * pw ? min(16u, n - 16 * pw) : 0u);
+                const uint32_t id = sh.ids[s & (kIdRing - 1)][16 * pw + (lane & 15)];
+                if (q >= uint32_t(kStages)) {
+                    BRR_SITE(221);
+                    for (;;) {
+                        if (mbar_test(&sh.empty[st], ((q >> 3) - 1u) & 1u)) break;
+                        if (ldv(&sh.finished) || spin_fail()) { ok = false; break; }
+                    }
+                    spin_ok();
+                    if (!ok) break;
+                }
+                PHASE(kPfPrEmpty);
+                // (no fence.proxy.async here: the entry's last readers released it through the mbarrier, which orders their generic-proxy
+                //  reads before these async-proxy writes)
+                if (lane == 0) mbar_arrive_expect_tx(&sh.full[st], nt * CB);
+                __syncwarp();
+                if (uint32_t(lane) < nt)
+                    bulk_g2s(stages + (size_t(st) * kTileRows + lane) * RS, p.codes + (size_t(id) * p.nCTA + cta) * PWT, CB, &sh.full[st]);
+                PHASE(kPfPrIssue);
             }
+            if (s == 0) continue;
+            // ---- tail work of block d = s - 1, tile pw ----
+            const uint32_t d = s - 1;
+            BRR_AUX(d);
+            if (!mbw(&sh.dec_bar[d & (kSeq - 1)], (d / kSeq) & 1u)) break;
+            const Blk6 &B = sh.blk[d & (kSeq - 1)];
+            const uint32_t action = B.action;
+            if (action == kActExit) break;
+            if (B.n_upd) { if (!mbw(&sh.apply_done, n_apply & 1u)) break; ++n_apply; }      // the residual this block's dot pass sees
+            const uint32_t st = (4 * d + pw) & (kStages - 1);
+            if (!mbw(&sh.full[st], (d >> 1) & 1u)) break;
             PHASE(kPfPrEmpty);
-            // (no fence.proxy.async here: the entry's last readers released it through the mbarrier, which orders their generic-proxy
-            //  reads before these async-proxy writes; the fence cost the producers ~a third of the kernel's stall samples as MEMBAR)
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&sh.full[st], nt * CB);
-#ifdef BRR_V6_DEBUG
-                stv(&sh.arm_cnt[st], (q >> 3) + 1u);
-#endif
+            if (action == kActDot && !(BRR_X & 2)) {
+                const uint32_t n = B.n, present = B.present;
+                const uint32_t *pk = stages + size_t(st) * kTileRows * RS;
+                int *slot = p.slots + size_t(B.c % kSlotRing) * kSlotInts5;
+                const uint32_t rr = lane >> 1, e2 = lane & 1u, m = 16 * pw + rr;
+                const uint32_t *rowa = pk + size_t(rr) * RS;
+                const uint16_t *tla = reinterpret_cast<const uint16_t *>(rowa + PW);
+                uint32_t cntm = 0;
+                long long qh = 0; unsigned long long ql = 0;
+                if (m < n) {
+                    cntm = tla[0];
+                    if (cntm <= 15u) {
+#pragma unroll 1
+                        for (uint32_t en = e2; en < cntm; en += 2) { const long long q = q_of(tla[1 + en]); qh += q >> 32; ql += (unsigned long long)(q & 0xffffffffLL); }
+                    } else {                                   // a long list: the two lanes scan the row's words
+#pragma unroll 1
+                        for (uint32_t w = e2; w < PW; w += 2) {
+                            const uint32_t x = rowa[w];
+                            uint32_t mm = x & (x >> 1) & 0x55555555u;
+                            while (mm) {
+                                const int bit = __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                const long long q = q_of(16 * w + (bit >> 1)); qh += q >> 32; ql += (unsigned long long)(q & 0xffffffffLL);
+                            }
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, cntm != 0u)) {
+                    qh += __shfl_xor_sync(0xffffffffu, qh, 1);
+                    ql += __shfl_xor_sync(0xffffffffu, ql, 1);
+                    if (e2 == 0 && m < n && cntm) {
+                        if (qh) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLSm + 2 * m) * kLine), (unsigned long long)qh);
+                        if (ql) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLSm + 2 * m + 1) * kLine), ql);
+                    }
+                }
+                PHASE(kPfDMiss);
+                if (present) {
+                    bool bad = false;
+                    for (uint32_t r = 0; r < uint32_t(kGramRows); ++r) {
+                        if (!((present >> r) & 1u)) continue;
+                        if (pw == 0) PCOUNT(kPfRowBlocks);
+                        const uint32_t back = D - r;
+                        const uint32_t hs = back ? B.back_seq[back - 1] : d;
+                        if (!mbw(&sh.stash_full[hs % kStashRing], (hs / kStashRing) & 1u)) { bad = true; break; }
+                        const uint32_t *rowj = stash + size_t(hs % kStashRing) * RS;
+                        const uint16_t *tlj = reinterpret_cast<const uint16_t *>(rowj + PW);
+                        const uint32_t cntj = tlj[0];
+                        const bool pair = m < n && !(back == 0u && B.rowk == m);            // (the row against itself: not needed)
+                        uint32_t z = 0, wv = 0, y = 0;
+                        if (pair) {
+                            if (cntj <= 15u && cntm <= 15u) {
+                                for (uint32_t en = e2; en < cntj; en += 2) {
+                                    const uint32_t ii = tlj[1 + en];
+                                    const uint32_t cc = (rowa[ii >> 4] >> (2 * (ii & 15u))) & 3u;
+                                    if (cc == 3u) ++wv; else z += cc;
+                                }
+                                for (uint32_t en = e2; en < cntm; en += 2) {
+                                    const uint32_t ii = tla[1 + en];
+                                    const uint32_t cc = (rowj[ii >> 4] >> (2 * (ii & 15u))) & 3u;
+                                    if (cc != 3u) y += cc;
+                                }
+                            } else if (cntj | cntm) {
+                                for (uint32_t w = e2; w < PW; w += 2) {
+                                    const uint32_t xj = rowj[w], xa = rowa[w];
+                                    const uint32_t mj = xj & (xj >> 1) & 0x55555555u, ma = xa & (xa >> 1) & 0x55555555u;
+                                    uint32_t mm = mj | ma;
+                                    while (mm) {
+                                        const int bit = __ffs(mm) - 1;
+                                        mm &= mm - 1;
+                                        const uint32_t cj2 = (xj >> bit) & 3u, ca2 = (xa >> bit) & 3u;
+                                        if (cj2 == 3u) { if (ca2 == 3u) ++wv; else z += ca2; }
+                                        else y += cj2;                               // column missing, row present
+                                    }
+                                }
+                            }
+                        }
+                        unsigned long long pk3 = (unsigned long long)wv | ((unsigned long long)y << 20) | ((unsigned long long)z << 40);
+                        pk3 += __shfl_xor_sync(0xffffffffu, pk3, 1);
+                        if (e2 == 0 && pair && pk3) {
+                            const unsigned long long wv4 = pk3 & 0xfffffULL, y4 = (pk3 >> 20) & 0xfffffULL, z4 = pk3 >> 40;
+                            unsigned long long *ln = reinterpret_cast<unsigned long long *>(slot + size_t(kLGram + r * kB + m) * kLine);
+                            if (wv4) atomicAdd(ln, wv4 << 32);
+                            if (y4 | z4) atomicAdd(ln + 1, y4 | (z4 << 32));
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, bad)) break;
+                }
             }
             __syncwarp();
-            if (uint32_t(lane) < nt)
-                bulk_g2s(stages + (size_t(st) * kTileRows + lane) * RS, p.codes + (size_t(id) * p.nCTA + cta) * PWT, CB, &sh.full[st]);
-            PHASE(kPfPrIssue);
+            if (lane == 0) mbar_arrive(&sh.empty[st]);
+            // (this warp arrives at acc_full: the phase of the set's previous block must be over, as for the dot warps)
+            if (d >= uint32_t(kAcc) && !mbw(&sh.acc_empty[d % kAcc], ((d / kAcc) - 1u) & 1u)) break;
+            if (lane == 0) mbar_arrive(&sh.acc_full[d % kAcc]);
+            PHASE(kPfDCross);
         }
     } else if (is_dot) {
         // ---- dot warps: tiles 2 tp, 2 tp + 1 of every block; the 128-individual chunks kp, kp + 4, ... --------------------------------
         const uint32_t tp = dw >> 2, kp = dw & 3u;
         uint32_t n_apply = 0;
+        // (profiling builds: where the first dot warp of EVERY CTA spends its cycles -- the CTAs wait for each other through the results)
+        const bool cta_prof = PROF && p.prof != nullptr && dw == 0 && lane == 0;
+        long long ct[6] = {0, 0, 0, 0, 0, 0}, ct_prev = 0; uint32_t ct_blocks = 0;
+        auto CT = [&](int k) { if (PROF && cta_prof) { const long long t = clock64(); ct[k] += t - ct_prev; ct_prev = t; } };
         for (uint32_t d = 0;; ++d) {
             PMARK();
             BRR_AUX(d);
+            if (PROF && cta_prof) ct_prev = clock64();
             if (!mbw(&sh.dec_bar[d & (kSeq - 1)], (d / kSeq) & 1u)) break;
+            CT(0);
             const Blk6 &B = sh.blk[d & (kSeq - 1)];
             const uint32_t action = B.action, n_upd = B.n_upd;
-            // the block's accumulator set (released by the publisher kAcc blocks ago): the change of sum q of an update goes there too
-            if (d >= uint32_t(kAcc) && !mbw(&sh.acc_empty[d % kAcc], ((d / kAcc) - 1u) & 1u)) break;
             PHASE(kPfDDec);
             if (n_upd) {
                 // ---- residual update (src/BayesRBase.cpp:375-378 for every update not yet applied, in chain order) ----
@@ -669,17 +845,23 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 PHASE(kPfDApply);
             }
             if (action == kActExit) break;
-            if (dw == 0 && lane < 2)        // sum q as this block's dot pass sees it (no update touches it before every dot warp has arrived at acc_full)
-                *(reinterpret_cast<unsigned long long *>(accs + size_t(d % kAcc) * kAccInts + kAccSumQ) + lane) = sh.sumq[lane];
+            // sum q as this block's dot pass sees it (no update touches it before every dot warp has arrived at acc_full): kept until the
+            // block's accumulator set is free (below)
+            unsigned long long sq_snap = 0;
+            if (dw == 0 && lane < 2) sq_snap = sh.sumq[lane];
             const uint32_t st0 = (4 * d + 2 * tp) & (kStages - 1);
             const uint32_t *pk = stages + size_t(st0) * kTileRows * RS;      // 32 rows: the two tiles are neighbours in the ring
             PHASE(kPfDPre);
+            CT(1);
             if (!mbw(&sh.full[st0], (d >> 1) & 1u)) break;
             if (!mbw(&sh.full[st0 + 1], (d >> 1) & 1u)) break;
+            CT(2);
             PHASE(kPfDFullOnly);
             if (action == kActSkip) {
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&sh.empty[st0]); mbar_arrive(&sh.empty[st0 + 1]); mbar_arrive(&sh.acc_full[d % kAcc]); }
+                if (lane == 0) { mbar_arrive(&sh.empty[st0]); mbar_arrive(&sh.empty[st0 + 1]); }
+                if (d >= uint32_t(kAcc) && !mbw(&sh.acc_empty[d % kAcc], ((d / kAcc) - 1u) & 1u)) break;
+                if (lane == 0) mbar_arrive(&sh.acc_full[d % kAcc]);
                 continue;
             }
             const uint32_t n = B.n, present = B.present;
@@ -708,7 +890,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[tl][cc][q] = 0;
             int gacc[2][4][4];
-            if (any) {
+            if (any && !(BRR_X & 1)) {
                 const uint32_t lo = gid * RS + tig;
                 uint32_t aR = smem_u32(pk + lo + 8 * kp);
                 const uint32_t dR8 = 32u * RS, dR16 = 64u * RS, dR24 = 96u * RS;       // byte offsets of rows + 8, + 16, + 24
@@ -792,127 +974,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                 }
             }
             if (present) { PHASE(kPfDLoopGram); } else { PHASE(kPfDLoop); }
-            bool early = false;
-            // ---- sums of q over the missing individuals of the pair's rows: 4 lanes per row, 8 rows per warp.  q is taken from the fp64
-            //      residual (the same rounding as the limbs: one load instead of eight) ----
-            {
-                const uint32_t rr = 8 * kp + (lane >> 2), e4 = lane & 3u, m = 32 * tp + rr;
-                uint32_t cntm = 0;
-                long long qh = 0; unsigned long long ql = 0;
-                auto q_of = [&](uint32_t i) -> long long { return __double2ll_rn(e_s[16 * (i >> 4) + 4 * (i & 3u) + ((i >> 2) & 3u)] * scale); };
-                // this lane's share of the row's list (entries e4, e4 + 4, ...) goes to registers first: with it, a block without Gram rows
-                // needs the code rows no longer, and the stages go back to the producers before the look-ups
-                const uint32_t *row = pk + size_t(rr) * RS;
-                const uint16_t *tail = reinterpret_cast<const uint16_t *>(row + PW);
-                uint32_t idv[4] = {0u, 0u, 0u, 0u};
-                if (m < n) {
-                    cntm = tail[0];
-                    if (cntm <= 15u) {
-#pragma unroll
-                        for (uint32_t k4 = 0; k4 < 4; ++k4) if (e4 + 4 * k4 < cntm) idv[k4] = tail[1 + e4 + 4 * k4];
-                    }
-                }
-                early = !present && __all_sync(0xffffffffu, cntm <= 15u);
-                if (early) {
-                    __syncwarp();
-                    if (lane == 0) { mbar_arrive(&sh.empty[st0]); mbar_arrive(&sh.empty[st0 + 1]); }
-                }
-                if (m < n) {
-                    if (cntm <= 15u) {
-#pragma unroll
-                        for (uint32_t k4 = 0; k4 < 4; ++k4)
-                            if (e4 + 4 * k4 < cntm) { const long long q = q_of(idv[k4]); qh += q >> 32; ql += (unsigned long long)(q & 0xffffffffLL); }
-                    } else {                                   // a long list: the four lanes scan the row's words
-#pragma unroll 1
-                        for (uint32_t w = e4; w < PW; w += 4) {
-                            const uint32_t x = row[w];
-                            uint32_t mm = x & (x >> 1) & 0x55555555u;
-                            while (mm) {
-                                const int bit = __ffs(mm) - 1;
-                                mm &= mm - 1;
-                                const long long q = q_of(16 * w + (bit >> 1)); qh += q >> 32; ql += (unsigned long long)(q & 0xffffffffLL);
-                            }
-                        }
-                    }
-                }
-                if (__any_sync(0xffffffffu, cntm != 0u)) {
-#pragma unroll
-                    for (int o2 = 1; o2 < 4; o2 <<= 1) {
-                        qh += __shfl_xor_sync(0xffffffffu, qh, o2);
-                        ql += __shfl_xor_sync(0xffffffffu, ql, o2);
-                    }
-                    if (e4 == 0 && m < n && cntm) {
-                        int *slot = p.slots + size_t(B.c % kSlotRing) * kSlotInts5;
-                        if (qh) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLSm + 2 * m) * kLine), (unsigned long long)qh);
-                        if (ql) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLSm + 2 * m + 1) * kLine), ql);
-                    }
-                }
-                PHASE(kPfDMiss);
-                // ---- missing-genotype cross counts of the (stashed row, this row) pairs: the row's four lanes share both lists ----
-                if (present) {
-                    bool bad = false;
-                    for (uint32_t r = 0; r < uint32_t(kGramRows); ++r) {
-                        if (!((present >> r) & 1u)) continue;
-                        PCOUNT(kPfRowBlocks);
-                        const uint32_t back = D - r;
-                        const uint32_t hs = back ? B.back_seq[back - 1] : d;
-                        if (!mbw(&sh.stash_full[hs % kStashRing], (hs / kStashRing) & 1u)) { bad = true; break; }
-                        const uint32_t *rowj = stash + size_t(hs % kStashRing) * RS;
-                        const uint16_t *tlj = reinterpret_cast<const uint16_t *>(rowj + PW);
-                        const uint32_t cntj = tlj[0];
-                        const bool pair = m < n && !(back == 0u && B.rowk == m);            // (the row against itself: not needed)
-                        uint32_t z = 0, wv = 0, y = 0;
-                        if (pair) {
-                            const uint32_t *rowa = pk + size_t(rr) * RS;
-                            if (cntj <= 15u && cntm <= 15u) {
-                                // (all look-ups of a lane issued together: its share of the row's list, then this row's list from idv)
-                                uint32_t idj[4], wj[4], wa[4];
-#pragma unroll
-                                for (uint32_t k4 = 0; k4 < 4; ++k4) idj[k4] = e4 + 4 * k4 < cntj ? tlj[1 + e4 + 4 * k4] : 0u;
-#pragma unroll
-                                for (uint32_t k4 = 0; k4 < 4; ++k4) {
-                                    wa[k4] = e4 + 4 * k4 < cntj ? rowa[idj[k4] >> 4] : 0u;
-                                    wj[k4] = e4 + 4 * k4 < cntm ? rowj[idv[k4] >> 4] : 0u;
-                                }
-#pragma unroll
-                                for (uint32_t k4 = 0; k4 < 4; ++k4) {
-                                    if (e4 + 4 * k4 < cntj) { const uint32_t cc = (wa[k4] >> (2 * (idj[k4] & 15u))) & 3u; if (cc == 3u) ++wv; else z += cc; }
-                                    if (e4 + 4 * k4 < cntm) { const uint32_t cc = (wj[k4] >> (2 * (idv[k4] & 15u))) & 3u; if (cc != 3u) y += cc; }
-                                }
-                            } else if (cntj | cntm) {
-                                for (uint32_t w = e4; w < PW; w += 4) {
-                                    const uint32_t xj = rowj[w], xa = rowa[w];
-                                    const uint32_t mj = xj & (xj >> 1) & 0x55555555u, ma = xa & (xa >> 1) & 0x55555555u;
-                                    uint32_t mm = mj | ma;
-                                    while (mm) {
-                                        const int bit = __ffs(mm) - 1;
-                                        mm &= mm - 1;
-                                        const uint32_t cj2 = (xj >> bit) & 3u, ca2 = (xa >> bit) & 3u;
-                                        if (cj2 == 3u) { if (ca2 == 3u) ++wv; else z += ca2; }
-                                        else y += cj2;                               // column missing, row present
-                                    }
-                                }
-                            }
-                        }
-                        unsigned long long pk3 = (unsigned long long)wv | ((unsigned long long)y << 20) | ((unsigned long long)z << 40);
-                        pk3 += __shfl_xor_sync(0xffffffffu, pk3, 1);
-                        pk3 += __shfl_xor_sync(0xffffffffu, pk3, 2);
-                        if (e4 == 0 && pair && pk3) {
-                            const unsigned long long wv4 = pk3 & 0xfffffULL, y4 = (pk3 >> 20) & 0xfffffULL, z4 = pk3 >> 40;
-                            int *slot = p.slots + size_t(B.c % kSlotRing) * kSlotInts5;
-                            unsigned long long *ln = reinterpret_cast<unsigned long long *>(slot + size_t(kLGram + r * kB + m) * kLine);
-                            if (wv4) atomicAdd(ln, wv4 << 32);
-                            if (y4 | z4) atomicAdd(ln + 1, y4 | (z4 << 32));
-                        }
-                    }
-                    if (__any_sync(0xffffffffu, bad)) break;
-                }
-            }
-            // the rows are no longer needed by this warp
+            CT(3);
+            // the rows are no longer needed by this warp (the tile's producer takes the missing sums / cross counts from them, beside this loop)
             __syncwarp();
-            if (!early && lane == 0) { mbar_arrive(&sh.empty[st0]); mbar_arrive(&sh.empty[st0 + 1]); }
-            PHASE(kPfDCross);
-            // ---- partial sums into the block's accumulator set ----
+            if (lane == 0) { mbar_arrive(&sh.empty[st0]); mbar_arrive(&sh.empty[st0 + 1]); }
+
+            // ---- partial sums into the block's accumulator set: released by the publisher kAcc blocks ago (waited for HERE, not at the top of
+            //      the block: the publisher has the whole dot pass of the next block to get through its REDs) ----
+            if (d >= uint32_t(kAcc) && !mbw(&sh.acc_empty[d % kAcc], ((d / kAcc) - 1u) & 1u)) break;
+            CT(4);
+            if (dw == 0 && lane < 2) *(reinterpret_cast<unsigned long long *>(accs + size_t(d % kAcc) * kAccInts + kAccSumQ) + lane) = sq_snap;
             {
                 int *aset = accs + size_t(d % kAcc) * kAccInts;
                 int *wacc = aset + dw * 256;
@@ -932,6 +1003,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.acc_full[d % kAcc]);
             PHASE(kPfDAcc);
+            CT(5); ++ct_blocks;
+        }
+        if (PROF && cta_prof) {
+            unsigned long long *o = p.prof + kPfN + size_t(cta) * 8;
+            for (int k = 0; k < 6; ++k) o[k] += (unsigned long long)ct[k];
+            o[6] += ct_blocks;
+            unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            o[7] = smid;
         }
     } else if (warp >= kWPub && warp < kWPub + kPubW) {
         // ---- publishers (two, alternating blocks): accumulator set -> the block's global slot, arrive at its counter; recycling of the global slots ----
@@ -975,7 +1054,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
 #pragma unroll
                         for (int kp2 = 0; kp2 < 4; ++kp2) { l0 += pv[rep][kp2][0].x; l2 += pv[rep][kp2][0].y; l1 += pv[rep][kp2][1].x; l3 += pv[rep][kp2][1].y; }
                         const long long v = (long long)l0 + (long long)l1 * 256LL + (long long)l2 * 65536LL + (long long)l3 * 16777216LL;
-                        if (v && m < n) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLDots + 2 * m + h) * kLine), (unsigned long long)v);
+                        if (v && m < n && !(BRR_X & 4)) atomicAdd(reinterpret_cast<unsigned long long *>(slot + size_t(kLDots + 2 * m + h) * kLine), (unsigned long long)v);
                     }
                 }
                 if (present) {
@@ -1195,12 +1274,13 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
                             uint32_t ctl = 1;
                             const int *line = p.results + size_t(hc % kResRing) * 32;
                             BRR_SITE(202);
-                            while (ld_acquire(reinterpret_cast<const unsigned *>(line)) != hc + 1u) {
+                            ulonglong2 rx;
+                            while (!res_valid(rx = res_load(line), hc)) {
                                 if (ldv(&sh.epoch_w) != b_epoch) { ctl = 2; break; }
                                 if (spin_fail()) { ctl = 0; break; }
                             }
                             spin_ok();
-                            if (ctl == 1) sh.bcast[1] = __ldcg(reinterpret_cast<const double *>(line + 2));
+                            if (ctl == 1) { res_acquire(); sh.bcast[1] = res_dB(rx); }
                             sh.w_ctl[2] = ctl;
                         }
                         bar_named(1, 64);
@@ -1254,14 +1334,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_dense6_kernel(const Sweep6P
             // ---- the result line: what every CTA needs to know about this block ----
             {
                 int *line = p.results + size_t(c % kResRing) * 32;
-                if (nrows && uint32_t(wk) == rowk) *reinterpret_cast<volatile double *>(line + 2) = dBm;
-                if (restart && uint32_t(wk) == n_final - 1u) *reinterpret_cast<volatile double *>(line + 4) = dBm;
-                if (tid == 0) {
-                    *reinterpret_cast<volatile int *>(line + 1) = int(n_final | (restart ? 0x10000u : 0u));
-                    if (!nrows) *reinterpret_cast<volatile double *>(line + 2) = 0.0;
-                }
+                if (nrows && uint32_t(wk) == rowk) sh.w_res = dBm;
+                if (restart && uint32_t(wk) == n_final - 1u) res_store_ne(line, dBm, c);
                 bar_named(1, 64);                                   // (the release below is cumulative over the writes this barrier orders before it)
-                if (tid == 0) { __threadfence(); st_release_gpu(reinterpret_cast<unsigned *>(line), c + 1u); }
+                if (tid == 0) res_store(line, nrows ? sh.w_res : 0.0, c, n_final, restart);
             }
             PHASE(kPfWFix);
             // ---- the block is part of the chain once this CTA's control warp has consumed its result in chain order ----

@@ -310,13 +310,13 @@ def main():
     if profiling and rank == 0 and 6 in kernels:      # version-6 kernel: cycles per block of the sweep, one warp per role of CTA 0 -> stderr
         pc = eng.profile_cycles6(reset=True)
         nblk = max(1, int(np.sum(blocks)))
-        cnts = ("blocks", "walks", "applies", "restarts", "gram_blocks", "row_blocks")
+        cnts = ("blocks", "walks", "applies", "restarts", "gram_blocks", "row_blocks", "c_iters")
         sys.stderr.write("v6 phase cycles/block over %d timed sweeps (%d blocks): " % (a.steps, nblk)
                          + "  ".join("%s=%d" % (k, pc[k] // nblk) for k in eng.PROFILE6 if k not in cnts and not k.startswith("w_"))
                          + " (d_full = d_pre [release of the set, snapshot] + d_fullonly [rows] + wait for stashed rows; d_loop = blocks without Gram rows, d_loopgram = with)"
                          + "  | per walk of CTA 0 (%d walks): " % pc["walks"] + "  ".join("%s=%d" % (k, pc[k] // max(1, pc["walks"])) for k in eng.PROFILE6 if k.startswith("w_"))
-                         + "  | per block: applies=%.3f  Gram rows on a dot pass=%.3f  walks with a row=%.3f of CTA 0's  restarts/sweep=%.1f\n" % (
-                             pc["applies"] / nblk, pc["row_blocks"] / nblk, pc["gram_blocks"] / max(1, pc["walks"]), float(np.mean(restarts))))
+                         + "  | per block: applies=%.3f  Gram rows on a dot pass=%.3f  walks with a row=%.3f of CTA 0's  restarts/sweep=%.1f  control-warp passes=%.2f\n" % (
+                             pc["applies"] / nblk, pc["row_blocks"] / nblk, pc["gram_blocks"] / max(1, pc["walks"]), float(np.mean(restarts)), pc["c_iters"] / nblk))
     if profiling and rank == 0 and 4 in kernels:      # phase breakdown of the timed sweeps (cycles of CTA 0 per block) -> stderr
         pc = eng.profile_cycles(reset=True)
         nblk = max(1, int(np.sum(blocks)))

@@ -230,6 +230,10 @@ int brr_gpu_profile_cycles5(brr_gpu_ctx *ctx, uint64_t *cycles24, int reset);
  * slot counter, read-back, rows of earlier blocks, sampling, in-block corrections + result line, validation); then counts:
  * -, blocks walked by CTA 0, residual updates, -, blocks walked with an in-model row. */
 int brr_gpu_profile_cycles6(brr_gpu_ctx *ctx, uint64_t *cycles32, int reset);
+/* Version-6 kernel, per CTA (the CTAs wait for each other through the block results, so the slowest one paces the sweep): 8 words per
+ * CTA, the first dot warp's cycles in {wait for the decision, residual update + bookkeeping, wait for the rows, MMA loop, wait for the
+ * accumulator set, store + arrive}, the blocks it went through, the SM it ran on.  words: [8 * max_ctas]; *n_ctas = CTAs written. */
+int brr_gpu_profile_ctas6(brr_gpu_ctx *ctx, uint64_t *words, uint32_t max_ctas, uint32_t *n_ctas, int reset);
 /* Which dense kernel the last sweep ran (4 = on-demand Gram rows, 5 = steady-state pipeline, 6 = steady-state pipeline with the
  * walk distributed over the CTAs; 0 = not dense) and, for versions 5 / 6, how often the pipeline restarted behind a marker that
  * entered the model.  The library chooses per sweep: version 6 (one GPU or several) when the sweep is synchronous and the previous

@@ -22,5 +22,15 @@ k, r = e.last_sweep_info()
 if os.environ.get("BRR_GPU_PROFILE") == "1" and k == 6:
     pc = e.profile_cycles6(reset=True)
     nblk = 6 * (M / 64)
-    sys.stderr.write("v6 quiet chain, cycles per block: " + "  ".join("%s=%d" % (kk, v / nblk) for kk, v in pc.items() if not kk.startswith("w_") and v > nblk) + "\n")
+    sys.stderr.write("v6 quiet chain, cycles per block: " + "  ".join("%s=%d" % (kk, v / nblk) for kk, v in pc.items() if not kk.startswith("w_") and kk != "c_iters" and v > nblk) + "  control-warp passes per block=%.2f\n" % (pc["c_iters"] / nblk))
+    a = e.profile_ctas6(reset=True).astype(np.float64)
+    per = a[:, :6] / np.maximum(1.0, a[:, 6:7])                        # cycles per block, per CTA
+    names = e.PROFILE6_CTA[:6]
+    sys.stderr.write("per CTA (first dot warp), cycles per block, min / median / max over %d CTAs: " % len(a)
+                     + "  ".join("%s=%d/%d/%d" % (n, per[:, i].min(), np.median(per[:, i]), per[:, i].max()) for i, n in enumerate(names)) + "\n")
+    o = np.argsort(per[:, 0])
+    sys.stderr.write("the 12 CTAs that wait least for decisions (cta:smid dec_wait rows_wait mma_loop acc_wait): "
+                     + "  ".join("%d:%d %d %d %d %d" % (c, a[c, 7], per[c, 0], per[c, 2], per[c, 3], per[c, 4]) for c in o[:12]) + "\n")
+    sys.stderr.write("the 6 that wait most: " + "  ".join("%d:%d %d %d %d %d" % (c, a[c, 7], per[c, 0], per[c, 2], per[c, 3], per[c, 4]) for c in o[-6:]) + "\n")
+    np.save(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "quiet_ctas6.npy"), a)
 print(json.dumps({"kernel": k, "dbg": os.environ.get("BRR_GPU_V5_DBG"), "ms_per_sweep": float(np.mean(ms[2:])), "us_per_block": 1e3 * float(np.mean(ms[2:])) / (M / 64), "M": M}))
