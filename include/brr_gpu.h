@@ -146,7 +146,11 @@ int brr_gpu_eps_reduce(brr_gpu_ctx *ctx, double *sum_out, double *sqnorm_out);
  * flight (Options::analysisTokens, src/options.hpp:33), T <= 64 for the dense layout, T <= 32 for the
  * ragged / eigen layouts (BRR_GPU_EINVAL beyond).
  * v (n_groups x K) and betasqn (n_groups) are OVERWRITTEN with this sweep's counts / sums
- * (runGibbs zeroes them before exec, src/BayesRBase.cpp:200-202). */
+ * (runGibbs zeroes them before exec, src/BayesRBase.cpp:200-202).
+ * Errors raised INSIDE the kernel (BRR_GPU_ESTATE: the residual grew past the fixed-point range of the
+ * sweep, a peer stopped taking part, a protocol time-out; brr_gpu_last_error names which) leave the
+ * device state of the chain (eps, beta, components, acum) undefined: the sweep updates it in place.
+ * A caller that wants to go on restores the last good state with brr_gpu_set_state. */
 int brr_gpu_sweep(brr_gpu_ctx *ctx, const uint32_t *marker_order, uint32_t n_order, const double *rand_uz,
                   const double *pi, const double *sigmaG, double sigmaE, double eps_sum_in,
                   uint32_t async_tokens, double *v, double *betasqn, brr_gpu_sweep_out *out);
