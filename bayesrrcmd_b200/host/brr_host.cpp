@@ -69,7 +69,8 @@ bool Options::inputOptions(int argc, const char *const argv[])
         if (a == "--analysis-type") {
             if (!(v = need(i))) return false;
             const std::string t = v;
-            analysisType = t == "ppbayes" ? AnalysisType::PpBayes : t == "asyncppbayes" ? AnalysisType::AsyncPpBayes : AnalysisType::Unknown;
+            analysisType = t == "ppbayes" ? AnalysisType::PpBayes : t == "asyncppbayes" ? AnalysisType::AsyncPpBayes
+                         : t == "preprocess" ? AnalysisType::Preprocess : AnalysisType::Unknown;      // src/options.cpp:7-21
         } else if (a == "--data-file") { if (!(v = need(i))) return false; dataFile = v; }
         else if (a == "--pheno") { if (!(v = need(i))) return false; phenotypeFile = v; }
         else if (a == "--mcmc-samples") { if (!(v = need(i))) return false; mcmcSampleFile = v; }
@@ -93,10 +94,10 @@ bool Options::inputOptions(int argc, const char *const argv[])
         else if (a == "--block-markers") { if (!(v = need(i))) return false; blockMarkers = unsigned(std::atoi(v)); }
         else if (a == "--sample-precision") { if (!(v = need(i))) return false; g_samplePrecision = std::atoi(v); }
         else if (a == "--no-epsilon") writeEpsilon = false;
-        // accepted for command-line compatibility; they configure the reference's TBB graphs / .ppbed cache, which do not exist here
+        // (the last group is accepted for command-line compatibility: it configures the reference's TBB graphs, which do not exist here)
         else if (a == "--marker-cache") useMarkerCache = true;       // genotypes from the reference's preprocessed files (markers.hpp)
         else if (a == "--compress") compress = true;
-        else if (a == "--preprocess") { }
+        else if (a == "--preprocess") analysisType = AnalysisType::Preprocess;      // src/options.cpp:111-114
         else if (a == "--thread" || a == "--thread-spawned" || a == "--decompression-concurrency" || a == "--decompression-tokens" ||
                  a == "--analysis-concurrency" || a == "--preprocess-chunks") { if (!need(i)) return false; }
         else { std::cerr << "Error: invalid option \"" << a << "\"." << std::endl; return false; }
@@ -547,8 +548,24 @@ int brr_main(int argc, const char *const argv[])
 {
     Options opt;
     if (!opt.inputOptions(argc, argv)) return 1;
+    if (opt.analysisType == AnalysisType::Preprocess) {
+        // `brr --preprocess` (src/analysisrunner.cpp:47-78, src/preprocessgraph.cpp:36-66): the .bed through the marker builders into the
+        // reference's preprocessed files, for users who keep that workflow (`--marker-cache` reads them back).  Host work only, in memory:
+        // not meant for data sets whose dense columns (8 N M bytes) do not fit -- the GPU path itself needs no preprocessing.
+        if (opt.dataFile.empty()) { std::cerr << "Error: --data-file <x.bed> is required" << std::endl; return 1; }
+        Data data;
+        if (!data.readFamFile(replaceExtension(opt.dataFile, ".fam")) || !data.readBimFile(replaceExtension(opt.dataFile, ".bim")) ||
+            !data.readBedFile(opt.dataFile))
+            return 1;
+        std::cout << "Start preprocessing " << opt.dataFile << std::endl;
+        MarkerCache cache;
+        cache.populateFromBed(data.bed.data(), data.colStride, opt.preprocessDataType, data.numSnps, data.numInds);
+        if (!cache.writeFiles(opt.dataFile, opt.preprocessDataType, opt.compress)) return 1;
+        std::cout << "Finished preprocessing the bed file: " << ppFileForType(opt.preprocessDataType, opt.dataFile) << std::endl;
+        return 0;
+    }
     if (opt.analysisType != AnalysisType::PpBayes && opt.analysisType != AnalysisType::AsyncPpBayes) {
-        std::cerr << "Error: --analysis-type must be ppbayes or asyncppbayes (preprocessing is not needed: the .bed is uploaded as it is)" << std::endl;
+        std::cerr << "Error: --analysis-type must be ppbayes, asyncppbayes or preprocess" << std::endl;
         return 1;
     }
     if (opt.dataFile.empty() || opt.phenotypeFile.empty()) {

@@ -40,7 +40,7 @@ namespace brrhost {
 using VectorXd = std::vector<double>;
 using VectorXdPtr = std::unique_ptr<VectorXd>;
 
-enum class AnalysisType { Unknown, PpBayes, AsyncPpBayes };
+enum class AnalysisType { Unknown, PpBayes, AsyncPpBayes, Preprocess };
 enum class PreprocessDataType { Dense, SparseEigen, SparseRagged };
 
 struct Options {                                   // src/options.hpp:20-112 (the fields of the ppbayes path, same defaults)

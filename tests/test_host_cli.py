@@ -62,8 +62,10 @@ def test_host_library_exports_entry_point(built):
 def test_command_line_errors(built, tmp_path):
     r = run(built, ["--no-such-option"])
     assert r.returncode == 1 and "invalid option" in r.stderr
-    r = run(built, ["--analysis-type", "preprocess", "--data-file", "x.bed", "--pheno", "x.phen"])
+    r = run(built, ["--analysis-type", "gauss", "--data-file", "x.bed", "--pheno", "x.phen"])
     assert r.returncode == 1 and "ppbayes" in r.stderr
+    r = run(built, ["--preprocess", "--data-file", str(tmp_path / "missing.bed")])
+    assert r.returncode == 1 and "can not open" in r.stderr
     r = run(built, ["--analysis-type", "ppbayes", "--data-file", str(tmp_path / "missing.bed"), "--pheno", "x.phen"])
     assert r.returncode == 1 and "can not open" in r.stderr
     r = run(built, ["--analysis-type", "ppbayes", "--S", "0.1,zzz"])
@@ -192,6 +194,39 @@ def test_posterior_on_test_gauss_agrees_with_the_reference_chain(built, tmp_path
     assert abs((beta ** 2).sum() - (ref ** 2).sum()) <= 0.5 * max((ref ** 2).sum(), 1e-12) + 1e-6
     top = np.argsort(-np.abs(ref))[:20]
     assert np.corrcoef(beta[top], ref[top])[0, 1] > 0.5 or n_same == iters
+
+
+@pytest.mark.parametrize("sparse", [None, "ragged", "eigen"])
+@pytest.mark.parametrize("compress", [False, True])
+def test_preprocess_writes_the_references_files(built, tmp_path, sparse, compress):
+    """`brr_gpu --preprocess [--compress] [--sparse-data ...]` (host work only, no GPU): the files equal what the REFERENCE's own markers
+    and index writer produce (oracle/_ref: Marker::write / compress, src/preprocessgraph.cpp:92-125) -- byte for byte for the index-list
+    layouts, to 1e-13 for the dense columns (the column mean is summed in another order)."""
+    import ref_lib as R
+    if not R.ref_available():
+        pytest.skip("oracle/_ref is not built")
+    g = Golden("missing_small")
+    base = write_plink(g, str(tmp_path))
+    layout, ext = {None: (0, ".ppbed"), "eigen": (2, ".eigen.sparsebed"), "ragged": (1, ".ragged.sparsebed")}[sparse]
+    r = run(built, ["--preprocess", "--data-file", base + ".bed"] + (["--compress"] if compress else []) + (["--sparse-data", sparse] if sparse else []))
+    assert r.returncode == 0, r.stderr
+    ref = str(tmp_path / "ref")
+    R.write_pp_files(g.bed, g.N, g.M, layout, int(compress), ref + ext, ref + ext + "index")
+    own_idx = np.fromfile(base + ext + "index", dtype=np.uint64).reshape(g.M, 3); ref_idx = np.fromfile(ref + ext + "index", dtype=np.uint64).reshape(g.M, 3)
+    assert np.array_equal(own_idx[:, 2], ref_idx[:, 2])                 # original sizes
+    if sparse is not None:
+        assert np.array_equal(own_idx, ref_idx)
+        assert open(base + ext, "rb").read() == open(ref + ext, "rb").read()
+    elif not compress:
+        assert np.array_equal(own_idx, ref_idx)
+        assert np.max(np.abs(np.fromfile(base + ext) - np.fromfile(ref + ext))) <= 1e-13
+    else:                                                               # deflated doubles that differ in the last bit: compare after inflation
+        import zlib
+        blob = open(base + ext, "rb").read(); rblob = open(ref + ext, "rb").read()
+        for j in (0, g.M // 2, g.M - 1):
+            a = np.frombuffer(zlib.decompress(blob[int(own_idx[j, 0]):int(own_idx[j, 0] + own_idx[j, 1])]), dtype=np.float64)
+            b = np.frombuffer(zlib.decompress(rblob[int(ref_idx[j, 0]):int(ref_idx[j, 0] + ref_idx[j, 1])]), dtype=np.float64)
+            assert a.size == g.N and np.max(np.abs(a - b)) <= 1e-13
 
 
 @pytest.mark.gpu
