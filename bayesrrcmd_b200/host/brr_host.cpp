@@ -66,6 +66,11 @@ bool Options::inputOptions(int argc, const char *const argv[])
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         const char *v = nullptr;
+        if (a == "--inp-file") {                                      // the options come from a file; the rest of the line is ignored (src/options.cpp:98-101)
+            if (!(v = need(i))) return false;
+            if (!readFile(v)) return false;
+            break;
+        }
         if (a == "--analysis-type") {
             if (!(v = need(i))) return false;
             const std::string t = v;
@@ -94,6 +99,11 @@ bool Options::inputOptions(int argc, const char *const argv[])
         else if (a == "--block-markers") { if (!(v = need(i))) return false; blockMarkers = unsigned(std::atoi(v)); }
         else if (a == "--sample-precision") { if (!(v = need(i))) return false; g_samplePrecision = std::atoi(v); }
         else if (a == "--no-epsilon") writeEpsilon = false;
+        else if (a == "--out") { if (!(v = need(i))) return false; title = v; }
+        else if (a == "--iterLog") { if (!(v = need(i))) return false; iterLog = true; iterLogFile = v; }
+        // --colLog: the reference logs, per marker, the microseconds of its three steps (src/BayesRBase.cpp:381-389).  A sweep is ONE kernel
+        // here, there are no per-marker host timings to log: the file gets its header and one line per sweep (markers, device ms).
+        else if (a == "--colLog") { if (!(v = need(i))) return false; colLog = true; colLogFile = v; }
         // (the last group is accepted for command-line compatibility: it configures the reference's TBB graphs, which do not exist here)
         else if (a == "--marker-cache") useMarkerCache = true;       // genotypes from the reference's preprocessed files (markers.hpp)
         else if (a == "--compress") compress = true;
@@ -104,6 +114,31 @@ bool Options::inputOptions(int argc, const char *const argv[])
     }
     if (seed == 0) seed = static_cast<unsigned>(std::time(nullptr));
     if (thin == 0) thin = 1;
+    return true;
+}
+
+bool Options::readFile(const std::string &file)
+{
+    optionFile = file;
+    title = file.substr(0, file.rfind('.'));                          // makeTitle, src/options.cpp:326-332
+    std::ifstream in(file);
+    if (!in) { std::cerr << "Error: can not open the file [" << file << "] to read." << std::endl; return false; }
+    std::string key, value;
+    while (in >> key >> value) {
+        if (key == "phenotypeFile") phenotypeFile = value;
+        else if (key == "analysisType")
+            analysisType = value == "ppbayes" ? AnalysisType::PpBayes : value == "asyncppbayes" ? AnalysisType::AsyncPpBayes
+                         : value == "preprocess" ? AnalysisType::Preprocess : AnalysisType::Unknown;
+        else if (key == "mcmcSampleFile") mcmcSampleFile = value;
+        else if (key == "chainLength") chainLength = unsigned(std::atoi(value.c_str()));
+        else if (key == "burnin") burnin = unsigned(std::atoi(value.c_str()));
+        else if (key == "seed") seed = unsigned(std::atoi(value.c_str()));
+        else if (key == "thin") thin = unsigned(std::atoi(value.c_str()));
+        else if (key == "S") { if (!parseVarianceComponents(value, S)) return false; }
+        else if (key == "numThread") { }
+        else if (key.substr(0, 2) == "//" || key.substr(0, 1) == "#") continue;
+        else { std::cerr << "Error: invalid option " << key << " " << value << std::endl; return false; }
+    }
     return true;
 }
 
@@ -385,6 +420,18 @@ int GpuBayesR::runGibbs(AnalysisGraph *analysis)
     std::vector<unsigned> markerI(M);
     std::iota(markerI.begin(), markerI.end(), 0);
     std::cout << "Number of groups: " << nGroups << std::endl << "Running Gibbs sampling" << std::endl;
+    std::ofstream iterLogger, colLogger;
+    if (m_opt->iterLog) {                                             // LogWriter::open, src/logwriter.cpp:6-24
+        std::cout << "Opening iteration log file " << m_opt->iterLogFile << std::endl;
+        iterLogger.open(m_opt->iterLogFile);
+        if (!iterLogger) { std::cerr << "Error: can not open the file [" << m_opt->iterLogFile << "] to write." << std::endl; return 1; }
+        iterLogger << "iter,m_0,sigmaG,sigmaE,mu,mu_upd_microS,sigmaG_upd_microS,sigmaE_upd_microS,flowgraph_milliS,iter_d_milliS" << std::endl;
+    }
+    if (m_opt->colLog) {
+        colLogger.open(m_opt->colLogFile);
+        if (!colLogger) { std::cerr << "Error: can not open the file [" << m_opt->colLogFile << "] to write." << std::endl; return 1; }
+        colLogger << "iter,markers,markers_changing_the_residual,sweep_device_milliS" << std::endl;
+    }
     const auto t1 = std::chrono::high_resolution_clock::now();
     double iterSeconds = 0, sweepSeconds = 0;
 
@@ -393,6 +440,7 @@ int GpuBayesR::runGibbs(AnalysisGraph *analysis)
         std::cout << "iteration " << iteration << ": ";
         const double old_mu = m_mu;
         if (!updateMu(old_mu, double(N))) { std::cerr << "Error: " << brr_gpu_last_error() << std::endl; return 1; }
+        const auto muTime = std::chrono::high_resolution_clock::now();
         prepareForAnylsis();
 #pragma GCC diagnostic push
 #pragma GCC diagnostic ignored "-Wdeprecated-declarations"
@@ -408,7 +456,10 @@ int GpuBayesR::runGibbs(AnalysisGraph *analysis)
         if (m_failed) return 1;
         if (nF > 0 && !updateFixedEffects(xI)) { std::cerr << "Error: " << brr_gpu_last_error() << std::endl; return 1; }
 
+        const auto sEstartTime = std::chrono::high_resolution_clock::now();
         m_sigmaE = m_dist.inv_scaled_chisq_rng(m_opt->v0E + N, (m_epsilonSqNorm + m_opt->v0E * m_opt->s02E) / (m_opt->v0E + N));   // :238-239
+        const auto sEendTime = std::chrono::high_resolution_clock::now();
+        const auto sGstartTime = std::chrono::high_resolution_clock::now();
         for (unsigned g = 0; g < nGroups; ++g) {                                                                                    // :243-247
             double rowSum = 0;
             for (int k = 0; k < K; ++k) rowSum += m_v[size_t(g) * K + k];
@@ -419,6 +470,7 @@ int GpuBayesR::runGibbs(AnalysisGraph *analysis)
             const auto pi = m_dist.dirichlet_rng(alpha);
             std::copy(pi.begin(), pi.end(), m_pi.begin() + size_t(g) * K);
         }
+        const auto sGendTime = std::chrono::high_resolution_clock::now();
 
         if (iteration >= m_opt->burnin && iteration % m_opt->thin == 0) {
             if (brr_gpu_get_state(m_dev->ctx(), m_opt->writeEpsilon ? m_epsilon.data() : nullptr, m_beta.data(), m_components.data(), m_acum.data())) {
@@ -431,6 +483,15 @@ int GpuBayesR::runGibbs(AnalysisGraph *analysis)
         const double it = std::chrono::duration<double>(endTime - startTime).count(), sw = std::chrono::duration<double>(sweepEnd - sweepStart).count();
         std::cout << it << "s (" << sw << "s)" << std::endl;
         iterSeconds += it; sweepSeconds += sw;
+        if (m_opt->iterLog) {       // src/BayesRBase.cpp:261-273 (the reference's 10-column line holds ONE sigmaG: with several groups, the last group's m_0 / sigmaG)
+            auto us = [](auto a, auto b) { return double(std::chrono::duration_cast<std::chrono::microseconds>(b - a).count()); };
+            iterLogger << iteration << "," << m_m0 << "," << m_sigmaG[nGroups - 1] << "," << m_sigmaE << "," << m_mu << "," << us(startTime, muTime) << ","
+                       << us(sGstartTime, sGendTime) << "," << us(sEstartTime, sEendTime) << "," << std::floor(sw * 1e3) << "," << std::floor(it * 1e3) << std::endl;
+        }
+        if (m_opt->colLog) {
+            const auto *g = dynamic_cast<GpuSweepGraph *>(analysis);
+            colLogger << iteration << "," << M << "," << (g ? g->last().n_nonskipped : 0u) << "," << (g ? g->last().kernel_ms : 0.0f) << std::endl;
+        }
     }
     if (brr_gpu_get_state(m_dev->ctx(), m_epsilon.data(), m_beta.data(), m_components.data(), m_acum.data())) {
         std::cerr << "Error: " << brr_gpu_last_error() << std::endl;

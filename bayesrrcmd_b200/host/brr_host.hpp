@@ -57,6 +57,9 @@ struct Options {                                   // src/options.hpp:20-112 (th
     int device = 0;                                // --gpu n
     unsigned blockMarkers = 0;                     // --block-markers n (0 = engine default)
     bool writeEpsilon = true;                      // --no-epsilon drops the N residual columns from the sample file
+    bool iterLog = false, colLog = false;          // --iterLog <file>: per-iteration log (src/logwriter.cpp); --colLog <file>: per-column timings (see brr_host.cpp)
+    std::string iterLogFile, colLogFile, title, optionFile;
+    bool readFile(const std::string &file);        // --inp-file: `key value` pairs (src/options.cpp:280-324)
     bool useMarkerCache = false;                   // --marker-cache: genotypes from the preprocessed files of --data-file (markers.hpp)
     bool compress = false;                         // --compress: those files hold deflated markers
     bool inputOptions(int argc, const char *const argv[]);   // false + message on std::cerr when the line is unusable

@@ -72,6 +72,22 @@ def test_command_line_errors(built, tmp_path):
     assert r.returncode == 1 and "variance component" in r.stderr
 
 
+def test_options_from_a_file(built, tmp_path):
+    """--inp-file (src/options.cpp:280-324): `key value` pairs; a pair whose key starts with # or // is a comment; unknown keys are errors."""
+    f = tmp_path / "run.txt"
+    f.write_text("#note x\nanalysisType ppbayes\nchainLength 3\nburnin 0\nthin 1\nseed 5\nS 0.1,0.01\nphenotypeFile %s\n" % (tmp_path / "x.phen"))
+    r = run(built, ["--inp-file", str(f)])
+    assert r.returncode == 1 and "--data-file" in r.stderr            # options accepted; the data file is what is missing
+    f.write_text("nonsense 3\n")
+    r = run(built, ["--inp-file", str(f)])
+    assert r.returncode == 1 and "invalid option nonsense" in r.stderr
+    r = run(built, ["--inp-file", str(tmp_path / "none.txt")])
+    assert r.returncode == 1 and "can not open" in r.stderr
+    for opt in ("--iterLog", "--colLog", "--out"):
+        r = run(built, [opt])
+        assert r.returncode == 1 and "needs a value" in r.stderr
+
+
 def test_reads_plink_files_then_requires_a_gpu(built, tmp_path):
     import torch
     if torch.cuda.is_available():
@@ -227,6 +243,29 @@ def test_preprocess_writes_the_references_files(built, tmp_path, sparse, compres
             a = np.frombuffer(zlib.decompress(blob[int(own_idx[j, 0]):int(own_idx[j, 0] + own_idx[j, 1])]), dtype=np.float64)
             b = np.frombuffer(zlib.decompress(rblob[int(ref_idx[j, 0]):int(ref_idx[j, 0] + ref_idx[j, 1])]), dtype=np.float64)
             assert a.size == g.N and np.max(np.abs(a - b)) <= 1e-13
+
+
+@pytest.mark.gpu
+def test_iteration_and_column_logs(built, tmp_path):
+    """--iterLog / --colLog (src/logwriter.cpp, src/BayesRBase.cpp:261-273): the iteration log has the reference's header and one line per
+    iteration whose sigmaG / sigmaE / mu are the chain's; the column log has one line per sweep."""
+    g = Golden("uk10k")
+    base = write_plink(g, str(tmp_path))
+    out, ilog, clog = str(tmp_path / "s.csv"), str(tmp_path / "iter.csv"), str(tmp_path / "col.csv")
+    r = run(built, ["--analysis-type", "ppbayes", "--data-file", base + ".bed", "--pheno", base + ".phen", "--chain-length", "3", "--burn-in", "0",
+                    "--thin", "1", "--seed", "3", "--S", ",".join("%.17g" % x for x in g.S[0]), "--mcmc-samples", out, "--sample-precision", "17",
+                    "--iterLog", ilog, "--colLog", clog, "--out", "run1", "--no-epsilon"])
+    assert r.returncode == 0, r.stderr + r.stdout
+    lines = open(ilog).read().strip().splitlines()
+    assert lines[0] == "iter,m_0,sigmaG,sigmaE,mu,mu_upd_microS,sigmaG_upd_microS,sigmaE_upd_microS,flowgraph_milliS,iter_d_milliS"
+    log = np.loadtxt(ilog, delimiter=",", skiprows=1, ndmin=2)
+    assert log.shape == (3, 10) and list(log[:, 0]) == [0, 1, 2]
+    rows = np.loadtxt(out, delimiter=",", skiprows=1, ndmin=2)
+    assert np.allclose(log[:, 4], rows[:, 1], rtol=1e-5)               # mu (the log is written with the stream's default precision)
+    assert np.allclose(log[:, 3], rows[:, 2 + g.M], rtol=1e-5)         # sigmaE
+    assert np.allclose(log[:, 2], rows[:, 3 + g.M], rtol=1e-5)         # sigmaG
+    col = np.loadtxt(clog, delimiter=",", skiprows=1, ndmin=2)
+    assert col.shape == (3, 4) and (col[:, 1] == g.M).all() and (col[:, 3] > 0).all()
 
 
 @pytest.mark.gpu
