@@ -32,5 +32,7 @@ if os.environ.get("BRR_GPU_PROFILE") == "1" and k == 6:
     sys.stderr.write("the 12 CTAs that wait least for decisions (cta:smid dec_wait rows_wait mma_loop acc_wait): "
                      + "  ".join("%d:%d %d %d %d %d" % (c, a[c, 7], per[c, 0], per[c, 2], per[c, 3], per[c, 4]) for c in o[:12]) + "\n")
     sys.stderr.write("the 6 that wait most: " + "  ".join("%d:%d %d %d %d %d" % (c, a[c, 7], per[c, 0], per[c, 2], per[c, 3], per[c, 4]) for c in o[-6:]) + "\n")
-    np.save(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "quiet_ctas6.npy"), a)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    np.save(os.path.join(out_dir, "quiet_ctas6.npy"), a)
 print(json.dumps({"kernel": k, "dbg": os.environ.get("BRR_GPU_V5_DBG"), "ms_per_sweep": float(np.mean(ms[2:])), "us_per_block": 1e3 * float(np.mean(ms[2:])) / (M / 64), "M": M}))
