@@ -130,6 +130,57 @@ def test_dense_column_back_to_codes(host):
         assert same.all() or np.allclose(lut[cls[~same]], lut[orig[~same]], atol=1e-9)   # (a class whose value coincides with the imputed one)
 
 
+def _pack(codes):
+    """(M, N) PLINK bit pairs (0 = two copies, 1 = missing, 2 = one copy, 3 = none) -> .bed payload rows."""
+    M, N = codes.shape
+    out = np.zeros((M, (N + 3) // 4), np.uint8)
+    for i in range(N):
+        out[:, i // 4] |= codes[:, i].astype(np.uint8) << (2 * (i % 4))
+    return out
+
+
+@needs_ref
+@pytest.mark.parametrize("N", [2, 3, 5, 17, 65])
+def test_ragged_sizes_and_sparse_columns_against_the_reference(host, tmp_path, N):
+    """Individual counts that are not multiples of 4, columns with one informative genotype among missing ones, all-heterozygous columns:
+    the files of the host's builders equal the reference's, and the reference's files are read back, for every layout, plain and deflated."""
+    rng = np.random.default_rng(N)
+    cols = [np.r_[0, np.full(N - 1, 1)], np.r_[2, np.full(N - 1, 1)], np.r_[0, np.full(N - 1, 3)], np.r_[2, 0, np.full(N - 2, 3)][:N],
+            np.r_[0, rng.integers(0, 4, N - 1)], np.r_[2, rng.choice([0, 1, 3], N - 1)], np.full(N, 2)]
+    bed = _pack(np.array(cols)); M = len(cols)
+    for name, L in LAYOUTS.items():
+        for compress in (0, 1):
+            ref, own = str(tmp_path / ("ref_%s%d" % (name, compress))), str(tmp_path / ("own_%s%d" % (name, compress)))
+            R.write_pp_files(bed, N, M, L, compress, ref + EXT[L], ref + EXT[L] + "index")
+            assert host.brr_host_cache_from_bed(_p(bed), bed.shape[1], L, M, N) == 0
+            assert host.brr_host_cache_write((own + ".bed").encode(), L, compress) == 0
+            a, b = open(ref + EXT[L], "rb").read(), open(own + EXT[L], "rb").read()
+            if name == "dense" and not compress:
+                assert np.allclose(np.frombuffer(a), np.frombuffer(b), atol=1e-13, equal_nan=True)
+            elif name != "dense":
+                assert a == b and open(ref + EXT[L] + "index", "rb").read() == open(own + EXT[L] + "index", "rb").read()
+            assert host.brr_host_cache_from_files((ref + ".bed").encode(), L, M, N, compress) == 0
+            if name == "ragged":
+                for j in range(M):
+                    got = _cached_marker(host, j, N, L)
+                    stats, ones, twos, missing = R.ragged_marker(bed[j], N)
+                    assert np.array_equal(got["stats"], stats, equal_nan=True)
+                    for x, y in zip(got["lists"], (ones, twos, missing)):
+                        assert np.array_equal(x, y)
+
+
+def test_a_marker_that_does_not_vary_is_refused_like_the_reference_does(host, tmp_path):
+    """src/raggedsparsemarker.cpp:68-77, src/eigensparsemarker.cpp:59-71: a sparse marker without a single 1 or 2 is not valid -- reading
+    a file that holds one fails (the reference prints "SNPs that do not vary ... should be removed prior to analysis")."""
+    N = 9
+    bed = _pack(np.array([np.r_[0, np.full(N - 1, 3)], np.full(N, 3), np.r_[2, np.full(N - 1, 3)]]))     # the second column: nobody carries the allele
+    for L in (1, 2):
+        base = str(tmp_path / ("mono%d" % L))
+        assert host.brr_host_cache_from_bed(_p(bed), bed.shape[1], L, 3, N) == 0
+        assert host.brr_host_cache_write((base + ".bed").encode(), L, 0) == 0
+        assert host.brr_host_cache_from_files((base + ".bed").encode(), L, 3, N, 0) != 0
+
+
 def test_missing_files_are_reported(host, tmp_path):
     assert host.brr_host_cache_from_files(str(tmp_path / "nothing.bed").encode(), 1, 5, 10, 0) != 0
 
