@@ -64,3 +64,36 @@ def test_chain_matches_reference_with_missing_and_groups():
             assert np.max(np.abs(eps - arr["eps_out"][it])) <= 1e-10
             assert np.max(np.abs(bs - arr["betasq_out"][it])) <= 1e-11
             assert abs(es - arr["epssum_out"][it]) <= 1e-9
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_chain_matches_reference_on_random_configurations(seed):
+    """Random shapes of the model -- individuals (also not a multiple of 4), markers, groups, mixture components, missing rate,
+    all three layouts: every sweep of the reference's chain is replayed by the restatement from the reference's inputs."""
+    O.build()
+    rng = np.random.default_rng(100 + seed)
+    N = int(rng.choice([33, 130, 402, 777])); M = int(rng.integers(20, 90))
+    nG = int(rng.integers(1, 4)); K1 = int(rng.integers(1, 5))
+    p_miss = float(rng.choice([0.0, 0.01, 0.15]))
+    bed = _random_bed(rng, N, M, p_miss)
+    beta_true = np.where(rng.random(M) < 0.2, rng.normal(size=M), 0.0)
+    cols = np.array([np.nan_to_num(O.dense_column(bed[j], N)) for j in range(M)])
+    y = (beta_true @ cols * 0.3 + rng.normal(size=N)).astype(np.float32)
+    groups = rng.integers(0, nG, M).astype(np.int32)
+    groups[:nG] = np.arange(nG)                                          # every group has a marker
+    S = np.sort(rng.uniform(1e-4, 0.5, size=(nG, K1)), axis=1)
+    iters = 3
+    for layout, name in ((0, "dense"), (1, "ragged"), (2, "eigen")):
+        arr, _ = R.run_chain(bed, N, M, y, S, seed=seed + 1, iterations=iters, layout=layout, groups=groups if nG > 1 else None)
+        for it in range(iters):
+            mdl = O.ModelArrays(N, S, arr["pi_in"][it], arr["sigmaG_in"][it], arr["sigmaE_in"][it])
+            eps = arr["eps_in"][it].copy(); beta = arr["beta_in"][it].copy()
+            comp = arr["comp_out"][it - 1].copy() if it else np.zeros(M)
+            acum = arr["acum_out"][it - 1].copy() if it else np.zeros(M)
+            v, bs, es = O.sweep(name, bed, M, arr["order"][it], arr["rand_uz"][it], mdl, groups if nG > 1 else np.zeros(M, np.int32), eps, beta, comp, acum,
+                                eps_sum=arr["epssum_in"][it])
+            scale = 1.0 + np.abs(arr["beta_out"][it]).max()
+            assert np.max(np.abs(beta - arr["beta_out"][it])) <= 1e-10 * scale, (name, it)
+            assert (comp == arr["comp_out"][it]).all() and (v == arr["v_out"][it]).all(), (name, it)
+            assert np.max(np.abs(acum - arr["acum_out"][it])) <= 1e-10
+            assert np.max(np.abs(eps - arr["eps_out"][it])) <= 1e-9 * (1.0 + np.abs(arr["eps_out"][it]).max())
